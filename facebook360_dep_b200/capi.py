@@ -1,0 +1,408 @@
+"""ctypes binding of include/derp_b200.h.
+
+The same binding drives both shared libraries that export the ABI:
+  * ``load_cuda()``   -> facebook360_dep_b200/libderp_b200.so (the product, sm_100a CUDA)
+  * ``load_oracle()`` -> oracle/libderp_oracle.so (TEST INFRASTRUCTURE: only tests/, smoke() and
+    bench.py's cpu_baseline may call it)
+
+There is deliberately no fallback between them: ``load_cuda()`` raises if the CUDA library is
+missing or reports a different backend.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+CUDA_LIB = os.path.join(_HERE, "libderp_b200.so")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "libderp_oracle.so")
+
+CAM_FTHETA, CAM_RECTILINEAR, CAM_EQUISOLID, CAM_ORTHOGRAPHIC = 0, 1, 2, 3
+CAM_TYPES = {"FTHETA": 0, "RECTILINEAR": 1, "EQUISOLID": 2, "ORTHOGRAPHIC": 3}
+
+OK, EINVAL, ECUDA, ENOMEM, ESTATE, ECOVERAGE = 0, -1, -2, -3, -4, -5
+
+
+class CameraDesc(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("has_principal", C.c_int32),
+        ("has_fov", C.c_int32),
+        ("reserved", C.c_int32),
+        ("origin", C.c_double * 3),
+        ("forward", C.c_double * 3),
+        ("up", C.c_double * 3),
+        ("right", C.c_double * 3),
+        ("resolution", C.c_double * 2),
+        ("principal", C.c_double * 2),
+        ("focal", C.c_double * 2),
+        ("distortion", C.c_double * 3),
+        ("fov", C.c_double),
+    ]
+
+
+class LevelParams(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32),
+        ("height", C.c_int32),
+        ("level", C.c_int32),
+        ("num_levels", C.c_int32),
+        ("full_width", C.c_int32),
+        ("full_height", C.c_int32),
+        ("var_noise_floor", C.c_float),
+        ("var_high_thresh", C.c_float),
+        ("use_foreground_masks", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class ProcessOpts(C.Structure):
+    _fields_ = [
+        ("num_depths", C.c_int32),
+        ("min_depth_m", C.c_float),
+        ("max_depth_m", C.c_float),
+        ("partial_coverage", C.c_int32),
+        ("random_proposals", C.c_int32),
+        ("ping_pong_iterations", C.c_int32),
+        ("mismatches_start_level", C.c_int32),
+        ("do_bilateral_filter", C.c_int32),
+        ("do_median_filter", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+def camera_desc_from_json(cam):
+    """One entry of the rig JSON's "cameras" array -> CameraDesc (Camera.cpp:30-75)."""
+    d = CameraDesc()
+    d.type = CAM_TYPES[cam["type"]]
+    for k in ("origin", "forward", "up", "right"):
+        for i in range(3):
+            getattr(d, k)[i] = float(cam[k][i])
+    for i in range(2):
+        d.resolution[i] = float(cam["resolution"][i])
+        d.focal[i] = float(cam["focal"][i])
+    if "principal" in cam:
+        d.has_principal = 1
+        for i in range(2):
+            d.principal[i] = float(cam["principal"][i])
+    dist = list(cam.get("distortion", []))
+    if len(dist) > 3:
+        raise ValueError("bad distortion")
+    for i in range(3):
+        d.distortion[i] = float(dist[i]) if i < len(dist) else 0.0
+    if "fov" in cam:
+        d.has_fov = 1
+        d.fov = float(cam["fov"])
+    return d
+
+
+def rig_descs(rig_json):
+    cams = rig_json["cameras"]
+    arr = (CameraDesc * len(cams))()
+    for i, c in enumerate(cams):
+        arr[i] = camera_desc_from_json(c)
+    return arr
+
+
+_p = C.POINTER
+_SIGS = {
+    "derp_backend": (C.c_char_p, []),
+    "derp_last_error": (C.c_char_p, []),
+    "derp_set_threads": (C.c_int, [C.c_int]),
+    "derp_create": (C.c_int, [_p(CameraDesc), C.c_int, _p(C.c_int32), C.c_int, C.c_int, _p(C.c_void_p)]),
+    "derp_destroy": (None, [C.c_void_p]),
+    "derp_level_begin": (C.c_int, [C.c_void_p, _p(LevelParams)]),
+    "derp_set_colors": (C.c_int, [C.c_void_p, _p(C.c_void_p)]),
+    "derp_set_foreground_masks": (C.c_int, [C.c_void_p, _p(C.c_void_p)]),
+    "derp_set_background_disparity": (C.c_int, [C.c_void_p, _p(C.c_void_p)]),
+    "derp_reproject": (C.c_int, [C.c_void_p, C.c_int]),
+    "derp_brute_force": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "derp_random_proposals": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]),
+    "derp_ping_pong": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "derp_mismatches": (C.c_int, [C.c_void_p]),
+    "derp_bilateral": (C.c_int, [C.c_void_p, C.c_int]),
+    "derp_median": (C.c_int, [C.c_void_p, C.c_int]),
+    "derp_mask_fov": (C.c_int, [C.c_void_p, C.c_int]),
+    "derp_upsample_from": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "derp_process_level": (C.c_int, [C.c_void_p, _p(ProcessOpts)]),
+    "derp_eval_cost": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "derp_set_disparity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "derp_get_disparity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "derp_get_fov_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "derp_get_mismatch_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "derp_get_variance": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "derp_get_var_noise_floor": (C.c_int, [C.c_void_p, _p(C.c_float)]),
+    "derp_get_proj_warp": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "derp_get_proj_color": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "derp_get_proj_bias": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "derp_get_counters": (C.c_int, [C.c_void_p, _p(C.c_uint64), _p(C.c_uint64)]),
+    "derp_temporal_filter": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p(C.c_void_p), _p(C.c_void_p),
+                                       _p(C.c_void_p), C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
+                                       C.c_float, C.c_void_p]),
+    "derp_joint_bilateral_f32": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "derp_upsample_disparity": (C.c_int, [C.c_int, _p(CameraDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+}
+
+ABI_SYMBOLS = sorted(_SIGS)
+
+
+class DerpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("derp error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Library:
+    """One loaded shared library exporting the derp_b200.h ABI."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "%s not found — build it first (python -c 'import __graft_entry__ as g; g.build()')" % path)
+        self.path = path
+        self.lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(self.lib, name)  # AttributeError if a declared symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        self.backend = self.lib.derp_backend().decode()
+
+    def check(self, rc):
+        if rc != 0:
+            raise DerpError(rc, self.lib.derp_last_error().decode())
+
+    def set_threads(self, n):
+        self.check(self.lib.derp_set_threads(int(n)))
+
+    # ---- stand-alone entry points ----------------------------------------------------------
+    def temporal_filter(self, guides, disps, masks, frame_offset, sigma, spatial_radius, w0, w1, w2, device=0):
+        T = len(guides)
+        H, W = disps[0].shape
+        g = [np.ascontiguousarray(x, np.uint16) for x in guides]
+        d = [np.ascontiguousarray(x, np.float32) for x in disps]
+        m = [np.ascontiguousarray(x, np.uint8) for x in masks]
+        out = np.empty((H, W), np.float32)
+        self.check(self.lib.derp_temporal_filter(
+            device, W, H, T, _ptr_array(g), _ptr_array(d), _ptr_array(m), frame_offset, sigma,
+            spatial_radius, w0, w1, w2, out.ctypes.data))
+        return out
+
+    def joint_bilateral_f32(self, image, guide, mask, radius, sigma, w0, w1, w2, device=0):
+        H, W = image.shape
+        image = np.ascontiguousarray(image, np.float32)
+        guide = np.ascontiguousarray(guide, np.float32)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        out = np.empty((H, W), np.float32)
+        self.check(self.lib.derp_joint_bilateral_f32(device, W, H, image.ctypes.data, guide.ctypes.data,
+                                                     mask.ctypes.data, radius, sigma, w0, w1, w2,
+                                                     out.ctypes.data))
+        return out
+
+    def upsample_disparity(self, cam_desc, coarse, out_w, out_h, background_up=None, coarse_mask=None,
+                           fine_mask=None, use_foreground_masks=False, device=0):
+        coarse = np.ascontiguousarray(coarse, np.float32)
+        ch, cw = coarse.shape
+        bg = None if background_up is None else np.ascontiguousarray(background_up, np.float32)
+        cm = None if coarse_mask is None else np.ascontiguousarray(coarse_mask, np.uint8)
+        fm = None if fine_mask is None else np.ascontiguousarray(fine_mask, np.uint8)
+        out = np.empty((out_h, out_w), np.float32)
+        self.check(self.lib.derp_upsample_disparity(
+            device, C.byref(cam_desc), coarse.ctypes.data, cw, ch, _dp(bg), _dp(cm), _dp(fm), out_w, out_h,
+            int(use_foreground_masks), out.ctypes.data))
+        return out
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data
+
+
+def _ptr_array(arrs):
+    pa = (C.c_void_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        pa[i] = a.ctypes.data
+    return pa
+
+
+class Context:
+    """One DerpCtx: a (frame, level) of a rig on one device."""
+
+    def __init__(self, library, descs, dst_to_src=None, device=0):
+        self.L = library
+        self.S = len(descs)
+        if dst_to_src is None:
+            dst_to_src = list(range(self.S))
+        self.dst_to_src = list(dst_to_src)
+        self.Sd = len(self.dst_to_src)
+        d2s = (C.c_int32 * self.Sd)(*self.dst_to_src)
+        h = C.c_void_p()
+        library.check(library.lib.derp_create(descs, self.S, d2s, self.Sd, device, C.byref(h)))
+        self.h = h
+        self.W = self.H = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.L.lib.derp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def level_begin(self, width, height, level=0, num_levels=1, full_width=None, full_height=None,
+                    var_noise_floor=4e-5, var_high_thresh=1e-3, use_foreground_masks=False):
+        p = LevelParams()
+        p.width, p.height, p.level, p.num_levels = width, height, level, num_levels
+        p.full_width = full_width if full_width else width
+        p.full_height = full_height if full_height else height
+        p.var_noise_floor, p.var_high_thresh = var_noise_floor, var_high_thresh
+        p.use_foreground_masks = int(use_foreground_masks)
+        self.L.check(self.L.lib.derp_level_begin(self.h, C.byref(p)))
+        self.W, self.H = width, height
+
+    def set_colors(self, colors):
+        a = [np.ascontiguousarray(c, np.uint16) for c in colors]
+        assert len(a) == self.S and all(x.shape == (self.H, self.W, 3) for x in a)
+        self.L.check(self.L.lib.derp_set_colors(self.h, _ptr_array(a)))
+
+    def set_foreground_masks(self, masks):
+        a = [np.ascontiguousarray(m, np.uint8) for m in masks]
+        assert len(a) == self.S
+        self.L.check(self.L.lib.derp_set_foreground_masks(self.h, _ptr_array(a)))
+
+    def set_background_disparity(self, bgs):
+        a = [np.ascontiguousarray(m, np.float32) for m in bgs]
+        assert len(a) == self.Sd
+        self.L.check(self.L.lib.derp_set_background_disparity(self.h, _ptr_array(a)))
+
+    def reproject(self, dst):
+        self.L.check(self.L.lib.derp_reproject(self.h, dst))
+
+    def brute_force(self, dst, num_depths=150, min_depth_m=0.5, max_depth_m=1e4, partial_coverage=True,
+                    want_index=True):
+        idx = np.empty((self.H, self.W), np.int32) if want_index else None
+        self.L.check(self.L.lib.derp_brute_force(self.h, dst, num_depths, min_depth_m, max_depth_m,
+                                                 int(partial_coverage), _dp(idx)))
+        return idx
+
+    def random_proposals(self, dst, n=2, min_depth_m=0.5, max_depth_m=1e4):
+        self.L.check(self.L.lib.derp_random_proposals(self.h, dst, n, min_depth_m, max_depth_m))
+
+    def ping_pong(self, dst, iterations=1):
+        self.L.check(self.L.lib.derp_ping_pong(self.h, dst, iterations))
+
+    def mismatches(self):
+        self.L.check(self.L.lib.derp_mismatches(self.h))
+
+    def bilateral(self, dst):
+        self.L.check(self.L.lib.derp_bilateral(self.h, dst))
+
+    def median(self, dst):
+        self.L.check(self.L.lib.derp_median(self.h, dst))
+
+    def mask_fov(self, dst):
+        self.L.check(self.L.lib.derp_mask_fov(self.h, dst))
+
+    def upsample_from(self, dst, coarse, coarse_mask=None, fine_mask=None):
+        coarse = np.ascontiguousarray(coarse, np.float32)
+        ch, cw = coarse.shape
+        cm = None if coarse_mask is None else np.ascontiguousarray(coarse_mask, np.uint8)
+        fm = None if fine_mask is None else np.ascontiguousarray(fine_mask, np.uint8)
+        self.L.check(self.L.lib.derp_upsample_from(self.h, dst, coarse.ctypes.data, cw, ch, _dp(cm), _dp(fm)))
+
+    def process_level(self, num_depths=150, min_depth_m=0.5, max_depth_m=1e4, partial_coverage=True,
+                      random_proposals=2, ping_pong_iterations=1, mismatches_start_level=-1,
+                      do_bilateral_filter=True, do_median_filter=True):
+        o = ProcessOpts()
+        o.num_depths, o.min_depth_m, o.max_depth_m = num_depths, min_depth_m, max_depth_m
+        o.partial_coverage = int(partial_coverage)
+        o.random_proposals, o.ping_pong_iterations = random_proposals, ping_pong_iterations
+        o.mismatches_start_level = mismatches_start_level
+        o.do_bilateral_filter, o.do_median_filter = int(do_bilateral_filter), int(do_median_filter)
+        self.L.check(self.L.lib.derp_process_level(self.h, C.byref(o)))
+
+    def eval_cost(self, dst, disparity):
+        d = np.ascontiguousarray(disparity, np.float32)
+        cost = np.empty((self.H, self.W), np.float32)
+        conf = np.empty((self.H, self.W), np.float32)
+        self.L.check(self.L.lib.derp_eval_cost(self.h, dst, d.ctypes.data, cost.ctypes.data, conf.ctypes.data))
+        return cost, conf
+
+    def set_disparity(self, dst, disparity=None, cost=None, confidence=None):
+        a = [None if x is None else np.ascontiguousarray(x, np.float32) for x in (disparity, cost, confidence)]
+        self.L.check(self.L.lib.derp_set_disparity(self.h, dst, _dp(a[0]), _dp(a[1]), _dp(a[2])))
+
+    def get_disparity(self, dst, want_cost=True):
+        d = np.empty((self.H, self.W), np.float32)
+        c = np.empty((self.H, self.W), np.float32) if want_cost else None
+        f = np.empty((self.H, self.W), np.float32) if want_cost else None
+        self.L.check(self.L.lib.derp_get_disparity(self.h, dst, d.ctypes.data, _dp(c), _dp(f)))
+        return (d, c, f) if want_cost else d
+
+    def get_fov_mask(self, dst):
+        m = np.empty((self.H, self.W), np.uint8)
+        self.L.check(self.L.lib.derp_get_fov_mask(self.h, dst, m.ctypes.data))
+        return m
+
+    def get_mismatch_mask(self, dst):
+        m = np.empty((self.H, self.W), np.uint8)
+        self.L.check(self.L.lib.derp_get_mismatch_mask(self.h, dst, m.ctypes.data))
+        return m
+
+    def get_variance(self, src):
+        v = np.empty((self.H, self.W), np.float32)
+        self.L.check(self.L.lib.derp_get_variance(self.h, src, v.ctypes.data))
+        return v
+
+    def get_var_noise_floor(self):
+        f = C.c_float()
+        self.L.check(self.L.lib.derp_get_var_noise_floor(self.h, C.byref(f)))
+        return f.value
+
+    def get_proj_warp(self, src):
+        w = np.empty((self.H, self.W, 2), np.float32)
+        self.L.check(self.L.lib.derp_get_proj_warp(self.h, src, w.ctypes.data))
+        return w
+
+    def get_proj_color(self, src):
+        w = np.empty((self.H, self.W, 3), np.uint16)
+        self.L.check(self.L.lib.derp_get_proj_color(self.h, src, w.ctypes.data))
+        return w
+
+    def get_proj_bias(self, src):
+        w = np.empty((self.H, self.W, 3), np.uint16)
+        self.L.check(self.L.lib.derp_get_proj_bias(self.h, src, w.ctypes.data))
+        return w
+
+    def get_counters(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.L.check(self.L.lib.derp_get_counters(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+_cache = {}
+
+
+def load_cuda():
+    """The product library. Fails loudly when it is missing — there is no CPU fallback."""
+    if "cuda" not in _cache:
+        lib = Library(CUDA_LIB)
+        if not lib.backend.startswith("cuda"):
+            raise RuntimeError("%s reports backend %r, expected the CUDA library" % (CUDA_LIB, lib.backend))
+        _cache["cuda"] = lib
+    return _cache["cuda"]
+
+
+def load_oracle():
+    """TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py cpu_baseline)."""
+    if "oracle" not in _cache:
+        lib = Library(ORACLE_LIB)
+        if lib.backend != "oracle-cpu":
+            raise RuntimeError("unexpected oracle backend %r" % lib.backend)
+        _cache["oracle"] = lib
+    return _cache["oracle"]

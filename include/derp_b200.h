@@ -1,0 +1,203 @@
+/*
+ * derp_b200.h — C ABI of the B200-native depth-estimation hot path.
+ *
+ * The reference (facebook360_dep, source/depth_estimation) has no FFI for this path: its
+ * stages are free functions over PyramidLevel<cv::Vec3w>& (Derp.h:57-161) linked statically
+ * into DerpCLI / TemporalBilateralFilter / UpsampleDisparity.  This header is the boundary a
+ * maintainer would bind instead: one opaque context per (GPU, stream) that owns all device
+ * buffers of one pyramid level of one frame, and one entry point per reference stage.
+ * Every entry point cites the reference function it replaces.
+ *
+ * Conventions
+ *   - all functions return 0 on success, a negative DERP_E* code on failure;
+ *     derp_last_error() returns a thread-local human readable message.
+ *   - the caller owns every host pointer; the library owns device memory inside DerpCtx.
+ *   - images are row-major, top row first, tightly packed:
+ *       colour  : uint16_t[H][W][3]  (B,G,R — cv::Vec3w, DerpUtil.h:19)
+ *       float   : float[H][W]
+ *       mask    : uint8_t[H][W]      (0 / non-zero — cv::Mat_<bool>)
+ *       warp    : float[H][W][2]     (x,y — cv::Vec2f)
+ *   - `dst` is an index into the destination list given to derp_create (rigDst),
+ *     `src` an index into the camera list (rigSrc).
+ *   - a context is not thread-safe; different contexts are independent.
+ *
+ * Two shared libraries export exactly this ABI:
+ *   facebook360_dep_b200/libderp_b200.so  — the product: hand-written sm_100a CUDA
+ *   oracle/libderp_oracle.so              — TEST INFRASTRUCTURE ONLY: CPU restatement
+ */
+#ifndef DERP_B200_H_
+#define DERP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DERP_OK 0
+#define DERP_EINVAL (-1)   /* bad argument / precondition (reference: glog CHECK failure) */
+#define DERP_ECUDA (-2)    /* CUDA runtime error */
+#define DERP_ENOMEM (-3)
+#define DERP_ESTATE (-4)   /* call sequence error (e.g. stage before derp_reproject) */
+#define DERP_ECOVERAGE (-5)/* Derp.cpp:339 CHECK(partialCoverage || useForegroundMasks) */
+
+/* Camera::Type, source/util/Camera.h:43 */
+#define DERP_CAM_FTHETA 0
+#define DERP_CAM_RECTILINEAR 1
+#define DERP_CAM_EQUISOLID 2
+#define DERP_CAM_ORTHOGRAPHIC 3
+
+/* One camera exactly as the rig JSON states it (Camera.cpp:30-75, docs/rig.md).
+ * Derived state (re-unitarised rotation Camera.cpp:77-87, distortionMax Camera.cpp:119-154,
+ * cosFov Camera.cpp:204-207) is computed inside the library. */
+typedef struct DerpCameraDesc {
+  int32_t type;           /* DERP_CAM_* */
+  int32_t has_principal;  /* 0 => principal = resolution / 2 (Camera.cpp:47-51) */
+  int32_t has_fov;        /* 0 => default fov (Camera.cpp:183-195) */
+  int32_t reserved;
+  double origin[3];
+  double forward[3];
+  double up[3];
+  double right[3];
+  double resolution[2];
+  double principal[2];
+  double focal[2];
+  double distortion[3];   /* missing trailing entries = 0 (Camera.cpp:53-63) */
+  double fov;             /* radians from the optical axis */
+} DerpCameraDesc;
+
+/* What PyramidLevel's constructor receives (PyramidLevel.h:93-167, DerpCLI.cpp:250-271). */
+typedef struct DerpLevelParams {
+  int32_t width, height;            /* sizeLevel */
+  int32_t level, num_levels;        /* brute force runs iff level == num_levels-1 */
+  int32_t full_width, full_height;  /* rigDst[0].resolution before normalisation (DerpCLI.cpp:212-214) */
+  float var_noise_floor;            /* --var_noise_floor (full-size); level value derived per PyramidLevel.h:232-236 */
+  float var_high_thresh;            /* --var_high_thresh */
+  int32_t use_foreground_masks;     /* --use_foreground_masks */
+  int32_t reserved;
+} DerpLevelParams;
+
+/* Arguments of processLevel (Derp.cpp:1005-1034) + the constants the north-star makes tunable. */
+typedef struct DerpProcessOpts {
+  int32_t num_depths;             /* kNumDepths, Derp.h:33 (reference: 150) */
+  float min_depth_m;              /* --min_depth_m */
+  float max_depth_m;              /* --max_depth_m */
+  int32_t partial_coverage;       /* --partial_coverage */
+  int32_t random_proposals;       /* --random_proposals */
+  int32_t ping_pong_iterations;   /* --ping_pong_iterations */
+  int32_t mismatches_start_level; /* --mismatches_start_level */
+  int32_t do_bilateral_filter;    /* --do_bilateral_filter */
+  int32_t do_median_filter;       /* --do_median_filter */
+  int32_t reserved;
+} DerpProcessOpts;
+
+typedef struct DerpCtx DerpCtx;
+
+/* Identification: "cuda-sm_100a" for the product, "oracle-cpu" for the test oracle. */
+const char* derp_backend(void);
+const char* derp_last_error(void);
+
+/* Number of host worker threads for CPU-side loops (oracle only; the CUDA library ignores it).
+ * Mirrors --threads (ThreadPool.h:30-45): -1 = hardware_concurrency, 0 = inline. */
+int derp_set_threads(int threads);
+
+/* rigSrc = cams[0..num_cams), rigDst[i] = cams[dst_to_src[i]] (DerpUtil.cpp:75-88 mapSrcToDstIndexes,
+ * ImageUtil.cpp:110-125 filterDestinations).  Cameras are given at full resolution; the library
+ * normalises them (Camera::normalizeRig, Camera.cpp:236-242) like DerpCLI.cpp:216-218. */
+int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_src, int num_dsts,
+                int device, DerpCtx** out);
+void derp_destroy(DerpCtx* ctx);
+
+/* Starts one (frame, level): allocates level buffers, zero-fills disparity/cost/confidence/
+ * mismatch mask (PyramidLevel.h:206-230) and builds the dst FOV masks
+ * (generateFovMasks, DerpUtil.cpp:259-276).  Invalidates everything from the previous level. */
+int derp_level_begin(DerpCtx* ctx, const DerpLevelParams* p);
+
+/* Source colours of all cameras, colors[s] = uint16_t[H][W][3]; also computes the per-source
+ * variance (PyramidLevel::computeVariances PyramidLevel.h:232-247, computeImageVariance
+ * DerpUtil.cpp:214-237). */
+int derp_set_colors(DerpCtx* ctx, const uint16_t* const* colors);
+/* Optional (use_foreground_masks): masks[s] per source camera, background[d] per destination. */
+int derp_set_foreground_masks(DerpCtx* ctx, const uint8_t* const* masks);
+int derp_set_background_disparity(DerpCtx* ctx, const float* const* background);
+
+/* reprojectColors + precomputeProjections for ONE destination (Derp.cpp:955-1003): builds, for
+ * every source s, projWarp(dst,s) (src px -> dst px at infinity), projColor(dst,s)
+ * (cv::remap INTER_CUBIC of the source through projWarpInv) and projColorBias (3x3 box mean).
+ * The tables of one destination are resident at a time; cost-evaluating stages below require
+ * them to be current for their `dst`. */
+int derp_reproject(DerpCtx* ctx, int dst);
+
+/* computeBruteForceDisparity (Derp.cpp:264-382): fused sweep + winner-takes-all.
+ * best_index (optional, int32_t[H][W]) receives the winning candidate index, -1 where no
+ * candidate had a finite cost, -2 outside FOV, -3 outside the foreground mask; border pixels get
+ * the index of the clamped interior pixel. */
+int derp_brute_force(DerpCtx* ctx, int dst, int num_depths, float min_depth_m, float max_depth_m,
+                     int partial_coverage, int32_t* best_index);
+/* randomProposal(s) (Derp.cpp:750-873) — no level test here; the caller decides (processLevel). */
+int derp_random_proposals(DerpCtx* ctx, int dst, int num_proposals, float min_depth_m,
+                          float max_depth_m);
+/* pingPong (Derp.cpp:480-538) */
+int derp_ping_pong(DerpCtx* ctx, int dst, int iterations);
+/* handleDisparityMismatches body for all destinations (Derp.cpp:685-748); needs num_dsts == num_cams. */
+int derp_mismatches(DerpCtx* ctx);
+/* bilateralFilter (Derp.cpp:875-902) / medianFilter (Derp.cpp:904-920) / maskFov (Derp.cpp:940-951) */
+int derp_bilateral(DerpCtx* ctx, int dst);
+int derp_median(DerpCtx* ctx, int dst);
+int derp_mask_fov(DerpCtx* ctx, int dst);
+
+/* upsampleDisparities for one destination (UpsampleDisparityLib.cpp:98-182): writes the level's
+ * disparity from a coarser map.  coarse_mask / fine_mask are the destination's foreground masks at
+ * both sizes (ignored unless use_foreground_masks). */
+int derp_upsample_from(DerpCtx* ctx, int dst, const float* coarse, int coarse_w, int coarse_h,
+                       const uint8_t* coarse_mask, const uint8_t* fine_mask);
+
+/* processLevel minus file output (Derp.cpp:1005-1034) for all destinations. */
+int derp_process_level(DerpCtx* ctx, const DerpProcessOpts* opts);
+
+/* Cost of one hypothesis per pixel: out_cost/out_conf[y][x] = computeCost(dst, disparity[y][x], x, y)
+ * (Derp.cpp:104-226) on interior pixels, NaN on the 1-px border.  Test/diagnostic entry. */
+int derp_eval_cost(DerpCtx* ctx, int dst, const float* disparity, float* out_cost, float* out_conf);
+
+/* Host <-> context state. NULL pointers are skipped. */
+int derp_set_disparity(DerpCtx* ctx, int dst, const float* disparity, const float* cost,
+                       const float* confidence);
+int derp_get_disparity(DerpCtx* ctx, int dst, float* disparity, float* cost, float* confidence);
+int derp_get_fov_mask(DerpCtx* ctx, int dst, uint8_t* mask);
+int derp_get_mismatch_mask(DerpCtx* ctx, int dst, uint8_t* mask);
+int derp_get_variance(DerpCtx* ctx, int src, float* variance);
+int derp_get_var_noise_floor(DerpCtx* ctx, float* out);
+/* Tables of the destination last passed to derp_reproject. */
+int derp_get_proj_warp(DerpCtx* ctx, int src, float* warp_xy);
+int derp_get_proj_color(DerpCtx* ctx, int src, uint16_t* bgr);
+int derp_get_proj_bias(DerpCtx* ctx, int src, uint16_t* bgr);
+/* Work counters of the last cost-evaluating stage: number of computeCost calls and the number
+ * of (call, source) pairs whose source camera saw the point (sum of ssdCount). */
+int derp_get_counters(DerpCtx* ctx, uint64_t* cost_evals, uint64_t* src_hits);
+
+/* temporalJointBilateralFilter (TemporalBilateralFilter.h:126-215) for one camera.
+ * guides[t] colour, disps[t] float, masks[t] uint8 (fg & fov of frame t), t in [0, num_frames). */
+int derp_temporal_filter(int device, int width, int height, int num_frames,
+                         const uint16_t* const* guides, const float* const* disps,
+                         const uint8_t* const* masks, int frame_offset, float sigma,
+                         int spatial_radius, float weight0, float weight1, float weight2,
+                         float* out);
+
+/* generalizedJointBilateralFilter<float, Vec3f> as UpsampleDisparity.cpp uses it
+ * (TemporalBilateralFilter.h:39-124): guide is float BGR in [0,1]. */
+int derp_joint_bilateral_f32(int device, int width, int height, const float* image,
+                             const float* guide_bgr, const uint8_t* mask, int radius, float sigma,
+                             float weight0, float weight1, float weight2, float* out);
+
+/* Stand-alone upsampling as the UpsampleDisparity app needs it (UpsampleDisparityLib.cpp:98-182)
+ * for one camera; fov masks are derived from `cam`. */
+int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* coarse, int coarse_w,
+                            int coarse_h, const float* background_up, const uint8_t* coarse_mask,
+                            const uint8_t* fine_mask, int out_w, int out_h,
+                            int use_foreground_masks, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DERP_B200_H_ */

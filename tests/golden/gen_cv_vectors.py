@@ -1,0 +1,75 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/cv_vectors.npz with the cv2 wheel of this image (cv2 4.13.0, single
+thread like source/test/DepUnitTest.cpp:14).  Pins the oracle's restatement of the OpenCV primitives
+the reference calls (OpenCV itself is not under /root/reference and the reference pins no version):
+  remap INTER_CUBIC BORDER_CONSTANT u16x3   (DerpUtil.cpp:199-205 project)
+  blur 3x3 u16x3                            (DerpUtil.cpp:208-210 colorBias, CvUtil.h:314-323)
+  computeImageVariance                      (DerpUtil.cpp:214-237) via the same cv2 calls
+  resize INTER_LANCZOS4 / INTER_NEAREST f32 (UpsampleDisparityLib.cpp:125,145)
+"""
+import os
+
+import cv2
+import numpy as np
+
+cv2.setNumThreads(1)
+
+
+def main():
+    rng = np.random.RandomState(12345)
+    out = {}
+    # ---- remap
+    sh, sw, dh, dw = 37, 53, 41, 47
+    src = rng.randint(0, 65536, size=(sh, sw, 3)).astype(np.uint16)
+    mp = np.empty((dh, dw, 2), np.float32)
+    mp[..., 0] = rng.uniform(-6, sw + 5, size=(dh, dw))
+    mp[..., 1] = rng.uniform(-6, sh + 5, size=(dh, dw))
+    # exact-grid and half-grid coordinates, NaNs, far outside
+    mp[0, :10, 0] = np.arange(10)
+    mp[0, :10, 1] = 5
+    mp[1, :10, 0] = np.arange(10) + 0.5
+    mp[1, :10, 1] = 5.5
+    mp[2, :8] = np.nan
+    mp[3, :4, 0] = 1e9
+    mp[3, 4:8, 1] = -1e9
+    mp[4, :16, 0] = np.arange(16) / 64.0 + 3  # 1/64 steps: exercises the 1/32 rounding (half-even)
+    mp[4, :16, 1] = 7.015625
+    out["remap_src"] = src
+    out["remap_map"] = mp
+    out["remap_dst"] = cv2.remap(src, mp, None, cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT)
+    # smooth-ish second case (values near saturation)
+    src2 = np.clip(rng.normal(60000, 6000, size=(sh, sw, 3)), 0, 65535).astype(np.uint16)
+    out["remap_src2"] = src2
+    out["remap_dst2"] = cv2.remap(src2, mp, None, cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT)
+    # ---- blur
+    img = rng.randint(0, 65536, size=(29, 31, 3)).astype(np.uint16)
+    out["blur_src"] = img
+    out["blur_dst"] = cv2.blur(img, (3, 3))
+    small = rng.randint(0, 12, size=(9, 7, 3)).astype(np.uint16)
+    out["blur_src_small"] = small
+    out["blur_dst_small"] = cv2.blur(small, (3, 3))
+    # ---- variance (same call sequence as the reference)
+    for tag, im in (("var", img), ("var_small", small),
+                    ("var_smooth", np.clip(rng.normal(30000, 900, size=(33, 35, 3)), 0, 65535).astype(np.uint16))):
+        # cv::Mat::convertTo(CV_32F, 1.0f/65535.0f) (CvUtil.h:171-183): float multiply
+        f = im.astype(np.float32) * (np.float32(1.0) / np.float32(65535.0))
+        mean = cv2.blur(f, (3, 3))
+        msq = cv2.blur(f * f, (3, 3))
+        v = msq - mean * mean
+        w = np.array([0.3333, 0.3334, 0.3333], np.float32)
+        var = v[..., 0] * w[2] + v[..., 1] * w[1] + v[..., 2] * w[0]
+        out[tag + "_src"] = im
+        out[tag + "_dst"] = var.astype(np.float32)
+    # ---- resize
+    d = rng.uniform(1e-4, 2.0, size=(23, 31)).astype(np.float32)
+    out["resize_src"] = d
+    for (W, H) in ((62, 46), (50, 37), (31, 23), (100, 80)):
+        out["lanczos_%dx%d" % (W, H)] = cv2.resize(d, (W, H), interpolation=cv2.INTER_LANCZOS4)
+        out["nearest_%dx%d" % (W, H)] = cv2.resize(d, (W, H), interpolation=cv2.INTER_NEAREST)
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cv_vectors.npz")
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, "cv2", cv2.__version__)
+
+
+if __name__ == "__main__":
+    main()
