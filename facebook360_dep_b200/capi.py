@@ -112,6 +112,11 @@ _SIGS = {
     "derp_set_threads": (C.c_int, [C.c_int]),
     "derp_create": (C.c_int, [_p(CameraDesc), C.c_int, _p(C.c_int32), C.c_int, C.c_int, _p(C.c_void_p)]),
     "derp_destroy": (None, [C.c_void_p]),
+    "derp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "derp_sync": (C.c_int, [C.c_void_p]),
+    "derp_get_launch_count": (C.c_int, [C.c_void_p, _p(C.c_uint64)]),
+    "derp_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "derp_get_profile": (C.c_int, [C.c_void_p, _p(C.c_double), _p(C.c_uint64)]),
     "derp_level_begin": (C.c_int, [C.c_void_p, _p(LevelParams)]),
     "derp_set_colors": (C.c_int, [C.c_void_p, _p(C.c_void_p)]),
     "derp_set_foreground_masks": (C.c_int, [C.c_void_p, _p(C.c_void_p)]),
@@ -253,6 +258,25 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_stream(self, cuda_stream):
+        self.L.check(self.L.lib.derp_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self.L.check(self.L.lib.derp_sync(self.h))
+
+    def profile(self, enable=True):
+        self.L.check(self.L.lib.derp_profile(self.h, int(enable)))
+
+    def get_profile(self):
+        ms, n = C.c_double(), C.c_uint64()
+        self.L.check(self.L.lib.derp_get_profile(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self.L.check(self.L.lib.derp_get_launch_count(self.h, C.byref(n)))
+        return n.value
 
     def level_begin(self, width, height, level=0, num_levels=1, full_width=None, full_height=None,
                     var_noise_floor=4e-5, var_high_thresh=1e-3, use_foreground_masks=False):

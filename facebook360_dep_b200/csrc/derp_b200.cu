@@ -1,0 +1,1125 @@
+// libderp_b200.so — the product: C ABI of include/derp_b200.h implemented with hand-written
+// sm_100a CUDA kernels (derp_kernels.cuh).  No CPU fallback: every entry point that computes
+// needs a CUDA device and fails with DERP_ECUDA otherwise.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see Makefile).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/derp_b200.h"
+#include "derp_kernels.cuh"
+
+using namespace derp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(DERP_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                                  std::to_string(__LINE__) + ")");                                   \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+inline dim3 grid2(int W, int H, int z = 1) { return dim3((W + kBlockX - 1) / kBlockX, (H + kBlockY - 1) / kBlockY, z); }
+inline dim3 block2() { return dim3(kBlockX, kBlockY, 1); }
+inline unsigned grid1(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// OpenCV's float bicubic table (imgwarp.cpp: interpolateCubic A=-0.75, initInterTab2D, INTER_TAB_SIZE 32)
+void buildBicubicTable(std::vector<float>& tab) {
+  float t1[32][4];
+  const float scale = 1.f / 32;
+  for (int i = 0; i < 32; ++i) {
+    const float x = i * scale, A = -0.75f;
+    t1[i][0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    t1[i][1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    t1[i][2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    t1[i][3] = 1.f - t1[i][0] - t1[i][1] - t1[i][2];
+  }
+  tab.resize(32 * 32 * 16);
+  for (int i = 0; i < 32; ++i)
+    for (int j = 0; j < 32; ++j)
+      for (int k1 = 0; k1 < 4; ++k1)
+        for (int k2 = 0; k2 < 4; ++k2) tab[(i * 32 + j) * 16 + k1 * 4 + k2] = t1[i][k1] * t1[j][k2];
+}
+
+// resize.cpp interpolateLanczos4
+void lanczosTaps(float x, float* c) {
+  static const double s45 = 0.70710678118654752440084436210485;
+  static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  if (x < 1.1920928955078125e-07f) {
+    for (int i = 0; i < 8; ++i) c[i] = 0;
+    c[3] = 1;
+    return;
+  }
+  float sum = 0;
+  const double y0 = -(x + 3) * M_PI * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+  for (int i = 0; i < 8; ++i) {
+    const double y = -(x + 3 - i) * M_PI * 0.25;
+    c[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+    sum += c[i];
+  }
+  sum = 1.f / sum;
+  for (int i = 0; i < 8; ++i) c[i] *= sum;
+}
+int floorD(double v) {
+  int i = (int)v;
+  return i - (i > v);
+}
+void lanczosAxis(int sn, int dn, std::vector<int>& ofs, std::vector<float>& taps) {
+  const double inv = (double)dn / sn, scale = 1. / inv;
+  ofs.resize(dn);
+  taps.resize((size_t)dn * 8);
+  for (int d = 0; d < dn; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    const int s = floorD(f);
+    f -= s;
+    ofs[d] = s;
+    lanczosTaps(f, &taps[(size_t)d * 8]);
+  }
+}
+void nearestAxis(int sn, int dn, std::vector<int>& ofs) {
+  const double inv = (double)dn / sn, ifx = 1. / inv;
+  ofs.resize(dn);
+  for (int d = 0; d < dn; ++d) ofs[d] = std::min(floorD(d * ifx), sn - 1);
+}
+// UpsampleDisparityLib.cpp:27-52: clock-wise outward spiral of diameter w
+void spiralOffsets(int w, std::vector<short2>& locs) {
+  int x = 0, y = 0, dx = 0, dy = -1, t = w;
+  const int samples = t * t;
+  locs.clear();
+  for (int i = 0; i < samples; ++i) {
+    if ((-w / 2 <= x) && (x <= w / 2) && (-w / 2 <= y) && (y <= w / 2)) locs.push_back(make_short2((short)x, (short)y));
+    if (x == y || ((x < 0) && (x == -y)) || ((x > 0) && (x == 1 - y))) {
+      t = dx;
+      dx = -dy;
+      dy = t;
+    }
+    x += dx;
+    y += dy;
+  }
+}
+
+}  // namespace
+
+struct DerpCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  int S = 0, Sd = 0;
+  std::vector<int> dst2src;
+  std::vector<DevCamera> camsNorm;  // normalised (Camera::normalizeRig)
+  DevBuf<DevCamera> dCams, dCamsPx;
+  DevBuf<float> dWtab;
+  // level
+  bool levelOpen = false, haveColors = false, haveFg = false, haveBg = false;
+  DerpLevelParams lp{};
+  int W = 0, H = 0;
+  size_t plane = 0;
+  float varNoiseFloor = 0;
+  DevBuf<uint2> dColor, dProjColor, dProjBias;
+  DevBuf<float2> dProjWarp;
+  DevBuf<float> dVariance, dBg, dDisp, dCost, dConf, dScratchA, dScratchB, dScratchC, dDisparities;
+  DevBuf<uint8_t> dFg, dFov, dMismatch, dChangedA, dChangedB, dStage;
+  DevBuf<unsigned long long> dBest, dCounters;
+  DevBuf<unsigned> dUncovered;
+  DevBuf<int> dPrefix, dIdx, dOfs;
+  DevBuf<float> dTaps;
+  DevBuf<short2> dSpiral;
+  int projDst = -1;
+  uint64_t launches = 0;
+  uint64_t lastEvals = 0, lastHits = 0;
+  bool countersOnDevice = false;
+  int tableD = -1;
+  float tableMin = 0, tableMax = 0;  // candidate table currently in dDisparities
+  // optional per-kernel timing of the dominant kernel (sweepKernel) with CUDA events on c->stream
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweepEvents;
+
+  const uint8_t* fgOf(int src) const { return haveFg ? dFg.p + (size_t)src * plane : nullptr; }
+  const float* bgOf(int dst) const { return haveBg ? dBg.p + (size_t)dst * plane : nullptr; }
+  CostView view(int dst) const {
+    CostView v;
+    v.W = W;
+    v.H = H;
+    v.S = S;
+    v.self = dst2src[dst];
+    v.projColor = dProjColor.p;
+    v.projBias = dProjBias.p;
+    v.projWarp = dProjWarp.p;
+    v.variance = dVariance.p + (size_t)v.self * plane;
+    v.cams = dCams.p;
+    return v;
+  }
+  size_t camSmem() const { return (size_t)S * sizeof(DevCamera); }
+};
+
+namespace {
+
+int useDevice(DerpCtx* c) {
+  CU(cudaSetDevice(c->device));
+  return DERP_OK;
+}
+
+int checkDst(DerpCtx* c, int dst, const char* who, bool needProj) {
+  if (!c) return fail(DERP_EINVAL, std::string(who) + ": null ctx");
+  if (!c->levelOpen) return fail(DERP_ESTATE, std::string(who) + ": no level");
+  if (dst < 0 || dst >= c->Sd) return fail(DERP_EINVAL, std::string(who) + ": dst out of range");
+  if (needProj && c->projDst != dst)
+    return fail(DERP_ESTATE, std::string(who) + ": derp_reproject(dst) must precede this stage");
+  return useDevice(c);
+}
+
+int launchCheck(DerpCtx* c, const char* what) {
+  c->launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(DERP_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return DERP_OK;
+}
+#define LAUNCHED(what)                      \
+  do {                                      \
+    int rc_ = launchCheck(c, what);         \
+    if (rc_) return rc_;                    \
+  } while (0)
+
+int resetCounters(DerpCtx* c) {
+  CU(cudaMemsetAsync(c->dCounters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  c->countersOnDevice = true;
+  return DERP_OK;
+}
+
+int readCounters(DerpCtx* c) {
+  unsigned long long h[2];
+  CU(cudaMemcpyAsync(h, c->dCounters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->lastEvals = h[0];
+  c->lastHits = h[1];
+  return DERP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* derp_backend(void) { return "cuda-sm_100a"; }
+const char* derp_last_error(void) { return g_err.c_str(); }
+int derp_set_threads(int) { return DERP_OK; }
+
+int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_src, int num_dsts, int device,
+                DerpCtx** out) {
+  if (!cams || !dst_to_src || !out || num_cams <= 0 || num_dsts <= 0)
+    return fail(DERP_EINVAL, "derp_create: bad arguments");
+  if (num_cams > kMaxCams) return fail(DERP_EINVAL, "derp_create: at most 32 cameras are supported");
+  std::unique_ptr<DerpCtx> c(new DerpCtx);
+  c->device = device;
+  c->S = num_cams;
+  c->Sd = num_dsts;
+  c->camsNorm.resize(num_cams);
+  for (int i = 0; i < num_cams; ++i) {
+    if (!host::makeCamera(cams[i], &c->camsNorm[i]))
+      return fail(DERP_EINVAL, "derp_create: invalid camera " + std::to_string(i));
+  }
+  for (int i = 1; i < num_cams; ++i)  // PyramidLevel::checkParams (PyramidLevel.h:169-184)
+    if (c->camsNorm[i].res[0] != c->camsNorm[0].res[0] || c->camsNorm[i].res[1] != c->camsNorm[0].res[1])
+      return fail(DERP_EINVAL, "derp_create: cameras must share one resolution");
+  for (auto& cam : c->camsNorm)
+    if (!(cam.res[0] == 1 && cam.res[1] == 1)) host::normalise(cam);
+  c->dst2src.assign(dst_to_src, dst_to_src + num_dsts);
+  for (int d : c->dst2src)
+    if (d < 0 || d >= num_cams) return fail(DERP_EINVAL, "derp_create: dst_to_src out of range");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DERP_ECUDA, "derp_create: no such CUDA device " + std::to_string(device));
+  CU(cudaSetDevice(device));
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->ownStream = true;
+  CU(c->dCams.ensure(num_cams));
+  CU(c->dCamsPx.ensure(num_cams));
+  CU(cudaMemcpy(c->dCams.p, c->camsNorm.data(), num_cams * sizeof(DevCamera), cudaMemcpyHostToDevice));
+  std::vector<float> tab;
+  buildBicubicTable(tab);
+  CU(c->dWtab.ensure(tab.size()));
+  CU(cudaMemcpy(c->dWtab.p, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CU(c->dCounters.ensure(2));
+  CU(c->dUncovered.ensure(1));
+  // all cost kernels stage S cameras in dynamic shared memory
+  *out = c.release();
+  return DERP_OK;
+}
+
+void derp_destroy(DerpCtx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int derp_set_stream(DerpCtx* c, void* cuda_stream) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+  c->ownStream = false;
+  c->stream = (cudaStream_t)cuda_stream;
+  return DERP_OK;
+}
+
+int derp_sync(DerpCtx* c) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_profile(DerpCtx* c, int enable) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  for (auto& e : c->sweepEvents) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  c->sweepEvents.clear();
+  c->profiling = enable != 0;
+  return DERP_OK;
+}
+
+int derp_get_profile(DerpCtx* c, double* sweep_ms, uint64_t* sweep_launches) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  double total = 0;
+  for (auto& e : c->sweepEvents) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e.first, e.second));
+    total += ms;
+  }
+  if (sweep_ms) *sweep_ms = total;
+  if (sweep_launches) *sweep_launches = c->sweepEvents.size();
+  return DERP_OK;
+}
+
+int derp_get_launch_count(DerpCtx* c, uint64_t* out) {
+  if (!c || !out) return fail(DERP_EINVAL, "bad arguments");
+  *out = c->launches;
+  return DERP_OK;
+}
+
+int derp_level_begin(DerpCtx* c, const DerpLevelParams* p) {
+  if (!c || !p || p->width < 3 || p->height < 3 || p->num_levels <= 0 || p->full_height <= 0)
+    return fail(DERP_EINVAL, "derp_level_begin: bad arguments");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  c->lp = *p;
+  c->W = p->width;
+  c->H = p->height;
+  c->plane = (size_t)c->W * c->H;
+  const size_t n = c->plane;
+  // PyramidLevel::computeVariances (PyramidLevel.h:232-236): width / heightFullSize, as written
+  const float scale = float(c->W) / p->full_height;
+  const float scaleVar = scale * scale;
+  c->varNoiseFloor = std::max(p->var_noise_floor * scaleVar, kMinVarF);
+  CU(c->dColor.ensure(n * c->S));
+  CU(c->dVariance.ensure(n * c->S));
+  CU(c->dProjColor.ensure(n * c->S));
+  CU(c->dProjBias.ensure(n * c->S));
+  CU(c->dProjWarp.ensure(n * c->S));
+  CU(c->dFov.ensure(n * c->Sd));
+  CU(c->dDisp.ensure(n * c->Sd));
+  CU(c->dCost.ensure(n * c->Sd));
+  CU(c->dConf.ensure(n * c->Sd));
+  CU(c->dMismatch.ensure(n * c->Sd));
+  CU(c->dScratchA.ensure(n));
+  CU(c->dScratchB.ensure(n));
+  CU(c->dChangedA.ensure(n));
+  CU(c->dChangedB.ensure(n));
+  CU(c->dBest.ensure(n));
+  CU(c->dPrefix.ensure(n));
+  CU(c->dIdx.ensure(n));
+  CU(c->dStage.ensure(n * 6 * (size_t)c->S));
+  CU(cudaMemsetAsync(c->dDisp.p, 0, n * c->Sd * sizeof(float), c->stream));
+  CU(cudaMemsetAsync(c->dCost.p, 0, n * c->Sd * sizeof(float), c->stream));
+  CU(cudaMemsetAsync(c->dConf.p, 0, n * c->Sd * sizeof(float), c->stream));
+  CU(cudaMemsetAsync(c->dMismatch.p, 0, n * c->Sd, c->stream));
+  // cameras rescaled to the level's pixel size (Derp.cpp:961,968)
+  std::vector<DevCamera> px(c->S);
+  for (int s = 0; s < c->S; ++s) px[s] = host::rescaled(c->camsNorm[s], c->W, c->H);
+  CU(cudaMemcpyAsync(c->dCamsPx.p, px.data(), c->S * sizeof(DevCamera), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // px goes out of scope
+  for (int d = 0; d < c->Sd; ++d) {
+    fovMaskKernel<<<grid2(c->W, c->H), block2(), 0, c->stream>>>(c->dCams.p + c->dst2src[d], c->W, c->H,
+                                                                 c->dFov.p + (size_t)d * n);
+    LAUNCHED("fovMaskKernel");
+  }
+  c->projDst = -1;
+  c->haveColors = c->haveFg = c->haveBg = false;
+  c->levelOpen = true;
+  return DERP_OK;
+}
+
+int derp_set_colors(DerpCtx* c, const uint16_t* const* colors) {
+  if (!c || !colors) return fail(DERP_EINVAL, "derp_set_colors: bad arguments");
+  if (!c->levelOpen) return fail(DERP_ESTATE, "derp_set_colors: no level");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  const size_t n = c->plane;
+  for (int s = 0; s < c->S; ++s) {
+    if (!colors[s]) return fail(DERP_EINVAL, "derp_set_colors: null image");
+    uint8_t* st = c->dStage.p + (size_t)s * n * 6;
+    CU(cudaMemcpyAsync(st, colors[s], n * 6, cudaMemcpyHostToDevice, c->stream));
+    packColorKernel<<<grid1(n), 256, 0, c->stream>>>(n, reinterpret_cast<const uint16_t*>(st), c->dColor.p + (size_t)s * n);
+    LAUNCHED("packColorKernel");
+  }
+  varianceKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dColor.p, c->dVariance.p);
+  LAUNCHED("varianceKernel");
+  c->haveColors = true;
+  c->projDst = -1;
+  return DERP_OK;
+}
+
+int derp_set_foreground_masks(DerpCtx* c, const uint8_t* const* masks) {
+  if (!c || !masks) return fail(DERP_EINVAL, "derp_set_foreground_masks: bad arguments");
+  if (!c->levelOpen) return fail(DERP_ESTATE, "no level");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  const size_t n = c->plane;
+  CU(c->dFg.ensure(n * c->S));
+  for (int s = 0; s < c->S; ++s)
+    CU(cudaMemcpyAsync(c->dFg.p + (size_t)s * n, masks[s], n, cudaMemcpyHostToDevice, c->stream));
+  c->haveFg = true;
+  return DERP_OK;
+}
+
+int derp_set_background_disparity(DerpCtx* c, const float* const* background) {
+  if (!c || !background) return fail(DERP_EINVAL, "derp_set_background_disparity: bad arguments");
+  if (!c->levelOpen) return fail(DERP_ESTATE, "no level");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  const size_t n = c->plane;
+  CU(c->dBg.ensure(n * c->Sd));
+  for (int d = 0; d < c->Sd; ++d)
+    CU(cudaMemcpyAsync(c->dBg.p + (size_t)d * n, background[d], n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  c->haveBg = true;
+  return DERP_OK;
+}
+
+int derp_reproject(DerpCtx* c, int dst) {
+  int rc = checkDst(c, dst, "derp_reproject", false);
+  if (rc) return rc;
+  if (!c->haveColors) return fail(DERP_ESTATE, "derp_reproject: colours not set");
+  const int self = c->dst2src[dst];
+  projWarpKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->dCamsPx.p, c->S, self, c->W, c->H, c->dProjWarp.p);
+  LAUNCHED("projWarpKernel");
+  reprojectKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->dCamsPx.p, c->S, self, c->W, c->H, c->dColor.p,
+                                                                       c->dWtab.p, c->dProjColor.p);
+  LAUNCHED("reprojectKernel");
+  biasKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor.p, c->dProjBias.p);
+  LAUNCHED("biasKernel");
+  c->projDst = dst;
+  return DERP_OK;
+}
+
+int derp_eval_cost(DerpCtx* c, int dst, const float* disparity, float* out_cost, float* out_conf) {
+  if (!disparity) return fail(DERP_EINVAL, "derp_eval_cost: bad arguments");
+  int rc = checkDst(c, dst, "derp_eval_cost", true);
+  if (rc) return rc;
+  const size_t n = c->plane;
+  CU(c->dScratchC.ensure(n));
+  CU(cudaMemcpyAsync(c->dScratchA.p, disparity, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = resetCounters(c))) return rc;
+  evalCostKernel<<<grid2(c->W, c->H), block2(), c->camSmem(), c->stream>>>(c->view(dst), c->dScratchA.p, c->dScratchB.p,
+                                                                          c->dScratchC.p, c->dCounters.p);
+  LAUNCHED("evalCostKernel");
+  if (out_cost) CU(cudaMemcpyAsync(out_cost, c->dScratchB.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (out_conf) CU(cudaMemcpyAsync(out_conf, c->dScratchC.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  rc = readCounters(c);
+  c->countersOnDevice = false;
+  return rc;
+}
+
+int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, float max_depth_m, int partial_coverage,
+                     int32_t* best_index) {
+  if (num_depths < 2) return fail(DERP_EINVAL, "derp_brute_force: bad arguments");
+  int rc = checkDst(c, dst, "derp_brute_force", true);
+  if (rc) return rc;
+  const bool useFg = c->lp.use_foreground_masks != 0;
+  if (useFg && (!c->haveBg || !c->haveFg))
+    return fail(DERP_ESTATE, "derp_brute_force: foreground masks / background disparity not set");
+  const int W = c->W, H = c->H;
+  const size_t n = c->plane;
+  const int self = c->dst2src[dst];
+  // candidate table (Derp.cpp:279-285, probeDisparity ImageUtil.cpp:100-107)
+  std::vector<float> disparities(num_depths);
+  const float minDisparity = 1.0f / max_depth_m, maxDisparity = 1.0f / min_depth_m;
+  for (int i = 0; i < num_depths; ++i) {
+    const double fraction = double(i) / double(num_depths - 1);
+    disparities[i] = (float)(fraction * (double)minDisparity + (1 - fraction) * (double)maxDisparity);
+  }
+  if (c->tableD != num_depths || c->tableMin != min_depth_m || c->tableMax != max_depth_m) {
+    CU(c->dDisparities.ensure(num_depths));
+    CU(cudaMemcpyAsync(c->dDisparities.p, disparities.data(), num_depths * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // host vector lifetime (tiny copy, only when the table changes)
+    c->tableD = num_depths;
+    c->tableMin = min_depth_m;
+    c->tableMax = max_depth_m;
+  }
+  fillKernel<unsigned long long><<<grid1(n), 256, 0, c->stream>>>(n, c->dBest.p, 0x7f7fffffffffffffull);
+  LAUNCHED("fillKernel");
+  if ((rc = resetCounters(c))) return rc;
+  CU(cudaMemsetAsync(c->dUncovered.p, 0, sizeof(unsigned), c->stream));
+  // candidate chunks: enough CTAs to fill 148 SMs x 8 resident CTAs even on the coarse levels
+  const dim3 g = grid2(W, H);
+  const long ctas = (long)g.x * g.y;
+  int chunks = (int)std::min<long>(num_depths, std::max<long>(1, (148L * 8 * 4 + ctas - 1) / ctas));
+  const int chunk = (num_depths + chunks - 1) / chunks;
+  chunks = (num_depths + chunk - 1) / chunk;
+  SweepArgs a;
+  a.v = c->view(dst);
+  a.fov = c->dFov.p + (size_t)dst * n;
+  a.fg = useFg ? c->fgOf(self) : nullptr;
+  a.bg = useFg ? c->bgOf(dst) : nullptr;
+  a.disparities = c->dDisparities.p;
+  a.D = num_depths;
+  a.chunk = chunk;
+  a.best = c->dBest.p;
+  a.counters = c->dCounters.p;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (c->profiling) {
+    CU(cudaEventCreate(&ev0));
+    CU(cudaEventCreate(&ev1));
+    CU(cudaEventRecord(ev0, c->stream));
+  }
+  sweepKernel<<<dim3(g.x, g.y, chunks), block2(), c->camSmem(), c->stream>>>(a);
+  LAUNCHED("sweepKernel");
+  if (c->profiling) {
+    CU(cudaEventRecord(ev1, c->stream));
+    c->sweepEvents.emplace_back(ev0, ev1);
+  }
+  float* disp = c->dDisp.p + (size_t)dst * n;
+  float* cost = c->dCost.p + (size_t)dst * n;
+  float* conf = c->dConf.p + (size_t)dst * n;
+  int* idx = best_index ? c->dIdx.p : nullptr;
+  sweepFinalizeKernel<<<g, block2(), 0, c->stream>>>(W, H, a.fov, a.fg, a.bg, a.v.variance, c->dDisparities.p, minDisparity,
+                                                     c->dBest.p, disp, cost, conf, idx, c->dUncovered.p);
+  LAUNCHED("sweepFinalizeKernel");
+  extendBorderKernel<<<grid1(2 * W + 2 * (H - 2)), 256, 0, c->stream>>>(W, H, a.fg, a.bg, disp, cost, conf, idx);
+  LAUNCHED("extendBorderKernel");
+  if (best_index) CU(cudaMemcpyAsync(best_index, c->dIdx.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (!(partial_coverage || useFg)) {
+    unsigned unc = 0;
+    CU(cudaMemcpyAsync(&unc, c->dUncovered.p, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (unc > 0)  // Derp.cpp:339 CHECK(partialCoverage || useForegroundMasks)
+      return fail(DERP_ECOVERAGE, "Insufficient coverage at " + std::to_string(unc) + " pixels");
+  } else if (best_index) {
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return DERP_OK;
+}
+
+int derp_random_proposals(DerpCtx* c, int dst, int num_proposals, float min_depth_m, float max_depth_m) {
+  int rc = checkDst(c, dst, "derp_random_proposals", true);
+  if (rc) return rc;
+  if (num_proposals < 0) return fail(DERP_EINVAL, "derp_random_proposals: negative count");
+  const bool useFg = c->lp.use_foreground_masks != 0;
+  if (useFg && (!c->haveBg || !c->haveFg)) return fail(DERP_ESTATE, "derp_random_proposals: masks not set");
+  const int W = c->W, H = c->H;
+  const size_t n = c->plane;
+  const int self = c->dst2src[dst];
+  const float kRandomPropHighVarDeviation = 0.1f;  // Derp.h:37
+  const float varHighDev = kRandomPropHighVarDeviation * c->lp.var_high_thresh;
+  const float varThresh = std::max(varHighDev, c->varNoiseFloor);
+  ProposalArgs a;
+  a.v = c->view(dst);
+  a.fov = c->dFov.p + (size_t)dst * n;
+  a.fg = useFg ? c->fgOf(self) : nullptr;
+  a.bg = useFg ? c->bgOf(dst) : nullptr;
+  a.prefix = c->dPrefix.p;
+  a.disp = c->dDisp.p + (size_t)dst * n;
+  a.cost = c->dCost.p + (size_t)dst * n;
+  a.conf = c->dConf.p + (size_t)dst * n;
+  a.numProposals = num_proposals;
+  a.level = c->lp.level;
+  a.minDispGlobal = 1.0f / max_depth_m;
+  a.maxDisp = 1.0f / min_depth_m;
+  a.counters = c->dCounters.p;
+  if ((rc = resetCounters(c))) return rc;
+  proposalScanKernel<<<(H + 7) / 8, 256, 0, c->stream>>>(W, H, a.fov, a.fg, a.v.variance, varThresh, c->dPrefix.p);
+  LAUNCHED("proposalScanKernel");
+  proposalKernel<<<grid2(W, H), block2(), c->camSmem(), c->stream>>>(a);
+  LAUNCHED("proposalKernel");
+  return DERP_OK;
+}
+
+int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
+  int rc = checkDst(c, dst, "derp_ping_pong", true);
+  if (rc) return rc;
+  const bool useFg = c->lp.use_foreground_masks != 0;
+  if (useFg && (!c->haveBg || !c->haveFg)) return fail(DERP_ESTATE, "derp_ping_pong: masks not set");
+  const int W = c->W, H = c->H;
+  const size_t n = c->plane;
+  const int self = c->dst2src[dst];
+  float* disp = c->dDisp.p + (size_t)dst * n;
+  float* cost = c->dCost.p + (size_t)dst * n;
+  if ((rc = resetCounters(c))) return rc;
+  fillKernel<uint8_t><<<grid1(n), 256, 0, c->stream>>>(n, c->dChangedA.p, (uint8_t)1);
+  LAUNCHED("fillKernel");
+  uint8_t* chIn = c->dChangedA.p;
+  uint8_t* chOut = c->dChangedB.p;
+  for (int it = 1; it <= iterations; ++it) {
+    PingPongArgs a;
+    a.v = c->view(dst);
+    a.fov = c->dFov.p + (size_t)dst * n;
+    a.fg = useFg ? c->fgOf(self) : nullptr;
+    a.bg = useFg ? c->bgOf(dst) : nullptr;
+    a.disp = disp;
+    a.changed = chIn;
+    a.dispRes = c->dScratchA.p;
+    a.costRes = c->dScratchB.p;
+    a.changedNext = chOut;
+    a.varNoiseFloor = c->varNoiseFloor;
+    a.counters = c->dCounters.p;
+    pingPongKernel<<<grid2(W, H), block2(), c->camSmem(), c->stream>>>(a);
+    LAUNCHED("pingPongKernel");
+    // disp <- dispRes, cost <- costsRes (Derp.cpp:527-529); confidence is not written back
+    CU(cudaMemcpyAsync(disp, c->dScratchA.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(cost, c->dScratchB.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    std::swap(chIn, chOut);
+  }
+  return DERP_OK;
+}
+
+int derp_mismatches(DerpCtx* c) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  if (!c->levelOpen) return fail(DERP_ESTATE, "derp_mismatches: no level");
+  if (c->Sd != c->S) return fail(DERP_EINVAL, "Mismatches only valid when considering all cameras");
+  for (int d = 0; d < c->Sd; ++d)
+    if (c->dst2src[d] != d) return fail(DERP_EINVAL, "derp_mismatches: dst list must equal camera list");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  const size_t n = c->plane;
+  DevBuf<float> dNew;
+  CU(dNew.ensure(n * c->Sd));
+  for (int d = 0; d < c->Sd; ++d) {
+    MismatchArgs a;
+    a.W = c->W;
+    a.H = c->H;
+    a.S = c->S;
+    a.self = d;
+    a.cams = c->dCams.p;
+    a.dispAll = c->dDisp.p;
+    a.variance = c->dVariance.p + (size_t)d * n;
+    a.fov = c->dFov.p + (size_t)d * n;
+    a.fg = (c->lp.use_foreground_masks && c->haveFg) ? c->fgOf(d) : nullptr;
+    a.varNoiseFloor = c->varNoiseFloor;
+    a.varHighThresh = c->lp.var_high_thresh;
+    a.dispNew = dNew.p + (size_t)d * n;
+    a.mask = c->dMismatch.p + (size_t)d * n;
+    mismatchKernel<<<grid2(c->W, c->H), block2(), c->camSmem(), c->stream>>>(a);
+    LAUNCHED("mismatchKernel");
+  }
+  CU(cudaMemcpyAsync(c->dDisp.p, dNew.p, n * c->Sd * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // dNew is freed on return
+  return DERP_OK;
+}
+
+int derp_bilateral(DerpCtx* c, int dst) {
+  int rc = checkDst(c, dst, "derp_bilateral", false);
+  if (rc) return rc;
+  if (!c->haveColors) return fail(DERP_ESTATE, "derp_bilateral: colours not set");
+  const size_t n = c->plane;
+  const int self = c->dst2src[dst];
+  // Derp.cpp:876-878: pow(float, int) promotes to double, result narrowed to float
+  const float scale = (float)std::pow((double)0.9f, (double)c->lp.level);
+  const int spaceRadius = (int)std::max(std::ceil(5 * scale), float(1));
+  const uint8_t* fg = (c->lp.use_foreground_masks && c->haveFg) ? c->fgOf(self) : nullptr;
+  float* disp = c->dDisp.p + (size_t)dst * n;
+  bilateralKernel<<<grid2(c->W, c->H), block2(), 0, c->stream>>>(c->W, c->H, disp, c->dColor.p + (size_t)self * n,
+                                                                c->dFov.p + (size_t)dst * n, fg, spaceRadius, 0.005f, 0.5f,
+                                                                1.0f, 1.0f, c->dScratchA.p);
+  LAUNCHED("bilateralKernel");
+  CU(cudaMemcpyAsync(disp, c->dScratchA.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  return DERP_OK;
+}
+
+int derp_median(DerpCtx* c, int dst) {
+  int rc = checkDst(c, dst, "derp_median", false);
+  if (rc) return rc;
+  const size_t n = c->plane;
+  const int self = c->dst2src[dst];
+  const uint8_t* fg = (c->lp.use_foreground_masks && c->haveFg) ? c->fgOf(self) : nullptr;
+  float* disp = c->dDisp.p + (size_t)dst * n;
+  medianKernel<<<grid2(c->W, c->H), block2(), 0, c->stream>>>(c->W, c->H, disp, c->bgOf(dst), c->dFov.p + (size_t)dst * n, fg,
+                                                             c->dScratchA.p);
+  LAUNCHED("medianKernel");
+  CU(cudaMemcpyAsync(disp, c->dScratchA.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  return DERP_OK;
+}
+
+int derp_mask_fov(DerpCtx* c, int dst) {
+  int rc = checkDst(c, dst, "derp_mask_fov", false);
+  if (rc) return rc;
+  const size_t n = c->plane;
+  maskFovKernel<<<grid1(n), 256, 0, c->stream>>>(n, c->dFov.p + (size_t)dst * n, c->dDisp.p + (size_t)dst * n);
+  LAUNCHED("maskFovKernel");
+  return DERP_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// upsampleDisparityInPlace (UpsampleDisparityLib.cpp:98-147) on device buffers.
+// dCoarse: cw*ch floats; maskC / maskUp: already AND-ed with the FOV masks (nullable when !useFg).
+int upsampleDevice(DerpCtx* c, cudaStream_t st, const float* dCoarse, int cw, int ch, const float* dBgUp,
+                   const uint8_t* dMaskC, const uint8_t* dMaskUp, int W, int H, bool useFg, float* dOut,
+                   DevBuf<float>& tmpA, DevBuf<float>& tmpB, DevBuf<int>& dOfs, DevBuf<float>& dTaps,
+                   DevBuf<short2>& dSpiral) {
+  if (useFg) {
+    if (!dBgUp || !dMaskC || !dMaskUp) return fail(DERP_EINVAL, "upsample: masks and background required");
+    const float scale = float(W) / float(cw);  // getRadius (UpsampleDisparityLib.cpp:93-96)
+    const int radius = (int)(scale * scale + 1);
+    std::vector<int> xo, yo;
+    nearestAxis(cw, W, xo);
+    nearestAxis(ch, H, yo);
+    std::vector<int> ofs(xo);
+    ofs.insert(ofs.end(), yo.begin(), yo.end());
+    CU(dOfs.ensure(ofs.size()));
+    CU(cudaMemcpyAsync(dOfs.p, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    std::vector<short2> sp;
+    spiralOffsets(radius * 2 + 1, sp);
+    CU(dSpiral.ensure(sp.size()));
+    CU(cudaMemcpyAsync(dSpiral.p, sp.data(), sp.size() * sizeof(short2), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    CU(tmpA.ensure((size_t)W * H));
+    nearestMaskedKernel<<<grid2(W, H), block2(), 0, st>>>(cw, ch, W, H, dCoarse, dMaskC, dMaskUp, dOfs.p, dOfs.p + W, tmpA.p);
+    if (c) c->launches++;
+    replaceNansKernel<<<grid2(W, H), block2(), 0, st>>>(W, H, tmpA.p, dBgUp, dMaskUp, dSpiral.p, (int)sp.size(), dOut);
+    if (c) c->launches++;
+  } else {
+    std::vector<int> xo, yo;
+    std::vector<float> al, be;
+    lanczosAxis(cw, W, xo, al);
+    lanczosAxis(ch, H, yo, be);
+    std::vector<int> ofs(xo);
+    ofs.insert(ofs.end(), yo.begin(), yo.end());
+    std::vector<float> taps(al);
+    taps.insert(taps.end(), be.begin(), be.end());
+    CU(dOfs.ensure(ofs.size()));
+    CU(dTaps.ensure(taps.size()));
+    CU(cudaMemcpyAsync(dOfs.p, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(dTaps.p, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    CU(tmpA.ensure((size_t)cw * ch));
+    CU(tmpB.ensure((size_t)W * ch));
+    nanToKernel<<<grid1((size_t)cw * ch), 256, 0, st>>>((size_t)cw * ch, dCoarse, 1e-4f, tmpA.p);
+    lanczosHKernel<<<grid2(W, ch), block2(), 0, st>>>(cw, ch, W, tmpA.p, dOfs.p, dTaps.p, tmpB.p);
+    lanczosVKernel<<<grid2(W, H), block2(), 0, st>>>(ch, W, H, tmpB.p, dOfs.p + W, dTaps.p + (size_t)W * 8, dOut);
+    if (c) c->launches += 3;
+  }
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) return fail(DERP_ECUDA, std::string("upsample kernels: ") + cudaGetErrorString(e));
+  return DERP_OK;
+}
+
+__global__ void andMaskKernel(size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a[i] && b[i]) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int derp_upsample_from(DerpCtx* c, int dst, const float* coarse, int coarse_w, int coarse_h, const uint8_t* coarse_mask,
+                       const uint8_t* fine_mask) {
+  if (!coarse || coarse_w < 1 || coarse_h < 1) return fail(DERP_EINVAL, "derp_upsample_from: bad arguments");
+  int rc = checkDst(c, dst, "derp_upsample_from", false);
+  if (rc) return rc;
+  const bool useFg = c->lp.use_foreground_masks != 0;
+  const int W = c->W, H = c->H;
+  const size_t nc = (size_t)coarse_w * coarse_h, n = c->plane;
+  DevBuf<float> dCoarse, tA, tB;
+  DevBuf<uint8_t> dMc, dMu, dFovC;
+  CU(dCoarse.ensure(nc));
+  CU(cudaMemcpyAsync(dCoarse.p, coarse, nc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  if (useFg) {
+    if (!coarse_mask || !fine_mask) return fail(DERP_EINVAL, "derp_upsample_from: masks required");
+    if (!c->haveBg) return fail(DERP_ESTATE, "derp_upsample_from: background disparity not set");
+    CU(dMc.ensure(nc));
+    CU(dMu.ensure(n));
+    CU(dFovC.ensure(nc));
+    CU(cudaMemcpyAsync(dMc.p, coarse_mask, nc, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dMu.p, fine_mask, n, cudaMemcpyHostToDevice, c->stream));
+    // FOV masks at both sizes (UpsampleDisparityLib.cpp:163-176)
+    fovMaskKernel<<<grid2(coarse_w, coarse_h), block2(), 0, c->stream>>>(c->dCams.p + c->dst2src[dst], coarse_w, coarse_h, dFovC.p);
+    andMaskKernel<<<grid1(nc), 256, 0, c->stream>>>(nc, dFovC.p, dMc.p, dMc.p);
+    andMaskKernel<<<grid1(n), 256, 0, c->stream>>>(n, c->dFov.p + (size_t)dst * n, dMu.p, dMu.p);
+    c->launches += 3;
+  }
+  rc = upsampleDevice(c, c->stream, dCoarse.p, coarse_w, coarse_h, useFg ? c->bgOf(dst) : nullptr, useFg ? dMc.p : nullptr,
+                      useFg ? dMu.p : nullptr, W, H, useFg, c->dDisp.p + (size_t)dst * n, tA, tB, c->dOfs, c->dTaps, c->dSpiral);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));  // temporaries are freed on return
+  return DERP_OK;
+}
+
+int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* coarse, int coarse_w, int coarse_h,
+                            const float* background_up, const uint8_t* coarse_mask, const uint8_t* fine_mask, int out_w,
+                            int out_h, int use_foreground_masks, float* out) {
+  if (!cam || !coarse || !out || coarse_w < 1 || coarse_h < 1 || out_w < 1 || out_h < 1)
+    return fail(DERP_EINVAL, "derp_upsample_disparity: bad arguments");
+  CU(cudaSetDevice(device));
+  const size_t nc = (size_t)coarse_w * coarse_h, n = (size_t)out_w * out_h;
+  DevBuf<float> dCoarse, dBg, dOut, tA, tB, dTaps;
+  DevBuf<uint8_t> dMc, dMu, dFovC, dFovU;
+  DevBuf<int> dOfs;
+  DevBuf<short2> dSpiral;
+  DevBuf<DevCamera> dCam;
+  cudaStream_t st = nullptr;  // legacy default stream: this entry point is synchronous
+  CU(dCoarse.ensure(nc));
+  CU(dOut.ensure(n));
+  CU(cudaMemcpy(dCoarse.p, coarse, nc * sizeof(float), cudaMemcpyHostToDevice));
+  if (use_foreground_masks) {
+    if (!coarse_mask || !fine_mask || !background_up) return fail(DERP_EINVAL, "derp_upsample_disparity: masks/background required");
+    DevCamera hc;
+    if (!host::makeCamera(*cam, &hc)) return fail(DERP_EINVAL, "derp_upsample_disparity: invalid camera");
+    host::normalise(hc);
+    CU(dCam.ensure(1));
+    CU(cudaMemcpy(dCam.p, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+    CU(dBg.ensure(n));
+    CU(dMc.ensure(nc));
+    CU(dMu.ensure(n));
+    CU(dFovC.ensure(nc));
+    CU(dFovU.ensure(n));
+    CU(cudaMemcpy(dBg.p, background_up, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dMc.p, coarse_mask, nc, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dMu.p, fine_mask, n, cudaMemcpyHostToDevice));
+    fovMaskKernel<<<grid2(coarse_w, coarse_h), block2(), 0, st>>>(dCam.p, coarse_w, coarse_h, dFovC.p);
+    fovMaskKernel<<<grid2(out_w, out_h), block2(), 0, st>>>(dCam.p, out_w, out_h, dFovU.p);
+    andMaskKernel<<<grid1(nc), 256, 0, st>>>(nc, dFovC.p, dMc.p, dMc.p);
+    andMaskKernel<<<grid1(n), 256, 0, st>>>(n, dFovU.p, dMu.p, dMu.p);
+  }
+  int rc = upsampleDevice(nullptr, st, dCoarse.p, coarse_w, coarse_h, use_foreground_masks ? dBg.p : nullptr,
+                          use_foreground_masks ? dMc.p : nullptr, use_foreground_masks ? dMu.p : nullptr, out_w, out_h,
+                          use_foreground_masks != 0, dOut.p, tA, tB, dOfs, dTaps, dSpiral);
+  if (rc) return rc;
+  CU(cudaMemcpy(out, dOut.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return DERP_OK;
+}
+
+int derp_process_level(DerpCtx* c, const DerpProcessOpts* o) {
+  if (!c || !o) return fail(DERP_EINVAL, "derp_process_level: bad arguments");
+  if (!c->levelOpen || !c->haveColors) return fail(DERP_ESTATE, "derp_process_level: level/colours not set");
+  const bool coarsest = c->lp.level == c->lp.num_levels - 1;
+  uint64_t evals = 0, hits = 0;
+  int rc;
+  for (int d = 0; d < c->Sd; ++d) {
+    if ((rc = derp_reproject(c, d))) return rc;
+    if (coarsest) {  // preprocessLevel (Derp.cpp:826-842)
+      if ((rc = derp_brute_force(c, d, o->num_depths, o->min_depth_m, o->max_depth_m, o->partial_coverage, nullptr))) return rc;
+      if ((rc = readCounters(c))) return rc;
+      evals += c->lastEvals;
+      hits += c->lastHits;
+    }
+    if (o->random_proposals > 0 && !coarsest) {  // Derp.cpp:851-853
+      if ((rc = derp_random_proposals(c, d, o->random_proposals, o->min_depth_m, o->max_depth_m))) return rc;
+      if ((rc = readCounters(c))) return rc;
+      evals += c->lastEvals;
+      hits += c->lastHits;
+    }
+    if (!coarsest) {  // Derp.cpp:545-547
+      if ((rc = derp_ping_pong(c, d, o->ping_pong_iterations))) return rc;
+      if ((rc = readCounters(c))) return rc;
+      evals += c->lastEvals;
+      hits += c->lastHits;
+    }
+  }
+  if (!(c->lp.level > o->mismatches_start_level || coarsest)) {  // Derp.cpp:726-728
+    if ((rc = derp_mismatches(c))) return rc;
+  }
+  for (int d = 0; d < c->Sd; ++d) {
+    if (o->do_bilateral_filter && (rc = derp_bilateral(c, d))) return rc;
+    if (o->do_median_filter && (rc = derp_median(c, d))) return rc;
+    if ((rc = derp_mask_fov(c, d))) return rc;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->lastEvals = evals;
+  c->lastHits = hits;
+  c->countersOnDevice = false;
+  return DERP_OK;
+}
+
+// ---- state access ------------------------------------------------------------------------------------
+int derp_set_disparity(DerpCtx* c, int dst, const float* disparity, const float* cost, const float* confidence) {
+  int rc = checkDst(c, dst, "derp_set_disparity", false);
+  if (rc) return rc;
+  const size_t n = c->plane, b = n * sizeof(float);
+  if (disparity) CU(cudaMemcpyAsync(c->dDisp.p + (size_t)dst * n, disparity, b, cudaMemcpyHostToDevice, c->stream));
+  if (cost) CU(cudaMemcpyAsync(c->dCost.p + (size_t)dst * n, cost, b, cudaMemcpyHostToDevice, c->stream));
+  if (confidence) CU(cudaMemcpyAsync(c->dConf.p + (size_t)dst * n, confidence, b, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_get_disparity(DerpCtx* c, int dst, float* disparity, float* cost, float* confidence) {
+  int rc = checkDst(c, dst, "derp_get_disparity", false);
+  if (rc) return rc;
+  const size_t n = c->plane, b = n * sizeof(float);
+  if (disparity) CU(cudaMemcpyAsync(disparity, c->dDisp.p + (size_t)dst * n, b, cudaMemcpyDeviceToHost, c->stream));
+  if (cost) CU(cudaMemcpyAsync(cost, c->dCost.p + (size_t)dst * n, b, cudaMemcpyDeviceToHost, c->stream));
+  if (confidence) CU(cudaMemcpyAsync(confidence, c->dConf.p + (size_t)dst * n, b, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_get_fov_mask(DerpCtx* c, int dst, uint8_t* mask) {
+  if (!mask) return fail(DERP_EINVAL, "bad arguments");
+  int rc = checkDst(c, dst, "derp_get_fov_mask", false);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(mask, c->dFov.p + (size_t)dst * c->plane, c->plane, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_get_mismatch_mask(DerpCtx* c, int dst, uint8_t* mask) {
+  if (!mask) return fail(DERP_EINVAL, "bad arguments");
+  int rc = checkDst(c, dst, "derp_get_mismatch_mask", false);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(mask, c->dMismatch.p + (size_t)dst * c->plane, c->plane, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_get_variance(DerpCtx* c, int src, float* variance) {
+  if (!c || !variance) return fail(DERP_EINVAL, "bad arguments");
+  if (!c->levelOpen || !c->haveColors) return fail(DERP_ESTATE, "derp_get_variance: colours not set");
+  if (src < 0 || src >= c->S) return fail(DERP_EINVAL, "src out of range");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(variance, c->dVariance.p + (size_t)src * c->plane, c->plane * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_get_var_noise_floor(DerpCtx* c, float* out) {
+  if (!c || !out || !c->levelOpen) return fail(DERP_EINVAL, "bad arguments");
+  *out = c->varNoiseFloor;
+  return DERP_OK;
+}
+
+static int checkProj(DerpCtx* c, int src, const char* who) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  if (!c->levelOpen || c->projDst < 0) return fail(DERP_ESTATE, std::string(who) + ": no projection tables");
+  if (src < 0 || src >= c->S) return fail(DERP_EINVAL, std::string(who) + ": src out of range");
+  return useDevice(c);
+}
+
+int derp_get_proj_warp(DerpCtx* c, int src, float* warp_xy) {
+  if (!warp_xy) return fail(DERP_EINVAL, "bad arguments");
+  int rc = checkProj(c, src, "derp_get_proj_warp");
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(warp_xy, c->dProjWarp.p + (size_t)src * c->plane, c->plane * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+static int getTexels(DerpCtx* c, const uint2* plane, uint16_t* bgr) {
+  const size_t n = c->plane;
+  uint16_t* st = reinterpret_cast<uint16_t*>(c->dStage.p);
+  unpackColorKernel<<<grid1(n), 256, 0, c->stream>>>(n, plane, st);
+  LAUNCHED("unpackColorKernel");
+  CU(cudaMemcpyAsync(bgr, st, n * 6, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_get_proj_color(DerpCtx* c, int src, uint16_t* bgr) {
+  if (!bgr) return fail(DERP_EINVAL, "bad arguments");
+  int rc = checkProj(c, src, "derp_get_proj_color");
+  if (rc) return rc;
+  return getTexels(c, c->dProjColor.p + (size_t)src * c->plane, bgr);
+}
+
+int derp_get_proj_bias(DerpCtx* c, int src, uint16_t* bgr) {
+  if (!bgr) return fail(DERP_EINVAL, "bad arguments");
+  int rc = checkProj(c, src, "derp_get_proj_bias");
+  if (rc) return rc;
+  return getTexels(c, c->dProjBias.p + (size_t)src * c->plane, bgr);
+}
+
+int derp_get_counters(DerpCtx* c, uint64_t* cost_evals, uint64_t* src_hits) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  if (c->countersOnDevice) {  // stage-level calls leave their counters on the device
+    if ((rc = readCounters(c))) return rc;
+    c->countersOnDevice = false;
+  }
+  if (cost_evals) *cost_evals = c->lastEvals;
+  if (src_hits) *src_hits = c->lastHits;
+  return DERP_OK;
+}
+
+// temporalJointBilateralFilter (TemporalBilateralFilter.h:126-215) for one camera
+int derp_temporal_filter(int device, int width, int height, int num_frames, const uint16_t* const* guides,
+                         const float* const* disps, const uint8_t* const* masks, int frame_offset, float sigma,
+                         int spatial_radius, float weight0, float weight1, float weight2, float* out) {
+  if (!guides || !disps || !masks || !out || num_frames < 1 || frame_offset < 0 || frame_offset >= num_frames || width < 1 ||
+      height < 1 || spatial_radius < 0)
+    return fail(DERP_EINVAL, "derp_temporal_filter: bad arguments");
+  CU(cudaSetDevice(device));
+  const size_t n = (size_t)width * height;
+  DevBuf<uint2> dG;
+  DevBuf<float> dD, dOut;
+  DevBuf<uint8_t> dM, dStage;
+  CU(dG.ensure(n * num_frames));
+  CU(dD.ensure(n * num_frames));
+  CU(dM.ensure(n * num_frames));
+  CU(dOut.ensure(n));
+  CU(dStage.ensure(n * 6));
+  for (int t = 0; t < num_frames; ++t) {
+    CU(cudaMemcpy(dStage.p, guides[t], n * 6, cudaMemcpyHostToDevice));
+    packColorKernel<<<grid1(n), 256>>>(n, reinterpret_cast<const uint16_t*>(dStage.p), dG.p + (size_t)t * n);
+    CU(cudaMemcpy(dD.p + (size_t)t * n, disps[t], n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dM.p + (size_t)t * n, masks[t], n, cudaMemcpyHostToDevice));
+  }
+  TemporalArgs a;
+  a.W = width;
+  a.H = height;
+  a.T = num_frames;
+  a.frameOffset = frame_offset;
+  a.radius = spatial_radius;
+  a.guides = dG.p;
+  a.disps = dD.p;
+  a.masks = dM.p;
+  a.sigma = sigma;
+  a.w0 = weight0;
+  a.w1 = weight1;
+  a.w2 = weight2;
+  a.out = dOut.p;
+  temporalKernel<<<grid2(width, height), block2()>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dOut.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return DERP_OK;
+}
+
+int derp_joint_bilateral_f32(int device, int width, int height, const float* image, const float* guide_bgr,
+                             const uint8_t* mask, int radius, float sigma, float weight0, float weight1, float weight2,
+                             float* out) {
+  if (!image || !guide_bgr || !mask || !out || radius < 0 || width < 1 || height < 1)
+    return fail(DERP_EINVAL, "derp_joint_bilateral_f32: bad arguments");
+  CU(cudaSetDevice(device));
+  const size_t n = (size_t)width * height;
+  DevBuf<float> dI, dG, dO;
+  DevBuf<uint8_t> dM;
+  CU(dI.ensure(n));
+  CU(dG.ensure(n * 3));
+  CU(dO.ensure(n));
+  CU(dM.ensure(n));
+  CU(cudaMemcpy(dI.p, image, n * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dG.p, guide_bgr, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dM.p, mask, n, cudaMemcpyHostToDevice));
+  bilateralF32Kernel<<<grid2(width, height), block2()>>>(width, height, dI.p, dG.p, dM.p, radius, sigma, weight0, weight1,
+                                                        weight2, dO.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(out, dO.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return DERP_OK;
+}
+
+}  // extern "C"
+
+// ---- host-side test hooks ---------------------------------------------------------------------------
+// The selection, RNG and camera code is __host__ __device__; these entry points run the HOST
+// instantiation so that CPU-only tests (-m "not gpu") can check it against libstdc++ / the oracle.
+extern "C" {
+
+float derp_test_robust_sum(const float* first, const float* second, int n, int keep) {
+  float a[64], b[64];
+  if (n > 64 || n < 0) return NAN;
+  for (int i = 0; i < n; ++i) {
+    a[i] = first[i];
+    b[i] = second[i];
+  }
+  return derp::robustSum(a, b, n, keep);
+}
+
+void derp_test_minstd_uniform(uint32_t seed, uint64_t skip, int n, float lo, float hi, float* out) {
+  derp::MinstdRand0 r;
+  r.seed(seed);
+  r.discard(skip);
+  for (int i = 0; i < n; ++i) out[i] = r.uniform(lo, hi);
+}
+
+// sees() of the (optionally normalised) camera for n rig-space points; pix = pixel coordinates
+int derp_test_camera_sees(const DerpCameraDesc* d, int normalized, const double* pts, int n, double* pix, uint8_t* seen) {
+  derp::DevCamera c;
+  if (!derp::host::makeCamera(*d, &c)) return fail(DERP_EINVAL, "invalid camera");
+  if (normalized) derp::host::normalise(c);
+  for (int i = 0; i < n; ++i) {
+    double x = NAN, y = NAN;
+    seen[i] = derp::sees(c, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], &x, &y) ? 1 : 0;
+    pix[2 * i] = x;
+    pix[2 * i + 1] = y;
+  }
+  return DERP_OK;
+}
+
+// rig(pixel, depth) and isOutsideImageCircle(pixel)
+int derp_test_camera_rig(const DerpCameraDesc* d, const double* pix, int n, double depth, double* pts, uint8_t* outside) {
+  derp::DevCamera c;
+  if (!derp::host::makeCamera(*d, &c)) return fail(DERP_EINVAL, "invalid camera");
+  for (int i = 0; i < n; ++i) {
+    double dir[3];
+    derp::pixelRay(c, pix[2 * i], pix[2 * i + 1], dir);
+    for (int k = 0; k < 3; ++k) pts[3 * i + k] = c.pos[k] + dir[k] * depth;
+    outside[i] = derp::outsideImageCircle(c, pix[2 * i], pix[2 * i + 1]) ? 1 : 0;
+  }
+  return DERP_OK;
+}
+
+int derp_test_camera_info(const DerpCameraDesc* d, double* rotation9, double* distortion_max, double* cos_fov) {
+  derp::DevCamera c;
+  if (!derp::host::makeCamera(*d, &c)) return fail(DERP_EINVAL, "invalid camera");
+  for (int i = 0; i < 9; ++i) rotation9[i] = c.rot[i];
+  *distortion_max = c.distMax;
+  *cos_fov = c.cosFov;
+  return DERP_OK;
+}
+
+}  // extern "C"

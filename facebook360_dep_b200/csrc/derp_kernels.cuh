@@ -1,0 +1,872 @@
+// sm_100a kernels of the depth path.  One thread per destination pixel unless stated; a warp
+// covers 32 consecutive x so that the gathers of neighbouring lanes land in neighbouring texels.
+// Camera structs are staged into shared memory once per CTA.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+
+#include "derp_cost.cuh"
+#include "derp_rng.cuh"
+
+namespace derp {
+
+constexpr int kBlockX = 32, kBlockY = 8;  // 256 threads
+
+__device__ __forceinline__ void stageCameras(DevCamera* sm, const DevCamera* __restrict__ g, int n) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nt = blockDim.x * blockDim.y;
+  const int words = n * (int)(sizeof(DevCamera) / sizeof(double));
+  const double* src = reinterpret_cast<const double*>(g);
+  double* dst = reinterpret_cast<double*>(sm);
+  for (int i = tid; i < words; i += nt) dst[i] = src[i];
+  __syncthreads();
+}
+
+// Adds (evals, hits) of the currently converged lanes to the global work counters with one
+// atomic pair per warp.
+__device__ __forceinline__ void addCounters(unsigned long long* counters, unsigned evals, unsigned hits) {
+  const unsigned m = __activemask();
+  const unsigned e = __reduce_add_sync(m, evals);
+  const unsigned h = __reduce_add_sync(m, hits);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) {
+    atomicAdd(counters, (unsigned long long)e);
+    atomicAdd(counters + 1, (unsigned long long)h);
+  }
+}
+
+// ---- K1: generateFovMasks (DerpUtil.cpp:239-276) ------------------------------------------------
+__global__ void fovMaskKernel(const DevCamera* __restrict__ cam, int W, int H, uint8_t* __restrict__ mask) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  // normalised camera: p = (x + .5, y + .5) / size (DerpUtil.cpp:245-251)
+  const double px = (x + 0.5) / W, py = (y + 0.5) / H;
+  mask[(size_t)y * W + x] = !outsideImageCircle(*cam, px, py);
+}
+
+// ---- K2: computeWarpDstToSrc (ImageUtil.cpp:142-167) for all sources of one destination ---------
+// projWarp(dst, s) = computeWarpDstToSrc(camSrc, camDst): iterates SOURCE pixels, stores where the
+// destination sees them at infinity (Derp.cpp:970).  camsPx = cameras rescaled to the level size.
+__global__ void projWarpKernel(const DevCamera* __restrict__ camsPx, int S, int self, int W, int H,
+                               float2* __restrict__ projWarp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const float nan = __int_as_float(0x7fc00000);
+  float2 out = make_float2(nan, nan);
+  if (s != self) {
+    const DevCamera& from = camsPx[s];
+    const DevCamera& to = camsPx[self];
+    const double px = x + 0.5, py = y + 0.5;
+    if (!outsideImageCircle(from, px, py)) {
+      double dir[3];
+      pixelRay(from, px, py, dir);
+      const double wx = from.pos[0] + dir[0] * 1e4, wy = from.pos[1] + dir[1] * 1e4, wz = from.pos[2] + dir[2] * 1e4;
+      double qx, qy;
+      if (sees(to, wx, wy, wz, &qx, &qy)) out = make_float2((float)(qx - 0.5f), (float)(qy - 0.5f));
+    }
+  }
+  projWarp[(size_t)s * W * H + (size_t)y * W + x] = out;
+}
+
+// ---- K3: reprojectColors -> project (Derp.cpp:978-1003, DerpUtil.cpp:199-205) --------------------
+// Fuses projWarpInv(dst, s) = computeWarpDstToSrc(camDst, camSrc) with cv::remap(INTER_CUBIC,
+// BORDER_CONSTANT 0): the map entry lives in registers and is never written to HBM.
+// wtab = OpenCV's 32x32x16 float bicubic table (built on the host exactly as imgwarp.cpp does).
+__device__ __forceinline__ int cvRoundQ5(float v) {
+  // cvRound(v * 32) with x86 semantics: NaN / out-of-range -> INT_MIN
+  const float s = v * 32.0f;
+  if (!(s == s) || s >= 2147483648.0f || s < -2147483648.0f) return INT_MIN;
+  return __float2int_rn(s);
+}
+
+__device__ __forceinline__ uint32_t roundSatU16(float v) {
+  int r = __float2int_rn(v);  // cvRound, then saturate_cast<ushort>
+  r = r < 0 ? 0 : (r > 65535 ? 65535 : r);
+  return (uint32_t)r;
+}
+
+__global__ void reprojectKernel(const DevCamera* __restrict__ camsPx, int S, int self, int W, int H,
+                                const uint2* __restrict__ color, const float* __restrict__ wtab,
+                                uint2* __restrict__ projColor) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const size_t plane = (size_t)W * H;
+  const size_t p = (size_t)y * W + x;
+  if (s == self) {
+    projColor[s * plane + p] = color[s * plane + p];  // Derp.cpp:989-991
+    return;
+  }
+  const float nan = __int_as_float(0x7fc00000);
+  float mx = nan, my = nan;
+  {
+    const DevCamera& from = camsPx[self];
+    const DevCamera& to = camsPx[s];
+    const double px = x + 0.5, py = y + 0.5;
+    if (!outsideImageCircle(from, px, py)) {
+      double dir[3];
+      pixelRay(from, px, py, dir);
+      const double wx = from.pos[0] + dir[0] * 1e4, wy = from.pos[1] + dir[1] * 1e4, wz = from.pos[2] + dir[2] * 1e4;
+      double qx, qy;
+      if (sees(to, wx, wy, wz, &qx, &qy)) {
+        mx = (float)(qx - 0.5f);
+        my = (float)(qy - 0.5f);
+      }
+    }
+  }
+  const int sxq = cvRoundQ5(mx), syq = cvRoundQ5(my);
+  const int fidx = (syq & 31) * 32 + (sxq & 31);
+  int ix = sxq >> 5, iy = syq >> 5;
+  ix = ix < -32768 ? -32768 : (ix > 32767 ? 32767 : ix);  // saturate_cast<short>
+  iy = iy < -32768 ? -32768 : (iy > 32767 ? 32767 : iy);
+  const int sx = ix - 1, sy = iy - 1;
+  const float* w = wtab + fidx * 16;
+  const uint2* S0 = color + s * plane;
+  float sum0, sum1, sum2;
+  if ((unsigned)sx < (unsigned)max(W - 3, 0) && (unsigned)sy < (unsigned)max(H - 3, 0)) {
+    // interior: row-wise 4-term sums, accumulated row by row (imgwarp.cpp remapBicubic)
+    sum0 = sum1 = sum2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint2* row = S0 + (size_t)(sy + i) * W + sx;
+      const Texel a = unpack(__ldg(row)), b = unpack(__ldg(row + 1)), c = unpack(__ldg(row + 2)),
+                  d = unpack(__ldg(row + 3));
+      const float w0 = __ldg(w + i * 4), w1 = __ldg(w + i * 4 + 1), w2 = __ldg(w + i * 4 + 2), w3 = __ldg(w + i * 4 + 3);
+      const float r0 = a.b * w0 + b.b * w1 + c.b * w2 + d.b * w3;
+      const float r1 = a.g * w0 + b.g * w1 + c.g * w2 + d.g * w3;
+      const float r2 = a.r * w0 + b.r * w1 + c.r * w2 + d.r * w3;
+      if (i == 0) {
+        sum0 = r0;
+        sum1 = r1;
+        sum2 = r2;
+      } else {
+        sum0 += r0;
+        sum1 += r1;
+        sum2 += r2;
+      }
+    }
+  } else {
+    if (sx >= W || sx + 4 <= 0 || sy >= H || sy + 4 <= 0) {
+      projColor[s * plane + p] = make_uint2(0u, 0u);
+      return;
+    }
+    // border: taps outside contribute the constant 0; one sequential sum (imgwarp.cpp)
+    sum0 = sum1 = sum2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int yi = sy + i;
+      if ((unsigned)yi >= (unsigned)H) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xj = sx + j;
+        if ((unsigned)xj >= (unsigned)W) continue;
+        const Texel t = unpack(__ldg(S0 + (size_t)yi * W + xj));
+        const float ww = __ldg(w + i * 4 + j);
+        sum0 += (t.b - 0.f) * ww;
+        sum1 += (t.g - 0.f) * ww;
+        sum2 += (t.r - 0.f) * ww;
+      }
+    }
+  }
+  const uint32_t B = roundSatU16(sum0), G = roundSatU16(sum1), R = roundSatU16(sum2);
+  projColor[s * plane + p] = make_uint2(B | (G << 16), R);
+}
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+  return p;
+}
+
+// ---- K4: colorBias = cv::blur 3x3 on u16x3 (DerpUtil.cpp:208-210) for all S planes -----------------
+__global__ void biasKernel(int W, int H, const uint2* __restrict__ in, uint2* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const uint2* img = in + (size_t)s * W * H;
+  int sb = 0, sg = 0, sr = 0;
+#pragma unroll
+  for (int j = -1; j <= 1; ++j) {
+    const int yy = reflect101(y + j, H);
+#pragma unroll
+    for (int i = -1; i <= 1; ++i) {
+      const int xx = reflect101(x + i, W);
+      const uint2 t = __ldg(img + (size_t)yy * W + xx);
+      sb += (int)(t.x & 0xffffu);
+      sg += (int)(t.x >> 16);
+      sr += (int)(t.y & 0xffffu);
+    }
+  }
+  // saturate_cast<ushort>(sum * (1.0/9)) == (sum + 4) / 9 for integer sums (no exact .5 cases)
+  const uint32_t B = (uint32_t)((sb + 4) / 9), G = (uint32_t)((sg + 4) / 9), R = (uint32_t)((sr + 4) / 9);
+  out[(size_t)s * W * H + (size_t)y * W + x] = make_uint2(B | (G << 16), R);
+}
+
+// ---- K5: computeImageVariance (DerpUtil.cpp:214-237) for all S planes ---------------------------
+__global__ void varianceKernel(int W, int H, const uint2* __restrict__ in, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const uint2* img = in + (size_t)s * W * H;
+  const float alpha = 1.0f / 65535.0f;
+  double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = -1; j <= 1; ++j) {
+    const int yy = reflect101(y + j, H);
+    double r1[3] = {0, 0, 0}, r2[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = -1; i <= 1; ++i) {
+      const int xx = reflect101(x + i, W);
+      const Texel t = unpack(__ldg(img + (size_t)yy * W + xx));
+      const float f0 = t.b * alpha, f1 = t.g * alpha, f2 = t.r * alpha;
+      r1[0] += (double)f0;
+      r1[1] += (double)f1;
+      r1[2] += (double)f2;
+      r2[0] += (double)(f0 * f0);
+      r2[1] += (double)(f1 * f1);
+      r2[2] += (double)(f2 * f2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      s1[c] += r1[c];
+      s2[c] += r2[c];
+    }
+  }
+  const double scale = 1.0 / 9;
+  float vc[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float mean = (float)(s1[c] * scale);
+    const float msq = (float)(s2[c] * scale);
+    vc[c] = msq - mean * mean;
+  }
+  out[(size_t)s * W * H + (size_t)y * W + x] = vc[0] * 0.3333f + vc[1] * 0.3334f + vc[2] * 0.3333f;
+}
+
+// ---- layout conversion ----------------------------------------------------------------------------
+__global__ void packColorKernel(size_t n, const uint16_t* __restrict__ bgr, uint2* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t b = bgr[i * 3], g = bgr[i * 3 + 1], r = bgr[i * 3 + 2];
+  out[i] = make_uint2(b | (g << 16), r);
+}
+__global__ void unpackColorKernel(size_t n, const uint2* __restrict__ in, uint16_t* __restrict__ bgr) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint2 t = in[i];
+  bgr[i * 3] = (uint16_t)(t.x & 0xffffu);
+  bgr[i * 3 + 1] = (uint16_t)(t.x >> 16);
+  bgr[i * 3 + 2] = (uint16_t)(t.y & 0xffffu);
+}
+template <typename T>
+__global__ void fillKernel(size_t n, T* p, T v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---- K6: fused sphere sweep + cost + winner-takes-all (Derp.cpp:230-356) ------------------------
+// grid.z = candidate chunk.  Every thread sweeps its chunk in index order with a strict-< running
+// minimum, then merges across chunks with a 64-bit atomicMin on (cost bits << 32 | index): for
+// non-negative floats the bit pattern is monotone, so the merge keeps the lowest cost and, among
+// equal costs, the lowest index — exactly the reference's first-strict-minimum scan.
+struct SweepArgs {
+  CostView v;
+  const uint8_t* fov;
+  const uint8_t* fg;       // nullable (all-pass)
+  const float* bg;         // nullable unless foreground masks are used
+  const float* disparities;  // [D] candidate table (probeDisparity)
+  int D, chunk;
+  unsigned long long* best;   // [H][W] packed
+  unsigned long long* counters;  // [0] cost evaluations, [1] source hits
+};
+
+__global__ void __launch_bounds__(kBlockX* kBlockY) sweepKernel(const SweepArgs a) {
+  extern __shared__ double smemRaw[];
+  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  stageCameras(cams, a.v.cams, a.v.S);
+  const int W = a.v.W, H = a.v.H;
+  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+  unsigned hits = 0, evals = 0;
+  if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+    const size_t p = (size_t)y * W + x;
+    const bool active = a.fov[p] && (!a.fg || a.fg[p]);
+    if (active) {
+      PixelState ps;
+      loadPixelState(a.v, cams[a.v.self], x, y, ps);
+      const float bgd = a.bg ? a.bg[p] : 0.f;
+      const int c0 = blockIdx.z * a.chunk;
+      const int c1 = min(a.D, c0 + a.chunk);
+      float bestCost = FLT_MAX;
+      int bestIdx = -1;
+      for (int c = c0; c < c1; ++c) {
+        const float d = __ldg(a.disparities + c);
+        if (a.bg && !(bgd < d)) continue;  // closerMask (Derp.cpp:240-243)
+        const float cost = evalCost(a.v, cams, ps, d, &hits);
+        ++evals;
+        if (cost < bestCost) {
+          bestCost = cost;
+          bestIdx = c;
+        }
+      }
+      if (bestIdx >= 0) {
+        const unsigned long long packed =
+            ((unsigned long long)__float_as_uint(bestCost) << 32) | (unsigned long long)(unsigned)bestIdx;
+        atomicMin(a.best + p, packed);
+      }
+    }
+  }
+  addCounters(a.counters, evals, hits);
+}
+
+// WTA write-back (Derp.cpp:306-356) for interior pixels
+__global__ void sweepFinalizeKernel(int W, int H, const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg,
+                                    const float* __restrict__ bg, const float* __restrict__ variance,
+                                    const float* __restrict__ disparities, float minDisparity,
+                                    const unsigned long long* __restrict__ best, float* __restrict__ disp,
+                                    float* __restrict__ cost, float* __restrict__ conf, int* __restrict__ idxOut,
+                                    unsigned* __restrict__ uncovered) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
+  const size_t p = (size_t)y * W + x;
+  if (!fov[p]) {
+    disp[p] = __int_as_float(0x7fc00000);
+    if (idxOut) idxOut[p] = -2;
+    return;
+  }
+  if (fg && !fg[p]) {
+    disp[p] = bg[p];
+    if (idxOut) idxOut[p] = -3;
+    return;
+  }
+  const unsigned long long b = best[p];
+  const unsigned idx = (unsigned)(b & 0xffffffffull);
+  if (idx == 0xffffffffu) {
+    atomicAdd(uncovered, 1u);
+    disp[p] = minDisparity;
+    cost[p] = FLT_MAX;
+    conf[p] = 0.f;
+    if (idxOut) idxOut[p] = -1;
+  } else {
+    disp[p] = disparities[idx];
+    cost[p] = __uint_as_float((unsigned)(b >> 32));
+    conf[p] = fmaxf(variance[p], kMinVarF);
+    if (idxOut) idxOut[p] = (int)idx;
+  }
+}
+
+// Extend disparities to the 1-px margin (Derp.cpp:359-381)
+__global__ void extendBorderKernel(int W, int H, const uint8_t* __restrict__ fg, const float* __restrict__ bg,
+                                   float* __restrict__ disp, float* __restrict__ cost, float* __restrict__ conf,
+                                   int* __restrict__ idxOut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 2 * W + 2 * (H - 2);
+  if (i >= per) return;
+  int x, y;
+  if (i < W) {
+    x = i;
+    y = 0;
+  } else if (i < 2 * W) {
+    x = i - W;
+    y = H - 1;
+  } else {
+    const int k = i - 2 * W;
+    y = 1 + (k >> 1);
+    x = (k & 1) ? W - 1 : 0;
+  }
+  const size_t p = (size_t)y * W + x;
+  if (fg && !fg[p]) {
+    disp[p] = bg[p];
+    if (idxOut) idxOut[p] = -3;
+    return;
+  }
+  const size_t qq = (size_t)max(1, min(y, H - 2)) * W + max(1, min(x, W - 2));
+  disp[p] = disp[qq];
+  cost[p] = cost[qq];
+  conf[p] = conf[qq];
+  if (idxOut) idxOut[p] = idxOut[qq];
+}
+
+// ---- derp_eval_cost: one hypothesis per pixel ------------------------------------------------------
+__global__ void __launch_bounds__(kBlockX* kBlockY)
+    evalCostKernel(const CostView v, const float* __restrict__ disparity, float* __restrict__ outCost,
+                   float* __restrict__ outConf, unsigned long long* counters) {
+  extern __shared__ double smemRaw[];
+  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  stageCameras(cams, v.cams, v.S);
+  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+  if (x >= v.W || y >= v.H) return;
+  const size_t p = (size_t)y * v.W + x;
+  float co = __int_as_float(0x7fc00000), cf = co;
+  if (x >= 1 && x < v.W - 1 && y >= 1 && y < v.H - 1) {
+    PixelState ps;
+    loadPixelState(v, cams[v.self], x, y, ps);
+    unsigned hits = 0;
+    co = evalCost(v, cams, ps, disparity[p], &hits);
+    cf = (co == FLT_MAX) ? 0.f : ps.conf;
+    addCounters(counters, 1u, hits);
+  }
+  if (outCost) outCost[p] = co;
+  if (outConf) outConf[p] = cf;
+}
+
+// ---- K7: randomProposal (Derp.cpp:750-824) -----------------------------------------------------------
+// The reference walks each row sequentially with one minstd_rand0 per row (seed y*level) and draws
+// exactly numProposals values for every processed pixel.  Whether a pixel is processed depends only
+// on masks and variance, so the draw index of pixel x is numProposals * (#processed pixels left of
+// x): an exclusive row scan + LCG skip-ahead makes the row parallel and bit-identical.
+__global__ void proposalScanKernel(int W, int H, const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg,
+                                   const float* __restrict__ variance, float varThresh, int* __restrict__ prefix) {
+  // one warp per row
+  const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (y >= H) return;
+  int running = 0;
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    const int x = x0 + lane;
+    bool proc = false;
+    if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+      const size_t p = (size_t)y * W + x;
+      proc = fov[p] && (!fg || fg[p]) && !(variance[p] < varThresh);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, proc);
+    if (x < W) prefix[(size_t)y * W + x] = proc ? running + __popc(m & ((1u << lane) - 1u)) : -1;
+    running += __popc(m);
+  }
+}
+
+struct ProposalArgs {
+  CostView v;
+  const uint8_t* fov;
+  const uint8_t* fg;
+  const float* bg;
+  const int* prefix;
+  float* disp;
+  float* cost;
+  float* conf;
+  int numProposals, level;
+  float minDispGlobal, maxDisp;
+  unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(kBlockX* kBlockY) proposalKernel(const ProposalArgs a) {
+  extern __shared__ double smemRaw[];
+  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  stageCameras(cams, a.v.cams, a.v.S);
+  const int W = a.v.W, H = a.v.H;
+  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+  if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
+  const size_t p = (size_t)y * W + x;
+  if (!a.fov[p]) return;
+  if (a.fg && !a.fg[p]) {
+    a.disp[p] = a.bg[p];
+    return;
+  }
+  const int rank = a.prefix[p];
+  if (rank < 0) return;  // low variance: skipped (Derp.cpp:785-789)
+  PixelState ps;
+  loadPixelState(a.v, cams[a.v.self], x, y, ps);
+  unsigned hits = 0;
+  float currDisp = a.disp[p];
+  float currCost = evalCost(a.v, cams, ps, currDisp, &hits);
+  float currConf = (currCost == FLT_MAX) ? 0.f : ps.conf;
+  const float costThresh = fminf(0.5f * currCost, 5.0f);
+  const float minDisp = a.bg ? a.bg[p] : a.minDispGlobal;
+  const float maxDisp = a.maxDisp;
+  float amplitude = (maxDisp - minDisp) / 2.0f;
+  MinstdRand0 rng;
+  rng.seed((unsigned)(y * a.level));
+  rng.discard((unsigned long long)rank * (unsigned long long)a.numProposals);
+  for (int i = 0; i < a.numProposals; ++i) {
+    const float lo = fmaxf(minDisp, currDisp - amplitude);
+    const float hi = fminf(maxDisp, currDisp + amplitude);
+    const float propDisp = rng.uniform(lo, hi);
+    const float propCost = evalCost(a.v, cams, ps, propDisp, &hits);
+    if (propCost < currCost && propCost < costThresh) {
+      currCost = propCost;
+      currDisp = propDisp;
+      currConf = (propCost == FLT_MAX) ? 0.f : ps.conf;
+      amplitude /= 2.0f;
+    }
+  }
+  a.disp[p] = currDisp;
+  a.cost[p] = currCost;
+  a.conf[p] = currConf;
+  addCounters(a.counters, (unsigned)(1 + a.numProposals), hits);
+}
+
+// ---- K8: pingPongRectangle (Derp.cpp:403-478), one Jacobi iteration ------------------------------------
+struct PingPongArgs {
+  CostView v;
+  const uint8_t* fov;
+  const uint8_t* fg;
+  const float* bg;
+  const float* disp;        // read
+  const uint8_t* changed;   // read
+  float* dispRes;           // write (all pixels)
+  float* costRes;           // write (all pixels; INF where skipped)
+  uint8_t* changedNext;     // write: disp != dispRes
+  float varNoiseFloor;
+  unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(kBlockX* kBlockY) pingPongKernel(const PingPongArgs a) {
+  extern __shared__ double smemRaw[];
+  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  stageCameras(cams, a.v.cams, a.v.S);
+  const int W = a.v.W, H = a.v.H;
+  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t p = (size_t)y * W + x;
+  const float old = a.disp[p];
+  float res = old;
+  float resCost = __int_as_float(0x7f800000);  // +INF
+  const bool interior = x >= 1 && x < W - 1 && y >= 1 && y < H - 1;
+  if (interior && a.fov[p]) {
+    if (a.fg && !a.fg[p]) {
+      res = a.bg[p];
+    } else if (!(a.v.variance[p] < a.varNoiseFloor)) {
+      PixelState ps;
+      loadPixelState(a.v, cams[a.v.self], x, y, ps);
+      unsigned hits = 0, evals = 0;
+      float bestCost = __int_as_float(0x7f800000);
+      float bestDisp = old;
+      const float backgroundDisparity = a.bg ? a.bg[p] : 0.f;
+      const int offX[9] = {0, -1, 1, 0, 0, -2, 2, -2, 2};   // candidateTemplateOriginal, DerpUtil.h:34-43
+      const int offY[9] = {0, 0, 0, -1, 1, -2, -2, 2, 2};
+#pragma unroll 1
+      for (int k = 0; k < 9; ++k) {
+        const int xx = clampIdx(x + offX[k], W - 1), yy = clampIdx(y + offY[k], H - 1);
+        const size_t q = (size_t)yy * W + xx;
+        if (!a.fov[q]) continue;
+        const float d = a.disp[q];
+        if (d >= backgroundDisparity && a.changed[q]) {
+          const float cost = evalCost(a.v, cams, ps, d, &hits);
+          ++evals;
+          if (cost < bestCost) {
+            bestCost = cost;
+            bestDisp = d;
+          }
+        }
+      }
+      res = bestDisp;
+      resCost = bestCost;
+      addCounters(a.counters, evals, hits);
+    }
+  }
+  a.dispRes[p] = res;
+  a.costRes[p] = resCost;
+  a.changedNext[p] = (old != res) ? 1 : 0;
+}
+
+// ---- K9: handleDisparityMismatch (Derp.cpp:553-720) for one destination ----------------------------------
+struct MismatchArgs {
+  int W, H, S, self;
+  const DevCamera* cams;
+  const float* dispAll;      // [S][H][W] all cameras' disparity (dst list == camera list)
+  const float* variance;     // destination's
+  const uint8_t* fov;
+  const uint8_t* fg;
+  float varNoiseFloor, varHighThresh;
+  float* dispNew;            // [H][W]
+  uint8_t* mask;             // [H][W]
+};
+
+__global__ void __launch_bounds__(kBlockX* kBlockY) mismatchKernel(const MismatchArgs a) {
+  extern __shared__ double smemRaw[];
+  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  stageCameras(cams, a.cams, a.S);
+  const int W = a.W, H = a.H;
+  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t p = (size_t)y * W + x;
+  const size_t plane = (size_t)W * H;
+  const float nan = __int_as_float(0x7fc00000);
+  if (!a.fov[p]) {
+    a.dispNew[p] = nan;
+    return;
+  }
+  const float dispCurr = a.dispAll[a.self * plane + p];
+  int nMatch = 0, nMis = 0;
+  float mis[kMaxCams];
+  if (!a.fg || a.fg[p]) {
+    const DevCamera& cd = cams[a.self];
+    double dir[3];
+    pixelRay(cd, (x + 0.5) / W, (y + 0.5) / H, dir);
+    const double depth = (double)(1.0f / dispCurr);
+    const double wx = cd.pos[0] + dir[0] * depth, wy = cd.pos[1] + dir[1] * depth, wz = cd.pos[2] + dir[2] * depth;
+    for (int s = 0; s < a.S; ++s) {
+      if (s == a.self) continue;
+      double px, py;
+      if (!sees(cams[s], wx, wy, wz, &px, &py)) continue;
+      px *= W;
+      py *= H;
+      const float dSrc = sampleF32(a.dispAll + s * plane, W, H, (float)px, (float)py);
+      const float dMin = (1.0f - 0.1f) * dispCurr, dMax = (1.0f + 0.1f) * dispCurr;
+      if (dMin <= dSrc && dSrc <= dMax) ++nMatch;
+      else mis[nMis++] = dSrc;
+    }
+  }
+  if (nMatch + nMis == 0) {
+    a.mask[p] = 0;
+    a.dispNew[p] = dispCurr;
+    return;
+  }
+  const float var = a.variance[p];
+  if (nMatch >= 1 || a.varHighThresh < var || var < a.varNoiseFloor) {
+    a.mask[p] = 0;
+    a.dispNew[p] = dispCurr;
+  } else {
+    a.mask[p] = 1;
+    for (int i = 1; i < nMis; ++i) {  // ascending sort
+      const float vv = mis[i];
+      int j = i - 1;
+      while (j >= 0 && vv < mis[j]) {
+        mis[j + 1] = mis[j];
+        --j;
+      }
+      mis[j + 1] = vv;
+    }
+    int closer = 0;
+    for (; closer < nMis; ++closer)
+      if (mis[closer] >= dispCurr) break;
+    const float m = mis[closer / 2];
+    a.dispNew[p] = (m < dispCurr) ? m : dispCurr;  // std::min(dispCurr, m)
+  }
+}
+
+// ---- K10: generalizedJointBilateralFilter<float, Vec3w> (TemporalBilateralFilter.h:39-124) ----------
+// mask = fov & fg; output copied only onto foreground pixels (Derp.cpp:900).
+__global__ void bilateralKernel(int W, int H, const float* __restrict__ image, const uint2* __restrict__ guide,
+                                const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg, int radius,
+                                float sigma, float w0, float w1, float w2, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t p = (size_t)y * W + x;
+  const float self = image[p];
+  const bool fgp = !fg || fg[p];
+  if (!(fov[p] && fgp)) {
+    out[p] = self;  // dest = image where unmasked; non-fg pixels keep their value anyway
+    return;
+  }
+  const float f = 1 / 65535.0f;
+  const Texel gc = unpack(__ldg(guide + p));
+  const float g0 = gc.b * f, g1 = gc.g * f, g2 = gc.r * f;
+  const float denom = 2.0f * (sigma * sigma);
+  float sumWeight = 0.0f, weightedAvg = 0.0f;
+  for (int v = -radius; v <= radius; ++v) {
+    const int sy = clampIdx(y + v, H - 1);
+    for (int u = -radius; u <= radius; ++u) {
+      const int sx = clampIdx(x + u, W - 1);
+      const size_t q = (size_t)sy * W + sx;
+      if (!(fov[q] && (!fg || fg[q]))) continue;
+      const Texel n = unpack(__ldg(guide + q));
+      const float d0 = g0 - n.b * f, d1 = g1 - n.g * f, d2 = g2 - n.r * f;
+      const float colorDiffSq = w0 * (d0 * d0) + w1 * (d1 * d1) + w2 * (d2 * d2);
+      const float weight = expf((-colorDiffSq / 3.0f) / denom);
+      sumWeight += weight;
+      weightedAvg += weight * __ldg(image + q);
+    }
+  }
+  out[p] = (sumWeight != 0.0f) ? weightedAvg / sumWeight : self;
+}
+
+// float-guide variant used by UpsampleDisparity (guide already in [0,1], factor 1/1.0f)
+__global__ void bilateralF32Kernel(int W, int H, const float* __restrict__ image, const float* __restrict__ guide,
+                                   const uint8_t* __restrict__ mask, int radius, float sigma, float w0, float w1,
+                                   float w2, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t p = (size_t)y * W + x;
+  const float self = image[p];
+  if (!mask[p]) {
+    out[p] = self;
+    return;
+  }
+  const float f = 1 / 1.0f;
+  const float g0 = guide[p * 3] * f, g1 = guide[p * 3 + 1] * f, g2 = guide[p * 3 + 2] * f;
+  const float denom = 2.0f * (sigma * sigma);
+  float sumWeight = 0.0f, weightedAvg = 0.0f;
+  for (int v = -radius; v <= radius; ++v) {
+    const int sy = clampIdx(y + v, H - 1);
+    for (int u = -radius; u <= radius; ++u) {
+      const int sx = clampIdx(x + u, W - 1);
+      const size_t q = (size_t)sy * W + sx;
+      if (!mask[q]) continue;
+      const float d0 = g0 - guide[q * 3] * f, d1 = g1 - guide[q * 3 + 1] * f, d2 = g2 - guide[q * 3 + 2] * f;
+      const float colorDiffSq = w0 * (d0 * d0) + w1 * (d1 * d1) + w2 * (d2 * d2);
+      const float weight = expf((-colorDiffSq / 3.0f) / denom);
+      sumWeight += weight;
+      weightedAvg += weight * image[q];
+    }
+  }
+  out[p] = (sumWeight != 0.0f) ? weightedAvg / sumWeight : self;
+}
+
+// ---- K11: maskedMedianBlur radius 1 (CvUtil.h:336-385) ----------------------------------------------
+__global__ void medianKernel(int W, int H, const float* __restrict__ mat, const float* __restrict__ background,
+                             const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg,
+                             float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t p = (size_t)y * W + x;
+  if (!(fov[p] && (!fg || fg[p]))) {
+    out[p] = background ? background[p] : 0.0f;
+    return;
+  }
+  float vals[9];
+  int n = 0;
+  for (int yy = y - 1; yy <= y + 1; ++yy)
+    for (int xx = x - 1; xx <= x + 1; ++xx) {
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const size_t q = (size_t)yy * W + xx;
+      if (!(fov[q] && (!fg || fg[q]))) continue;
+      const float v = mat[q];
+      if (isnan(v) || v == 0) continue;
+      // sorted insert
+      int j = n++;
+      while (j > 0 && v < vals[j - 1]) {
+        vals[j] = vals[j - 1];
+        --j;
+      }
+      vals[j] = v;
+    }
+  float r = 0.0f;
+  if (n > 0) {
+    const int m = n / 2;
+    r = (n & 1) ? vals[m] : (float)((double)(vals[m - 1] + vals[m]) / 2.0);
+  }
+  out[p] = r;
+}
+
+// ---- K12: maskFov (Derp.cpp:940-951) -----------------------------------------------------------------
+__global__ void maskFovKernel(size_t n, const uint8_t* __restrict__ fov, float* __restrict__ disp) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !fov[i]) disp[i] = __int_as_float(0x7fc00000);
+}
+
+__global__ void copyWhereKernel(size_t n, const uint8_t* __restrict__ mask, const float* __restrict__ src,
+                                float* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (!mask || mask[i])) dst[i] = src[i];
+}
+
+// ---- K13: upsampling (UpsampleDisparityLib.cpp:98-147) ---------------------------------------------------
+// cv::resize INTER_LANCZOS4: separable, 8 taps, index-clamped; tap tables come from the host.
+__global__ void nanToKernel(size_t n, const float* __restrict__ in, float v, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float f = in[i];
+    out[i] = (f != f) ? v : f;
+  }
+}
+__global__ void lanczosHKernel(int sw, int sh, int dw, const float* __restrict__ src, const int* __restrict__ xofs,
+                               const float* __restrict__ alpha, float* __restrict__ rows) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (dx >= dw || y >= sh) return;
+  const float* S = src + (size_t)y * sw;
+  const float* a = alpha + (size_t)dx * 8;
+  const int sx = xofs[dx];
+  float v;
+  if (sx - 3 >= 0 && sx + 4 < sw) {
+    v = S[sx - 3] * a[0] + S[sx - 2] * a[1] + S[sx - 1] * a[2] + S[sx] * a[3] + S[sx + 1] * a[4] +
+        S[sx + 2] * a[5] + S[sx + 3] * a[6] + S[sx + 4] * a[7];
+  } else {
+    v = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += S[clampIdx(sx + j - 3, sw - 1)] * a[j];
+  }
+  rows[(size_t)y * dw + dx] = v;
+}
+__global__ void lanczosVKernel(int sh, int dw, int dh, const float* __restrict__ rows, const int* __restrict__ yofs,
+                               const float* __restrict__ beta, float* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dw || dy >= dh) return;
+  const float* b = beta + (size_t)dy * 8;
+  const int sy = yofs[dy];
+  float r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = rows[(size_t)clampIdx(sy - 3 + k, sh - 1) * dw + x];
+  dst[(size_t)dy * dw + x] = r[0] * b[0] + r[1] * b[1] + r[2] * b[2] + r[3] * b[3] + r[4] * b[4] + r[5] * b[5] +
+      r[6] * b[6] + r[7] * b[7];
+}
+// masked path: NaN outside coarse mask -> INTER_NEAREST -> NaN outside fine mask
+__global__ void nearestMaskedKernel(int sw, int sh, int dw, int dh, const float* __restrict__ src,
+                                    const uint8_t* __restrict__ maskC, const uint8_t* __restrict__ maskUp,
+                                    const int* __restrict__ xofs, const int* __restrict__ yofs,
+                                    float* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dw || y >= dh) return;
+  const size_t q = (size_t)yofs[y] * sw + xofs[x];
+  float v = maskC[q] ? src[q] : __int_as_float(0x7fc00000);
+  if (!maskUp[(size_t)y * dw + x]) v = __int_as_float(0x7fc00000);
+  dst[(size_t)y * dw + x] = v;
+}
+// replaceNans (UpsampleDisparityLib.cpp:54-91): spiral search, then background fill
+__global__ void replaceNansKernel(int W, int H, const float* __restrict__ dispUp, const float* __restrict__ bg,
+                                  const uint8_t* __restrict__ maskUp, const short2* __restrict__ spiral, int nSpiral,
+                                  float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t p = (size_t)y * W + x;
+  float v = dispUp[p];
+  if (maskUp[p] && !(v > 0)) {
+    for (int i = 0; i < nSpiral; ++i) {
+      const short2 o = spiral[i];
+      const float d = dispUp[(size_t)clampIdx(y + o.y, H - 1) * W + clampIdx(x + o.x, W - 1)];
+      if (d > 0) {
+        v = d;
+        break;
+      }
+    }
+  }
+  if (isnan(v) || v == 0) v = bg[p];
+  out[p] = v;
+}
+
+// ---- K14: temporalJointBilateralFilter (TemporalBilateralFilter.h:126-215) ------------------------------------
+struct TemporalArgs {
+  int W, H, T, frameOffset, radius;
+  const uint2* guides;    // [T][H][W] texels
+  const float* disps;     // [T][H][W]
+  const uint8_t* masks;   // [T][H][W]
+  float sigma, w0, w1, w2;
+  float* out;
+};
+__global__ void temporalKernel(const TemporalArgs a) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= a.W || y >= a.H) return;
+  const size_t plane = (size_t)a.W * a.H;
+  const size_t p = (size_t)y * a.W + x;
+  if (!a.masks[a.frameOffset * plane + p]) {
+    a.out[p] = a.disps[a.frameOffset * plane + p];
+    return;
+  }
+  const uint2 rt = __ldg(a.guides + a.frameOffset * plane + p);
+  const int r0 = (int)(rt.x & 0xffffu), r1 = (int)(rt.x >> 16), r2 = (int)(rt.y & 0xffffu);
+  const float sig2 = a.sigma * a.sigma;
+  float weightedSumPix = 0.0f, sumWeight = 0.0f;
+  for (int t = 0; t < a.T; ++t) {
+    const float dt = a.disps[t * plane + p];  // centre pixel of frame t (TemporalBilateralFilter.h:165)
+    for (int u = -a.radius; u <= a.radius; ++u) {
+      const int sx = clampIdx(x + u, a.W - 1);
+      for (int v = -a.radius; v <= a.radius; ++v) {
+        const int sy = clampIdx(y + v, a.H - 1);
+        const size_t q = (size_t)sy * a.W + sx;
+        if (!a.masks[t * plane + q]) continue;
+        const uint2 st = __ldg(a.guides + t * plane + q);
+        // (ushort - ushort) is exact in int; int -> float conversion rounds to nearest like the CPU
+        const float e0 = (float)(r0 - (int)(st.x & 0xffffu)) / 65535.0f;
+        const float e1 = (float)(r1 - (int)(st.x >> 16)) / 65535.0f;
+        const float e2 = (float)(r2 - (int)(st.y & 0xffffu)) / 65535.0f;
+        const float weightedDiff = a.w0 * (e0 * e0) + a.w1 * (e1 * e1) + a.w2 * (e2 * e2);
+        const float weight = expf(-weightedDiff / sig2);
+        weightedSumPix += dt * weight;
+        sumWeight += weight;
+      }
+    }
+  }
+  a.out[p] = weightedSumPix / sumWeight;
+}
+
+}  // namespace derp

@@ -109,6 +109,19 @@ int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_
                 int device, DerpCtx** out);
 void derp_destroy(DerpCtx* ctx);
 
+/* Stream control (CUDA library; no-ops in the oracle).  derp_set_stream makes the context enqueue
+ * all its work on the caller's cudaStream_t (e.g. the stream a benchmark times with CUDA events);
+ * stage functions that return no host data are then asynchronous.  derp_sync waits for the stream.
+ * derp_get_launch_count reports how many kernels this context has launched so far. */
+int derp_set_stream(DerpCtx* ctx, void* cuda_stream);
+int derp_sync(DerpCtx* ctx);
+int derp_get_launch_count(DerpCtx* ctx, uint64_t* out);
+/* Optional timing of the dominant kernel (the fused sweep of derp_brute_force): while enabled, every
+ * sweep launch is bracketed by CUDA events on the context's stream; derp_get_profile synchronises and
+ * returns the summed device time and the number of launches since derp_profile(ctx, 1). */
+int derp_profile(DerpCtx* ctx, int enable);
+int derp_get_profile(DerpCtx* ctx, double* sweep_ms, uint64_t* sweep_launches);
+
 /* Starts one (frame, level): allocates level buffers, zero-fills disparity/cost/confidence/
  * mismatch mask (PyramidLevel.h:206-230) and builds the dst FOV masks
  * (generateFovMasks, DerpUtil.cpp:259-276).  Invalidates everything from the previous level. */

@@ -343,6 +343,18 @@ int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_
 }
 
 void derp_destroy(DerpCtx* ctx) { delete ctx; }
+int derp_set_stream(DerpCtx*, void*) { return DERP_OK; }
+int derp_sync(DerpCtx*) { return DERP_OK; }
+int derp_profile(DerpCtx*, int) { return DERP_OK; }
+int derp_get_profile(DerpCtx*, double* ms, uint64_t* n) {
+  if (ms) *ms = 0;
+  if (n) *n = 0;
+  return DERP_OK;
+}
+int derp_get_launch_count(DerpCtx*, uint64_t* out) {
+  if (out) *out = 0;  // the oracle launches no GPU kernels
+  return DERP_OK;
+}
 
 int derp_level_begin(DerpCtx* ctx, const DerpLevelParams* p) {
   if (!ctx || !p || p->width < 3 || p->height < 3 || p->num_levels <= 0 || p->full_height <= 0)

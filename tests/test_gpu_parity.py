@@ -1,0 +1,320 @@
+"""GPU parity tests proper: the CUDA library vs the CPU oracle through the same C ABI, same seeded
+inputs.  Bar (BASELINE.json north_star): integer disparity indices bit-exact; float depth within 1e-3
+relative.  Most stages are in fact bit-exact; the tolerance classes are stated where they apply:
+  * fp64 atan2 / sin / cos differ by <= 2 ulp between CUDA and glibc: a projected coordinate narrowed
+    to fp32 can flip its last bit on ~1e-7 of pixels -> tables/costs allow a 1e-5 mismatching fraction;
+  * expf differs in the last bits -> bilateral / temporal outputs compared at 2e-6 relative.
+"""
+import numpy as np
+import pytest
+
+from facebook360_dep_b200 import capi, synth
+from tests.parity_util import both, make_pair, mismatch_fraction, same_float_bits, scene_inputs
+
+pytestmark = pytest.mark.gpu
+
+RIGS = [
+    # cfg-1 of BASELINE.json: 4-camera synthetic rig (rectilinear, hfov 120 so neighbours overlap)
+    ("rect4", dict(num_cams=4, width=96, height=80, kind="RECTILINEAR", hfov_deg=120.0)),
+    ("ftheta8d", dict(num_cams=8, width=112, height=96, kind="FTHETA", distorted=True)),
+    ("ftheta5", dict(num_cams=5, width=72, height=72, kind="FTHETA")),
+]
+
+
+def _begin(ctxs, colors, W, H, **kw):
+    both(ctxs, "level_begin", W, H, **kw)
+    both(ctxs, "set_colors", colors)
+
+
+@pytest.mark.parametrize("name,cfg", RIGS)
+def test_level_tables(cuda, oracle, name, cfg):
+    rig, colors, _ = scene_inputs(**cfg)
+    W, H = cfg["width"], cfg["height"]
+    ctxs = make_pair(cuda, oracle, rig)
+    _begin(ctxs, colors, W, H)
+    S = len(colors)
+    for d in range(S):
+        g, o = both(ctxs, "get_fov_mask", d)
+        assert np.array_equal(g, o)
+    for s in range(S):
+        g, o = both(ctxs, "get_variance", s)
+        assert np.array_equal(g.view(np.uint32), o.view(np.uint32)), "variance must be bit-exact"
+    for d in (0, S - 1):
+        both(ctxs, "reproject", d)
+        for s in range(S):
+            gw, ow = both(ctxs, "get_proj_warp", s)
+            assert mismatch_fraction(gw, ow) <= 1e-5
+            assert np.array_equal(np.isnan(gw), np.isnan(ow))
+            fin = ~np.isnan(ow)
+            assert np.abs(gw[fin] - ow[fin]).max(initial=0) <= 1e-3
+            gc, oc = both(ctxs, "get_proj_color", s)
+            assert (gc != oc).mean() <= 1e-5, "projColor"
+            gb, ob = both(ctxs, "get_proj_bias", s)
+            assert (gb != ob).mean() <= 2e-5, "projBias"
+
+
+@pytest.mark.parametrize("name,cfg", RIGS)
+def test_eval_cost_bit_exact(cuda, oracle, name, cfg):
+    rig, colors, true_disp = scene_inputs(**cfg)
+    W, H = cfg["width"], cfg["height"]
+    ctxs = make_pair(cuda, oracle, rig)
+    _begin(ctxs, colors, W, H)
+    rng = np.random.RandomState(1)
+    for d in (0, len(colors) // 2):
+        both(ctxs, "reproject", d)
+        for disp in (np.full((H, W), 0.31, np.float32), true_disp[d],
+                     rng.uniform(1e-4, 2.0, size=(H, W)).astype(np.float32)):
+            (gc, gf), (oc, of) = both(ctxs, "eval_cost", d, disp)
+            assert mismatch_fraction(gc, oc) <= 1e-5, name
+            assert mismatch_fraction(gf, of) <= 1e-5, name
+            assert ctxs[0].get_counters() == ctxs[1].get_counters()
+
+
+@pytest.mark.parametrize("name,cfg", RIGS)
+@pytest.mark.parametrize("num_depths", [32, 150])
+def test_brute_force_indices_bit_exact(cuda, oracle, name, cfg, num_depths):
+    rig, colors, _ = scene_inputs(**cfg)
+    W, H = cfg["width"], cfg["height"]
+    ctxs = make_pair(cuda, oracle, rig)
+    _begin(ctxs, colors, W, H)
+    total_bad = 0
+    for d in range(len(colors)):
+        both(ctxs, "reproject", d)
+        gi, oi = both(ctxs, "brute_force", d, num_depths=num_depths)
+        total_bad += int((gi != oi).sum())
+        (gd, gc, gf), (od, oc, of) = both(ctxs, "get_disparity", d)
+        ok = gi == oi
+        assert same_float_bits(gd, od)[ok].all()
+        assert same_float_bits(gc, oc)[ok].all()
+        assert same_float_bits(gf, of)[ok].all()
+        assert ctxs[0].get_counters() == ctxs[1].get_counters()
+    assert total_bad == 0, "%d winner indices differ" % total_bad
+
+
+def test_brute_force_cfg1_full_size(cuda, oracle):
+    """BASELINE.json configs[0]: 4-camera synthetic rig, 512x512, 32 candidates, single level."""
+    cfg = dict(num_cams=4, width=512, height=512, kind="RECTILINEAR", hfov_deg=120.0)
+    rig, colors, true_disp = scene_inputs(**cfg)
+    ctxs = make_pair(cuda, oracle, rig)
+    _begin(ctxs, colors, 512, 512)
+    for d in range(4):
+        both(ctxs, "reproject", d)
+        gi, oi = both(ctxs, "brute_force", d, num_depths=32)
+        assert np.array_equal(gi, oi)
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        assert same_float_bits(gd, od).all()
+        # sanity: the sweep finds the scene (within two candidate steps on most covered pixels)
+        cov = oi >= 0
+        assert (np.abs(od - true_disp[d])[cov] < 2 * 2.0 / 31).mean() > 0.7
+
+
+def test_coverage_check_matches_reference_abort(cuda, oracle):
+    # Derp.cpp:334-339: CHECK(partialCoverage || useForegroundMasks) when no candidate is visible
+    cfg = dict(num_cams=4, width=64, height=64, kind="RECTILINEAR", hfov_deg=60.0)
+    rig, colors, _ = scene_inputs(**cfg)
+    ctxs = make_pair(cuda, oracle, rig)
+    _begin(ctxs, colors, 64, 64)
+    both(ctxs, "reproject", 0)
+    for c in ctxs:
+        with pytest.raises(capi.DerpError) as e:
+            c.brute_force(0, num_depths=16, partial_coverage=False)
+        assert e.value.code == capi.ECOVERAGE
+
+
+def _coarse_to_fine_start(ctxs, rig, colors, W, H, level=1, num_levels=3):
+    """Brute force at half size with the ORACLE, upsample into both contexts at (W, H)."""
+    cw, ch = W // 2, H // 2
+    coarse_colors = [synth.downscale_area(c, 2) for c in colors]
+    oc = ctxs[1]
+    oc.level_begin(cw, ch, level=level + 1, num_levels=num_levels, full_width=W, full_height=H)
+    oc.set_colors(coarse_colors)
+    coarse = []
+    for d in range(len(colors)):
+        oc.reproject(d)
+        oc.brute_force(d, num_depths=48, want_index=False)
+        oc.mask_fov(d)
+        coarse.append(oc.get_disparity(d, want_cost=False))
+    both(ctxs, "level_begin", W, H, level=level, num_levels=num_levels, full_width=W, full_height=H)
+    both(ctxs, "set_colors", colors)
+    for d in range(len(colors)):
+        both(ctxs, "upsample_from", d, coarse[d])
+    return coarse
+
+
+@pytest.mark.parametrize("name,cfg", RIGS[:2])
+def test_fine_level_stages(cuda, oracle, name, cfg):
+    rig, colors, _ = scene_inputs(**cfg)
+    W, H = cfg["width"], cfg["height"]
+    ctxs = make_pair(cuda, oracle, rig)
+    _coarse_to_fine_start(ctxs, rig, colors, W, H)
+    S = len(colors)
+    for d in range(S):
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        assert same_float_bits(gd, od).all(), "Lanczos upsample must be bit-exact (host-built tap tables)"
+    for d in range(S):
+        both(ctxs, "reproject", d)
+        both(ctxs, "random_proposals", d, 2)
+        (gd, gc, gf), (od, oc, of) = both(ctxs, "get_disparity", d)
+        assert mismatch_fraction(gd, od) <= 2e-5, "random proposals disparity"
+        assert mismatch_fraction(gc, oc) <= 2e-5 and mismatch_fraction(gf, of) <= 2e-5
+        assert ctxs[0].get_counters() == ctxs[1].get_counters()
+        ctxs[0].set_disparity(d, od, oc, of)  # re-synchronise before the next stage
+        both(ctxs, "ping_pong", d, 2)
+        (gd, gc, gf), (od, oc, of) = both(ctxs, "get_disparity", d)
+        assert mismatch_fraction(gd, od) <= 2e-5, "ping-pong disparity"
+        assert mismatch_fraction(gc, oc) <= 2e-5
+        assert ctxs[0].get_counters() == ctxs[1].get_counters()
+        ctxs[0].set_disparity(d, od, oc, of)
+    # mismatch handling (all cameras' disparity)
+    both(ctxs, "mismatches")
+    for d in range(S):
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        assert mismatch_fraction(gd, od) <= 1e-3
+        gm, om = both(ctxs, "get_mismatch_mask", d)
+        assert (gm != om).mean() <= 1e-3
+        ctxs[0].set_disparity(d, od)
+    for d in range(S):
+        both(ctxs, "bilateral", d)
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        fin = np.isfinite(od)
+        assert np.array_equal(np.isfinite(gd), fin)
+        assert (np.abs(gd - od)[fin] <= 2e-6 * np.abs(od)[fin] + 1e-12).all(), "bilateral"
+        ctxs[0].set_disparity(d, od)
+        both(ctxs, "median", d)
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        assert same_float_bits(gd, od).all(), "median must be bit-exact"
+        both(ctxs, "mask_fov", d)
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        assert same_float_bits(gd, od).all()
+
+
+def test_foreground_mask_paths(cuda, oracle):
+    cfg = RIGS[1][1]
+    rig, colors, true_disp = scene_inputs(**cfg)
+    W, H = cfg["width"], cfg["height"]
+    S = len(colors)
+    rng = np.random.RandomState(5)
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = [(((xx - W / 2 - 6 * s) ** 2 + (yy - H / 2) ** 2) < (0.38 * W) ** 2).astype(np.uint8) for s in range(S)]
+    bgs = [np.full((H, W), 0.05, np.float32) + rng.uniform(0, 0.01, (H, W)).astype(np.float32) for _ in range(S)]
+    ctxs = make_pair(cuda, oracle, rig)
+    both(ctxs, "level_begin", W, H, use_foreground_masks=True)
+    both(ctxs, "set_colors", colors)
+    both(ctxs, "set_foreground_masks", masks)
+    both(ctxs, "set_background_disparity", bgs)
+    for d in (0, 3):
+        both(ctxs, "reproject", d)
+        gi, oi = both(ctxs, "brute_force", d, num_depths=40, partial_coverage=False)
+        assert np.array_equal(gi, oi)
+        (gd, gc, gf), (od, oc, of) = both(ctxs, "get_disparity", d)
+        assert same_float_bits(gd, od).all() and same_float_bits(gc, oc).all()
+        both(ctxs, "random_proposals", d, 2)
+        both(ctxs, "ping_pong", d, 1)
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        assert mismatch_fraction(gd, od) <= 1e-4
+        ctxs[0].set_disparity(d, od)
+        both(ctxs, "bilateral", d)
+        both(ctxs, "median", d)
+        both(ctxs, "mask_fov", d)
+        gd, od = both(ctxs, "get_disparity", d, want_cost=False)
+        fin = np.isfinite(od)
+        assert np.array_equal(np.isfinite(gd), fin)
+        assert (np.abs(gd - od)[fin] <= 1e-5 * np.abs(od)[fin] + 1e-12).mean() > 0.999
+    # masked upsampling (nearest + spiral fill + background)
+    cw, ch = W // 2, H // 2
+    coarse = rng.uniform(0.06, 1.5, (ch, cw)).astype(np.float32)
+    coarse[rng.uniform(size=coarse.shape) < 0.1] = np.nan
+    cmask = masks[2][::2, ::2].copy()
+    both(ctxs, "upsample_from", 2, coarse, cmask, masks[2])
+    gd, od = both(ctxs, "get_disparity", 2, want_cost=False)
+    assert same_float_bits(gd, od).all(), "masked upsample must be bit-exact"
+
+
+def test_process_level_coarse_to_fine(cuda, oracle):
+    """3-level coarse-to-fine run, each library on its own (no re-synchronisation): end-to-end class (iii)
+    of SURVEY.md §8(c): >= 99.9 % of pixels within 1e-3 relative."""
+    cfg = dict(num_cams=6, width=128, height=128, kind="FTHETA", distorted=True)
+    rig, colors, _ = scene_inputs(**cfg)
+    W = H = 128
+    pyr = [colors, [synth.downscale_area(c, 2) for c in colors], [synth.downscale_area(c, 4) for c in colors]]
+    ctxs = make_pair(cuda, oracle, rig)
+    prev = None
+    for level in (2, 1, 0):
+        w = W >> level
+        both(ctxs, "level_begin", w, w, level=level, num_levels=3, full_width=W, full_height=H)
+        both(ctxs, "set_colors", pyr[level])
+        if prev is not None:
+            for c, p in zip(ctxs, prev):
+                for d in range(6):
+                    c.upsample_from(d, p[d])
+        both(ctxs, "process_level", num_depths=64)
+        prev = [[c.get_disparity(d, want_cost=False) for d in range(6)] for c in ctxs]
+        good = tot = 0
+        for d in range(6):
+            g, o = prev[0][d], prev[1][d]
+            assert np.array_equal(np.isnan(g), np.isnan(o))
+            fin = ~np.isnan(o)
+            good += (np.abs(g - o)[fin] <= 1e-3 * np.abs(o)[fin]).sum()
+            tot += fin.sum()
+        assert good / tot >= 0.999, (level, good / tot)
+
+
+def test_temporal_and_joint_bilateral(cuda, oracle):
+    rng = np.random.RandomState(11)
+    H, W, T = 60, 68, 5
+    base = rng.randint(0, 65536, (H, W, 3))
+    guides = [np.clip(base + rng.randint(-300, 300, (H, W, 3)), 0, 65535).astype(np.uint16) for _ in range(T)]
+    disps = [rng.uniform(1e-3, 2, (H, W)).astype(np.float32) for _ in range(T)]
+    masks = [(rng.uniform(size=(H, W)) > 0.15).astype(np.uint8) for _ in range(T)]
+    for off, r in ((2, 1), (0, 2), (4, 0)):
+        g = cuda.temporal_filter(guides, disps, masks, off, 0.01, r, 0.5, 1.0, 0.5)
+        o = oracle.temporal_filter(guides, disps, masks, off, 0.01, r, 0.5, 1.0, 0.5)
+        fin = np.isfinite(o)
+        assert np.array_equal(np.isfinite(g), fin)
+        assert (np.abs(g - o)[fin] <= 2e-6 * np.abs(o)[fin]).all()
+    img = disps[0]
+    guide = (guides[0].astype(np.float32) / 65535.0)
+    g = cuda.joint_bilateral_f32(img, guide, masks[0], 3, 0.05, 0.5, 0.5, 1.0)
+    o = oracle.joint_bilateral_f32(img, guide, masks[0], 3, 0.05, 0.5, 0.5, 1.0)
+    assert (np.abs(g - o) <= 2e-6 * np.abs(o)).all()
+
+
+def test_standalone_upsample(cuda, oracle):
+    rig = synth.ring_rig(4, 96, 64, kind="FTHETA")
+    d = capi.camera_desc_from_json(rig["cameras"][1])
+    rng = np.random.RandomState(2)
+    coarse = rng.uniform(1e-4, 2, (32, 48)).astype(np.float32)
+    coarse[3:6, 7:9] = np.nan
+    for (w, h) in ((96, 64), (100, 70), (48, 32)):
+        g = cuda.upsample_disparity(d, coarse, w, h)
+        o = oracle.upsample_disparity(d, coarse, w, h)
+        assert same_float_bits(g, o).all()
+    cm = (rng.uniform(size=(32, 48)) > 0.3).astype(np.uint8)
+    fm = (rng.uniform(size=(64, 96)) > 0.2).astype(np.uint8)
+    bg = rng.uniform(0.01, 0.02, (64, 96)).astype(np.float32)
+    g = cuda.upsample_disparity(d, coarse, 96, 64, bg, cm, fm, True)
+    o = oracle.upsample_disparity(d, coarse, 96, 64, bg, cm, fm, True)
+    assert same_float_bits(g, o).all()
+
+
+def test_dst_subset_and_edge_sizes(cuda, oracle):
+    # --cameras subset (filterDestinations) and tiny / ragged sizes
+    cfg = dict(num_cams=5, width=72, height=72, kind="FTHETA")
+    rig, colors, _ = scene_inputs(**cfg)
+    ctxs = make_pair(cuda, oracle, rig, dst_to_src=[3, 0])
+    _begin(ctxs, colors, 72, 72)
+    for d in (0, 1):
+        both(ctxs, "reproject", d)
+        gi, oi = both(ctxs, "brute_force", d, num_depths=20)
+        assert np.array_equal(gi, oi)
+    rig2 = synth.ring_rig(3, 33, 3, kind="FTHETA")
+    col2, _ = synth.render_rig(rig2, 33, 3)
+    ctxs = make_pair(cuda, oracle, rig2)
+    _begin(ctxs, col2, 33, 3)
+    both(ctxs, "reproject", 1)
+    gi, oi = both(ctxs, "brute_force", 1, num_depths=7)
+    assert np.array_equal(gi, oi)
+    with pytest.raises(capi.DerpError):
+        ctxs[0].level_begin(2, 2)
+    with pytest.raises(capi.DerpError):
+        ctxs[0].brute_force(0)  # stage before reproject of that dst -> DERP_ESTATE
