@@ -1,0 +1,354 @@
+// DerpCLI — drop-in for facebook360_dep's source/depth_estimation/DerpCLI.cpp on B200.
+// Same flags (names, types, defaults, help), same input/output directory tree, same rig JSON, same
+// PFM/PNG outputs; the per-level work runs through libderp_b200.so (sm_100a CUDA kernels).
+// Additions (surface extensions, defaults reproduce the reference): --num_depths (kNumDepths, Derp.h:33),
+// --gpus / --gpu (frames are sharded across the GPUs of one box: frames are independent,
+// DerpCLI.cpp:229-320).  There is no CPU fallback: without a CUDA device the process aborts.
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+#include "io.h"
+
+const std::string kUsageMessage = R"(
+ - Runs depth estimation on a set of frames. We assume the inputs have already been resized into
+ the appropriate pyramid level widths before execution. See scripts/render/config.py to see
+ the assumed widths.
+
+ - Example:
+   ./DerpCLI \
+   --input_root=/path/to/ \
+   --output_root=/path/to/output \
+   --rig=/path/to/rigs/rig.json \
+   --first=000000 \
+   --last=000000
+ )";
+
+DEFINE_string(background_disp, "", "path to background disparities");
+DEFINE_string(background_frame, "000000", "background frame (lexical)");
+DEFINE_string(cameras, "", "comma-separated destinations to render (empty for all)");
+DEFINE_string(color, "", "path to input color images");
+DEFINE_bool(do_bilateral_filter, true, "apply bilateral filter at each level");
+DEFINE_bool(do_median_filter, true, "apply median filter to disparity at each level");
+DEFINE_string(first, "000000", "first frame to process (lexical)");
+DEFINE_string(foreground_masks, "", "path to foreground masks");
+DEFINE_string(input_root, "", "path to input data (required)");
+DEFINE_string(last, "000000", "last frame to process (lexical)");
+DEFINE_int32(level_end, -1, "level to end at (-1 = finest)");
+DEFINE_int32(level_start, -1, "level to start at (-1 = coarsest)");
+DEFINE_double(max_depth_m, 1e4, "max depth (m)");
+DEFINE_double(min_depth_m, .50, "min depth (m)");
+DEFINE_int32(mismatches_start_level, -1, "(-1 = no mismatch handling)");
+DEFINE_int32(num_levels, -1, "number of levels in the pyramid (-1 = uses highest level)");
+DEFINE_string(output_formats, "", "saved formats, comma separated (exr, png, pfm supported)");
+DEFINE_string(output_root, "", "path to output directory (required)");
+DEFINE_bool(partial_coverage, false, "set to true if no 360 coverage");
+DEFINE_int32(ping_pong_iterations, 1, "number of spatial propagation iterations");
+DEFINE_int32(random_proposals, 2, "number of proposed random disparities before propagation");
+DEFINE_int32(resolution, 2048, "Output resolution (width in pixels)");
+DEFINE_string(rig, "", "path to camera rig .json");
+DEFINE_bool(save_debug_images, false, "if true, save debugging output images");
+DEFINE_int32(threads, -1, "number of threads (-1 = auto, 0 = none)");
+DEFINE_bool(use_foreground_masks, false, "use pre-computed foreground masks");
+DEFINE_double(var_high_thresh, 1e-3, "ignore variances higher than this threshold");
+DEFINE_double(var_noise_floor, 4e-5, "noise variance floor on original, full-size images");
+// B200 extensions
+DEFINE_int32(num_depths, 150, "number of brute-force depth candidates (reference constant kNumDepths)");
+DEFINE_int32(gpus, 1, "number of GPUs of this box to shard frames across");
+DEFINE_int32(gpu, 0, "first CUDA device to use");
+
+#define DERP_CALL(expr)                                                 \
+  do {                                                                  \
+    const int rc_ = (expr);                                             \
+    if (rc_ != 0) LOG(FATAL) << #expr << " failed: " << derp_last_error(); \
+  } while (0)
+
+static void verifyInputs() {  // DerpCLI.cpp:69-118
+  CHECK_NE(FLAGS_input_root, "");
+  CHECK_NE(FLAGS_output_root, "");
+  if (FLAGS_level_start >= 0 && FLAGS_level_end >= 0) CHECK_GE(FLAGS_level_start, FLAGS_level_end);
+  if (FLAGS_rig.empty()) FLAGS_rig = FLAGS_input_root + "/rigs/rig_calibrated.json";
+  if (FLAGS_color.empty()) FLAGS_color = FLAGS_input_root + "/" + io::kColorLevels;
+  if (FLAGS_background_disp.empty()) FLAGS_background_disp = FLAGS_input_root + "/" + io::kBackgroundDispLevels;
+  if (FLAGS_foreground_masks.empty()) FLAGS_foreground_masks = FLAGS_input_root + "/" + io::kForegroundMasksLevels;
+  CHECK_GE(FLAGS_random_proposals, 0);
+  CHECK_LE(FLAGS_first, FLAGS_last);
+  CHECK_GE(FLAGS_num_depths, 2);
+  CHECK(fs::is_directory(FLAGS_color)) << "No images in " << FLAGS_color;
+  if (FLAGS_use_foreground_masks) {
+    CHECK(fs::is_directory(FLAGS_background_disp))
+        << "Asked to use background but no background disparities found in " << FLAGS_background_disp;
+    CHECK(fs::is_directory(FLAGS_foreground_masks))
+        << "Asked to use foreground masks but no foreground masks found in " << FLAGS_foreground_masks;
+  }
+  std::stringstream ss(FLAGS_output_formats);
+  std::string fmt;
+  while (std::getline(ss, fmt, ','))
+    CHECK(fmt.empty() || fmt == "exr" || fmt == "png" || fmt == "pfm") << "Invalid output format specified: " << fmt;
+}
+
+// image size from the file header only
+static bool imageSize(const fs::path& p, int* w, int* h) {
+  std::ifstream f(p, std::ios::binary);
+  if (!f.good()) return false;
+  if (p.extension() == ".pfm") {
+    std::string fmt;
+    std::getline(f, fmt);
+    f >> *w >> *h;
+    return f.good();
+  }
+  uint8_t hdr[24];
+  f.read(reinterpret_cast<char*>(hdr), 24);
+  if (!f.good() || std::memcmp(hdr + 12, "IHDR", 4) != 0) return false;
+  *w = (int)io::be32(hdr + 16);
+  *h = (int)io::be32(hdr + 20);
+  return true;
+}
+
+// getPyramidLevelSizes (Derp.cpp:72-99): first non-.tar file found under each level_<L> directory
+static void getPyramidLevelSizes(std::map<int, std::pair<int, int>>& sizes, const fs::path& imageDir) {
+  if (!fs::exists(imageDir)) return;
+  for (const auto& entry : fs::directory_iterator(imageDir)) {
+    const fs::path p = entry.path();
+    if (!fs::is_directory(entry) || io::isHidden(p)) continue;
+    const std::string name = p.filename().string();
+    if (name.rfind("level_", 0) != 0) continue;
+    std::vector<fs::path> files;
+    for (const auto& e : fs::recursive_directory_iterator(p))
+      if (fs::is_regular_file(e) && !io::isHidden(e.path()) && e.path().extension() != ".tar") files.push_back(e.path());
+    if (files.empty()) continue;
+    std::sort(files.begin(), files.end());
+    int w = 0, h = 0;
+    CHECK(imageSize(files[0], &w, &h)) << "cannot read image header: " << files[0].string();
+    sizes[std::stoi(name.substr(6))] = {w, h};
+  }
+}
+
+// verifyImagePaths (ImageUtil.cpp:62-94)
+static void verifyImagePaths(const fs::path& dir, const io::Rig& rig, const std::vector<int>& cams,
+                             const std::string& first, const std::string& last) {
+  int a = 0, b = 0;
+  try {
+    a = std::stoi(first);
+  } catch (...) {
+    LOG(FATAL) << "Invalid frame name: " << first;
+  }
+  try {
+    b = std::stoi(last);
+  } catch (...) {
+    LOG(FATAL) << "Invalid frame name: " << last;
+  }
+  CHECK_LE(a, b);
+  CHECK_GT(cams.size(), 0u);
+  const std::string ext = io::firstExtension(dir / rig.ids[cams[0]]);
+  for (int c : cams)
+    for (int f = a; f <= b; ++f) {
+      const fs::path p = dir / rig.ids[c] / (io::zeroPad(f) + ext);
+      CHECK(fs::is_regular_file(p)) << "Missing file: " << p.string();
+    }
+}
+
+struct Shared {
+  io::Rig rig;
+  std::vector<int> dst;  // indices into rig
+  std::map<int, std::pair<int, int>> sizes;
+  int numLevels = 0, levelStart = 0, levelEnd = 0, widthFull = 0, heightFull = 0, firstFrame = 0, numFrames = 0;
+};
+
+static void saveLevel(const Shared& sh, DerpCtx* ctx, int level, const std::string& frameName, int W, int H) {
+  // saveResults (Derp.cpp:922-938, PyramidLevel.h:487-529): pfm always; png/exr on request
+  std::vector<std::string> formats = {"pfm"};
+  std::stringstream ss(FLAGS_output_formats);
+  std::string f;
+  while (std::getline(ss, f, ','))
+    if (!f.empty() && f != "pfm") formats.push_back(f);
+  std::vector<float> disp((size_t)W * H), cost, conf;
+  if (FLAGS_save_debug_images) {
+    cost.resize(disp.size());
+    conf.resize(disp.size());
+  }
+  for (size_t d = 0; d < sh.dst.size(); ++d) {
+    DERP_CALL(derp_get_disparity(ctx, (int)d, disp.data(), cost.empty() ? nullptr : cost.data(),
+                                 conf.empty() ? nullptr : conf.data()));
+    const std::string& id = sh.rig.ids[sh.dst[d]];
+    const fs::path stem = fs::path(io::levelDir(FLAGS_output_root + "/" + io::kDisparityLevels, level)) / id / frameName;
+    for (const auto& ext : formats) io::saveDisparity(stem, ext, disp.data(), W, H);
+    if (FLAGS_save_debug_images) {  // saveDebugImages (PyramidLevel.h:418-461): scaled 16-bit previews
+      auto scaled = [&](const std::vector<float>& src, float s) {
+        std::vector<float> o(src.size());
+        for (size_t i = 0; i < o.size(); ++i) o[i] = src[i] * s / 65535.0f;  // written as raw u16 of value*scale
+        return o;
+      };
+      const auto c = scaled(cost, 255.0f / 100.0f), q = scaled(conf, 255.0f * 100.0f);
+      io::saveDisparity(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kCost, level)) / id / frameName, "png",
+                        c.data(), W, H);
+      io::saveDisparity(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kConfidence, level)) / id / frameName,
+                        "png", q.data(), W, H);
+    }
+  }
+}
+
+// One (level, frame): DerpCLI.cpp:229-320
+static void processFrame(const Shared& sh, DerpCtx* ctx, int level, int iFrame) {
+  const std::string frameName = io::zeroPad(iFrame + sh.firstFrame);
+  const int W = sh.sizes.at(level).first, H = sh.sizes.at(level).second;
+  const int S = (int)sh.rig.cams.size(), Sd = (int)sh.dst.size();
+  DerpLevelParams lp{};
+  lp.width = W;
+  lp.height = H;
+  lp.level = level;
+  lp.num_levels = sh.numLevels;
+  lp.full_width = sh.widthFull;
+  lp.full_height = sh.heightFull;
+  lp.var_noise_floor = (float)FLAGS_var_noise_floor;
+  lp.var_high_thresh = (float)FLAGS_var_high_thresh;
+  lp.use_foreground_masks = FLAGS_use_foreground_masks ? 1 : 0;
+  DERP_CALL(derp_level_begin(ctx, &lp));
+
+  const std::string colorDir = io::levelDir(FLAGS_color, level);
+  std::vector<std::vector<uint16_t>> colors(S);
+  std::vector<const uint16_t*> cptr(S);
+  for (int s = 0; s < S; ++s) {
+    int w, h;
+    colors[s] = io::loadColor16(io::imagePath(colorDir, sh.rig.ids[s], frameName), &w, &h);
+    CHECK(w == W && h == H) << "unexpected image size for " << sh.rig.ids[s] << " at level " << level;
+    cptr[s] = colors[s].data();
+  }
+  DERP_CALL(derp_set_colors(ctx, cptr.data()));
+
+  std::vector<std::vector<uint8_t>> masks, masksCoarse;
+  if (FLAGS_use_foreground_masks) {
+    const std::string maskDir = io::levelDir(FLAGS_foreground_masks, level);
+    masks.resize(S);
+    std::vector<const uint8_t*> mptr(S);
+    for (int s = 0; s < S; ++s) {
+      int w, h;
+      masks[s] = io::loadMask(io::imagePath(maskDir, sh.rig.ids[s], frameName), &w, &h);
+      CHECK(w == W && h == H) << "unexpected mask size";
+      mptr[s] = masks[s].data();
+    }
+    DERP_CALL(derp_set_foreground_masks(ctx, mptr.data()));
+    const std::string bgDir = io::levelDir(FLAGS_background_disp, level);
+    std::vector<std::vector<float>> bgs(Sd);
+    std::vector<const float*> bptr(Sd);
+    for (int d = 0; d < Sd; ++d) {
+      int w, h;
+      bgs[d] = io::loadFloat(io::imagePath(bgDir, sh.rig.ids[sh.dst[d]], FLAGS_background_frame), &w, &h);
+      CHECK(w == W && h == H) << "unexpected background disparity size";
+      bptr[d] = bgs[d].data();
+    }
+    DERP_CALL(derp_set_background_disparity(ctx, bptr.data()));
+  }
+
+  if (level < sh.numLevels - 1) {  // DerpCLI.cpp:276-303: coarser disparity comes from disk
+    const std::string coarseDir = io::levelDir(FLAGS_output_root + "/" + io::kDisparityLevels, level + 1);
+    for (int d = 0; d < Sd; ++d) {
+      const std::string& id = sh.rig.ids[sh.dst[d]];
+      int cw, ch;
+      const std::vector<float> coarse = io::loadFloat(io::imagePath(coarseDir, id, frameName), &cw, &ch);
+      std::vector<uint8_t> mc;
+      const uint8_t* mfine = nullptr;
+      if (FLAGS_use_foreground_masks) {
+        int w, h;
+        mc = io::loadMask(io::imagePath(io::levelDir(FLAGS_foreground_masks, level + 1), id, frameName), &w, &h);
+        CHECK(w == cw && h == ch) << "coarse mask / disparity size mismatch";
+        mfine = masks[sh.dst[d]].data();
+      }
+      DERP_CALL(derp_upsample_from(ctx, d, coarse.data(), cw, ch, mc.empty() ? nullptr : mc.data(), mfine));
+    }
+  }
+
+  DerpProcessOpts o{};
+  o.num_depths = FLAGS_num_depths;
+  o.min_depth_m = (float)FLAGS_min_depth_m;
+  o.max_depth_m = (float)FLAGS_max_depth_m;
+  o.partial_coverage = FLAGS_partial_coverage ? 1 : 0;
+  o.random_proposals = FLAGS_random_proposals;
+  o.ping_pong_iterations = FLAGS_ping_pong_iterations;
+  o.mismatches_start_level = FLAGS_mismatches_start_level;
+  o.do_bilateral_filter = FLAGS_do_bilateral_filter ? 1 : 0;
+  o.do_median_filter = FLAGS_do_median_filter ? 1 : 0;
+  LOG(INFO) << "Processing " << frameName << " level " << level;
+  DERP_CALL(derp_process_level(ctx, &o));
+  saveLevel(sh, ctx, level, frameName, W, H);
+}
+
+int main(int argc, char* argv[]) {
+  flags::initDep(argc, argv, kUsageMessage);
+  const auto t0 = std::chrono::steady_clock::now();
+  verifyInputs();
+
+  Shared sh;
+  sh.rig = io::loadRig(FLAGS_rig);
+  CHECK_GT(sh.rig.cams.size(), 0u) << "no source cameras!";
+  sh.dst = io::filterDestinations(sh.rig, FLAGS_cameras);
+  CHECK_GT(sh.dst.size(), 0u) << "no destination cameras!";
+
+  getPyramidLevelSizes(sh.sizes, FLAGS_color);
+  getPyramidLevelSizes(sh.sizes, FLAGS_output_root + "/" + io::kDisparityLevels);
+  CHECK(!sh.sizes.empty()) << "no level_<n> directories under " << FLAGS_color;
+  sh.numLevels = FLAGS_num_levels == -1 ? sh.sizes.rbegin()->first + 1 : FLAGS_num_levels;
+  sh.levelStart = FLAGS_level_start >= 0 ? FLAGS_level_start : sh.numLevels - 1;
+  // getLevelEnd (DerpCLI.cpp:158-177): first level whose width <= --resolution
+  sh.levelEnd = 0;
+  for (const auto& kv : sh.sizes)
+    if (kv.second.first <= FLAGS_resolution) {
+      sh.levelEnd = kv.first;
+      break;
+    }
+  if (FLAGS_level_end >= 0)
+    CHECK_GE(FLAGS_level_end, sh.levelEnd) << "Requested end level " << FLAGS_level_end
+                                           << " is larger than requested resolution (" << FLAGS_resolution << ")";
+  sh.levelEnd = std::max(sh.levelEnd, FLAGS_level_end);
+  CHECK_LE(FLAGS_level_start, sh.numLevels);
+  sh.firstFrame = std::stoi(FLAGS_first);
+  sh.numFrames = std::stoi(FLAGS_last) - sh.firstFrame + 1;
+
+  // verifyInputImagePaths (DerpCLI.cpp:136-156)
+  std::vector<int> all(sh.rig.cams.size());
+  for (size_t i = 0; i < all.size(); ++i) all[i] = (int)i;
+  verifyImagePaths(io::levelDir(FLAGS_color, sh.levelStart), sh.rig, all, FLAGS_first, FLAGS_last);
+  if (FLAGS_use_foreground_masks) {
+    verifyImagePaths(io::levelDir(FLAGS_background_disp, sh.levelStart), sh.rig, sh.dst, FLAGS_background_frame,
+                     FLAGS_background_frame);
+    verifyImagePaths(io::levelDir(FLAGS_foreground_masks, sh.levelStart), sh.rig, sh.dst, FLAGS_first, FLAGS_last);
+  }
+  if (sh.levelStart < sh.numLevels - 1)
+    verifyImagePaths(io::levelDir(FLAGS_output_root + "/" + io::kDisparityLevels, sh.levelStart + 1), sh.rig, sh.dst,
+                     FLAGS_first, FLAGS_last);
+  fs::create_directories(FLAGS_output_root);
+  sh.widthFull = (int)sh.rig.cams[sh.dst[0]].resolution[0];
+  sh.heightFull = (int)sh.rig.cams[sh.dst[0]].resolution[1];
+
+  // one context per GPU; frames are sharded in contiguous blocks
+  const int G = std::max(1, std::min(FLAGS_gpus, sh.numFrames));
+  std::vector<DerpCtx*> ctxs(G, nullptr);
+  std::vector<int32_t> d2s(sh.dst.begin(), sh.dst.end());
+  for (int g = 0; g < G; ++g)
+    DERP_CALL(derp_create(sh.rig.cams.data(), (int)sh.rig.cams.size(), d2s.data(), (int)d2s.size(), FLAGS_gpu + g, &ctxs[g]));
+  LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s), " << sh.numFrames << " frame(s), levels "
+            << sh.levelStart << " -> " << sh.levelEnd;
+
+  for (int level = sh.levelStart; level >= sh.levelEnd; --level) {
+    CHECK(sh.sizes.count(level)) << "no images for level " << level;
+    for (int d : sh.dst) {  // createLevelOutputDirs (DerpUtil.cpp:311-330)
+      fs::create_directories(fs::path(FLAGS_output_root) / io::kDisparity / sh.rig.ids[d]);
+      if (FLAGS_save_debug_images)
+        for (const char* t : {io::kDisparityLevels, io::kCost, io::kConfidence, io::kMismatches})
+          fs::create_directories(fs::path(io::levelDir(FLAGS_output_root + "/" + t, level)) / sh.rig.ids[d]);
+    }
+    std::vector<std::thread> workers;
+    const int per = (sh.numFrames + G - 1) / G;
+    for (int g = 0; g < G; ++g)
+      workers.emplace_back([&, g] {
+        for (int i = g * per; i < std::min(sh.numFrames, (g + 1) * per); ++i) processFrame(sh, ctxs[g], level, i);
+      });
+    for (auto& w : workers) w.join();  // per-level barrier, like the render pipeline (pipeline.py:364-380)
+    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    LOG(INFO) << "-- Elapsed time: " << el << "s wall";
+  }
+  for (auto* c : ctxs) derp_destroy(c);
+  const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  LOG(INFO) << "-- TOTAL: " << el << "s wall";
+  return EXIT_SUCCESS;
+}

@@ -1,0 +1,575 @@
+// Host-side file formats of the drop-in apps: rig JSON (Camera.cpp:30-75, 244-258), PFM
+// (CvUtil.cpp:39-73), PNG via zlib (the reference uses cv::imread / cv::imwrite, CvUtil.cpp:22-37),
+// the directory layout (ImageTypes.h:16-47, DerpUtil.cpp:278-330) and the per-camera image loaders
+// (ImageUtil.h:42-107, CvUtil.h:227-284 convertImage semantics).
+#pragma once
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <iomanip>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../../include/derp_b200.h"
+#include "flags.h"
+
+namespace fs = std::filesystem;
+
+namespace io {
+
+// ---- JSON (just enough for rig files) ----------------------------------------------------------------
+struct Json {
+  enum Type { Null, Bool, Num, Str, Arr, Obj } type = Null;
+  double num = 0;
+  bool b = false;
+  std::string str;
+  std::vector<Json> arr;
+  std::vector<std::pair<std::string, Json>> obj;
+  const Json* find(const std::string& k) const {
+    for (auto& kv : obj)
+      if (kv.first == k) return &kv.second;
+    return nullptr;
+  }
+  const Json& at(const std::string& k) const {
+    const Json* j = find(k);
+    CHECK(j != nullptr) << "missing JSON key: " << k;
+    return *j;
+  }
+};
+
+class JsonParser {
+ public:
+  explicit JsonParser(const std::string& s) : s_(s) {}
+  Json parse() {
+    Json j = value();
+    ws();
+    CHECK(p_ == s_.size()) << "trailing characters in JSON at offset " << p_;
+    return j;
+  }
+
+ private:
+  const std::string& s_;
+  size_t p_ = 0;
+  void ws() {
+    while (p_ < s_.size() && (s_[p_] == ' ' || s_[p_] == '\n' || s_[p_] == '\t' || s_[p_] == '\r')) ++p_;
+  }
+  char peek() {
+    ws();
+    CHECK(p_ < s_.size()) << "unexpected end of JSON";
+    return s_[p_];
+  }
+  void expect(char c) {
+    CHECK(peek() == c) << "JSON: expected '" << c << "' at offset " << p_;
+    ++p_;
+  }
+  std::string string() {
+    expect('"');
+    std::string out;
+    while (true) {
+      CHECK(p_ < s_.size()) << "unterminated JSON string";
+      char c = s_[p_++];
+      if (c == '"') break;
+      if (c == '\\') {
+        CHECK(p_ < s_.size()) << "bad escape";
+        char e = s_[p_++];
+        switch (e) {
+          case 'n': out += '\n'; break;
+          case 't': out += '\t'; break;
+          case 'r': out += '\r'; break;
+          case 'b': out += '\b'; break;
+          case 'f': out += '\f'; break;
+          case 'u': {
+            CHECK(p_ + 4 <= s_.size()) << "bad \\u escape";
+            unsigned cp = (unsigned)std::stoul(s_.substr(p_, 4), nullptr, 16);
+            p_ += 4;
+            if (cp < 0x80) out += (char)cp;
+            else if (cp < 0x800) {
+              out += (char)(0xC0 | (cp >> 6));
+              out += (char)(0x80 | (cp & 0x3F));
+            } else {
+              out += (char)(0xE0 | (cp >> 12));
+              out += (char)(0x80 | ((cp >> 6) & 0x3F));
+              out += (char)(0x80 | (cp & 0x3F));
+            }
+            break;
+          }
+          default: out += e;
+        }
+      } else {
+        out += c;
+      }
+    }
+    return out;
+  }
+  Json value() {
+    char c = peek();
+    Json j;
+    if (c == '{') {
+      j.type = Json::Obj;
+      ++p_;
+      if (peek() == '}') {
+        ++p_;
+        return j;
+      }
+      while (true) {
+        std::string k = string();
+        expect(':');
+        j.obj.emplace_back(k, value());
+        if (peek() == ',') {
+          ++p_;
+          continue;
+        }
+        expect('}');
+        break;
+      }
+    } else if (c == '[') {
+      j.type = Json::Arr;
+      ++p_;
+      if (peek() == ']') {
+        ++p_;
+        return j;
+      }
+      while (true) {
+        j.arr.push_back(value());
+        if (peek() == ',') {
+          ++p_;
+          continue;
+        }
+        expect(']');
+        break;
+      }
+    } else if (c == '"') {
+      j.type = Json::Str;
+      j.str = string();
+    } else if (s_.compare(p_, 4, "true") == 0) {
+      j.type = Json::Bool;
+      j.b = true;
+      p_ += 4;
+    } else if (s_.compare(p_, 5, "false") == 0) {
+      j.type = Json::Bool;
+      p_ += 5;
+    } else if (s_.compare(p_, 4, "null") == 0) {
+      p_ += 4;
+    } else {
+      const char* b = s_.c_str() + p_;
+      char* e = nullptr;
+      j.type = Json::Num;
+      j.num = std::strtod(b, &e);
+      CHECK(e != b) << "bad JSON number at offset " << p_;
+      p_ += (size_t)(e - b);
+    }
+    return j;
+  }
+};
+
+// ---- rig ----------------------------------------------------------------------------------------------
+struct Rig {
+  std::vector<DerpCameraDesc> cams;
+  std::vector<std::string> ids;
+};
+
+inline double jnum(const Json& j) {
+  if (j.type == Json::Str) return std::stod(j.str);  // folly asDouble accepts numeric strings
+  CHECK(j.type == Json::Num) << "expected a number in rig JSON";
+  return j.num;
+}
+template <int N>
+inline void jvec(const Json& j, double* out) {
+  CHECK_EQ((int)j.arr.size(), N) << "bad vector";
+  for (int i = 0; i < N; ++i) out[i] = jnum(j.arr[i]);
+}
+
+inline Rig loadRig(const std::string& path) {  // Camera::loadRig (Camera.cpp:244-258)
+  std::ifstream f(path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  const std::string text = ss.str();
+  CHECK(!text.empty()) << "could not read JSON file: " << path;
+  const Json root = JsonParser(text).parse();
+  Rig rig;
+  for (const Json& c : root.at("cameras").arr) {
+    DerpCameraDesc d;
+    std::memset(&d, 0, sizeof(d));
+    CHECK_GE(jnum(c.at("version")), 1.0);
+    const std::string type = c.at("type").str;
+    static const char* names[] = {"FTHETA", "RECTILINEAR", "EQUISOLID", "ORTHOGRAPHIC"};
+    d.type = -1;
+    for (int i = 0; i < 4; ++i)
+      if (type == names[i]) d.type = i;
+    CHECK_GE(d.type, 0) << "unknown camera type " << type;
+    jvec<3>(c.at("origin"), d.origin);
+    jvec<3>(c.at("forward"), d.forward);
+    jvec<3>(c.at("up"), d.up);
+    jvec<3>(c.at("right"), d.right);
+    jvec<2>(c.at("resolution"), d.resolution);
+    jvec<2>(c.at("focal"), d.focal);
+    if (const Json* p = c.find("principal")) {
+      d.has_principal = 1;
+      jvec<2>(*p, d.principal);
+    }
+    if (const Json* p = c.find("distortion")) {
+      CHECK_LE((int)p->arr.size(), 3) << "bad distortion";
+      for (size_t i = 0; i < p->arr.size(); ++i) d.distortion[i] = jnum(p->arr[i]);
+    }
+    if (const Json* p = c.find("fov")) {
+      d.has_fov = 1;
+      d.fov = jnum(*p);
+    }
+    rig.cams.push_back(d);
+    rig.ids.push_back(c.at("id").str);
+  }
+  return rig;
+}
+
+// image_util::filterDestinations (ImageUtil.cpp:110-125): indices into rig, in the requested order
+inline std::vector<int> filterDestinations(const Rig& rig, const std::string& destinations) {
+  std::vector<int> out;
+  if (destinations.empty()) {
+    for (size_t i = 0; i < rig.ids.size(); ++i) out.push_back((int)i);
+    return out;
+  }
+  std::stringstream ss(destinations);
+  std::string dest;
+  while (std::getline(ss, dest, ','))
+    for (size_t i = 0; i < rig.ids.size(); ++i)
+      if (rig.ids[i] == dest) out.push_back((int)i);
+  return out;
+}
+
+// ---- directory layout (ImageTypes.h:16-47) ------------------------------------------------------------
+inline const char* kColorLevels = "video/color_levels";
+inline const char* kForegroundMasksLevels = "video/foreground_masks_levels";
+inline const char* kBackgroundDispLevels = "background/disparity_levels";
+inline const char* kDisparity = "disparity";
+inline const char* kDisparityLevels = "disparity_levels";
+inline const char* kDisparityTimeFilteredLevels = "disparity_time_filtered_levels";
+inline const char* kCost = "cost";
+inline const char* kConfidence = "confidence";
+inline const char* kMismatches = "mismatches";
+
+inline std::string levelDir(const std::string& dir, int level) { return dir + "/level_" + std::to_string(level); }
+
+inline std::string zeroPad(int x, int padlen = 6) {  // ImageUtil.h:42-46
+  std::ostringstream ss;
+  ss << std::setw(padlen) << std::setfill('0') << x;
+  return ss.str();
+}
+
+inline bool isHidden(const fs::path& p) { return p.filename().string()[0] == '.'; }
+
+inline std::vector<fs::path> visibleFilesSorted(const fs::path& dir) {  // FilesystemUtil.h:53-68
+  std::vector<fs::path> r;
+  for (const auto& e : fs::directory_iterator(dir))
+    if (fs::is_regular_file(e) && !isHidden(e.path())) r.push_back(e.path());
+  std::sort(r.begin(), r.end());
+  return r;
+}
+
+inline std::string firstExtension(const fs::path& dir) {  // FilesystemUtil.h:91-95
+  const auto files = visibleFilesSorted(dir);
+  CHECK_GT(files.size(), 0u) << "no visible files in " << dir.string();
+  return files[0].extension().string();
+}
+
+inline fs::path imagePath(const fs::path& dir, const std::string& camId, const std::string& frame,
+                          const std::string& extension = "") {  // ImageUtil.h:48-56
+  const fs::path camDir = dir / camId;
+  const std::string ext = extension.empty() ? firstExtension(camDir) : extension;
+  return camDir / (frame + ext);
+}
+
+// ---- PFM (CvUtil.cpp:39-73): "Pf\n<W> <H>\n-1.0\n" + little-endian rows, top row first -------------
+inline void writePfm(const fs::path& path, const float* data, int w, int h) {
+  std::ofstream f(path, std::ios::binary);
+  CHECK(f.good()) << "cannot write " << path.string();
+  f << "Pf\n" << w << " " << h << "\n-1.0\n";
+  f.write(reinterpret_cast<const char*>(data), (std::streamsize)w * h * sizeof(float));
+}
+
+inline std::vector<float> readPfm(const fs::path& path, int* w, int* h) {
+  std::ifstream f(path, std::ios::binary);
+  CHECK(f.good()) << "cannot load file: " << path.string();
+  std::string format;
+  std::getline(f, format);
+  CHECK(format == "Pf") << "expected 'Pf' in 1-channel .pfm file header: " << path.string();
+  double endian;
+  f >> *w >> *h >> endian;
+  CHECK_LE(endian, 0.0) << "only little endian .pfm files supported: " << path.string();
+  f.ignore();
+  std::vector<float> m((size_t)*w * *h);
+  f.read(reinterpret_cast<char*>(m.data()), (std::streamsize)m.size() * sizeof(float));
+  return m;
+}
+
+// ---- PNG (zlib) ---------------------------------------------------------------------------------------
+struct Image {
+  int w = 0, h = 0, channels = 0, bits = 0;  // bits: 8, 16 (integer) or 32 (float, from .pfm)
+  std::vector<uint16_t> u;                   // integer samples (8-bit values stored as-is), interleaved
+  std::vector<float> f;                      // float samples (PFM)
+};
+
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+inline Image readPng(const fs::path& path) {
+  std::ifstream f(path, std::ios::binary);
+  CHECK(f.good()) << "failed to load image: " << path.string();
+  std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  CHECK(buf.size() > 8 && std::memcmp(buf.data(), sig, 8) == 0) << "not a PNG file: " << path.string();
+  size_t p = 8;
+  int w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+  std::vector<uint8_t> idat, palette;
+  while (p + 8 <= buf.size()) {
+    const uint32_t len = be32(&buf[p]);
+    const std::string type(reinterpret_cast<char*>(&buf[p + 4]), 4);
+    const uint8_t* data = &buf[p + 8];
+    CHECK(p + 12 + len <= buf.size()) << "truncated PNG: " << path.string();
+    if (type == "IHDR") {
+      w = (int)be32(data);
+      h = (int)be32(data + 4);
+      depth = data[8];
+      ctype = data[9];
+      interlace = data[12];
+    } else if (type == "PLTE") {
+      palette.assign(data, data + len);
+    } else if (type == "IDAT") {
+      idat.insert(idat.end(), data, data + len);
+    } else if (type == "IEND") {
+      break;
+    }
+    p += 12 + len;
+  }
+  CHECK(w > 0 && h > 0) << "bad PNG header: " << path.string();
+  CHECK_EQ(interlace, 0) << "interlaced PNG not supported: " << path.string();
+  CHECK(depth == 8 || depth == 16) << "PNG bit depth " << depth << " not supported: " << path.string();
+  int ch = 0;
+  switch (ctype) {
+    case 0: ch = 1; break;
+    case 2: ch = 3; break;
+    case 3: ch = 1; break;  // palette index, expanded below
+    case 4: ch = 2; break;
+    case 6: ch = 4; break;
+    default: LOG(FATAL) << "bad PNG colour type";
+  }
+  const int bpp = ch * depth / 8;
+  const size_t stride = (size_t)w * bpp;
+  std::vector<uint8_t> raw((stride + 1) * h);
+  uLongf outLen = (uLongf)raw.size();
+  const int zr = uncompress(raw.data(), &outLen, idat.data(), (uLong)idat.size());
+  CHECK(zr == Z_OK && outLen == raw.size()) << "PNG inflate failed: " << path.string();
+  std::vector<uint8_t> pix(stride * h);
+  for (int y = 0; y < h; ++y) {
+    const uint8_t ft = raw[y * (stride + 1)];
+    const uint8_t* in = &raw[y * (stride + 1) + 1];
+    uint8_t* out = &pix[y * stride];
+    const uint8_t* up = y ? out - stride : nullptr;
+    for (size_t i = 0; i < stride; ++i) {
+      const int a = i >= (size_t)bpp ? out[i - bpp] : 0;
+      const int b = up ? up[i] : 0;
+      const int c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
+      int v = in[i];
+      switch (ft) {
+        case 0: break;
+        case 1: v += a; break;
+        case 2: v += b; break;
+        case 3: v += (a + b) >> 1; break;
+        case 4: {
+          const int pa = std::abs(b - c), pb = std::abs(a - c), pc = std::abs(a + b - 2 * c);
+          v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+          break;
+        }
+        default: LOG(FATAL) << "bad PNG filter";
+      }
+      out[i] = (uint8_t)v;
+    }
+  }
+  Image img;
+  img.w = w;
+  img.h = h;
+  img.bits = depth;
+  if (ctype == 3) {  // palette -> RGB 8 bit
+    CHECK_EQ(depth, 8);
+    img.channels = 3;
+    img.u.resize((size_t)w * h * 3);
+    for (size_t i = 0; i < (size_t)w * h; ++i)
+      for (int c = 0; c < 3; ++c) img.u[i * 3 + c] = palette[pix[i] * 3 + c];
+  } else {
+    img.channels = ch;
+    img.u.resize((size_t)w * h * ch);
+    for (size_t i = 0; i < img.u.size(); ++i)
+      img.u[i] = depth == 8 ? pix[i] : (uint16_t)((pix[2 * i] << 8) | pix[2 * i + 1]);
+  }
+  // PNG stores RGB(A); OpenCV hands out BGR(A) (cv::imread IMREAD_UNCHANGED)
+  if (img.channels >= 3)
+    for (size_t i = 0; i < (size_t)w * h; ++i) std::swap(img.u[i * img.channels], img.u[i * img.channels + 2]);
+  return img;
+}
+
+inline void pngChunk(std::ofstream& f, const char* type, const std::vector<uint8_t>& data) {
+  uint8_t len[4] = {(uint8_t)(data.size() >> 24), (uint8_t)(data.size() >> 16), (uint8_t)(data.size() >> 8),
+                    (uint8_t)data.size()};
+  f.write(reinterpret_cast<char*>(len), 4);
+  f.write(type, 4);
+  if (!data.empty()) f.write(reinterpret_cast<const char*>(data.data()), (std::streamsize)data.size());
+  uLong crc = crc32(0L, reinterpret_cast<const Bytef*>(type), 4);
+  if (!data.empty()) crc = crc32(crc, data.data(), (uInt)data.size());
+  uint8_t c[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+  f.write(reinterpret_cast<char*>(c), 4);
+}
+
+// 16-bit PNG, `channels` = 1 (gray) or 3 (BGR input, written as RGB)
+inline void writePng16(const fs::path& path, const uint16_t* data, int w, int h, int channels) {
+  std::ofstream f(path, std::ios::binary);
+  CHECK(f.good()) << "failed to save image: " << path.string();
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  f.write(reinterpret_cast<const char*>(sig), 8);
+  std::vector<uint8_t> ihdr(13);
+  ihdr[0] = w >> 24; ihdr[1] = w >> 16; ihdr[2] = w >> 8; ihdr[3] = w;
+  ihdr[4] = h >> 24; ihdr[5] = h >> 16; ihdr[6] = h >> 8; ihdr[7] = h;
+  ihdr[8] = 16;
+  ihdr[9] = channels == 1 ? 0 : 2;
+  pngChunk(f, "IHDR", ihdr);
+  const size_t stride = (size_t)w * channels * 2;
+  std::vector<uint8_t> raw((stride + 1) * h);
+  for (int y = 0; y < h; ++y) {
+    uint8_t* out = &raw[y * (stride + 1)];
+    *out++ = 0;
+    for (int x = 0; x < w; ++x)
+      for (int c = 0; c < channels; ++c) {
+        const int sc = channels == 3 ? 2 - c : c;
+        const uint16_t v = data[((size_t)y * w + x) * channels + sc];
+        *out++ = (uint8_t)(v >> 8);
+        *out++ = (uint8_t)v;
+      }
+  }
+  uLongf clen = compressBound((uLong)raw.size());
+  std::vector<uint8_t> comp(clen);
+  CHECK(compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 3) == Z_OK) << "PNG deflate failed";
+  comp.resize(clen);
+  pngChunk(f, "IDAT", comp);
+  pngChunk(f, "IEND", {});
+}
+
+// ---- cv_util::loadImage<T> semantics (CvUtil.h:171-284) -----------------------------------------------
+inline Image loadUnchanged(const fs::path& path) {
+  const std::string ext = path.extension().string();
+  if (ext == ".pfm") {
+    Image img;
+    img.channels = 1;
+    img.bits = 32;
+    img.f = readPfm(path, &img.w, &img.h);
+    return img;
+  }
+  CHECK(ext == ".png") << "only .png and .pfm inputs are supported by this build (got " << path.string() << ")";
+  return readPng(path);
+}
+
+inline int cvRoundD(double v) { return (int)std::lrint(v); }
+
+// loadImage<cv::Vec3w>: depth -> 16U (8U scaled by 65535/255 = 257, float by 65535 with rounding and
+// saturation), then channels -> 3 (gray replicated, alpha dropped)
+inline std::vector<uint16_t> loadColor16(const fs::path& path, int* w, int* h) {
+  const Image img = loadUnchanged(path);
+  *w = img.w;
+  *h = img.h;
+  const size_t n = (size_t)img.w * img.h;
+  std::vector<uint16_t> out(n * 3);
+  auto conv = [&](size_t idx) -> uint16_t {
+    if (img.bits == 16) return img.u[idx];
+    if (img.bits == 8) return (uint16_t)cvRoundD(img.u[idx] * (double)(65535.0f / 255.0f));
+    const double v = (double)img.f[idx] * 65535.0;
+    const int r = v != v ? 0 : cvRoundD(v);
+    return (uint16_t)(r < 0 ? 0 : r > 65535 ? 65535 : r);
+  };
+  for (size_t i = 0; i < n; ++i)
+    for (int c = 0; c < 3; ++c) {
+      const int sc = img.channels >= 3 ? c : 0;
+      out[i * 3 + c] = conv(i * img.channels + sc);
+    }
+  return out;
+}
+
+// loadImage<float>: .pfm as-is; integer images scaled by 1/max
+inline std::vector<float> loadFloat(const fs::path& path, int* w, int* h) {
+  const Image img = loadUnchanged(path);
+  *w = img.w;
+  *h = img.h;
+  const size_t n = (size_t)img.w * img.h;
+  if (img.bits == 32) return img.f;
+  std::vector<float> out(n);
+  const float scale = 1.0f / (img.bits == 16 ? 65535.0f : 255.0f);
+  for (size_t i = 0; i < n; ++i) {
+    if (img.channels >= 3) {  // BGR2GRAY
+      const float b = img.u[i * img.channels] * scale, g = img.u[i * img.channels + 1] * scale,
+                  r = img.u[i * img.channels + 2] * scale;
+      out[i] = 0.114f * b + 0.587f * g + 0.299f * r;
+    } else {
+      out[i] = img.u[i * img.channels] * scale;
+    }
+  }
+  return out;
+}
+
+// loadImage<bool>: depth -> 8U, threshold > 127 -> 1 (CvUtil.h:236-239), first channel / gray
+inline std::vector<uint8_t> loadMask(const fs::path& path, int* w, int* h) {
+  const Image img = loadUnchanged(path);
+  *w = img.w;
+  *h = img.h;
+  const size_t n = (size_t)img.w * img.h;
+  std::vector<uint8_t> out(n);
+  for (size_t i = 0; i < n; ++i) {
+    int v8;
+    if (img.bits == 32) {
+      const double v = (double)img.f[i] * 255.0;
+      v8 = std::min(255, std::max(0, v != v ? 0 : cvRoundD(v)));
+    } else {
+      int v;
+      if (img.channels >= 3) {
+        const int b = img.u[i * img.channels], g = img.u[i * img.channels + 1], r = img.u[i * img.channels + 2];
+        v = (int)std::lrint(0.114 * b + 0.587 * g + 0.299 * r);
+      } else {
+        v = img.u[i * img.channels];
+      }
+      v8 = img.bits == 16 ? std::min(255, cvRoundD(v * (double)(255.0f / 65535.0f))) : v;
+    }
+    out[i] = v8 > 127 ? 1 : 0;
+  }
+  return out;
+}
+
+// cv_util::convertTo<uint16_t>(disparity) for the png outputs: clamp(d,0,1)*65535, NaN -> 0
+inline std::vector<uint16_t> disparityTo16(const float* d, size_t n) {
+  std::vector<uint16_t> out(n);
+  for (size_t i = 0; i < n; ++i) {
+    const float v = d[i] * 65535.0f;
+    const int r = v != v ? 0 : (v >= 2147483648.0f ? 65535 : (v <= -2147483648.0f ? 0 : (int)std::lrintf(v)));
+    out[i] = (uint16_t)(r < 0 ? 0 : r > 65535 ? 65535 : r);
+  }
+  return out;
+}
+
+// output_formats handling shared by the three apps (pfm always for DerpCLI/TemporalBilateralFilter)
+inline void saveDisparity(const fs::path& stem, const std::string& ext, const float* d, int w, int h) {
+  fs::create_directories(stem.parent_path());
+  if (ext == "pfm") {
+    writePfm(stem.string() + ".pfm", d, w, h);
+  } else if (ext == "png") {
+    const auto v = disparityTo16(d, (size_t)w * h);
+    writePng16(stem.string() + ".png", v.data(), w, h, 1);
+  } else if (ext == "exr") {
+    LOG(WARNING) << "exr output is not supported by this build; skipping " << stem.string() << ".exr";
+  } else {
+    LOG(FATAL) << "Invalid type: " << ext;
+  }
+}
+
+}  // namespace io

@@ -197,8 +197,10 @@ int derp_temporal_filter(int device, int width, int height, int num_frames,
                          int spatial_radius, float weight0, float weight1, float weight2,
                          float* out);
 
-/* generalizedJointBilateralFilter<float, Vec3f> as UpsampleDisparity.cpp uses it
- * (TemporalBilateralFilter.h:39-124): guide is float BGR in [0,1]. */
+/* generalizedJointBilateralFilter<float, Vec3f> exactly as UpsampleDisparity.cpp:118-128 calls it
+ * (that file re-defines PixelType = cv::Vec3f, UpsampleDisparity.cpp:57; TemporalBilateralFilter.h:39-124):
+ * guide = float BGR in [0,1] as cv_util::loadImage<Vec3f> produces it (u16 * (1/65535.f), u8 * (1/255.f)),
+ * mask as given (not AND-ed with the FOV mask), weights passed as (weight_b, weight_g, weight_r). */
 int derp_joint_bilateral_f32(int device, int width, int height, const float* image,
                              const float* guide_bgr, const uint8_t* mask, int radius, float sigma,
                              float weight0, float weight1, float weight2, float* out);
