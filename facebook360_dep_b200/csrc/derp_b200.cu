@@ -150,7 +150,8 @@ struct DerpCtx {
   int W = 0, H = 0;
   size_t plane = 0;
   float varNoiseFloor = 0;
-  DevBuf<uint2> dColor, dProjColor, dProjBias;
+  DevBuf<uint2> dColor;
+  DevBuf<float4> dProjColor, dProjBias;  // integer-valued float texels (see derp_cost.cuh)
   DevBuf<float2> dProjWarp;
   DevBuf<float> dVariance, dBg, dDisp, dCost, dConf, dScratchA, dScratchB, dScratchC, dDisparities;
   DevBuf<uint8_t> dFg, dFov, dMismatch, dChangedA, dChangedB, dStage;
@@ -182,9 +183,12 @@ struct DerpCtx {
     v.projWarp = dProjWarp.p;
     v.variance = dVariance.p + (size_t)v.self * plane;
     v.cams = dCams.p;
+    v.one = 1.0f;
+    v.b23 = 8388608.0f;
     return v;
   }
-  size_t camSmem() const { return (size_t)S * sizeof(DevCamera); }
+  // dynamic smem of the cost kernels: S cameras + the destination patch tile
+  size_t camSmem() const { return (size_t)S * sizeof(DevCamera) + kTileFloats * sizeof(float); }
 };
 
 namespace {
@@ -959,11 +963,11 @@ int derp_get_proj_warp(DerpCtx* c, int src, float* warp_xy) {
   return DERP_OK;
 }
 
-static int getTexels(DerpCtx* c, const uint2* plane, uint16_t* bgr) {
+static int getTexels(DerpCtx* c, const float4* plane, uint16_t* bgr) {
   const size_t n = c->plane;
   uint16_t* st = reinterpret_cast<uint16_t*>(c->dStage.p);
-  unpackColorKernel<<<grid1(n), 256, 0, c->stream>>>(n, plane, st);
-  LAUNCHED("unpackColorKernel");
+  unpackTexelF32Kernel<<<grid1(n), 256, 0, c->stream>>>(n, plane, st);
+  LAUNCHED("unpackTexelF32Kernel");
   CU(cudaMemcpyAsync(bgr, st, n * 6, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return DERP_OK;

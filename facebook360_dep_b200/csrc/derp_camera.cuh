@@ -271,11 +271,47 @@ DERP_HD double undistort(const DevCamera& c, double y) {  // Camera.h:243-284
   return x0;
 }
 
+// atan2(y, x) for y >= 0 (y is a norm), result in [0, pi].
+// Device version: one division + fdlibm's degree-11 minimax polynomial (|t| <= tan(pi/8) after folding the
+// argument with atan(a/b) = pi/4 + atan((a-b)/(a+b))), coefficients as constant-bank operands.  CUDA's
+// libdevice atan2 materialises ~25 64-bit immediates with two UMOVs each inside the sweep's inner loop
+// (profiles/README.md); this one issues ~45 instructions in total.  Error < 1.5 ulp, i.e. the same
+// tolerance class as CUDA-vs-glibc atan2 (the value is narrowed to fp32 pixel coordinates afterwards).
+#if defined(__CUDACC__)
+__constant__ double kAtanT[11] = {
+    3.33333333333329318027e-01,  -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+    -1.11111104054623557880e-01, 9.09088713343650656196e-02,  -7.69187620504482999495e-02,
+    6.66107313738753120669e-02,  -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+    -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+#endif
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double atan2Pos(double y, double x) {
+  const double ax = fabs(x);
+  const double hi = fmax(ax, y), lo = fmin(ax, y);
+  // region 0: lo/hi <= tan(pi/8): t = lo/hi;  region 1: t = (lo-hi)/(lo+hi), atan(lo/hi) = pi/4 + atan(t)
+  const bool fold = lo > 0.41421356237309503 * hi;
+  const double num = fold ? lo - hi : lo;
+  const double den = fold ? lo + hi : hi;
+  double t = num / den;
+  if (!(den > 0)) t = 0;  // atan2(0, 0) = 0 like the C library (x = +0)
+  const double z = t * t, w = z * z;
+  const double s1 = z * fma(w, fma(w, fma(w, fma(w, fma(w, kAtanT[10], kAtanT[8]), kAtanT[6]), kAtanT[4]), kAtanT[2]), kAtanT[0]);
+  const double s2 = w * fma(w, fma(w, fma(w, fma(w, kAtanT[9], kAtanT[7]), kAtanT[5]), kAtanT[3]), kAtanT[1]);
+  double a = t - t * (s1 + s2);                       // atan(t), |t| <= 0.4143
+  if (fold) a += 7.85398163397448278999e-01;          // + pi/4
+  if (y > ax) a = 1.57079632679489655800e+00 - a;     // atan(y/ax) = pi/2 - atan(ax/y)
+  if (x < 0) a = 3.14159265358979311600e+00 - a;      // second quadrant
+  return a;
+}
+#else
+inline double atan2Pos(double y, double x) { return atan2(y, x); }
+#endif
+
 // Camera.h:301-341. `cam` = rotation * (rig - position).
 DERP_HD void cameraToSensor(const DevCamera& c, double cx, double cy, double cz, double* sx, double* sy) {
   if (c.type == DERP_CAM_FTHETA) {
     const double xy = sqrt(cx * cx + cy * cy);
-    const double r = atan2(xy, -cz);
+    const double r = atan2Pos(xy, -cz);
     const double f = distort(c, r) / xy;
     *sx = f * cx;
     *sy = f * cy;

@@ -8,8 +8,11 @@
 //   * SSD accumulation order dx outer / dy inner / channel 0..2, cv::Matx::dot order;
 //   * robust camera mean in libstdc++'s nth_element order (derp_select.cuh).
 //
-// HBM layout: every colour image is W*H texels of 4 x u16 (B,G,R,0) = 8 B, so one texel is one
-// aligned 64-bit load; warp tables are W*H x float2.
+// HBM layout: the source colour images are W*H texels of 4 x u16 (B,G,R,0) = 8 B; the per-destination
+// pair tables the cost reads (projColor, projBias) hold the same integer values pre-converted to
+// float4 (B,G,R,0) = one aligned 128-bit load per texel and no u16->f32 conversion in the inner loop
+// (the sweep is instruction-issue bound, not bandwidth bound: profiles/README.md); warp tables are
+// W*H x float2.
 #pragma once
 
 #include <cfloat>
@@ -26,11 +29,15 @@ constexpr float kMinVarF = 1.0f / 12.0f / 65025.0f;  // DerpUtil.h:32
 // One (frame, level, destination) as the cost function sees it.
 struct CostView {
   int W, H, S, self;
-  const uint2* projColor;   // [S][H][W] texels (self slot = the destination's own colour)
-  const uint2* projBias;    // [S][H][W]
+  const float4* projColor;  // [S][H][W] texels (self slot = the destination's own colour)
+  const float4* projBias;   // [S][H][W]
   const float2* projWarp;   // [S][H][W]  src px -> dst px at infinity (self slot unused)
   const float* variance;    // destination's own variance [H][W]
   const DevCamera* cams;    // [S] normalised cameras (global memory; staged to smem by kernels)
+  // 1.0f and 2^23 passed as kernel parameters: they reach the packed instructions as constant-bank /
+  // uniform-register operands, and because ptxas cannot see their values it can neither fold
+  // fma(p, one, q) back into an add nor contract it with the multiply that produced p (see f32x2 notes).
+  float one, b23;
 };
 
 __device__ __forceinline__ int clampIdx(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
@@ -42,8 +49,12 @@ __device__ __forceinline__ float u16lo(uint32_t w) {
 __device__ __forceinline__ float u16hi(uint32_t w) {
   return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f;
 }
-// (float)(ushort)v for 0 <= v < 2^23: adding 2^23 with round-toward-zero drops the fraction.
-__device__ __forceinline__ float truncU16(float v) { return __fadd_rz(v, 8388608.0f) - 8388608.0f; }
+// (ushort)v for 0 <= v < 2^23, returned as the float 2^23 + trunc(v): adding 2^23 with
+// round-toward-zero drops the fraction.  The cost only ever uses DIFFERENCES of such truncated values
+// and integer texels, so everything on the dst side is biased by 2^23 as well (exact: all values are
+// integers below 2^24) and the second FADD is never needed.
+constexpr float kBias23 = 8388608.0f;
+__device__ __forceinline__ float truncBiased(float v) { return __fadd_rz(v, kBias23); }
 
 struct Texel {
   float b, g, r;
@@ -56,22 +67,25 @@ __device__ __forceinline__ float bilerp1(float p00, float p01, float p10, float 
   return w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11;  // left-to-right, no FMA (-fmad=false)
 }
 
-// getPixelBilinear on a Vec3w image: per-channel truncated result (CvUtil.h:90-120)
-__device__ __forceinline__ Texel sampleTexelTrunc(const uint2* __restrict__ img, int W, int H, float x, float y) {
+__device__ __forceinline__ Texel texelOf(float4 t) { return Texel{t.x, t.y, t.z}; }
+
+// getPixelBilinear on a Vec3w image: per-channel truncated result (CvUtil.h:90-120), biased by 2^23.
+// Generic path: per-tap clamp-to-edge.
+__device__ __forceinline__ Texel sampleTexelTruncBiased(const float4* __restrict__ img, int W, int H, float x, float y) {
   const float xf = roundf(x), yf = roundf(y);
   const int xi = (int)xf, yi = (int)yf;
   const int x0 = clampIdx(xi - 1, W - 1), x1 = clampIdx(xi, W - 1);
   const int y0 = clampIdx(yi - 1, H - 1), y1 = clampIdx(yi, H - 1);
   const float xw = x - xf + 0.5f, yw = y - yf + 0.5f;
   const float w00 = (1 - xw) * (1 - yw), w01 = xw * (1 - yw), w10 = (1 - xw) * yw, w11 = xw * yw;
-  const Texel p00 = unpack(__ldg(img + (size_t)y0 * W + x0));
-  const Texel p01 = unpack(__ldg(img + (size_t)y0 * W + x1));
-  const Texel p10 = unpack(__ldg(img + (size_t)y1 * W + x0));
-  const Texel p11 = unpack(__ldg(img + (size_t)y1 * W + x1));
+  const Texel p00 = texelOf(__ldg(img + (size_t)y0 * W + x0));
+  const Texel p01 = texelOf(__ldg(img + (size_t)y0 * W + x1));
+  const Texel p10 = texelOf(__ldg(img + (size_t)y1 * W + x0));
+  const Texel p11 = texelOf(__ldg(img + (size_t)y1 * W + x1));
   Texel o;
-  o.b = truncU16(bilerp1(p00.b, p01.b, p10.b, p11.b, w00, w01, w10, w11));
-  o.g = truncU16(bilerp1(p00.g, p01.g, p10.g, p11.g, w00, w01, w10, w11));
-  o.r = truncU16(bilerp1(p00.r, p01.r, p10.r, p11.r, w00, w01, w10, w11));
+  o.b = truncBiased(bilerp1(p00.b, p01.b, p10.b, p11.b, w00, w01, w10, w11));
+  o.g = truncBiased(bilerp1(p00.g, p01.g, p10.g, p11.g, w00, w01, w10, w11));
+  o.r = truncBiased(bilerp1(p00.r, p01.r, p10.r, p11.r, w00, w01, w10, w11));
   return o;
 }
 
@@ -105,88 +119,355 @@ __device__ __forceinline__ float sampleF32(const float* __restrict__ img, int W,
                  img[(size_t)y1 * W + x1], w00, w01, w10, w11);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2) ---------------------------------------------
+// The sweep is instruction-issue bound and ~40 % of its instructions are the fp32 mul/add of the
+// truncated-bilinear SSD.  Blackwell's packed f32x2 instructions do two IEEE fp32 operations per issue slot
+// with per-lane rounding, so results stay bit-identical to the scalar reference arithmetic, PROVIDED no
+// multiply is contracted into a following add.  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+// even with explicit .rn and -fmad=false (verified on SASS), so every add whose operand is a product is
+// written as fma(p, one, q) with an opaque one (CostView::one): RN(p*1+q) == RN(p+q) exactly, and an FMA
+// cannot absorb a second multiply.  Adds of non-products use add/sub directly.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v) {
+  float a, b;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  (void)b;
+  return a;
+}
+__device__ __forceinline__ float hi2(f32x2 v) {
+  float a, b;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  (void)a;
+  return b;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {  // operands must NOT be products
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {  // operands must NOT be products
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 addrz2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 addp2(f32x2 p, f32x2 q, f32x2 one2) {  // p + q where p and/or q are products
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p), "l"(one2), "l"(q));
+  return r;
+}
+__device__ __forceinline__ float addp(float p, float q, float one) { return __fmaf_rn(p, one, q); }
+
+// bilerp of CvUtil.h:83-86 on two lanes: ((w00*p00 + w01*p01) + w10*p10) + w11*p11, per-lane RN after every op
+__device__ __forceinline__ f32x2 bilerp2(f32x2 p00, f32x2 p01, f32x2 p10, f32x2 p11, f32x2 w00, f32x2 w01, f32x2 w10,
+                                         f32x2 w11, f32x2 one2) {
+  f32x2 s = addp2(mul2(p01, w01), mul2(p00, w00), one2);
+  s = addp2(mul2(p10, w10), s, one2);
+  return addp2(mul2(p11, w11), s, one2);
+}
+
+// ---- destination patch tile in shared memory ----------------------------------------------------------
+// The 3x3 dst colour patches of a CTA's 32x8 pixels overlap: one (32+2)x(8+2) tile of the destination's
+// own colour (+2^23, see truncBiased) serves all of them and keeps 27 values per thread out of registers.
+// Two float2 planes so that the packed arithmetic gets its operands with 64-bit shared loads:
+//   bg[row][col] = (B, G),   rr[row][col] = (R(row), R(row+1))   (vertical pair: see the R channel below)
+constexpr int kTileW = 32 + 2, kTileH = 8 + 2;
+constexpr int kTileFloats = 2 * kTileH * kTileW * 2;
+
+__device__ __forceinline__ void loadDstTile(float* tile, const CostView& v, int x0, int y0) {
+  const float4* col = v.projColor + (size_t)v.self * v.W * v.H;
+  float2* bg = reinterpret_cast<float2*>(tile);
+  float2* rr = bg + kTileH * kTileW;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+  for (int i = tid; i < kTileW * kTileH; i += nt) {
+    const int ty = i / kTileW, tx = i - ty * kTileW;
+    const int gx = clampIdx(x0 + tx - 1, v.W - 1), gy = clampIdx(y0 + ty - 1, v.H - 1);
+    const int gy1 = clampIdx(y0 + ty, v.H - 1);
+    const float4 t = __ldg(col + (size_t)gy * v.W + gx);
+    const float4 t1 = __ldg(col + (size_t)gy1 * v.W + gx);
+    bg[i] = make_float2(t.x + kBias23, t.y + kBias23);
+    rr[i] = make_float2(t.z + kBias23, t1.z + kBias23);
+  }
+  __syncthreads();
+}
+
 // Candidate-independent state of one destination pixel.
 struct PixelState {
-  float cD[27];     // dst colour patch, [dx+1][dy+1][channel] (computeSSD loop order)
-  float dBias[3];   // projColorBias(dst,self)(y,x)
-  float conf;       // max(variance(y,x), kMinVar)
-  double dir[3];    // ray direction of the pixel in rig space
-  double org[3];    // destination camera position
+  const float2* bg;    // &bg[threadIdx.y][threadIdx.x]: patch(dx,dy) = bg[(dy+1)*kTileW + dx+1]
+  const float2* rr;    // same indexing, (R(dy), R(dy+1))
+  float dBias[3];      // projColorBias(dst,self)(y,x) + 2^23
+  float conf;          // max(variance(y,x), kMinVar)
+  double dir[3];       // ray direction of the pixel in rig space
 };
 
-__device__ __forceinline__ void loadPixelState(const CostView& v, const DevCamera& camDst, int x, int y,
-                                               PixelState& ps) {
-  const uint2* col = v.projColor + (size_t)v.self * v.W * v.H;
-#pragma unroll
-  for (int dx = -1; dx <= 1; ++dx)
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const Texel t = unpack(__ldg(col + (size_t)(y + dy) * v.W + (x + dx)));
-      const int k = ((dx + 1) * 3 + (dy + 1)) * 3;
-      ps.cD[k] = t.b;
-      ps.cD[k + 1] = t.g;
-      ps.cD[k + 2] = t.r;
-    }
-  const Texel tb = unpack(__ldg(v.projBias + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x));
-  ps.dBias[0] = tb.b;
-  ps.dBias[1] = tb.g;
-  ps.dBias[2] = tb.r;
+__device__ __forceinline__ void loadPixelState(const CostView& v, const DevCamera& camDst, const float* tile, int x,
+                                               int y, PixelState& ps) {
+  ps.bg = reinterpret_cast<const float2*>(tile) + threadIdx.y * kTileW + threadIdx.x;
+  ps.rr = ps.bg + kTileH * kTileW;
+  const float4 tb = __ldg(v.projBias + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
+  ps.dBias[0] = tb.x + kBias23;
+  ps.dBias[1] = tb.y + kBias23;
+  ps.dBias[2] = tb.z + kBias23;
   ps.conf = fmaxf(__ldg(v.variance + (size_t)y * v.W + x), kMinVarF);
   // dstToWorldPoint (DerpUtil.cpp:38-52): normalised pixel centre, ray through it
   const double px = (x + 0.5) / v.W, py = (y + 0.5) / v.H;
   pixelRay(camDst, px, py, ps.dir);
-  ps.org[0] = camDst.pos[0];
-  ps.org[1] = camDst.pos[1];
-  ps.org[2] = camDst.pos[2];
 }
 
-// computeSSD (DerpUtil.cpp:126-162) against one projected source
-__device__ __forceinline__ void ssdAgainst(const uint2* __restrict__ srcColor, int W, int H, const PixelState& ps,
-                                           float xDstSrc, float yDstSrc, const Texel& srcBias, float* ssdB,
-                                           float* ssdU) {
-  const float bias0 = ps.dBias[0] - srcBias.b, bias1 = ps.dBias[1] - srcBias.g, bias2 = ps.dBias[2] - srcBias.r;
+// isOutsideFov (Camera.h:154-164) for a world point; true = the cone test passes (camera may see it)
+__device__ __forceinline__ bool insideCone(const DevCamera& c, double wx, double wy, double wz) {
+  if (c.cosFov == -1) return true;
+  const double vx = wx - c.pos[0], vy = wy - c.pos[1], vz = wz - c.pos[2];
+  const double camz = c.rot[6] * vx + c.rot[7] * vy + c.rot[8] * vz;
+  if (c.cosFov == 0) return !(camz >= 0);  // !isBehind
+  const double dot = -camz;
+  const double n2 = vx * vx + vy * vy + vz * vz;
+  return !(dot * fabs(dot) <= c.cosFov * fabs(c.cosFov) * n2);
+}
+
+// pixel() + isOutsideSensor + de-normalisation + narrowing (Camera.h:121-128,180-190, DerpUtil.cpp:56-73,
+// Derp.cpp:175) for a point that already passed the cone test.  Straight-line code (no early exit) so that
+// the scheduler can interleave it with the fp32 SSD of the previous source.
+struct SrcPoint {
+  float x, y;
+  bool ok;
+};
+__device__ __forceinline__ SrcPoint projectToSource(const DevCamera& c, double wx, double wy, double wz, int W, int H) {
+  const double vx = wx - c.pos[0], vy = wy - c.pos[1], vz = wz - c.pos[2];
+  const double camx = c.rot[0] * vx + c.rot[1] * vy + c.rot[2] * vz;
+  const double camy = c.rot[3] * vx + c.rot[4] * vy + c.rot[5] * vz;
+  const double camz = c.rot[6] * vx + c.rot[7] * vy + c.rot[8] * vz;
+  double sx, sy;
+  cameraToSensor(c, camx, camy, camz, &sx, &sy);
+  double px = c.focal[0] * sx + c.principal[0];
+  double py = c.focal[1] * sy + c.principal[1];
+  SrcPoint o;
+  o.ok = !(0 > px || px >= c.res[0] || 0 > py || py >= c.res[1]);
+  px *= W;  // worldToSrcPoint: de-normalise (cameras are normalised, DerpUtil.cpp:67-71)
+  py *= H;
+  o.x = (float)px;
+  o.y = (float)py;
+  return o;
+}
+
+// Generic (border / inconsistent-rounding / invalid) path of one source: returns false if the source
+// contributes no SSD (warp entry NaN).  Kept out of line: it runs for a few pixels per image.
+__device__ __noinline__ bool ssdSlowPath(const float4* __restrict__ srcColor, const float4* __restrict__ srcBiasImg,
+                                         int W, int H, const float2* bg, const float2* rr, float dBias0, float dBias1,
+                                         float dBias2, float xDstSrc, float yDstSrc, float* ssdB, float* ssdU) {
+  if (isnan(xDstSrc) || isnan(yDstSrc)) return false;
+  const Texel sbias = sampleTexelTruncBiased(srcBiasImg, W, H, xDstSrc, yDstSrc);
+  const float bias0 = dBias0 - sbias.b, bias1 = dBias1 - sbias.g, bias2 = dBias2 - sbias.r;
   float sB = 0.0f, sU = 0.0f;
-#pragma unroll
-  for (int dx = -1; dx <= 1; ++dx) {
-    const float xs = xDstSrc + (float)dx;
-#pragma unroll
+  for (int dx = -1; dx <= 1; ++dx)
     for (int dy = -1; dy <= 1; ++dy) {
-      const Texel cs = sampleTexelTrunc(srcColor, W, H, xs, yDstSrc + (float)dy);
-      const int k = ((dx + 1) * 3 + (dy + 1)) * 3;
-      const float d0 = ps.cD[k] - cs.b, d1 = ps.cD[k + 1] - cs.g, d2 = ps.cD[k + 2] - cs.r;
+      const Texel cs = sampleTexelTruncBiased(srcColor, W, H, xDstSrc + (float)dx, yDstSrc + (float)dy);
+      const float2 pbg = bg[(dy + 1) * kTileW + dx + 1];
+      const float pr = rr[(dy + 1) * kTileW + dx + 1].x;
+      const float d0 = pbg.x - cs.b, d1 = pbg.y - cs.g, d2 = pr - cs.r;
       const float u0 = d0 - bias0, u1 = d1 - bias1, u2 = d2 - bias2;
       sB += d0 * d0 + d1 * d1 + d2 * d2;
       sU += u0 * u0 + u1 * u1 + u2 * u2;
     }
-  }
   const float scaleFactor = 1.0f / (65535.0f * 65535.0f);
   *ssdB = sB * scaleFactor;
   *ssdU = sU * scaleFactor;
+  return true;
 }
 
-// computeCost (Derp.cpp:104-226).  `cams` should point to shared memory.  Returns the cost;
-// confidence is ps.conf when the return value is not FLT_MAX, 0 otherwise.
+// roundf(p) for both lanes of p when 0 <= p < 2^22, returned biased by 2^23 (so the integer index is a
+// plain integer subtract of the bit patterns): floor(RZ(p + .5)) == floor(p + .5) == roundf(p) for p >= 0.
+__device__ __forceinline__ f32x2 roundBiased2(f32x2 p, f32x2 half2, f32x2 b23) { return addrz2(addrz2(p, half2), b23); }
+
+// computeCost (Derp.cpp:104-226).  `cams` points to shared memory.  Returns the cost; confidence is
+// ps.conf when the return value is not FLT_MAX, 0 otherwise.
+//
+// Structure (instruction-issue bound kernel, see profiles/README.md):
+//   phase A  cone test of every source -> bitmask (short independent fp64 chains, unrolled);
+//   phase B  for each set bit: the fp64 projection of the NEXT source is issued in the same basic block as
+//            the fp32 SSD of the CURRENT one, so the long dependent fp64 chain (sqrt, atan2, divide) and the
+//            two dependent gathers (warp entry -> 4x4 block) hide behind each other.
+// SSD fast path: the 36 taps of the nine 2x2 footprints are one interior 4x4 block read column by column
+// (= the reference's accumulation order, dx outer / dy inner).  Channels B,G ride the two lanes of the
+// packed instructions; channel R rides them as (sample dy=-1, sample dy=0) thanks to the table's w lane
+// holding R of the texel below; the dy=+1 R sample is scalar.  Weights are formed per sample exactly like
+// the reference, so the result is bit-identical to the generic per-tap path.
 __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __restrict__ cams,
                                           const PixelState& ps, float disparity, unsigned* hits) {
   const double depth = (double)(1.0f / disparity);
-  const double wx = ps.org[0] + ps.dir[0] * depth;
-  const double wy = ps.org[1] + ps.dir[1] * depth;
-  const double wz = ps.org[2] + ps.dir[2] * depth;
+  const DevCamera& cd = cams[v.self];
+  const double wx = cd.pos[0] + ps.dir[0] * depth;
+  const double wy = cd.pos[1] + ps.dir[1] * depth;
+  const double wz = cd.pos[2] + ps.dir[2] * depth;
+  const int W = v.W, H = v.H;
+  const size_t plane = (size_t)W * H;
+  const float one = v.one, b23 = v.b23;
+  const f32x2 one2 = pk(one, one), b232 = pk(b23, b23), half2 = pk(0.5f, 0.5f);
+
+  unsigned mask = 0;
+#pragma unroll 4
+  for (int s = 0; s < v.S; ++s)
+    if (insideCone(cams[s], wx, wy, wz)) mask |= 1u << s;
+  mask &= ~(1u << v.self);
+
   float ssdB[kMaxCams], ssdU[kMaxCams];
   int n = 0;
-  const size_t plane = (size_t)v.W * v.H;
-  for (int s = 0; s < v.S; ++s) {
-    if (s == v.self) continue;
-    double px, py;
-    if (!sees(cams[s], wx, wy, wz, &px, &py)) continue;
-    px *= v.W;  // worldToSrcPoint: de-normalise (DerpUtil.cpp:67-71)
-    py *= v.H;
-    const float2 pd = sampleWarp(v.projWarp + s * plane, v.W, v.H, (float)px, (float)py);
-    const float xDstSrc = pd.x + 0.5f, yDstSrc = pd.y + 0.5f;
-    if (isnan(xDstSrc) || isnan(yDstSrc)) continue;
-    const Texel srcBias = sampleTexelTrunc(v.projBias + s * plane, v.W, v.H, xDstSrc, yDstSrc);
-    ssdAgainst(v.projColor + s * plane, v.W, v.H, ps, xDstSrc, yDstSrc, srcBias, &ssdB[n], &ssdU[n]);
-    ++n;
+  if (mask) {
+    int s = __ffs(mask) - 1;
+    mask &= mask - 1;
+    SrcPoint cur = projectToSource(cams[s], wx, wy, wz, W, H);
+    while (true) {
+      const int sNext = mask ? __ffs(mask) - 1 : s;  // tail: harmless re-projection of the same source
+      const bool more = mask != 0;
+      mask &= mask - 1;
+      // ---- current source: warp entry (getPixelBilinear on the Vec2f table, CvUtil.h:107-120) ---------
+      // cur is inside the sensor when cur.ok, so its coordinates are >= 0 and the RZ rounding applies; when
+      // !cur.ok the (clamped, harmless) fetch result is discarded below.
+      f32x2 P = pk(cur.x, cur.y);
+      f32x2 T = roundBiased2(P, half2, b232);
+      f32x2 Wt = add2(sub2(P, sub2(T, b232)), half2);  // (xw, yw) = p - round(p) + 0.5
+      const int wxi = __float_as_int(lo2(T)) - 0x4B000000, wyi = __float_as_int(hi2(T)) - 0x4B000000;
+      float2 pd;
+      {
+        const float2* wt = v.projWarp + s * plane;
+        const int x0 = clampIdx(wxi - 1, W - 1), x1 = clampIdx(wxi, W - 1);
+        const int y0 = clampIdx(wyi - 1, H - 1), y1 = clampIdx(wyi, H - 1);
+        const float2 p00 = __ldg(wt + (size_t)y0 * W + x0), p01 = __ldg(wt + (size_t)y0 * W + x1);
+        const float2 p10 = __ldg(wt + (size_t)y1 * W + x0), p11 = __ldg(wt + (size_t)y1 * W + x1);
+        const float xw = lo2(Wt), yw = hi2(Wt);
+        const float xm = 1 - xw, ym = 1 - yw;
+        const f32x2 r = bilerp2(pk(p00.x, p00.y), pk(p01.x, p01.y), pk(p10.x, p10.y), pk(p11.x, p11.y),
+                                pk(xm * ym, xm * ym), pk(xw * ym, xw * ym), pk(xm * yw, xm * yw), pk(xw * yw, xw * yw), one2);
+        pd.x = lo2(r);
+        pd.y = hi2(r);
+      }
+      const float xDstSrc = pd.x + 0.5f, yDstSrc = pd.y + 0.5f;
+      // ---- footprint of the nine samples: (x,y) pairs for d = -1, 0, +1 ----------------------------------
+      const f32x2 C = pk(xDstSrc, yDstSrc);
+      const f32x2 P0 = add2(C, pk(-1.0f, -1.0f)), P2 = add2(C, pk(1.0f, 1.0f));  // xDstSrc + dx as float adds
+      const f32x2 T0 = roundBiased2(P0, half2, b232), T1 = roundBiased2(C, half2, b232), T2 = roundBiased2(P2, half2, b232);
+      const f32x2 W0 = add2(sub2(P0, sub2(T0, b232)), half2), W1 = add2(sub2(C, sub2(T1, b232)), half2),
+                  W2 = add2(sub2(P2, sub2(T2, b232)), half2);
+      const int xi0 = __float_as_int(lo2(T0)) - 0x4B000000, yi0 = __float_as_int(hi2(T0)) - 0x4B000000;
+      const int xi1 = __float_as_int(lo2(T1)) - 0x4B000000, yi1 = __float_as_int(hi2(T1)) - 0x4B000000;
+      const int xi2 = __float_as_int(lo2(T2)) - 0x4B000000, yi2 = __float_as_int(hi2(T2)) - 0x4B000000;
+      const int X0 = xi0 - 1, Y0 = yi0 - 1;
+      // the RZ rounding needs 0 <= p < 2^22; NaN fails every comparison -> slow path, which rejects it
+      const bool fast = (xDstSrc >= 1.5f) & (yDstSrc >= 1.5f) & (xDstSrc < 4.0e6f) & (yDstSrc < 4.0e6f) &
+          (xi1 == xi0 + 1) & (xi2 == xi0 + 2) & (yi1 == yi0 + 1) & (yi2 == yi0 + 2) & (X0 + 3 <= W - 1) & (Y0 + 3 <= H - 1);
+      const float4* srcColor = v.projColor + s * plane;
+      const float4* srcBiasImg = v.projBias + s * plane;
+      SrcPoint nxt;
+      if (cur.ok) {
+        if (fast) {
+          // ---- main block: 20 gathers + fp32 SSD of source s, fp64 projection of source sNext --------------
+          const size_t off = (size_t)Y0 * W + X0;
+          const float4* r0 = srcColor + off;
+          const float4* r1 = r0 + W;
+          const float4* r2 = r1 + W;
+          const float4* r3 = r2 + W;
+          const float4* b1 = srcBiasImg + off + W + 1;  // bias sample = centre sample's 2x2 footprint
+          const float4 q00 = __ldg(b1), q01 = __ldg(b1 + 1), q10 = __ldg(b1 + W), q11 = __ldg(b1 + W + 1);
+          float4 colA[4], colB[4];
+          colA[0] = __ldg(r0);
+          colA[1] = __ldg(r1);
+          colA[2] = __ldg(r2);
+          colA[3] = __ldg(r3);
+          nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+          // y weights: per sample row r (dy = r-1): yw, 1-yw; rows 0,1 also as a packed pair for channel R
+          const float yw0 = hi2(W0), yw1 = hi2(W1), yw2 = hi2(W2);
+          const float ym0 = 1 - yw0, ym1 = 1 - yw1, ym2 = 1 - yw2;
+          const f32x2 ywP = pk(yw0, yw1), ymP = pk(ym0, ym1);
+          const float xwv[3] = {lo2(W0), lo2(W1), lo2(W2)};
+          // bias = float(dstBias) - float(srcBias): both carry +2^23, the difference is exact
+          f32x2 biasBG;
+          float biasR;
+          {
+            const float xwc = xwv[1], xwm = 1 - xwc;
+            const float w00 = xwm * ym1, w01 = xwc * ym1, w10 = xwm * yw1, w11 = xwc * yw1;
+            const f32x2 sbg = addrz2(bilerp2(pk(q00.x, q00.y), pk(q01.x, q01.y), pk(q10.x, q10.y), pk(q11.x, q11.y),
+                                            pk(w00, w00), pk(w01, w01), pk(w10, w10), pk(w11, w11), one2), b232);
+            biasBG = sub2(pk(ps.dBias[0], ps.dBias[1]), sbg);
+            biasR = ps.dBias[2] - truncBiased(bilerp1(q00.z, q01.z, q10.z, q11.z, w00, w01, w10, w11));
+          }
+          const f32x2 biasRR = pk(biasR, biasR);
+          float sB = 0.0f, sU = 0.0f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {  // dx = c-1: texel columns c and c+1
+            colB[0] = __ldg(r0 + c + 1);
+            colB[1] = __ldg(r1 + c + 1);
+            colB[2] = __ldg(r2 + c + 1);
+            colB[3] = __ldg(r3 + c + 1);
+            const float xwc = xwv[c], xwm = 1 - xwc;
+            const f32x2 xwc2 = pk(xwc, xwc), xwm2 = pk(xwm, xwm);
+            // weights of samples dy=-1,0 as pairs (lane = sample), dy=+1 scalar: w00=(1-xw)(1-yw) ...
+            const f32x2 w00P = mul2(ymP, xwm2), w01P = mul2(ymP, xwc2), w10P = mul2(ywP, xwm2), w11P = mul2(ywP, xwc2);
+            const float w00s = xwm * ym2, w01s = xwc * ym2, w10s = xwm * yw2, w11s = xwc * yw2;
+            // channel R of samples dy=-1 and dy=0 in one go: the texels' (z,w) lanes are (R(row), R(row+1))
+            const f32x2 sR01 = addrz2(bilerp2(pk(colA[0].z, colA[0].w), pk(colB[0].z, colB[0].w), pk(colA[1].z, colA[1].w),
+                                              pk(colB[1].z, colB[1].w), w00P, w01P, w10P, w11P, one2), b232);
+            const float sR2 = truncBiased(bilerp1(colA[2].z, colB[2].z, colA[3].z, colB[3].z, w00s, w01s, w10s, w11s));
+            const f32x2 pR01 = *reinterpret_cast<const f32x2*>(ps.rr + c);
+            const float pR2 = ps.rr[2 * kTileW + c].x;
+            const f32x2 dR01 = sub2(pR01, sR01);
+            const f32x2 uR01 = sub2(dR01, biasRR);
+            const f32x2 ddR01 = mul2(dR01, dR01), uuR01 = mul2(uR01, uR01);
+            const float dR2 = pR2 - sR2, uR2 = dR2 - biasR;
+            const float ddR[3] = {lo2(ddR01), hi2(ddR01), dR2 * dR2};
+            const float uuR[3] = {lo2(uuR01), hi2(uuR01), uR2 * uR2};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {  // dy = r-1: texel rows r and r+1; channels (B,G) on the two lanes
+              const float w00 = r == 0 ? lo2(w00P) : (r == 1 ? hi2(w00P) : w00s);
+              const float w01 = r == 0 ? lo2(w01P) : (r == 1 ? hi2(w01P) : w01s);
+              const float w10 = r == 0 ? lo2(w10P) : (r == 1 ? hi2(w10P) : w10s);
+              const float w11 = r == 0 ? lo2(w11P) : (r == 1 ? hi2(w11P) : w11s);
+              const f32x2 sBG = addrz2(bilerp2(pk(colA[r].x, colA[r].y), pk(colB[r].x, colB[r].y), pk(colA[r + 1].x, colA[r + 1].y),
+                                               pk(colB[r + 1].x, colB[r + 1].y), pk(w00, w00), pk(w01, w01), pk(w10, w10),
+                                               pk(w11, w11), one2), b232);
+              const f32x2 pBG = *reinterpret_cast<const f32x2*>(ps.bg + r * kTileW + c);
+              const f32x2 dBG = sub2(pBG, sBG);
+              const f32x2 uBG = sub2(dBG, biasBG);
+              const f32x2 dd = mul2(dBG, dBG), uu = mul2(uBG, uBG);
+              // cv::Matx::dot order (d0*d0 + d1*d1) + d2*d2, then ssd += s (DerpUtil.cpp:150-151)
+              const float s1 = addp(ddR[r], addp(hi2(dd), lo2(dd), one), one);
+              const float s2 = addp(uuR[r], addp(hi2(uu), lo2(uu), one), one);
+              sB += s1;
+              sU += s2;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) colA[j] = colB[j];
+          }
+          const float scaleFactor = 1.0f / (65535.0f * 65535.0f);
+          ssdB[n] = sB * scaleFactor;
+          ssdU[n] = sU * scaleFactor;
+          ++n;
+        } else {
+          nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+          if (ssdSlowPath(srcColor, srcBiasImg, W, H, ps.bg, ps.rr, ps.dBias[0], ps.dBias[1], ps.dBias[2], xDstSrc, yDstSrc,
+                          &ssdB[n], &ssdU[n]))
+            ++n;
+        }
+      } else {
+        nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+      }
+      if (!more) break;
+      cur = nxt;
+      s = sNext;
+    }
   }
   *hits += n;
   if (n < 1) return FLT_MAX;  // kMinOverlappingCams - 1

@@ -80,22 +80,23 @@ __device__ __forceinline__ int cvRoundQ5(float v) {
   return __float2int_rn(s);
 }
 
-__device__ __forceinline__ uint32_t roundSatU16(float v) {
-  int r = __float2int_rn(v);  // cvRound, then saturate_cast<ushort>
+__device__ __forceinline__ float roundSatU16(float v) {
+  int r = __float2int_rn(v);  // cvRound, then saturate_cast<ushort>; stored as an integer-valued float
   r = r < 0 ? 0 : (r > 65535 ? 65535 : r);
-  return (uint32_t)r;
+  return (float)r;
 }
 
 __global__ void reprojectKernel(const DevCamera* __restrict__ camsPx, int S, int self, int W, int H,
                                 const uint2* __restrict__ color, const float* __restrict__ wtab,
-                                uint2* __restrict__ projColor) {
+                                float4* __restrict__ projColor) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   const int s = blockIdx.z;
   if (x >= W || y >= H) return;
   const size_t plane = (size_t)W * H;
   const size_t p = (size_t)y * W + x;
-  if (s == self) {
-    projColor[s * plane + p] = color[s * plane + p];  // Derp.cpp:989-991
+  if (s == self) {  // Derp.cpp:989-991: the destination's own colour
+    const Texel t = unpack(color[s * plane + p]);
+    projColor[s * plane + p] = make_float4(t.b, t.g, t.r, 0.f);
     return;
   }
   const float nan = __int_as_float(0x7fc00000);
@@ -148,7 +149,7 @@ __global__ void reprojectKernel(const DevCamera* __restrict__ camsPx, int S, int
     }
   } else {
     if (sx >= W || sx + 4 <= 0 || sy >= H || sy + 4 <= 0) {
-      projColor[s * plane + p] = make_uint2(0u, 0u);
+      projColor[s * plane + p] = make_float4(0.f, 0.f, 0.f, 0.f);
       return;
     }
     // border: taps outside contribute the constant 0; one sequential sum (imgwarp.cpp)
@@ -169,8 +170,7 @@ __global__ void reprojectKernel(const DevCamera* __restrict__ camsPx, int S, int
       }
     }
   }
-  const uint32_t B = roundSatU16(sum0), G = roundSatU16(sum1), R = roundSatU16(sum2);
-  projColor[s * plane + p] = make_uint2(B | (G << 16), R);
+  projColor[s * plane + p] = make_float4(roundSatU16(sum0), roundSatU16(sum1), roundSatU16(sum2), 0.f);
 }
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -180,27 +180,34 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 // ---- K4: colorBias = cv::blur 3x3 on u16x3 (DerpUtil.cpp:208-210) for all S planes -----------------
-__global__ void biasKernel(int W, int H, const uint2* __restrict__ in, uint2* __restrict__ out) {
+// The texels are integer-valued floats (< 2^16), so the 9-term sums are exact in fp32 (< 2^24) and equal
+// OpenCV's integer row/column sums.
+// Also fills the w lane of every projColor texel with R of the texel below, which lets the cost kernel run
+// channel R of two vertically adjacent samples on the two lanes of the packed fp32x2 instructions
+// (derp_cost.cuh).  Only the 4 bytes of w are written, so concurrent readers of x,y,z are unaffected.
+__global__ void biasKernel(int W, int H, float4* in, float4* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   const int s = blockIdx.z;
   if (x >= W || y >= H) return;
-  const uint2* img = in + (size_t)s * W * H;
-  int sb = 0, sg = 0, sr = 0;
+  float4* img = in + (size_t)s * W * H;
+  float sb = 0, sg = 0, sr = 0;
 #pragma unroll
   for (int j = -1; j <= 1; ++j) {
     const int yy = reflect101(y + j, H);
 #pragma unroll
     for (int i = -1; i <= 1; ++i) {
       const int xx = reflect101(x + i, W);
-      const uint2 t = __ldg(img + (size_t)yy * W + xx);
-      sb += (int)(t.x & 0xffffu);
-      sg += (int)(t.x >> 16);
-      sr += (int)(t.y & 0xffffu);
+      const float* t = reinterpret_cast<const float*>(img + (size_t)yy * W + xx);
+      sb += t[0];
+      sg += t[1];
+      sr += t[2];
     }
   }
   // saturate_cast<ushort>(sum * (1.0/9)) == (sum + 4) / 9 for integer sums (no exact .5 cases)
-  const uint32_t B = (uint32_t)((sb + 4) / 9), G = (uint32_t)((sg + 4) / 9), R = (uint32_t)((sr + 4) / 9);
-  out[(size_t)s * W * H + (size_t)y * W + x] = make_uint2(B | (G << 16), R);
+  const int B = ((int)sb + 4) / 9, G = ((int)sg + 4) / 9, R = ((int)sr + 4) / 9;
+  out[(size_t)s * W * H + (size_t)y * W + x] = make_float4((float)B, (float)G, (float)R, 0.f);
+  const float below = (y + 1 < H) ? reinterpret_cast<const float*>(img + (size_t)(y + 1) * W + x)[2] : 0.f;
+  reinterpret_cast<float*>(img + (size_t)y * W + x)[3] = below;
 }
 
 // ---- K5: computeImageVariance (DerpUtil.cpp:214-237) for all S planes ---------------------------
@@ -259,6 +266,14 @@ __global__ void unpackColorKernel(size_t n, const uint2* __restrict__ in, uint16
   bgr[i * 3 + 1] = (uint16_t)(t.x >> 16);
   bgr[i * 3 + 2] = (uint16_t)(t.y & 0xffffu);
 }
+__global__ void unpackTexelF32Kernel(size_t n, const float4* __restrict__ in, uint16_t* __restrict__ bgr) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 t = in[i];
+  bgr[i * 3] = (uint16_t)t.x;
+  bgr[i * 3 + 1] = (uint16_t)t.y;
+  bgr[i * 3 + 2] = (uint16_t)t.z;
+}
 template <typename T>
 __global__ void fillKernel(size_t n, T* p, T v) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,7 +299,9 @@ struct SweepArgs {
 __global__ void __launch_bounds__(kBlockX* kBlockY) sweepKernel(const SweepArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  float* tile = reinterpret_cast<float*>(cams + a.v.S);
   stageCameras(cams, a.v.cams, a.v.S);
+  loadDstTile(tile, a.v, blockIdx.x * kBlockX, blockIdx.y * kBlockY);
   const int W = a.v.W, H = a.v.H;
   const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
   unsigned hits = 0, evals = 0;
@@ -293,7 +310,7 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) sweepKernel(const SweepArgs 
     const bool active = a.fov[p] && (!a.fg || a.fg[p]);
     if (active) {
       PixelState ps;
-      loadPixelState(a.v, cams[a.v.self], x, y, ps);
+      loadPixelState(a.v, cams[a.v.self], tile, x, y, ps);
       const float bgd = a.bg ? a.bg[p] : 0.f;
       const int c0 = blockIdx.z * a.chunk;
       const int c1 = min(a.D, c0 + a.chunk);
@@ -393,14 +410,16 @@ __global__ void __launch_bounds__(kBlockX* kBlockY)
                    float* __restrict__ outConf, unsigned long long* counters) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  float* tile = reinterpret_cast<float*>(cams + v.S);
   stageCameras(cams, v.cams, v.S);
+  loadDstTile(tile, v, blockIdx.x * kBlockX, blockIdx.y * kBlockY);
   const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
   if (x >= v.W || y >= v.H) return;
   const size_t p = (size_t)y * v.W + x;
   float co = __int_as_float(0x7fc00000), cf = co;
   if (x >= 1 && x < v.W - 1 && y >= 1 && y < v.H - 1) {
     PixelState ps;
-    loadPixelState(v, cams[v.self], x, y, ps);
+    loadPixelState(v, cams[v.self], tile, x, y, ps);
     unsigned hits = 0;
     co = evalCost(v, cams, ps, disparity[p], &hits);
     cf = (co == FLT_MAX) ? 0.f : ps.conf;
@@ -452,7 +471,9 @@ struct ProposalArgs {
 __global__ void __launch_bounds__(kBlockX* kBlockY) proposalKernel(const ProposalArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  float* tile = reinterpret_cast<float*>(cams + a.v.S);
   stageCameras(cams, a.v.cams, a.v.S);
+  loadDstTile(tile, a.v, blockIdx.x * kBlockX, blockIdx.y * kBlockY);
   const int W = a.v.W, H = a.v.H;
   const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
   if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
@@ -465,7 +486,7 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) proposalKernel(const Proposa
   const int rank = a.prefix[p];
   if (rank < 0) return;  // low variance: skipped (Derp.cpp:785-789)
   PixelState ps;
-  loadPixelState(a.v, cams[a.v.self], x, y, ps);
+  loadPixelState(a.v, cams[a.v.self], tile, x, y, ps);
   unsigned hits = 0;
   float currDisp = a.disp[p];
   float currCost = evalCost(a.v, cams, ps, currDisp, &hits);
@@ -513,7 +534,9 @@ struct PingPongArgs {
 __global__ void __launch_bounds__(kBlockX* kBlockY) pingPongKernel(const PingPongArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  float* tile = reinterpret_cast<float*>(cams + a.v.S);
   stageCameras(cams, a.v.cams, a.v.S);
+  loadDstTile(tile, a.v, blockIdx.x * kBlockX, blockIdx.y * kBlockY);
   const int W = a.v.W, H = a.v.H;
   const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
   if (x >= W || y >= H) return;
@@ -527,7 +550,7 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) pingPongKernel(const PingPon
       res = a.bg[p];
     } else if (!(a.v.variance[p] < a.varNoiseFloor)) {
       PixelState ps;
-      loadPixelState(a.v, cams[a.v.self], x, y, ps);
+      loadPixelState(a.v, cams[a.v.self], tile, x, y, ps);
       unsigned hits = 0, evals = 0;
       float bestCost = __int_as_float(0x7f800000);
       float bestDisp = old;

@@ -1,0 +1,43 @@
+// Test helper (not a reference app): loads an image with the apps' loaders and dumps the converted
+// samples, so tests can compare the PNG/PFM readers and writers with cv2.
+#include "io.h"
+
+DEFINE_string(in, "", "input image");
+DEFINE_string(mode, "color", "color | float | mask | rig");
+DEFINE_string(out, "", "output file (raw samples, or .png/.pfm for mode=float)");
+
+int main(int argc, char** argv) {
+  flags::initDep(argc, argv, "IoSelfTest --in=<image> --mode=color|float|mask|rig --out=<file>");
+  int w = 0, h = 0;
+  std::ofstream o;
+  if (FLAGS_mode == "color") {
+    const auto v = io::loadColor16(FLAGS_in, &w, &h);
+    o.open(FLAGS_out, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size() * 2);
+  } else if (FLAGS_mode == "float") {
+    const auto v = io::loadFloat(FLAGS_in, &w, &h);
+    const fs::path outp(FLAGS_out);
+    const std::string ext = outp.extension().string();
+    if (ext == ".png" || ext == ".pfm") {
+      fs::path stem = outp;
+      stem.replace_extension("");
+      io::saveDisparity(stem, ext.substr(1), v.data(), w, h);
+    } else {
+      o.open(FLAGS_out, std::ios::binary);
+      o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size() * 4);
+    }
+  } else if (FLAGS_mode == "mask") {
+    const auto v = io::loadMask(FLAGS_in, &w, &h);
+    o.open(FLAGS_out, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size());
+  } else if (FLAGS_mode == "rig") {
+    const io::Rig rig = io::loadRig(FLAGS_in);
+    o.open(FLAGS_out, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(rig.cams.data()), (std::streamsize)(rig.cams.size() * sizeof(DerpCameraDesc)));
+    for (const auto& id : rig.ids) std::printf("%s\n", id.c_str());
+  } else {
+    LOG(FATAL) << "bad mode";
+  }
+  std::printf("%d %d\n", w, h);
+  return 0;
+}

@@ -1,0 +1,162 @@
+// TemporalBilateralFilter — drop-in for source/depth_estimation/TemporalBilateralFilter.cpp on B200.
+// Same flags, same directory contract (reads <disparity>/level_L/<cam>/<frame>, writes
+// <output_root>/disparity_time_filtered_levels/level_L/<cam>/<frame>.{pfm,png}); the filter itself is
+// the temporalKernel of libderp_b200.so (derp_temporal_filter).
+// Reproduced verbatim (parity > elegance): weights are passed as (weight_b, weight_g, weight_b) and
+// --weight_r is ignored (TemporalBilateralFilter.cpp:176-178).
+#include "io.h"
+
+static const int kTemporalSpaceRadiusMin = 1;
+static const int kTemporalSpaceRadiusMax = 1;
+
+const std::string kUsageMessage = R"(
+  - Runs temporal filter across disparity frames using corresponding color frames as guides.
+
+  - Example:
+    ./TemporalBilateralFilter \
+    --input_root=/path/to/ \
+    --output_root=/path/to/output \
+    --rig=/path/to/rigs/rig.json \
+    --first=000000 \
+    --last=000000
+)";
+
+DEFINE_string(color, "", "color directory");
+DEFINE_string(cameras, "", "destination cameras");
+DEFINE_string(disparity, "", "disparity directory");
+DEFINE_string(first, "000000", "first frame to process (lexical)");
+DEFINE_string(foreground_masks, "", "foreground masks directory");
+DEFINE_string(input_root, "", "output root directory (required)");
+DEFINE_string(last, "000000", "last frame to process (lexical)");
+DEFINE_int32(level, 0, "pyramid level being processed");
+DEFINE_string(output_formats, "", "saved formats, comma separated (exr, png, pfm supported)");
+DEFINE_string(output_root, "", "output root directory (required)");
+DEFINE_int32(resolution, 2048, "8192, 4096, 2048, 1024, 512, 256");
+DEFINE_string(rig, "", "path to camera rig .json (required)");
+DEFINE_double(sigma, 0.01, "spatio-temporal smoothing");
+DEFINE_int32(space_radius, -1, "space filtering radius");
+DEFINE_int32(threads, -1, "number of threads (-1 = auto, 0 = none)");
+DEFINE_int32(time_radius, 2, "temporal filtering radius");
+DEFINE_bool(use_foreground_masks, false, "use pre-computed foreground masks");
+DEFINE_double(weight_b, 0.5, "Blue channel weight");
+DEFINE_double(weight_g, 1.0, "Green channel weight");
+DEFINE_double(weight_r, 1.0, "Red channel weight");
+DEFINE_int32(gpu, 0, "CUDA device to use");
+
+#define DERP_CALL(expr)                                                 \
+  do {                                                                  \
+    const int rc_ = (expr);                                             \
+    if (rc_ != 0) LOG(FATAL) << #expr << " failed: " << derp_last_error(); \
+  } while (0)
+
+// populateMinMaxFrame (TemporalBilateralFilter.cpp:96-119)
+static void populateMinMaxFrame(const std::string& dir, int level, const std::string& camId, int cur, int& first,
+                                int& last) {
+  const std::string levelDir = io::levelDir(dir, level) + "/" + camId;
+  const std::string ext = io::firstExtension(levelDir);
+  int localFirst = INT32_MAX, localLast = 0;
+  for (int f = cur - FLAGS_time_radius; f <= cur + FLAGS_time_radius; ++f)
+    if (fs::exists(fs::path(levelDir) / (io::zeroPad(f) + ext))) {
+      localFirst = std::min(f, localFirst);
+      localLast = std::max(f, localLast);
+    }
+  first = std::max(localFirst, first);
+  last = std::min(localLast, last);
+}
+
+// FOV mask of one destination at the level size, through the library (generateFovMasks)
+static std::vector<std::vector<uint8_t>> fovMasks(const io::Rig& rig, const std::vector<int>& dst, int W, int H) {
+  std::vector<int32_t> d2s(dst.begin(), dst.end());
+  DerpCtx* ctx = nullptr;
+  DERP_CALL(derp_create(rig.cams.data(), (int)rig.cams.size(), d2s.data(), (int)d2s.size(), FLAGS_gpu, &ctx));
+  DerpLevelParams lp{};
+  lp.width = W;
+  lp.height = H;
+  lp.num_levels = 1;
+  lp.full_width = W;
+  lp.full_height = H;
+  DERP_CALL(derp_level_begin(ctx, &lp));
+  std::vector<std::vector<uint8_t>> out(dst.size(), std::vector<uint8_t>((size_t)W * H));
+  for (size_t d = 0; d < dst.size(); ++d) DERP_CALL(derp_get_fov_mask(ctx, (int)d, out[d].data()));
+  derp_destroy(ctx);
+  return out;
+}
+
+static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst) {  // :121-184
+  int first = 0, last = INT32_MAX;
+  const std::string& ref = rig.ids[dst[0]];
+  populateMinMaxFrame(FLAGS_color, FLAGS_level, ref, cur, first, last);
+  populateMinMaxFrame(FLAGS_disparity, FLAGS_level, ref, cur, first, last);
+  if (FLAGS_use_foreground_masks) populateMinMaxFrame(FLAGS_foreground_masks, FLAGS_level, ref, cur, first, last);
+  CHECK_LE(first, last) << "no frames available around " << cur;
+  const int T = last - first + 1;
+  const float scale = (float)std::pow((double)0.9f, (double)FLAGS_level);
+  const int spaceRadius = FLAGS_space_radius == -1
+      ? (int)std::max(std::ceil(kTemporalSpaceRadiusMax * scale), float(kTemporalSpaceRadiusMin))
+      : FLAGS_space_radius;
+  std::vector<std::vector<uint8_t>> fov;
+  for (size_t ci = 0; ci < dst.size(); ++ci) {
+    const std::string& id = rig.ids[dst[ci]];
+    std::vector<std::vector<uint16_t>> colors(T);
+    std::vector<std::vector<float>> disps(T);
+    std::vector<std::vector<uint8_t>> masks(T);
+    int W = 0, H = 0;
+    for (int t = 0; t < T; ++t) {
+      const std::string frame = io::zeroPad(first + t);
+      int w, h;
+      colors[t] = io::loadColor16(io::imagePath(io::levelDir(FLAGS_color, FLAGS_level), id, frame), &w, &h);
+      W = w;
+      H = h;
+      disps[t] = io::loadFloat(io::imagePath(io::levelDir(FLAGS_disparity, FLAGS_level), id, frame), &w, &h);
+      CHECK(w == W && h == H) << "colour / disparity size mismatch";
+      if (fov.empty()) fov = fovMasks(rig, dst, W, H);
+      if (FLAGS_use_foreground_masks) {
+        masks[t] = io::loadMask(io::imagePath(io::levelDir(FLAGS_foreground_masks, FLAGS_level), id, frame), &w, &h);
+        CHECK(w == W && h == H) << "mask size mismatch";
+        for (size_t i = 0; i < masks[t].size(); ++i) masks[t][i] = masks[t][i] & fov[ci][i];
+      } else {
+        masks[t] = fov[ci];
+      }
+    }
+    std::vector<const uint16_t*> g(T);
+    std::vector<const float*> dp(T);
+    std::vector<const uint8_t*> mp(T);
+    for (int t = 0; t < T; ++t) {
+      g[t] = colors[t].data();
+      dp[t] = disps[t].data();
+      mp[t] = masks[t].data();
+    }
+    std::vector<float> out((size_t)W * H);
+    DERP_CALL(derp_temporal_filter(FLAGS_gpu, W, H, T, g.data(), dp.data(), mp.data(), cur - first, (float)FLAGS_sigma,
+                                   spaceRadius, (float)FLAGS_weight_b, (float)FLAGS_weight_g, (float)FLAGS_weight_b,
+                                   out.data()));
+    // saveDisparity (:61-94): pfm always
+    std::vector<std::string> formats = {"pfm"};
+    std::stringstream ss(FLAGS_output_formats);
+    std::string f;
+    while (std::getline(ss, f, ','))
+      if ((f == "png" || f == "exr") && std::find(formats.begin(), formats.end(), f) == formats.end()) formats.push_back(f);
+    const fs::path stem = fs::path(io::levelDir(FLAGS_output_root + "/" + io::kDisparityTimeFilteredLevels, FLAGS_level)) /
+        id / io::zeroPad(cur);
+    for (const auto& ext : formats) io::saveDisparity(stem, ext, out.data(), W, H);
+  }
+}
+
+int main(int argc, char** argv) {
+  flags::initDep(argc, argv, kUsageMessage);
+  CHECK_NE(FLAGS_rig, "");
+  CHECK_NE(FLAGS_input_root, "");
+  CHECK_NE(FLAGS_output_root, "");
+  if (FLAGS_color.empty()) FLAGS_color = FLAGS_input_root + "/" + io::kColorLevels;
+  if (FLAGS_foreground_masks.empty()) FLAGS_foreground_masks = FLAGS_input_root + "/" + io::kForegroundMasksLevels;
+  if (FLAGS_disparity.empty()) FLAGS_disparity = FLAGS_output_root + "/" + io::kDisparityLevels;
+  const io::Rig rig = io::loadRig(FLAGS_rig);
+  const std::vector<int> dst = io::filterDestinations(rig, FLAGS_cameras);
+  CHECK_GT(dst.size(), 0u) << "no destination cameras!";
+  LOG(INFO) << "backend " << derp_backend();
+  for (int f = std::stoi(FLAGS_first); f <= std::stoi(FLAGS_last); ++f) {
+    LOG(INFO) << "Filtering images... frame " << io::zeroPad(f);
+    filterFrame(f, rig, dst);
+  }
+  return EXIT_SUCCESS;
+}

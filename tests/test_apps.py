@@ -1,0 +1,248 @@
+"""The drop-in executables (facebook360_dep_b200/bin): flag surface, file formats, and — on the GPU box —
+end-to-end runs over a synthetic dataset laid out like the reference's input tree."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from facebook360_dep_b200 import capi, synth
+
+ROOT = capi.ROOT
+BIN = os.path.join(ROOT, "facebook360_dep_b200", "bin")
+HOST = os.path.join(ROOT, "facebook360_dep_b200", "csrc", "host")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built_apps():
+    subprocess.check_call(["make", "-C", HOST], stdout=subprocess.DEVNULL)
+
+
+def run(app, *args, check=True):
+    p = subprocess.run([os.path.join(BIN, app)] + list(args), capture_output=True, text=True)
+    if check and p.returncode != 0:
+        raise AssertionError("%s failed (%d):\n%s" % (app, p.returncode, p.stderr[-2000:]))
+    return p
+
+
+# flag tables of the reference apps: name -> (type, default) (DerpCLI.cpp:40-67,
+# TemporalBilateralFilter.cpp:40-59, UpsampleDisparity.cpp:37-55)
+REF_FLAGS = {
+    "DerpCLI": {
+        "background_disp": ("string", ""), "background_frame": ("string", "000000"), "cameras": ("string", ""),
+        "color": ("string", ""), "do_bilateral_filter": ("bool", "true"), "do_median_filter": ("bool", "true"),
+        "first": ("string", "000000"), "foreground_masks": ("string", ""), "input_root": ("string", ""),
+        "last": ("string", "000000"), "level_end": ("int32", "-1"), "level_start": ("int32", "-1"),
+        "max_depth_m": ("double", "1e4"), "min_depth_m": ("double", ".50"), "mismatches_start_level": ("int32", "-1"),
+        "num_levels": ("int32", "-1"), "output_formats": ("string", ""), "output_root": ("string", ""),
+        "partial_coverage": ("bool", "false"), "ping_pong_iterations": ("int32", "1"),
+        "random_proposals": ("int32", "2"), "resolution": ("int32", "2048"), "rig": ("string", ""),
+        "save_debug_images": ("bool", "false"), "threads": ("int32", "-1"), "use_foreground_masks": ("bool", "false"),
+        "var_high_thresh": ("double", "1e-3"), "var_noise_floor": ("double", "4e-5"),
+    },
+    "TemporalBilateralFilter": {
+        "color": ("string", ""), "cameras": ("string", ""), "disparity": ("string", ""), "first": ("string", "000000"),
+        "foreground_masks": ("string", ""), "input_root": ("string", ""), "last": ("string", "000000"),
+        "level": ("int32", "0"), "output_formats": ("string", ""), "output_root": ("string", ""),
+        "resolution": ("int32", "2048"), "rig": ("string", ""), "sigma": ("double", "0.01"),
+        "space_radius": ("int32", "-1"), "threads": ("int32", "-1"), "time_radius": ("int32", "2"),
+        "use_foreground_masks": ("bool", "false"), "weight_b": ("double", "0.5"), "weight_g": ("double", "1.0"),
+        "weight_r": ("double", "1.0"),
+    },
+    "UpsampleDisparity": {
+        "background_disp": ("string", ""), "background_frame": ("string", "000000"), "cameras": ("string", ""),
+        "color": ("string", ""), "disparity": ("string", ""), "first": ("string", "000000"),
+        "foreground_masks_in": ("string", ""), "foreground_masks_out": ("string", ""), "height": ("int32", "-1"),
+        "last": ("string", "000000"), "output": ("string", ""), "output_formats": ("string", ""),
+        "resolution": ("int32", "-1"), "rig": ("string", ""), "sigma": ("double", "0.05"), "threads": ("int32", "-1"),
+        "weight_b": ("double", "0.5"), "weight_g": ("double", "0.5"), "weight_r": ("double", "1.0"),
+    },
+}
+
+
+@pytest.mark.parametrize("app", sorted(REF_FLAGS))
+def test_flag_surface_matches_reference(app):
+    """The render pipeline learns an app's flags by scraping DEFINE_ lines from its .cpp
+    (scripts/util/system_util.py:123-176): the same scrape of our sources must yield the reference's flags
+    with the reference's types and defaults (extra B200 flags allowed)."""
+    src = open(os.path.join(HOST, app + ".cpp")).read()
+    found = {}
+    for m in re.finditer(r"DEFINE_(\w+)\(\s*(\w+)\s*,\s*([^,]*?)\s*,\s*\"", src):
+        found[m.group(2)] = (m.group(1), m.group(3).strip().strip('"'))
+    for name, (typ, default) in REF_FLAGS[app].items():
+        assert name in found, name
+        assert found[name][0] == typ, name
+        if typ == "double":
+            assert float(found[name][1]) == float(default), name
+        else:
+            assert found[name][1] == default, name
+    extra = set(found) - set(REF_FLAGS[app])
+    assert extra <= {"num_depths", "gpus", "gpu"}, extra
+    h = run(app, "--help", check=False)
+    for name in REF_FLAGS[app]:
+        assert "-" + name + " " in h.stdout
+
+
+def test_png_pfm_io_matches_cv2(tmp_path):
+    rng = np.random.RandomState(0)
+    cases = {
+        "c16": rng.randint(0, 65536, (13, 17, 3)).astype(np.uint16),
+        "c8": rng.randint(0, 256, (11, 9, 3)).astype(np.uint8),
+        "g16": rng.randint(0, 65536, (7, 21)).astype(np.uint16),
+        "a8": rng.randint(0, 256, (9, 10, 4)).astype(np.uint8),
+    }
+    for name, img in cases.items():
+        p = str(tmp_path / (name + ".png"))
+        assert cv2.imwrite(p, img)
+        out = str(tmp_path / (name + ".raw"))
+        r = run("IoSelfTest", "--in=" + p, "--mode=color", "--out=" + out)
+        w, h = map(int, r.stdout.split()[-2:])
+        got = np.fromfile(out, np.uint16).reshape(h, w, 3)
+        # cv_util::loadImage<Vec3w>: depth -> 16U (x257 for 8 bit), gray -> BGR, alpha dropped (CvUtil.h:227-284)
+        ref = img if img.dtype == np.uint16 else img.astype(np.uint16) * 257
+        if ref.ndim == 2:
+            ref = np.repeat(ref[..., None], 3, axis=2)
+        assert np.array_equal(got, ref[..., :3]), name
+    # masks: threshold 127 on the 8-bit value
+    m = rng.randint(0, 256, (8, 12)).astype(np.uint8)
+    p = str(tmp_path / "m.png")
+    cv2.imwrite(p, m)
+    out = str(tmp_path / "m.raw")
+    run("IoSelfTest", "--in=" + p, "--mode=mask", "--out=" + out)
+    assert np.array_equal(np.fromfile(out, np.uint8).reshape(8, 12), (m > 127).astype(np.uint8))
+    # PFM: header + top-down little-endian rows (CvUtil.cpp:39-49); png = u16(clamp(d,0,1)*65535), NaN -> 0
+    d = rng.uniform(-0.2, 1.3, (6, 5)).astype(np.float32)
+    d[2, 3] = np.nan
+    pf = tmp_path / "d.pfm"
+    with open(pf, "wb") as f:
+        f.write(b"Pf\n5 6\n-1.0\n")
+        f.write(d.tobytes())
+    run("IoSelfTest", "--in=" + str(pf), "--mode=float", "--out=" + str(tmp_path / "o.pfm"))
+    assert open(tmp_path / "o.pfm", "rb").read() == open(pf, "rb").read()
+    run("IoSelfTest", "--in=" + str(pf), "--mode=float", "--out=" + str(tmp_path / "o.png"))
+    png = cv2.imread(str(tmp_path / "o.png"), cv2.IMREAD_UNCHANGED)
+    ref = np.nan_to_num(np.clip(d, 0, 1) * 65535.0, nan=0.0)
+    assert png.dtype == np.uint16 and np.array_equal(png, np.rint(ref).astype(np.uint16))
+
+
+def test_rig_json_parser_matches_python_binding(tmp_path):
+    rig = json.load(open(os.path.join(ROOT, "tests", "golden", "camera_vectors.json")))
+    cams = [c["json"] for c in rig["cameras"][:16]]
+    p = tmp_path / "rig.json"
+    json.dump({"cameras": cams}, open(p, "w"))
+    out = tmp_path / "rig.bin"
+    r = run("IoSelfTest", "--in=" + str(p), "--mode=rig", "--out=" + str(out))
+    ids = r.stdout.split()[:16]
+    assert ids == [c["id"] for c in cams]
+    raw = open(out, "rb").read()
+    descs = capi.rig_descs({"cameras": cams})
+    assert raw == bytes(descs)
+
+
+def write_dataset(root, rig, frames, levels, masks=None):
+    """<root>/video/color_levels/level_L/<cam>/<frame>.png + rigs/rig_calibrated.json (ImageTypes.h:16-47)."""
+    os.makedirs(os.path.join(root, "rigs"), exist_ok=True)
+    json.dump(rig, open(os.path.join(root, "rigs", "rig_calibrated.json"), "w"))
+    for f, colors in enumerate(frames):
+        for L in range(levels):
+            for cam, img in zip(rig["cameras"], colors):
+                d = os.path.join(root, "video", "color_levels", "level_%d" % L, cam["id"])
+                os.makedirs(d, exist_ok=True)
+                im = img if L == 0 else synth.downscale_area(img, 1 << L)
+                assert cv2.imwrite(os.path.join(d, "%06d.png" % f), im)
+
+
+def read_pfm(path):
+    with open(path, "rb") as f:
+        assert f.readline() == b"Pf\n"
+        w, h = map(int, f.readline().split())
+        f.readline()
+        return np.frombuffer(f.read(), np.float32).reshape(h, w)
+
+
+def test_derpcli_aborts_without_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rig = synth.ring_rig(3, 32, 32)
+    colors, _ = synth.render_rig(rig, 32, 32)
+    write_dataset(str(tmp_path / "in"), rig, [colors], 1)
+    p = run("DerpCLI", "--input_root=" + str(tmp_path / "in"), "--output_root=" + str(tmp_path / "out"),
+            "--partial_coverage", check=False)
+    assert p.returncode != 0 and "CUDA" in p.stderr  # glog-style FATAL + abort: no CPU fallback
+
+
+@pytest.mark.gpu
+def test_apps_end_to_end(tmp_path, cuda, oracle):
+    W = H = 96
+    S, F = 5, 3
+    rig = synth.ring_rig(S, W, H, kind="FTHETA")
+    frames = []
+    for f in range(F):
+        colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=42, shift=(0.01 * f, 0, 0)))
+        frames.append(colors)
+    inp, out = str(tmp_path / "in"), str(tmp_path / "out")
+    write_dataset(inp, rig, frames, 2)
+    run("DerpCLI", "--input_root=" + inp, "--output_root=" + out, "--first=000000", "--last=000002",
+        "--partial_coverage=true", "--num_depths=48", "--output_formats=png", "--gpus=1")
+    # same pipeline through the Python binding of the same library: PFMs must be byte-identical
+    descs = capi.rig_descs(rig)
+    for lib, exact in ((cuda, True), (oracle, False)):
+        ctx = capi.Context(lib, descs)
+        for f in range(F):
+            coarse = [synth.downscale_area(c, 2) for c in frames[f]]
+            ctx.level_begin(W // 2, H // 2, level=1, num_levels=2, full_width=W, full_height=H)
+            ctx.set_colors(coarse)
+            ctx.process_level(num_depths=48)
+            c1 = [ctx.get_disparity(d, want_cost=False) for d in range(S)]
+            ctx.level_begin(W, H, level=0, num_levels=2, full_width=W, full_height=H)
+            ctx.set_colors(frames[f])
+            for d in range(S):
+                if exact:  # the app re-reads the coarser level from its PFM, which is lossless
+                    ctx.upsample_from(d, c1[d])
+                else:
+                    ctx.upsample_from(d, c1[d])
+            ctx.process_level(num_depths=48)
+            for L, disps in ((1, c1), (0, [ctx.get_disparity(d, want_cost=False) for d in range(S)])):
+                for d in range(S):
+                    got = read_pfm(os.path.join(out, "disparity_levels", "level_%d" % L, "cam%d" % d, "%06d.pfm" % f))
+                    ref = disps[d]
+                    if exact:
+                        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (L, d, f)
+                    else:
+                        assert np.array_equal(np.isnan(got), np.isnan(ref))
+                        fin = ~np.isnan(ref)
+                        assert (np.abs(got - ref)[fin] <= 1e-3 * np.abs(ref)[fin]).mean() >= 0.999
+        ctx.close()
+    png = cv2.imread(os.path.join(out, "disparity_levels", "level_0", "cam0", "000001.png"), cv2.IMREAD_UNCHANGED)
+    assert png is not None and png.dtype == np.uint16 and png.shape == (H, W)
+    # temporal filter over the 3 frames, level 0
+    run("TemporalBilateralFilter", "--input_root=" + inp, "--output_root=" + out, "--rig=" + inp + "/rigs/rig_calibrated.json",
+        "--first=000001", "--last=000001", "--level=0", "--time_radius=2")
+    tf = read_pfm(os.path.join(out, "disparity_time_filtered_levels", "level_0", "cam2", "000001.pfm"))
+    ctx = capi.Context(oracle, descs)
+    ctx.level_begin(W, H)
+    fov = ctx.get_fov_mask(2)
+    guides = [frames[f][2] for f in range(F)]
+    disps = [read_pfm(os.path.join(out, "disparity_levels", "level_0", "cam2", "%06d.pfm" % f)) for f in range(F)]
+    ref = oracle.temporal_filter(guides, disps, [fov] * F, 1, 0.01, 1, 0.5, 1.0, 0.5)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(tf), fin)
+    assert (np.abs(tf - ref)[fin] <= 2e-6 * np.abs(ref)[fin]).all()
+    # upsample level-1 disparity to 96 wide with colour guidance
+    run("UpsampleDisparity", "--rig=" + inp + "/rigs/rig_calibrated.json", "--disparity=" + out + "/disparity_levels/level_1",
+        "--output=" + out + "/disparity_upsample", "--resolution=96", "--color=" + inp + "/video/color_levels/level_0",
+        "--first=000000", "--last=000000", "--cameras=cam1,cam3")
+    up = read_pfm(os.path.join(out, "disparity_upsample", "cam3", "000000.pfm"))
+    coarse = read_pfm(os.path.join(out, "disparity_levels", "level_1", "cam3", "000000.pfm"))
+    d3 = capi.camera_desc_from_json(rig["cameras"][3])
+    ref = oracle.upsample_disparity(d3, coarse, 96, 96)
+    guide = frames[0][3].astype(np.float32) * (np.float32(1.0) / np.float32(65535.0))
+    ref = oracle.joint_bilateral_f32(ref, guide, np.ones((96, 96), np.uint8), 5, 0.05, 0.5, 0.5, 1.0)
+    assert not os.path.exists(os.path.join(out, "disparity_upsample", "cam0"))
+    # Lanczos ringing next to the NaN->1e-4 fill gives values near zero: absolute floor on the tolerance
+    assert (np.abs(up - ref) <= 2e-6 * np.abs(ref) + 2e-7).all()
