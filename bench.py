@@ -138,8 +138,8 @@ def cpu_sample(workload, rig, colors, steps=1, warmup=0):
     from facebook360_dep_b200 import capi
     S, W, H, D, kind = WORKLOADS[workload]
     oracle = capi.load_oracle()  # bench.py's cpu_baseline / --impl reference legs only
-    oracle.set_threads(-1)
-    cores = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
+    oracle.set_threads(ncpu)
     ctx = capi.Context(oracle, capi.rig_descs(rig))
     ctx.level_begin(W, H)
     ctx.set_colors(colors)
@@ -147,6 +147,18 @@ def cpu_sample(workload, rig, colors, steps=1, warmup=0):
     rates = []
     vbar = None
     ncand = 8 if W >= 1024 else D
+    # all the host threads it can use: SMT siblings can hurt this fp-heavy loop, so calibrate on 2 candidates
+    cores, best = ncpu, 0.0
+    for t in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
+        oracle.set_threads(t)
+        t0 = time.perf_counter()
+        ctx.brute_force(0, num_depths=2, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True,
+                        want_index=False)
+        r = ctx.get_counters()[0] / (time.perf_counter() - t0)
+        if r > best:
+            best, cores = r, t
+    oracle.set_threads(cores)
+    log("[bench] cpu baseline uses %d of %d host threads" % (cores, ncpu))
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         ctx.brute_force(0, num_depths=ncand, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True,
@@ -169,7 +181,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    rig, colors = make_inputs(args.workload, "cpu")
+    # input generation is not part of the measurement: render on the GPU when there is one (torchrun pins
+    # OMP_NUM_THREADS=1, which makes the CPU renderer take minutes), else on all host threads
+    import torch
+    if torch.cuda.is_available():
+        gen_dev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+    else:
+        torch.set_num_threads(os.cpu_count() or 1)
+        gen_dev = "cpu"
+    rig, colors = make_inputs(args.workload, gen_dev)
     t0 = time.perf_counter()
     rates, cores, sample, vbar = cpu_sample(args.workload, rig, colors, steps=args.steps, warmup=min(args.warmup, 1))
     total = time.perf_counter() - t0
@@ -302,19 +322,10 @@ def main():
         barrier()
         e2e_ms = e0.elapsed_time(e1)
 
-    # ---- max over ranks ----
-    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else 0.0, float(evals_step), float(hits_step)], device=dev,
-                     dtype=torch.float64)
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, e2e_max = float(tmax[0]), float(tmax[1])
-        evals_all = float(tsum[2])
-    else:
-        e2e_max = float(t[1])
-        evals_all = float(evals_step)
+    # ---- max over ranks (time) / sum over ranks (work): facebook360_dep_b200/shard.py ----
+    from facebook360_dep_b200 import shard
+    ms, evals_all = shard.reduce_step(ms, evals_step, dev)
+    e2e_max, _ = shard.reduce_step(e2e_ms if e2e_ms is not None else 0.0, 0.0, dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

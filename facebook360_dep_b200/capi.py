@@ -15,7 +15,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-CUDA_LIB = os.path.join(_HERE, "libderp_b200.so")
+# DERP_B200_LIB: kernel-tuning experiments load an alternative build of the SAME CUDA library
+CUDA_LIB = os.environ.get("DERP_B200_LIB") or os.path.join(_HERE, "libderp_b200.so")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libderp_oracle.so")
 
 CAM_FTHETA, CAM_RECTILINEAR, CAM_EQUISOLID, CAM_ORTHOGRAPHIC = 0, 1, 2, 3

@@ -296,7 +296,10 @@ struct SweepArgs {
   unsigned long long* counters;  // [0] cost evaluations, [1] source hits
 };
 
-__global__ void __launch_bounds__(kBlockX* kBlockY) sweepKernel(const SweepArgs a) {
+#ifndef DERP_SWEEP_MINB
+#define DERP_SWEEP_MINB 3  // 80 regs, 24 warps/SM: measured best of 1..5 (profiles/README.md)
+#endif
+__global__ void __launch_bounds__(kBlockX* kBlockY, DERP_SWEEP_MINB) sweepKernel(const SweepArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
   float* tile = reinterpret_cast<float*>(cams + a.v.S);
