@@ -175,6 +175,40 @@ def cpu_sample(workload, rig, colors, steps=1, warmup=0):
     return rates, cores, sample, vbar
 
 
+def coarse_to_fine(ctx, colors, S, W, H, D, stream, levels=5):
+    """BASELINE.json configs[1] as the reference runs it (DerpCLI defaults): brute force with D candidates at the
+    coarsest of 5 levels, then random proposals (2) + ping-pong (1) + joint bilateral + median on every finer
+    level, levels handed over in HBM->host->HBM like the PFM round trip.  Reported beside the headline; the
+    second of two passes is timed (geometry caches warm, as from the second frame of a sequence on)."""
+    import torch
+    from facebook360_dep_b200 import synth
+    pyr = [colors]
+    for _ in range(1, levels):
+        pyr.append([synth.downscale_area(c, 2) for c in pyr[-1]])
+    out = None
+    for rep in range(2):
+        prev, tot_ms, tot_e = None, 0.0, 0
+        for level in range(levels - 1, -1, -1):
+            w, h = W >> level, H >> level
+            ctx.level_begin(w, h, level=level, num_levels=levels, full_width=W, full_height=H)
+            ctx.set_colors(pyr[level])
+            if prev is not None:
+                for d in range(S):
+                    ctx.upsample_from(d, prev[d])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.process_level(num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            tot_ms += e0.elapsed_time(e1)
+            tot_e += ctx.get_counters()[0]
+            prev = [ctx.get_disparity(d, want_cost=False) for d in range(S)]
+        out = {"ms_per_frame": tot_ms, "cost_evaluations": tot_e, "value": tot_e / tot_ms / 1e3, "unit": "Mpix·cand/s",
+               "levels": levels, "note": "process_level time only (uploads / level hand-over excluded)"}
+    return out
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU implementation of the path.  The reference cannot be compiled in this
     image (OpenCV C++/Eigen/Boost/gflags/glog/folly absent), so this is the oracle port, all host threads."""
@@ -220,6 +254,7 @@ def main():
     ap.add_argument("--workload", default="bf128_l0", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c2f", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -362,6 +397,8 @@ def main():
                     "FP32/FP64-issue bound, not HBM bound - see DESIGN.md",
             "triples_per_s": hits_step / S / (sweep_ms_launch / 1e3) if sweep_n else None},
     }
+    if world == 1 and args.workload == "bf128_l0" and not args.no_c2f:
+        line["coarse_to_fine_5level"] = coarse_to_fine(ctx, colors, S, W, H, D, stream)
     if world == 1 and not args.no_cpu_baseline:
         cpu_colors = [np.ascontiguousarray(c) for c in colors]
         rates, cores, sample, cvbar = cpu_sample(args.workload, rig, cpu_colors, steps=1, warmup=0)

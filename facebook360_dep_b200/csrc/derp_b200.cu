@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -152,12 +153,22 @@ struct DerpCtx {
   float varNoiseFloor = 0;
   DevBuf<uint2> dColor;
   DevBuf<float4> dProjColor, dProjBias;  // integer-valued float texels (see derp_cost.cuh)
-  DevBuf<float2> dProjWarp;
+  DevBuf<float2> dProjWarp, dWarpInv;  // per-destination scratch when the geometry cache is off
+  // geometry cache: projWarp / projWarpInv of every (dst, src) pair depend on the rig and the level size only
+  // one cache per level size (all levels of cfg-2 together: 21 GB), so both level-major (DerpCLI) and
+  // frame-major pipelines hit it from the second frame on
+  struct GeomCache {
+    DevBuf<float2> buf;  // [Sd][2][S][H][W]
+    std::vector<uint8_t> valid;
+  };
+  std::map<std::pair<int, int>, std::unique_ptr<GeomCache>> geomCaches;
+  GeomCache* geom = nullptr;  // cache of the current level size, or null (maps go to the scratch buffers)
+  bool geomCached = false;
   DevBuf<float> dVariance, dBg, dDisp, dCost, dConf, dScratchA, dScratchB, dScratchC, dDisparities;
   DevBuf<uint8_t> dFg, dFov, dMismatch, dChangedA, dChangedB, dStage;
   DevBuf<unsigned long long> dBest, dCounters;
   DevBuf<unsigned> dUncovered;
-  DevBuf<int> dPrefix, dIdx, dOfs;
+  DevBuf<int> dPrefix, dIdx, dOfs, dRowCount, dRowOffset, dList;
   DevBuf<float> dTaps;
   DevBuf<short2> dSpiral;
   int projDst = -1;
@@ -170,6 +181,8 @@ struct DerpCtx {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweepEvents;
 
+  float2* warpOf(int dst) const { return geomCached ? geom->buf.p + (size_t)dst * 2 * S * plane : dProjWarp.p; }
+  float2* warpInvOf(int dst) const { return geomCached ? geom->buf.p + ((size_t)dst * 2 + 1) * S * plane : dWarpInv.p; }
   const uint8_t* fgOf(int src) const { return haveFg ? dFg.p + (size_t)src * plane : nullptr; }
   const float* bgOf(int dst) const { return haveBg ? dBg.p + (size_t)dst * plane : nullptr; }
   CostView view(int dst) const {
@@ -180,7 +193,7 @@ struct DerpCtx {
     v.self = dst2src[dst];
     v.projColor = dProjColor.p;
     v.projBias = dProjBias.p;
-    v.projWarp = dProjWarp.p;
+    v.projWarp = warpOf(dst);
     v.variance = dVariance.p + (size_t)v.self * plane;
     v.cams = dCams.p;
     v.one = 1.0f;
@@ -189,6 +202,8 @@ struct DerpCtx {
   }
   // dynamic smem of the cost kernels: S cameras + the destination patch tile
   size_t camSmem() const { return (size_t)S * sizeof(DevCamera) + kTileFloats * sizeof(float); }
+  // compacted kernels: S cameras + one 3x3 patch per thread
+  size_t patchSmem() const { return (size_t)S * sizeof(DevCamera) + kPatchFloats * sizeof(float); }
 };
 
 namespace {
@@ -231,6 +246,18 @@ int readCounters(DerpCtx* c) {
   CU(cudaStreamSynchronize(c->stream));
   c->lastEvals = h[0];
   c->lastHits = h[1];
+  return DERP_OK;
+}
+
+// list of active pixels of one destination (activeScan -> rowOffset -> scatter), left in dList / dRowOffset[H]
+int buildActiveList(DerpCtx* c, const uint8_t* fov, const uint8_t* fg, const float* variance, float varThresh) {
+  const int W = c->W, H = c->H;
+  activeScanKernel<<<(H + 7) / 8, 256, 0, c->stream>>>(W, H, fov, fg, variance, varThresh, c->dPrefix.p, c->dRowCount.p);
+  LAUNCHED("activeScanKernel");
+  rowOffsetKernel<<<1, 1024, 0, c->stream>>>(H, c->dRowCount.p, c->dRowOffset.p);
+  LAUNCHED("rowOffsetKernel");
+  activeScatterKernel<<<grid2(W, H), block2(), 0, c->stream>>>(W, H, c->dPrefix.p, c->dRowOffset.p, c->dList.p);
+  LAUNCHED("activeScatterKernel");
   return DERP_OK;
 }
 
@@ -362,7 +389,28 @@ int derp_level_begin(DerpCtx* c, const DerpLevelParams* p) {
   CU(c->dVariance.ensure(n * c->S));
   CU(c->dProjColor.ensure(n * c->S));
   CU(c->dProjBias.ensure(n * c->S));
-  CU(c->dProjWarp.ensure(n * c->S));
+  {  // geometry cache of this level size: create it if all pairs' maps fit in (half of the free) HBM
+    const auto key = std::make_pair(c->W, c->H);
+    auto it = c->geomCaches.find(key);
+    if (it == c->geomCaches.end()) {
+      size_t freeB = 0, totalB = 0;
+      CU(cudaMemGetInfo(&freeB, &totalB));
+      const size_t need = (size_t)c->Sd * 2 * c->S * n * sizeof(float2);
+      const size_t levelBuffers = n * (size_t)c->S * 64;  // what the rest of this function is about to allocate
+      std::unique_ptr<DerpCtx::GeomCache> g(new DerpCtx::GeomCache);
+      if (need + levelBuffers < freeB / 2 && g->buf.ensure(need / sizeof(float2)) == cudaSuccess) {
+        g->valid.assign(c->Sd, 0);
+        it = c->geomCaches.emplace(key, std::move(g)).first;
+      }
+      cudaGetLastError();
+    }
+    c->geom = it == c->geomCaches.end() ? nullptr : it->second.get();
+    c->geomCached = c->geom != nullptr;
+  }
+  if (!c->geomCached) {
+    CU(c->dProjWarp.ensure(n * c->S));
+    CU(c->dWarpInv.ensure(n * c->S));
+  }
   CU(c->dFov.ensure(n * c->Sd));
   CU(c->dDisp.ensure(n * c->Sd));
   CU(c->dCost.ensure(n * c->Sd));
@@ -374,6 +422,9 @@ int derp_level_begin(DerpCtx* c, const DerpLevelParams* p) {
   CU(c->dChangedB.ensure(n));
   CU(c->dBest.ensure(n));
   CU(c->dPrefix.ensure(n));
+  CU(c->dList.ensure(n));
+  CU(c->dRowCount.ensure(c->H));
+  CU(c->dRowOffset.ensure(c->H + 1));
   CU(c->dIdx.ensure(n));
   CU(c->dStage.ensure(n * 6 * (size_t)c->S));
   CU(cudaMemsetAsync(c->dDisp.p, 0, n * c->Sd * sizeof(float), c->stream));
@@ -447,9 +498,14 @@ int derp_reproject(DerpCtx* c, int dst) {
   if (rc) return rc;
   if (!c->haveColors) return fail(DERP_ESTATE, "derp_reproject: colours not set");
   const int self = c->dst2src[dst];
-  projWarpKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->dCamsPx.p, c->S, self, c->W, c->H, c->dProjWarp.p);
-  LAUNCHED("projWarpKernel");
-  reprojectKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->dCamsPx.p, c->S, self, c->W, c->H, c->dColor.p,
+  if (!c->geomCached || !c->geom->valid[dst]) {  // rig + level size only: computed once per destination when cached
+    projWarpKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->dCamsPx.p, c->S, self, c->W, c->H, c->warpOf(dst));
+    LAUNCHED("projWarpKernel");
+    warpInvKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->dCamsPx.p, c->S, self, c->W, c->H, c->warpInvOf(dst));
+    LAUNCHED("warpInvKernel");
+    if (c->geomCached) c->geom->valid[dst] = 1;
+  }
+  reprojectKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->warpInvOf(dst), c->S, self, c->W, c->H, c->dColor.p,
                                                                        c->dWtab.p, c->dProjColor.p);
   LAUNCHED("reprojectKernel");
   biasKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor.p, c->dProjBias.p);
@@ -582,10 +638,15 @@ int derp_random_proposals(DerpCtx* c, int dst, int num_proposals, float min_dept
   a.minDispGlobal = 1.0f / max_depth_m;
   a.maxDisp = 1.0f / min_depth_m;
   a.counters = c->dCounters.p;
+  a.list = c->dList.p;
+  a.listCount = c->dRowOffset.p + H;
   if ((rc = resetCounters(c))) return rc;
-  proposalScanKernel<<<(H + 7) / 8, 256, 0, c->stream>>>(W, H, a.fov, a.fg, a.v.variance, varThresh, c->dPrefix.p);
-  LAUNCHED("proposalScanKernel");
-  proposalKernel<<<grid2(W, H), block2(), c->camSmem(), c->stream>>>(a);
+  if ((rc = buildActiveList(c, a.fov, a.fg, a.v.variance, varThresh))) return rc;
+  if (useFg) {
+    backgroundFillKernel<<<grid2(W, H), block2(), 0, c->stream>>>(W, H, a.fov, a.fg, a.bg, a.disp);
+    LAUNCHED("backgroundFillKernel");
+  }
+  proposalKernel<<<grid1((size_t)(W - 2) * (H - 2), kPatchThreads), kPatchThreads, c->patchSmem(), c->stream>>>(a);
   LAUNCHED("proposalKernel");
   return DERP_OK;
 }
@@ -600,25 +661,33 @@ int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
   const int self = c->dst2src[dst];
   float* disp = c->dDisp.p + (size_t)dst * n;
   float* cost = c->dCost.p + (size_t)dst * n;
+  const uint8_t* fov = c->dFov.p + (size_t)dst * n;
+  const uint8_t* fg = useFg ? c->fgOf(self) : nullptr;
+  const float* bg = useFg ? c->bgOf(dst) : nullptr;
   if ((rc = resetCounters(c))) return rc;
+  // active pixels: interior, in FOV, foreground, variance >= noise floor (Derp.cpp:420-437)
+  if ((rc = buildActiveList(c, fov, fg, c->view(dst).variance, c->varNoiseFloor))) return rc;
   fillKernel<uint8_t><<<grid1(n), 256, 0, c->stream>>>(n, c->dChangedA.p, (uint8_t)1);
   LAUNCHED("fillKernel");
   uint8_t* chIn = c->dChangedA.p;
   uint8_t* chOut = c->dChangedB.p;
   for (int it = 1; it <= iterations; ++it) {
+    pingPongInitKernel<<<grid2(W, H), block2(), 0, c->stream>>>(W, H, fov, fg, bg, disp, c->dScratchA.p, c->dScratchB.p, chOut);
+    LAUNCHED("pingPongInitKernel");
     PingPongArgs a;
     a.v = c->view(dst);
-    a.fov = c->dFov.p + (size_t)dst * n;
-    a.fg = useFg ? c->fgOf(self) : nullptr;
-    a.bg = useFg ? c->bgOf(dst) : nullptr;
+    a.fov = fov;
+    a.fg = fg;
+    a.bg = bg;
     a.disp = disp;
     a.changed = chIn;
     a.dispRes = c->dScratchA.p;
     a.costRes = c->dScratchB.p;
     a.changedNext = chOut;
-    a.varNoiseFloor = c->varNoiseFloor;
+    a.list = c->dList.p;
+    a.listCount = c->dRowOffset.p + H;
     a.counters = c->dCounters.p;
-    pingPongKernel<<<grid2(W, H), block2(), c->camSmem(), c->stream>>>(a);
+    pingPongKernel<<<grid1((size_t)(W - 2) * (H - 2), kPatchThreads), kPatchThreads, c->patchSmem(), c->stream>>>(a);
     LAUNCHED("pingPongKernel");
     // disp <- dispRes, cost <- costsRes (Derp.cpp:527-529); confidence is not written back
     CU(cudaMemcpyAsync(disp, c->dScratchA.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
@@ -958,7 +1027,7 @@ int derp_get_proj_warp(DerpCtx* c, int src, float* warp_xy) {
   if (!warp_xy) return fail(DERP_EINVAL, "bad arguments");
   int rc = checkProj(c, src, "derp_get_proj_warp");
   if (rc) return rc;
-  CU(cudaMemcpyAsync(warp_xy, c->dProjWarp.p + (size_t)src * c->plane, c->plane * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(warp_xy, c->warpOf(c->projDst) + (size_t)src * c->plane, c->plane * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return DERP_OK;
 }

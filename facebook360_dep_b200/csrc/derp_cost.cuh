@@ -228,6 +228,42 @@ __device__ __forceinline__ void loadPixelState(const CostView& v, const DevCamer
   pixelRay(camDst, px, py, ps.dir);
 }
 
+// Compacted kernels (one thread per ACTIVE pixel, pixels of a CTA are not a rectangle): every thread keeps its
+// own 3x3 patch in shared memory, laid out [row][col][thread] so that a warp reads consecutive words.
+constexpr int kPatchThreads = 256;
+constexpr int kPatchRP = 3 * kPatchThreads, kPatchCP = kPatchThreads;
+constexpr int kPatchFloats = 2 * 9 * kPatchThreads * 2;
+
+__device__ __forceinline__ void loadPixelStateCompact(const CostView& v, const DevCamera& camDst, float* patches, int x,
+                                                      int y, PixelState& ps) {
+  const int tid = threadIdx.x;
+  float2* bg = reinterpret_cast<float2*>(patches) + tid;
+  float2* rr = bg + 9 * kPatchThreads;
+  const float4* col = v.projColor + (size_t)v.self * v.W * v.H;
+  float rz[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // rows y-1 .. y+1 (interior pixel: always in bounds)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 t = __ldg(col + (size_t)(y - 1 + r) * v.W + (x - 1 + c));
+      bg[r * kPatchRP + c * kPatchCP] = make_float2(t.x + kBias23, t.y + kBias23);
+      // rr[r] = (R(row r), R(row r+1)); the fast path reads rr[0] (both lanes) and rr[2].x, the slow path rr[r].x
+      if (r >= 1) rr[(r - 1) * kPatchRP + c * kPatchCP] = make_float2(rz[c] + kBias23, t.z + kBias23);
+      if (r == 2) rr[2 * kPatchRP + c * kPatchCP] = make_float2(t.z + kBias23, 0.f);
+      rz[c] = t.z;
+    }
+  }
+  ps.bg = bg;
+  ps.rr = rr;
+  const float4 tb = __ldg(v.projBias + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
+  ps.dBias[0] = tb.x + kBias23;
+  ps.dBias[1] = tb.y + kBias23;
+  ps.dBias[2] = tb.z + kBias23;
+  ps.conf = fmaxf(__ldg(v.variance + (size_t)y * v.W + x), kMinVarF);
+  const double px = (x + 0.5) / v.W, py = (y + 0.5) / v.H;
+  pixelRay(camDst, px, py, ps.dir);
+}
+
 // isOutsideFov (Camera.h:154-164) for a world point; true = the cone test passes (camera may see it)
 __device__ __forceinline__ bool insideCone(const DevCamera& c, double wx, double wy, double wz) {
   if (c.cosFov == -1) return true;
@@ -267,8 +303,9 @@ __device__ __forceinline__ SrcPoint projectToSource(const DevCamera& c, double w
 // Generic (border / inconsistent-rounding / invalid) path of one source: returns false if the source
 // contributes no SSD (warp entry NaN).  Kept out of line: it runs for a few pixels per image.
 __device__ __noinline__ bool ssdSlowPath(const float4* __restrict__ srcColor, const float4* __restrict__ srcBiasImg,
-                                         int W, int H, const float2* bg, const float2* rr, float dBias0, float dBias1,
-                                         float dBias2, float xDstSrc, float yDstSrc, float* ssdB, float* ssdU) {
+                                         int W, int H, const float2* bg, const float2* rr, int rowPitch, int colPitch,
+                                         float dBias0, float dBias1, float dBias2, float xDstSrc, float yDstSrc,
+                                         float* ssdB, float* ssdU) {
   if (isnan(xDstSrc) || isnan(yDstSrc)) return false;
   const Texel sbias = sampleTexelTruncBiased(srcBiasImg, W, H, xDstSrc, yDstSrc);
   const float bias0 = dBias0 - sbias.b, bias1 = dBias1 - sbias.g, bias2 = dBias2 - sbias.r;
@@ -276,8 +313,8 @@ __device__ __noinline__ bool ssdSlowPath(const float4* __restrict__ srcColor, co
   for (int dx = -1; dx <= 1; ++dx)
     for (int dy = -1; dy <= 1; ++dy) {
       const Texel cs = sampleTexelTruncBiased(srcColor, W, H, xDstSrc + (float)dx, yDstSrc + (float)dy);
-      const float2 pbg = bg[(dy + 1) * kTileW + dx + 1];
-      const float pr = rr[(dy + 1) * kTileW + dx + 1].x;
+      const float2 pbg = bg[(dy + 1) * rowPitch + (dx + 1) * colPitch];
+      const float pr = rr[(dy + 1) * rowPitch + (dx + 1) * colPitch].x;
       const float d0 = pbg.x - cs.b, d1 = pbg.y - cs.g, d2 = pr - cs.r;
       const float u0 = d0 - bias0, u1 = d1 - bias1, u2 = d2 - bias2;
       sB += d0 * d0 + d1 * d1 + d2 * d2;
@@ -306,6 +343,9 @@ __device__ __forceinline__ f32x2 roundBiased2(f32x2 p, f32x2 half2, f32x2 b23) {
 // packed instructions; channel R rides them as (sample dy=-1, sample dy=0) thanks to the table's w lane
 // holding R of the texel below; the dy=+1 R sample is scalar.  Weights are formed per sample exactly like
 // the reference, so the result is bit-identical to the generic per-tap path.
+// RP / CP: row and column pitch (in float2) of the thread's 3x3 destination patch in shared memory —
+// (kTileW, 1) for the dense CTA tile, (3*256, 256) for the per-thread patches of the compacted kernels.
+template <int RP, int CP>
 __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __restrict__ cams,
                                           const PixelState& ps, float disparity, unsigned* hits) {
   const double depth = (double)(1.0f / disparity);
@@ -421,8 +461,8 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
             const f32x2 sR01 = addrz2(bilerp2(pk(colA[0].z, colA[0].w), pk(colB[0].z, colB[0].w), pk(colA[1].z, colA[1].w),
                                               pk(colB[1].z, colB[1].w), w00P, w01P, w10P, w11P, one2), b232);
             const float sR2 = truncBiased(bilerp1(colA[2].z, colB[2].z, colA[3].z, colB[3].z, w00s, w01s, w10s, w11s));
-            const f32x2 pR01 = *reinterpret_cast<const f32x2*>(ps.rr + c);
-            const float pR2 = ps.rr[2 * kTileW + c].x;
+            const f32x2 pR01 = *reinterpret_cast<const f32x2*>(ps.rr + c * CP);
+            const float pR2 = ps.rr[2 * RP + c * CP].x;
             const f32x2 dR01 = sub2(pR01, sR01);
             const f32x2 uR01 = sub2(dR01, biasRR);
             const f32x2 ddR01 = mul2(dR01, dR01), uuR01 = mul2(uR01, uR01);
@@ -438,7 +478,7 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
               const f32x2 sBG = addrz2(bilerp2(pk(colA[r].x, colA[r].y), pk(colB[r].x, colB[r].y), pk(colA[r + 1].x, colA[r + 1].y),
                                                pk(colB[r + 1].x, colB[r + 1].y), pk(w00, w00), pk(w01, w01), pk(w10, w10),
                                                pk(w11, w11), one2), b232);
-              const f32x2 pBG = *reinterpret_cast<const f32x2*>(ps.bg + r * kTileW + c);
+              const f32x2 pBG = *reinterpret_cast<const f32x2*>(ps.bg + r * RP + c * CP);
               const f32x2 dBG = sub2(pBG, sBG);
               const f32x2 uBG = sub2(dBG, biasBG);
               const f32x2 dd = mul2(dBG, dBG), uu = mul2(uBG, uBG);
@@ -457,8 +497,8 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           ++n;
         } else {
           nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
-          if (ssdSlowPath(srcColor, srcBiasImg, W, H, ps.bg, ps.rr, ps.dBias[0], ps.dBias[1], ps.dBias[2], xDstSrc, yDstSrc,
-                          &ssdB[n], &ssdU[n]))
+          if (ssdSlowPath(srcColor, srcBiasImg, W, H, ps.bg, ps.rr, RP, CP, ps.dBias[0], ps.dBias[1], ps.dBias[2], xDstSrc,
+                          yDstSrc, &ssdB[n], &ssdU[n]))
             ++n;
         }
       } else {

@@ -12,6 +12,11 @@
 namespace derp {
 
 constexpr int kBlockX = 32, kBlockY = 8;  // 256 threads
+// resident CTAs per SM requested for the cost kernels: 3 -> 80 registers, 24 warps/SM; measured best of
+// 1..5 on the sweep (15.0 / 20.8 / 21.2 / 17.1 / 10.9 G triples/s at 1024^2, profiles/README.md)
+#ifndef DERP_SWEEP_MINB
+#define DERP_SWEEP_MINB 3
+#endif
 
 __device__ __forceinline__ void stageCameras(DevCamera* sm, const DevCamera* __restrict__ g, int n) {
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -69,9 +74,34 @@ __global__ void projWarpKernel(const DevCamera* __restrict__ camsPx, int S, int 
   projWarp[(size_t)s * W * H + (size_t)y * W + x] = out;
 }
 
+// ---- K2b: projWarpInv(dst, s) = computeWarpDstToSrc(camDst, camSrc) (Derp.cpp:971) -------------------------
+// Destination pixel -> source pixel at infinity, OpenCV convention (-0.5), NaN where unseen.  Like projWarp it
+// depends on the rig and the level size only, so both maps are kept across frames when they fit in HBM
+// (DerpCtx geometry cache) and the per-frame work of reprojectColors is the pure gather below.
+__global__ void warpInvKernel(const DevCamera* __restrict__ camsPx, int S, int self, int W, int H,
+                              float2* __restrict__ warpInv) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const float nan = __int_as_float(0x7fc00000);
+  float2 out = make_float2(nan, nan);
+  if (s != self) {
+    const DevCamera& from = camsPx[self];
+    const DevCamera& to = camsPx[s];
+    const double px = x + 0.5, py = y + 0.5;
+    if (!outsideImageCircle(from, px, py)) {
+      double dir[3];
+      pixelRay(from, px, py, dir);
+      const double wx = from.pos[0] + dir[0] * 1e4, wy = from.pos[1] + dir[1] * 1e4, wz = from.pos[2] + dir[2] * 1e4;
+      double qx, qy;
+      if (sees(to, wx, wy, wz, &qx, &qy)) out = make_float2((float)(qx - 0.5f), (float)(qy - 0.5f));
+    }
+  }
+  warpInv[(size_t)s * W * H + (size_t)y * W + x] = out;
+}
+
 // ---- K3: reprojectColors -> project (Derp.cpp:978-1003, DerpUtil.cpp:199-205) --------------------
-// Fuses projWarpInv(dst, s) = computeWarpDstToSrc(camDst, camSrc) with cv::remap(INTER_CUBIC,
-// BORDER_CONSTANT 0): the map entry lives in registers and is never written to HBM.
+// cv::remap(src colour, projWarpInv, INTER_CUBIC, BORDER_CONSTANT 0).
 // wtab = OpenCV's 32x32x16 float bicubic table (built on the host exactly as imgwarp.cpp does).
 __device__ __forceinline__ int cvRoundQ5(float v) {
   // cvRound(v * 32) with x86 semantics: NaN / out-of-range -> INT_MIN
@@ -86,7 +116,7 @@ __device__ __forceinline__ float roundSatU16(float v) {
   return (float)r;
 }
 
-__global__ void reprojectKernel(const DevCamera* __restrict__ camsPx, int S, int self, int W, int H,
+__global__ void reprojectKernel(const float2* __restrict__ warpInv, int S, int self, int W, int H,
                                 const uint2* __restrict__ color, const float* __restrict__ wtab,
                                 float4* __restrict__ projColor) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -99,23 +129,8 @@ __global__ void reprojectKernel(const DevCamera* __restrict__ camsPx, int S, int
     projColor[s * plane + p] = make_float4(t.b, t.g, t.r, 0.f);
     return;
   }
-  const float nan = __int_as_float(0x7fc00000);
-  float mx = nan, my = nan;
-  {
-    const DevCamera& from = camsPx[self];
-    const DevCamera& to = camsPx[s];
-    const double px = x + 0.5, py = y + 0.5;
-    if (!outsideImageCircle(from, px, py)) {
-      double dir[3];
-      pixelRay(from, px, py, dir);
-      const double wx = from.pos[0] + dir[0] * 1e4, wy = from.pos[1] + dir[1] * 1e4, wz = from.pos[2] + dir[2] * 1e4;
-      double qx, qy;
-      if (sees(to, wx, wy, wz, &qx, &qy)) {
-        mx = (float)(qx - 0.5f);
-        my = (float)(qy - 0.5f);
-      }
-    }
-  }
+  const float2 m = __ldg(warpInv + s * plane + p);
+  const float mx = m.x, my = m.y;
   const int sxq = cvRoundQ5(mx), syq = cvRoundQ5(my);
   const int fidx = (syq & 31) * 32 + (sxq & 31);
   int ix = sxq >> 5, iy = syq >> 5;
@@ -296,9 +311,6 @@ struct SweepArgs {
   unsigned long long* counters;  // [0] cost evaluations, [1] source hits
 };
 
-#ifndef DERP_SWEEP_MINB
-#define DERP_SWEEP_MINB 3  // 80 regs, 24 warps/SM: measured best of 1..5 (profiles/README.md)
-#endif
 __global__ void __launch_bounds__(kBlockX* kBlockY, DERP_SWEEP_MINB) sweepKernel(const SweepArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(kBlockX* kBlockY, DERP_SWEEP_MINB) sweepKernel
       for (int c = c0; c < c1; ++c) {
         const float d = __ldg(a.disparities + c);
         if (a.bg && !(bgd < d)) continue;  // closerMask (Derp.cpp:240-243)
-        const float cost = evalCost(a.v, cams, ps, d, &hits);
+        const float cost = evalCost<kTileW, 1>(a.v, cams, ps, d, &hits);
         ++evals;
         if (cost < bestCost) {
           bestCost = cost;
@@ -408,7 +420,7 @@ __global__ void extendBorderKernel(int W, int H, const uint8_t* __restrict__ fg,
 }
 
 // ---- derp_eval_cost: one hypothesis per pixel ------------------------------------------------------
-__global__ void __launch_bounds__(kBlockX* kBlockY)
+__global__ void __launch_bounds__(kBlockX* kBlockY, DERP_SWEEP_MINB)
     evalCostKernel(const CostView v, const float* __restrict__ disparity, float* __restrict__ outCost,
                    float* __restrict__ outConf, unsigned long long* counters) {
   extern __shared__ double smemRaw[];
@@ -424,7 +436,7 @@ __global__ void __launch_bounds__(kBlockX* kBlockY)
     PixelState ps;
     loadPixelState(v, cams[v.self], tile, x, y, ps);
     unsigned hits = 0;
-    co = evalCost(v, cams, ps, disparity[p], &hits);
+    co = evalCost<kTileW, 1>(v, cams, ps, disparity[p], &hits);
     cf = (co == FLT_MAX) ? 0.f : ps.conf;
     addCounters(counters, 1u, hits);
   }
@@ -432,13 +444,15 @@ __global__ void __launch_bounds__(kBlockX* kBlockY)
   if (outConf) outConf[p] = cf;
 }
 
-// ---- K7: randomProposal (Derp.cpp:750-824) -----------------------------------------------------------
-// The reference walks each row sequentially with one minstd_rand0 per row (seed y*level) and draws
-// exactly numProposals values for every processed pixel.  Whether a pixel is processed depends only
-// on masks and variance, so the draw index of pixel x is numProposals * (#processed pixels left of
-// x): an exclusive row scan + LCG skip-ahead makes the row parallel and bit-identical.
-__global__ void proposalScanKernel(int W, int H, const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg,
-                                   const float* __restrict__ variance, float varThresh, int* __restrict__ prefix) {
+// ---- active-pixel compaction for the fine-level stages ---------------------------------------------------
+// randomProposal and pingPong skip pixels outside the FOV / foreground mask and below a variance threshold
+// (Derp.cpp:765-789, 422-437).  With one thread per pixel those lanes idle while their neighbours run ~10^4
+// instructions per cost evaluation, so the stages first build the list of active pixels (row scan ->
+// row offsets -> scatter) and then run one thread per ACTIVE pixel.  `prefix` doubles as the per-row draw
+// index of randomProposal's sequential RNG (see below).
+__global__ void activeScanKernel(int W, int H, const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg,
+                                 const float* __restrict__ variance, float varThresh, int* __restrict__ prefix,
+                                 int* __restrict__ rowCount) {
   // one warp per row
   const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -455,14 +469,66 @@ __global__ void proposalScanKernel(int W, int H, const uint8_t* __restrict__ fov
     if (x < W) prefix[(size_t)y * W + x] = proc ? running + __popc(m & ((1u << lane) - 1u)) : -1;
     running += __popc(m);
   }
+  if (lane == 0) rowCount[y] = running;
 }
 
+// exclusive scan of the row counts (H <= a few thousand: one CTA); rowOffset[H] = total
+__global__ void rowOffsetKernel(int H, const int* __restrict__ rowCount, int* __restrict__ rowOffset) {
+  __shared__ int warpSums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < H; base += blockDim.x) {
+    const int i = base + tid;
+    int v = i < H ? rowCount[i] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    if (lane == 31) warpSums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int ws = lane < (blockDim.x >> 5) ? warpSums[lane] : 0;
+      int wi = ws;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += n;
+      }
+      warpSums[lane] = wi - ws;  // exclusive
+    }
+    __syncthreads();
+    const int excl = carry + warpSums[wid] + incl - v;
+    if (i < H) rowOffset[i] = excl;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) rowOffset[H] = carry;
+}
+
+__global__ void activeScatterKernel(int W, int H, const int* __restrict__ prefix, const int* __restrict__ rowOffset,
+                                    int* __restrict__ list) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const int r = prefix[(size_t)y * W + x];
+  if (r >= 0) list[rowOffset[y] + r] = y * W + x;
+}
+
+// ---- K7: randomProposal (Derp.cpp:750-824) -----------------------------------------------------------
+// The reference walks each row sequentially with one minstd_rand0 per row (seed y*level) and draws
+// exactly numProposals values for every processed pixel.  Whether a pixel is processed depends only
+// on masks and variance, so the draw index of pixel x is numProposals * (#processed pixels left of
+// x) = numProposals * prefix[x]: the row scan + LCG skip-ahead makes the row parallel and bit-identical.
 struct ProposalArgs {
   CostView v;
   const uint8_t* fov;
   const uint8_t* fg;
   const float* bg;
   const int* prefix;
+  const int* list;       // active pixels
+  const int* listCount;  // &rowOffset[H]
   float* disp;
   float* cost;
   float* conf;
@@ -471,28 +537,30 @@ struct ProposalArgs {
   unsigned long long* counters;
 };
 
-__global__ void __launch_bounds__(kBlockX* kBlockY) proposalKernel(const ProposalArgs a) {
-  extern __shared__ double smemRaw[];
-  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
-  float* tile = reinterpret_cast<float*>(cams + a.v.S);
-  stageCameras(cams, a.v.cams, a.v.S);
-  loadDstTile(tile, a.v, blockIdx.x * kBlockX, blockIdx.y * kBlockY);
-  const int W = a.v.W, H = a.v.H;
-  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+// pixels outside the foreground mask take the background disparity (Derp.cpp:768-771)
+__global__ void backgroundFillKernel(int W, int H, const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg,
+                                     const float* __restrict__ bg, float* __restrict__ disp) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
   const size_t p = (size_t)y * W + x;
-  if (!a.fov[p]) return;
-  if (a.fg && !a.fg[p]) {
-    a.disp[p] = a.bg[p];
-    return;
-  }
-  const int rank = a.prefix[p];
-  if (rank < 0) return;  // low variance: skipped (Derp.cpp:785-789)
+  if (fov[p] && !fg[p]) disp[p] = bg[p];
+}
+
+__global__ void __launch_bounds__(kPatchThreads, DERP_SWEEP_MINB) proposalKernel(const ProposalArgs a) {
+  extern __shared__ double smemRaw[];
+  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  float* patches = reinterpret_cast<float*>(cams + a.v.S);
+  stageCameras(cams, a.v.cams, a.v.S);
+  const int i = blockIdx.x * kPatchThreads + threadIdx.x;
+  if (i >= *a.listCount) return;
+  const int W = a.v.W;
+  const int p = a.list[i];
+  const int y = p / W, x = p - y * W;
   PixelState ps;
-  loadPixelState(a.v, cams[a.v.self], tile, x, y, ps);
+  loadPixelStateCompact(a.v, cams[a.v.self], patches, x, y, ps);
   unsigned hits = 0;
   float currDisp = a.disp[p];
-  float currCost = evalCost(a.v, cams, ps, currDisp, &hits);
+  float currCost = evalCost<kPatchRP, kPatchCP>(a.v, cams, ps, currDisp, &hits);
   float currConf = (currCost == FLT_MAX) ? 0.f : ps.conf;
   const float costThresh = fminf(0.5f * currCost, 5.0f);
   const float minDisp = a.bg ? a.bg[p] : a.minDispGlobal;
@@ -500,12 +568,13 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) proposalKernel(const Proposa
   float amplitude = (maxDisp - minDisp) / 2.0f;
   MinstdRand0 rng;
   rng.seed((unsigned)(y * a.level));
-  rng.discard((unsigned long long)rank * (unsigned long long)a.numProposals);
-  for (int i = 0; i < a.numProposals; ++i) {
+  rng.discard((unsigned long long)a.prefix[p] * (unsigned long long)a.numProposals);
+#pragma unroll 1
+  for (int k = 0; k < a.numProposals; ++k) {
     const float lo = fmaxf(minDisp, currDisp - amplitude);
     const float hi = fminf(maxDisp, currDisp + amplitude);
     const float propDisp = rng.uniform(lo, hi);
-    const float propCost = evalCost(a.v, cams, ps, propDisp, &hits);
+    const float propCost = evalCost<kPatchRP, kPatchCP>(a.v, cams, ps, propDisp, &hits);
     if (propCost < currCost && propCost < costThresh) {
       currCost = propCost;
       currDisp = propDisp;
@@ -527,62 +596,71 @@ struct PingPongArgs {
   const float* bg;
   const float* disp;        // read
   const uint8_t* changed;   // read
-  float* dispRes;           // write (all pixels)
-  float* costRes;           // write (all pixels; INF where skipped)
+  float* dispRes;           // write
+  float* costRes;           // write (INF where skipped)
   uint8_t* changedNext;     // write: disp != dispRes
-  float varNoiseFloor;
+  const int* list;
+  const int* listCount;
   unsigned long long* counters;
 };
 
-__global__ void __launch_bounds__(kBlockX* kBlockY) pingPongKernel(const PingPongArgs a) {
-  extern __shared__ double smemRaw[];
-  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
-  float* tile = reinterpret_cast<float*>(cams + a.v.S);
-  stageCameras(cams, a.v.cams, a.v.S);
-  loadDstTile(tile, a.v, blockIdx.x * kBlockX, blockIdx.y * kBlockY);
-  const int W = a.v.W, H = a.v.H;
-  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+// every pixel: the values a skipped pixel ends up with (Derp.cpp:420-437, 486-487, 525-529)
+__global__ void pingPongInitKernel(int W, int H, const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg,
+                                   const float* __restrict__ bg, const float* __restrict__ disp,
+                                   float* __restrict__ dispRes, float* __restrict__ costRes,
+                                   uint8_t* __restrict__ changedNext) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
   const size_t p = (size_t)y * W + x;
-  const float old = a.disp[p];
+  const float old = disp[p];
   float res = old;
-  float resCost = __int_as_float(0x7f800000);  // +INF
   const bool interior = x >= 1 && x < W - 1 && y >= 1 && y < H - 1;
-  if (interior && a.fov[p]) {
-    if (a.fg && !a.fg[p]) {
-      res = a.bg[p];
-    } else if (!(a.v.variance[p] < a.varNoiseFloor)) {
-      PixelState ps;
-      loadPixelState(a.v, cams[a.v.self], tile, x, y, ps);
-      unsigned hits = 0, evals = 0;
-      float bestCost = __int_as_float(0x7f800000);
-      float bestDisp = old;
-      const float backgroundDisparity = a.bg ? a.bg[p] : 0.f;
-      const int offX[9] = {0, -1, 1, 0, 0, -2, 2, -2, 2};   // candidateTemplateOriginal, DerpUtil.h:34-43
-      const int offY[9] = {0, 0, 0, -1, 1, -2, -2, 2, 2};
+  if (interior && fov[p] && fg && !fg[p]) res = bg[p];
+  dispRes[p] = res;
+  costRes[p] = __int_as_float(0x7f800000);  // +INF
+  changedNext[p] = (old != res) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kPatchThreads, DERP_SWEEP_MINB) pingPongKernel(const PingPongArgs a) {
+  extern __shared__ double smemRaw[];
+  DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
+  float* patches = reinterpret_cast<float*>(cams + a.v.S);
+  stageCameras(cams, a.v.cams, a.v.S);
+  const int i = blockIdx.x * kPatchThreads + threadIdx.x;
+  if (i >= *a.listCount) return;
+  const int W = a.v.W, H = a.v.H;
+  const int p = a.list[i];
+  const int y = p / W, x = p - y * W;
+  PixelState ps;
+  loadPixelStateCompact(a.v, cams[a.v.self], patches, x, y, ps);
+  const float old = a.disp[p];
+  unsigned hits = 0, evals = 0;
+  float bestCost = __int_as_float(0x7f800000);
+  float bestDisp = old;
+  const float backgroundDisparity = a.bg ? a.bg[p] : 0.f;
 #pragma unroll 1
-      for (int k = 0; k < 9; ++k) {
-        const int xx = clampIdx(x + offX[k], W - 1), yy = clampIdx(y + offY[k], H - 1);
-        const size_t q = (size_t)yy * W + xx;
-        if (!a.fov[q]) continue;
-        const float d = a.disp[q];
-        if (d >= backgroundDisparity && a.changed[q]) {
-          const float cost = evalCost(a.v, cams, ps, d, &hits);
-          ++evals;
-          if (cost < bestCost) {
-            bestCost = cost;
-            bestDisp = d;
-          }
-        }
+  for (int k = 0; k < 9; ++k) {
+    // candidateTemplateOriginal (DerpUtil.h:34-43): centre, 4-neighbours, 4 diagonals at +-2
+    // offsets + 2 packed as nibbles, k = 0..8:  x: 0,-1,1,0,0,-2,2,-2,2   y: 0,0,0,-1,1,-2,-2,2,2
+    const int ox = (int)((0x404022312ull >> (4 * k)) & 0xF) - 2;
+    const int oy = (int)((0x440031222ull >> (4 * k)) & 0xF) - 2;
+    const int xx = clampIdx(x + ox, W - 1), yy = clampIdx(y + oy, H - 1);
+    const size_t q = (size_t)yy * W + xx;
+    if (!a.fov[q]) continue;
+    const float d = a.disp[q];
+    if (d >= backgroundDisparity && a.changed[q]) {
+      const float cost = evalCost<kPatchRP, kPatchCP>(a.v, cams, ps, d, &hits);
+      ++evals;
+      if (cost < bestCost) {
+        bestCost = cost;
+        bestDisp = d;
       }
-      res = bestDisp;
-      resCost = bestCost;
-      addCounters(a.counters, evals, hits);
     }
   }
-  a.dispRes[p] = res;
-  a.costRes[p] = resCost;
-  a.changedNext[p] = (old != res) ? 1 : 0;
+  a.dispRes[p] = bestDisp;
+  a.costRes[p] = bestCost;
+  a.changedNext[p] = (old != bestDisp) ? 1 : 0;
+  addCounters(a.counters, evals, hits);
 }
 
 // ---- K9: handleDisparityMismatch (Derp.cpp:553-720) for one destination ----------------------------------
