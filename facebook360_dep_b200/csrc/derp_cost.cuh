@@ -185,15 +185,17 @@ __device__ __forceinline__ f32x2 bilerp2(f32x2 p00, f32x2 p01, f32x2 p10, f32x2 
 // own colour (+2^23, see truncBiased) serves all of them and keeps 27 values per thread out of registers.
 // Two float2 planes so that the packed arithmetic gets its operands with 64-bit shared loads:
 //   bg[row][col] = (B, G),   rr[row][col] = (R(row), R(row+1))   (vertical pair: see the R channel below)
-constexpr int kTileW = 32 + 2, kTileH = 8 + 2;
-constexpr int kTileFloats = 2 * kTileH * kTileW * 2;
+constexpr int kTileW = 32 + 2;
+constexpr int kMaxTileH = 24 + 2;  // tallest CTA the sweep is launched with (32 x 24 threads)
+constexpr int kTileFloats = 2 * kMaxTileH * kTileW * 2;
 
 __device__ __forceinline__ void loadDstTile(float* tile, const CostView& v, int x0, int y0) {
   const float4* col = v.projColor + (size_t)v.self * v.W * v.H;
   float2* bg = reinterpret_cast<float2*>(tile);
-  float2* rr = bg + kTileH * kTileW;
+  const int tileH = blockDim.y + 2;
+  float2* rr = bg + tileH * kTileW;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
-  for (int i = tid; i < kTileW * kTileH; i += nt) {
+  for (int i = tid; i < kTileW * tileH; i += nt) {
     const int ty = i / kTileW, tx = i - ty * kTileW;
     const int gx = clampIdx(x0 + tx - 1, v.W - 1), gy = clampIdx(y0 + ty - 1, v.H - 1);
     const int gy1 = clampIdx(y0 + ty, v.H - 1);
@@ -217,7 +219,7 @@ struct PixelState {
 __device__ __forceinline__ void loadPixelState(const CostView& v, const DevCamera& camDst, const float* tile, int x,
                                                int y, PixelState& ps) {
   ps.bg = reinterpret_cast<const float2*>(tile) + threadIdx.y * kTileW + threadIdx.x;
-  ps.rr = ps.bg + kTileH * kTileW;
+  ps.rr = ps.bg + (blockDim.y + 2) * kTileW;
   const float4 tb = __ldg(v.projBias + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
   ps.dBias[0] = tb.x + kBias23;
   ps.dBias[1] = tb.y + kBias23;

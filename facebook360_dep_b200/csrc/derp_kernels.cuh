@@ -311,14 +311,16 @@ struct SweepArgs {
   unsigned long long* counters;  // [0] cost evaluations, [1] source hits
 };
 
-__global__ void __launch_bounds__(kBlockX* kBlockY, DERP_SWEEP_MINB) sweepKernel(const SweepArgs a) {
+// Launched with 32 x BY threads, BY in {8, 16, 24}: 85 registers allow 768 threads per SM either way; a taller
+// CTA shares more texel rows between its warps (per-warp footprint (BY+3)/BY rows instead of 11/8).
+__global__ void __launch_bounds__(768, 1) sweepKernel(const SweepArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
   float* tile = reinterpret_cast<float*>(cams + a.v.S);
   stageCameras(cams, a.v.cams, a.v.S);
-  loadDstTile(tile, a.v, blockIdx.x * kBlockX, blockIdx.y * kBlockY);
+  loadDstTile(tile, a.v, blockIdx.x * kBlockX, blockIdx.y * blockDim.y);
   const int W = a.v.W, H = a.v.H;
-  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
+  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   unsigned hits = 0, evals = 0;
   if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
     const size_t p = (size_t)y * W + x;

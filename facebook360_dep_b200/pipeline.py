@@ -1,0 +1,100 @@
+"""Frame-sharded temporal filtering (BASELINE.json configs[4]: 16-camera x 30-frame sequence with temporal
+depth smoothing on 8 GPUs) — the one stage of the path with a real cross-rank exchange.
+
+DerpCLI's frames are independent, so ranks own contiguous frame blocks (shard.frame_block) and estimate their
+disparities with no communication.  TemporalBilateralFilter then needs, for every frame, the colour, disparity
+and mask of the +-time_radius neighbouring frames (TemporalBilateralFilter.cpp:96-160): frames near a block
+boundary live on the neighbouring rank(s).  The reference moves them as files (pipeline.py:382-408); here the
+halo frames travel rank-to-rank with point-to-point send/recv on the process group — NCCL over NVLink when the
+tensors are CUDA tensors (one process per GPU), gloo in the CPU tests.  The filter itself is
+derp_temporal_filter of whichever library is passed in (CUDA product / CPU oracle in tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import shard
+
+
+def _pack(frame, H, W):
+    """frame = list over cameras of (color u16 HxWx3, disparity f32 HxW, mask u8 HxW) -> flat uint8 tensor."""
+    parts = []
+    for color, disp, mask in frame:
+        parts.append(np.ascontiguousarray(color, np.uint16).view(np.uint8).ravel())
+        parts.append(np.ascontiguousarray(disp, np.float32).view(np.uint8).ravel())
+        parts.append(np.ascontiguousarray(mask, np.uint8).ravel())
+    return torch.from_numpy(np.concatenate(parts))
+
+
+def _unpack(buf, num_cams, H, W):
+    a = buf.cpu().numpy()
+    out, o = [], 0
+    n = H * W
+    for _ in range(num_cams):
+        color = a[o:o + n * 6].view(np.uint16).reshape(H, W, 3)
+        o += n * 6
+        disp = a[o:o + n * 4].view(np.float32).reshape(H, W)
+        o += n * 4
+        mask = a[o:o + n].reshape(H, W)
+        o += n
+        out.append((color, disp, mask))
+    return out
+
+
+def exchange_halos(local_frames, num_frames, time_radius, device):
+    """local_frames: {frame_index: [(color, disp, mask) per camera]} for this rank's block.
+    Returns a dict with the halo frames this rank needs from other ranks (empty when world size is 1)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return {}
+    world, rank = dist.get_world_size(), dist.get_rank()
+    first, last = shard.frame_block(num_frames, world, rank)
+    some = next(iter(local_frames.values()))
+    num_cams = len(some)
+    H, W = some[0][1].shape
+    nbytes = num_cams * H * W * 11
+
+    def owner(f):
+        per = (num_frames + world - 1) // world
+        return f // per
+
+    ops, recv_bufs, keep = [], {}, []
+    # what every other rank needs from me / what I need from them is a pure function of (F, world, radius)
+    for r in range(world):
+        left, right = shard.halo_frames(num_frames, world, r, time_radius)
+        for f in left + right:
+            o = owner(f)
+            if o == rank and r != rank:
+                t = _pack(local_frames[f], H, W).to(device)
+                keep.append(t)
+                ops.append(dist.P2POp(dist.isend, t, r))
+            elif r == rank and o != rank:
+                t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+                recv_bufs[f] = t
+                ops.append(dist.P2POp(dist.irecv, t, o))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return {f: _unpack(t, num_cams, H, W) for f, t in recv_bufs.items()}
+
+
+def temporal_filter_block(lib, local_frames, num_frames, time_radius=2, sigma=0.01, space_radius=1,
+                          weight_b=0.5, weight_g=1.0, device=None, gpu=0):
+    """Temporal joint-bilateral filtering of this rank's frames.  Weights follow the reference app:
+    (weight_b, weight_g, weight_b) (TemporalBilateralFilter.cpp:176-178).  Returns {frame: [filtered per camera]}."""
+    device = device or torch.device("cpu")
+    halos = exchange_halos(local_frames, num_frames, time_radius, device)
+    frames = dict(local_frames)
+    frames.update(halos)
+    out = {}
+    for f in sorted(local_frames):
+        lo, hi = max(0, f - time_radius), min(num_frames - 1, f + time_radius)
+        window = [frames[t] for t in range(lo, hi + 1)]
+        res = []
+        for cam in range(len(local_frames[f])):
+            guides = [w[cam][0] for w in window]
+            disps = [w[cam][1] for w in window]
+            masks = [w[cam][2] for w in window]
+            res.append(lib.temporal_filter(guides, disps, masks, f - lo, sigma, space_radius, weight_b, weight_g,
+                                           weight_b, device=gpu))
+        out[f] = res
+    return out
