@@ -1,0 +1,18 @@
+#!/bin/bash
+# DerpCLI --gpus=2 must write byte-identical PFMs to --gpus=1 (frames are sharded, nothing else changes)
+set -e
+T=$(mktemp -d)
+python - "$T" <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd())
+from facebook360_dep_b200 import synth
+from tests.test_apps import write_dataset
+rig = synth.ring_rig(5, 96, 96, kind="FTHETA")
+frames = [synth.render_rig(rig, 96, 96, scene=synth.Scene(seed=42, shift=(0.01 * f, 0, 0)))[0] for f in range(4)]
+write_dataset(sys.argv[1] + "/in", rig, frames, 2)
+PY
+B=facebook360_dep_b200/bin/DerpCLI
+$B --input_root=$T/in --output_root=$T/out1 --first=000000 --last=000003 --partial_coverage --num_depths=32 --gpus=1 2>/dev/null
+$B --input_root=$T/in --output_root=$T/out2 --first=000000 --last=000003 --partial_coverage --num_depths=32 --gpus=2 2>/dev/null
+diff -r $T/out1 $T/out2 && echo "DerpCLI --gpus=2 == --gpus=1 : $(find $T/out2 -name '*.pfm' | wc -l) PFMs identical"
+rm -rf $T
