@@ -169,7 +169,7 @@ struct DerpCtx {
   DevBuf<uint8_t> dFg, dFov, dMismatch, dChangedA, dChangedB, dStage;
   DevBuf<unsigned long long> dBest, dCounters;
   DevBuf<unsigned> dUncovered;
-  DevBuf<int> dPrefix, dIdx, dOfs, dRowCount, dRowOffset, dList;
+  DevBuf<int> dPrefix, dIdx, dOfs, dRowCount, dTileCount, dTileOffset, dList;
   DevBuf<float> dTaps;
   DevBuf<short2> dSpiral;
   int projDst = -1;
@@ -250,16 +250,25 @@ int readCounters(DerpCtx* c) {
   return DERP_OK;
 }
 
-// list of active pixels of one destination (activeScan -> rowOffset -> scatter), left in dList / dRowOffset[H]
+// list of active pixels of one destination, tile-major (activeScan -> tile counts -> offsets -> scatter);
+// left in dList, the total in dTileOffset[numTiles] (see listCountPtr)
 int buildActiveList(DerpCtx* c, const uint8_t* fov, const uint8_t* fg, const float* variance, float varThresh) {
   const int W = c->W, H = c->H;
+  const dim3 tg = grid2(W, H);
+  const int numTiles = (int)(tg.x * tg.y);
   activeScanKernel<<<(H + 7) / 8, 256, 0, c->stream>>>(W, H, fov, fg, variance, varThresh, c->dPrefix.p, c->dRowCount.p);
   LAUNCHED("activeScanKernel");
-  rowOffsetKernel<<<1, 1024, 0, c->stream>>>(H, c->dRowCount.p, c->dRowOffset.p);
+  tileCountKernel<<<tg, block2(), 0, c->stream>>>(W, H, c->dPrefix.p, c->dTileCount.p);
+  LAUNCHED("tileCountKernel");
+  rowOffsetKernel<<<1, 1024, 0, c->stream>>>(numTiles, c->dTileCount.p, c->dTileOffset.p);
   LAUNCHED("rowOffsetKernel");
-  activeScatterKernel<<<grid2(W, H), block2(), 0, c->stream>>>(W, H, c->dPrefix.p, c->dRowOffset.p, c->dList.p);
+  activeScatterKernel<<<tg, block2(), 0, c->stream>>>(W, H, c->dPrefix.p, c->dTileOffset.p, c->dList.p);
   LAUNCHED("activeScatterKernel");
   return DERP_OK;
+}
+const int* listCountPtr(DerpCtx* c) {
+  const dim3 tg = grid2(c->W, c->H);
+  return c->dTileOffset.p + (size_t)tg.x * tg.y;
 }
 
 }  // namespace
@@ -425,7 +434,11 @@ int derp_level_begin(DerpCtx* c, const DerpLevelParams* p) {
   CU(c->dPrefix.ensure(n));
   CU(c->dList.ensure(n));
   CU(c->dRowCount.ensure(c->H));
-  CU(c->dRowOffset.ensure(c->H + 1));
+  {
+    const dim3 tg = grid2(c->W, c->H);
+    CU(c->dTileCount.ensure((size_t)tg.x * tg.y));
+    CU(c->dTileOffset.ensure((size_t)tg.x * tg.y + 1));
+  }
   CU(c->dIdx.ensure(n));
   CU(c->dStage.ensure(n * 6 * (size_t)c->S));
   CU(cudaMemsetAsync(c->dDisp.p, 0, n * c->Sd * sizeof(float), c->stream));
@@ -650,7 +663,7 @@ int derp_random_proposals(DerpCtx* c, int dst, int num_proposals, float min_dept
   a.maxDisp = 1.0f / min_depth_m;
   a.counters = c->dCounters.p;
   a.list = c->dList.p;
-  a.listCount = c->dRowOffset.p + H;
+  a.listCount = listCountPtr(c);
   if ((rc = resetCounters(c))) return rc;
   if ((rc = buildActiveList(c, a.fov, a.fg, a.v.variance, varThresh))) return rc;
   if (useFg) {
@@ -696,7 +709,7 @@ int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
     a.costRes = c->dScratchB.p;
     a.changedNext = chOut;
     a.list = c->dList.p;
-    a.listCount = c->dRowOffset.p + H;
+    a.listCount = listCountPtr(c);
     a.counters = c->dCounters.p;
     pingPongKernel<<<grid1((size_t)(W - 2) * (H - 2), kPatchThreads), kPatchThreads, c->patchSmem(), c->stream>>>(a);
     LAUNCHED("pingPongKernel");

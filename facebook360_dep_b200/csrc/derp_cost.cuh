@@ -423,7 +423,12 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           const float4* r2 = r1 + W;
           const float4* r3 = r2 + W;
           const float4* b1 = srcBiasImg + off + W + 1;  // bias sample = centre sample's 2x2 footprint
+#ifdef DERP_EXPERIMENT_NOBIAS  // measurement-only variant (breaks parity): upper bound of not reading the bias table
+          const float4 q00 = make_float4(1.f, 2.f, 3.f, 0.f), q01 = q00, q10 = q00, q11 = q00;
+          (void)b1;
+#else
           const float4 q00 = __ldg(b1), q01 = __ldg(b1 + 1), q10 = __ldg(b1 + W), q11 = __ldg(b1 + W + 1);
+#endif
           float4 colA[4], colB[4];
           colA[0] = __ldg(r0);
           colA[1] = __ldg(r1);
