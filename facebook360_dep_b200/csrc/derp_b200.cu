@@ -202,9 +202,14 @@ struct DerpCtx {
     return v;
   }
   // dynamic smem of the cost kernels: S cameras + the destination patch tile
-  size_t camSmem() const { return (size_t)S * sizeof(DevCamera) + kTileFloats * sizeof(float); }
-  // compacted kernels: S cameras + one 3x3 patch per thread
-  size_t patchSmem() const { return (size_t)S * sizeof(DevCamera) + kPatchFloats * sizeof(float); }
+  // + kSelSlots (ssdB, ssdU) pairs per thread for the robust camera mean
+  size_t camSmem(int threads = kBlockX * kBlockY) const {
+    return (size_t)S * sizeof(DevCamera) + kTileFloats * sizeof(float) + (size_t)kSelSlots * threads * sizeof(float2);
+  }
+  // compacted kernels: S cameras + one 3x3 patch per thread + the selection slots
+  size_t patchSmem() const {
+    return (size_t)S * sizeof(DevCamera) + kPatchFloats * sizeof(float) + (size_t)kSelSlots * kPatchThreads * sizeof(float2);
+  }
 };
 
 namespace {
@@ -316,7 +321,12 @@ int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_
   CU(cudaMemcpy(c->dWtab.p, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
   CU(c->dCounters.ensure(2));
   CU(c->dUncovered.ensure(1));
-  // all cost kernels stage S cameras in dynamic shared memory
+  // the cost kernels keep cameras, the destination patch tile / per-thread patches and the selection slots in
+  // dynamic shared memory: up to ~70 KB per CTA, above the 48 KB default
+  CU(cudaFuncSetAttribute(sweepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CU(cudaFuncSetAttribute(evalCostKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CU(cudaFuncSetAttribute(proposalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  CU(cudaFuncSetAttribute(pingPongKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   *out = c.release();
   return DERP_OK;
 }
@@ -608,7 +618,7 @@ int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, flo
     CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, c->stream));
   }
-  sweepKernel<<<dim3(gs.x, gs.y, chunks), dim3(kBlockX, sweepBY, 1), c->camSmem(), c->stream>>>(a);
+  sweepKernel<<<dim3(gs.x, gs.y, chunks), dim3(kBlockX, sweepBY, 1), c->camSmem(kBlockX * sweepBY), c->stream>>>(a);
   LAUNCHED("sweepKernel");
   if (c->profiling) {
     CU(cudaEventRecord(ev1, c->stream));

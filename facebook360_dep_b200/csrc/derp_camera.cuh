@@ -17,15 +17,17 @@
 
 namespace derp {
 
-struct DevCamera {
+// 16-byte aligned and a multiple of 16 bytes long so that pairs of doubles can move with one 128-bit shared load
+struct alignas(16) DevCamera {
   double pos[3];
+  double cosFov;        // next to pos: the cone test reads pos, cosFov, rot[6..8]
   double rot[9];        // row-major; rows: right, up, backward (Camera.h:77-85)
+  double distMax;
   double principal[2];
   double focal[2];
   double res[2];
   double dist[3];
-  double distMax;
-  double cosFov;
+  double pad0;
   int type;
   int defaultFov;       // cosFov == getDefaultCosFov(type) (Camera.cpp:206-208)
   int zeroDist;         // getDistortion().isZero() (Camera.h:256)

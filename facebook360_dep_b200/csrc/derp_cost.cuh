@@ -214,12 +214,29 @@ struct PixelState {
   float dBias[3];      // projColorBias(dst,self)(y,x) + 2^23
   float conf;          // max(variance(y,x), kMinVar)
   double dir[3];       // ray direction of the pixel in rig space
+  float2* sel;         // this thread's (ssdB, ssdU) slots in shared memory: entry i at sel[i * selStride]
+  int selStride;       // = threads per CTA
+};
+
+// The per-source (biased, unbiased) SSD pairs of one cost evaluation live in shared memory, [slot][thread], for
+// the first kSelSlots sources; evaluations with more visible sources overflow into local memory.
+constexpr int kSelSlots = 8;
+struct SmemPairs {
+  float2* p;
+  int stride;
+  __device__ __forceinline__ PairVal get(int i) const {
+    const float2 t = p[i * stride];
+    return PairVal{t.x, t.y};
+  }
+  __device__ __forceinline__ void set(int i, PairVal v) const { p[i * stride] = make_float2(v.a, v.b); }
 };
 
 __device__ __forceinline__ void loadPixelState(const CostView& v, const DevCamera& camDst, const float* tile, int x,
                                                int y, PixelState& ps) {
   ps.bg = reinterpret_cast<const float2*>(tile) + threadIdx.y * kTileW + threadIdx.x;
   ps.rr = ps.bg + (blockDim.y + 2) * kTileW;
+  ps.selStride = blockDim.x * blockDim.y;
+  ps.sel = reinterpret_cast<float2*>(const_cast<float*>(tile) + kTileFloats) + threadIdx.y * blockDim.x + threadIdx.x;
   const float4 tb = __ldg(v.projBias + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
   ps.dBias[0] = tb.x + kBias23;
   ps.dBias[1] = tb.y + kBias23;
@@ -257,6 +274,8 @@ __device__ __forceinline__ void loadPixelStateCompact(const CostView& v, const D
   }
   ps.bg = bg;
   ps.rr = rr;
+  ps.selStride = kPatchThreads;
+  ps.sel = reinterpret_cast<float2*>(patches + kPatchFloats) + tid;
   const float4 tb = __ldg(v.projBias + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
   ps.dBias[0] = tb.x + kBias23;
   ps.dBias[1] = tb.y + kBias23;
@@ -366,8 +385,13 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     if (insideCone(cams[s], wx, wy, wz)) mask |= 1u << s;
   mask &= ~(1u << v.self);
 
-  float ssdB[kMaxCams], ssdU[kMaxCams];
+  float2 overflow[kMaxCams - kSelSlots];  // touched only when more than kSelSlots sources see the point
   int n = 0;
+  auto pushPair = [&](float b, float u) {
+    if (n < kSelSlots) ps.sel[n * ps.selStride] = make_float2(b, u);
+    else overflow[n - kSelSlots] = make_float2(b, u);
+    ++n;
+  };
   if (mask) {
     int s = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -499,14 +523,13 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
             for (int j = 0; j < 4; ++j) colA[j] = colB[j];
           }
           const float scaleFactor = 1.0f / (65535.0f * 65535.0f);
-          ssdB[n] = sB * scaleFactor;
-          ssdU[n] = sU * scaleFactor;
-          ++n;
+          pushPair(sB * scaleFactor, sU * scaleFactor);
         } else {
           nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+          float slowB, slowU;
           if (ssdSlowPath(srcColor, srcBiasImg, W, H, ps.bg, ps.rr, RP, CP, ps.dBias[0], ps.dBias[1], ps.dBias[2], xDstSrc,
-                          yDstSrc, &ssdB[n], &ssdU[n]))
-            ++n;
+                          yDstSrc, &slowB, &slowU))
+            pushPair(slowB, slowU);
         }
       } else {
         nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
@@ -521,9 +544,17 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
   const int keep = n - 2 > 1 ? n - 2 : 1;
   float cost;
   if (n == 1) {
-    cost = 0.0f + ssdU[0];
-  } else {
-    cost = robustSum(ssdB, ssdU, n, keep);
+    cost = 0.0f + ps.sel[0].y;
+  } else if (n <= kSelSlots) {
+    cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);
+  } else {  // rare: gather everything into local arrays
+    float la[kMaxCams], lb[kMaxCams];
+    for (int i = 0; i < n; ++i) {
+      const float2 t = i < kSelSlots ? ps.sel[i * ps.selStride] : overflow[i - kSelSlots];
+      la[i] = t.x;
+      lb[i] = t.y;
+    }
+    cost = robustSum(la, lb, n, keep);
   }
   cost /= (float)keep;
   const float trustCoef = 1.0f / (float)keep;

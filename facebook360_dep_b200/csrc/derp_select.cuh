@@ -17,102 +17,111 @@
 
 namespace derp {
 
-struct PairRef {
-  float* a;  // first  (biased SSD)
-  float* b;  // second (unbiased SSD)
+// Element access is abstracted so that the same code runs on plain arrays (host unit test, device fallback in
+// local memory) and on the strided per-thread slots in shared memory the cost kernels use: local-memory
+// arrays get evicted from L1 by the texel gathers and every compare then waits on L2 (26 % of the sweep's
+// stall samples before this change, profiles/README.md).
+struct PairVal {
+  float a, b;  // first (biased SSD), second (unbiased SSD)
+};
+
+struct ArrayPairs {  // two separate float arrays
+  float* a;
+  float* b;
+  DERP_SEL_HD PairVal get(int i) const { return PairVal{a[i], b[i]}; }
+  DERP_SEL_HD void set(int i, PairVal v) const {
+    a[i] = v.a;
+    b[i] = v.b;
+  }
 };
 
 DERP_SEL_HD bool pairLess(float a0, float b0, float a1, float b1) {
   return a0 < a1 || (!(a1 < a0) && b0 < b1);
 }
+DERP_SEL_HD bool pairLess(PairVal x, PairVal y) { return pairLess(x.a, x.b, y.a, y.b); }
 
-DERP_SEL_HD bool lessAt(const PairRef& v, int i, int j) { return pairLess(v.a[i], v.b[i], v.a[j], v.b[j]); }
+template <class V>
+DERP_SEL_HD bool lessAt(const V& v, int i, int j) {
+  return pairLess(v.get(i), v.get(j));
+}
 
-DERP_SEL_HD void swapAt(const PairRef& v, int i, int j) {
-  const float ta = v.a[i], tb = v.b[i];
-  v.a[i] = v.a[j];
-  v.b[i] = v.b[j];
-  v.a[j] = ta;
-  v.b[j] = tb;
+template <class V>
+DERP_SEL_HD void swapAt(const V& v, int i, int j) {
+  const PairVal x = v.get(i), y = v.get(j);
+  v.set(i, y);
+  v.set(j, x);
 }
 
 // std::__insertion_sort on [first, last)
-DERP_SEL_HD void insertionSort(const PairRef& v, int first, int last) {
+template <class V>
+DERP_SEL_HD void insertionSort(const V& v, int first, int last) {
   if (first == last) return;
   for (int i = first + 1; i != last; ++i) {
-    const float va = v.a[i], vb = v.b[i];
-    if (pairLess(va, vb, v.a[first], v.b[first])) {
-      for (int k = i; k > first; --k) {
-        v.a[k] = v.a[k - 1];
-        v.b[k] = v.b[k - 1];
-      }
-      v.a[first] = va;
-      v.b[first] = vb;
+    const PairVal val = v.get(i);
+    if (pairLess(val, v.get(first))) {
+      for (int k = i; k > first; --k) v.set(k, v.get(k - 1));
+      v.set(first, val);
     } else {
       int last2 = i, next = i - 1;
-      while (pairLess(va, vb, v.a[next], v.b[next])) {
-        v.a[last2] = v.a[next];
-        v.b[last2] = v.b[next];
+      while (pairLess(val, v.get(next))) {
+        v.set(last2, v.get(next));
         last2 = next;
         --next;
       }
-      v.a[last2] = va;
-      v.b[last2] = vb;
+      v.set(last2, val);
     }
   }
 }
 
 // std::__adjust_heap (max-heap under pairLess) on [first, first+len)
-DERP_SEL_HD void adjustHeap(const PairRef& v, int first, int holeIndex, int len, float va, float vb) {
+template <class V>
+DERP_SEL_HD void adjustHeap(const V& v, int first, int holeIndex, int len, PairVal val) {
   const int topIndex = holeIndex;
   int secondChild = holeIndex;
   while (secondChild < (len - 1) / 2) {
     secondChild = 2 * (secondChild + 1);
     if (lessAt(v, first + secondChild, first + (secondChild - 1))) secondChild--;
-    v.a[first + holeIndex] = v.a[first + secondChild];
-    v.b[first + holeIndex] = v.b[first + secondChild];
+    v.set(first + holeIndex, v.get(first + secondChild));
     holeIndex = secondChild;
   }
   if ((len & 1) == 0 && secondChild == (len - 2) / 2) {
     secondChild = 2 * (secondChild + 1);
-    v.a[first + holeIndex] = v.a[first + (secondChild - 1)];
-    v.b[first + holeIndex] = v.b[first + (secondChild - 1)];
+    v.set(first + holeIndex, v.get(first + (secondChild - 1)));
     holeIndex = secondChild - 1;
   }
   // __push_heap
   int parent = (holeIndex - 1) / 2;
-  while (holeIndex > topIndex && pairLess(v.a[first + parent], v.b[first + parent], va, vb)) {
-    v.a[first + holeIndex] = v.a[first + parent];
-    v.b[first + holeIndex] = v.b[first + parent];
+  while (holeIndex > topIndex && pairLess(v.get(first + parent), val)) {
+    v.set(first + holeIndex, v.get(first + parent));
     holeIndex = parent;
     parent = (holeIndex - 1) / 2;
   }
-  v.a[first + holeIndex] = va;
-  v.b[first + holeIndex] = vb;
+  v.set(first + holeIndex, val);
 }
 
 // std::__heap_select(first, middle, last)
-DERP_SEL_HD void heapSelect(const PairRef& v, int first, int middle, int last) {
+template <class V>
+DERP_SEL_HD void heapSelect(const V& v, int first, int middle, int last) {
   const int len = middle - first;
   if (len >= 2) {  // __make_heap
     int parent = (len - 2) / 2;
     while (true) {
-      adjustHeap(v, first, parent, len, v.a[first + parent], v.b[first + parent]);
+      adjustHeap(v, first, parent, len, v.get(first + parent));
       if (parent == 0) break;
       parent--;
     }
   }
   for (int i = middle; i < last; ++i)
     if (lessAt(v, i, first)) {  // __pop_heap(first, middle, i)
-      const float va = v.a[i], vb = v.b[i];
-      v.a[i] = v.a[first];
-      v.b[i] = v.b[first];
-      adjustHeap(v, first, 0, len, va, vb);
+      const PairVal val = v.get(i);
+      v.set(i, v.get(first));
+      adjustHeap(v, first, 0, len, val);
     }
 }
 
 // std::nth_element(v, v+nth, v+n) with libstdc++'s algorithm.
-DERP_SEL_HD void nthElement(const PairRef& v, int nth, int n) {
+template <class V>
+DERP_SEL_HD void nthElement(const V& v, int nth, int n) {
   if (n == 0 || nth == n) return;
   int first = 0, last = n;
   int depth = 0;  // 2 * floor(log2(n))
@@ -128,24 +137,27 @@ DERP_SEL_HD void nthElement(const PairRef& v, int nth, int n) {
     const int mid = first + (last - first) / 2;
     {  // __move_median_to_first(first, first+1, mid, last-1)
       const int a = first + 1, b = mid, c = last - 1;
-      if (lessAt(v, a, b)) {
-        if (lessAt(v, b, c)) swapAt(v, first, b);
-        else if (lessAt(v, a, c)) swapAt(v, first, c);
-        else swapAt(v, first, a);
-      } else if (lessAt(v, a, c)) {
-        swapAt(v, first, a);
-      } else if (lessAt(v, b, c)) {
-        swapAt(v, first, c);
+      const PairVal va = v.get(a), vb = v.get(b), vc = v.get(c);
+      int m;
+      if (pairLess(va, vb)) {
+        if (pairLess(vb, vc)) m = b;
+        else if (pairLess(va, vc)) m = c;
+        else m = a;
+      } else if (pairLess(va, vc)) {
+        m = a;
+      } else if (pairLess(vb, vc)) {
+        m = c;
       } else {
-        swapAt(v, first, b);
+        m = b;
       }
+      swapAt(v, first, m);
     }
     int lo = first + 1, hi = last;
-    const float pa = v.a[first], pb = v.b[first];
+    const PairVal pivot = v.get(first);
     while (true) {
-      while (pairLess(v.a[lo], v.b[lo], pa, pb)) ++lo;
+      while (pairLess(v.get(lo), pivot)) ++lo;
       --hi;
-      while (pairLess(pa, pb, v.a[hi], v.b[hi])) --hi;
+      while (pairLess(pivot, v.get(hi))) --hi;
       if (!(lo < hi)) break;
       swapAt(v, lo, hi);
       ++lo;
@@ -158,12 +170,14 @@ DERP_SEL_HD void nthElement(const PairRef& v, int nth, int n) {
 }
 
 // cost numerator of computeCost: sum of the `keep` kept unbiased SSDs in nth_element's order.
-DERP_SEL_HD float robustSum(float* a, float* b, int n, int keep) {
-  PairRef v{a, b};
+template <class V>
+DERP_SEL_HD float robustSum(const V& v, int n, int keep) {
   nthElement(v, keep, n);
   float cost = 0;
-  for (int i = 0; i < keep; ++i) cost += b[i];
+  for (int i = 0; i < keep; ++i) cost += v.get(i).b;
   return cost;
 }
+
+DERP_SEL_HD float robustSum(float* a, float* b, int n, int keep) { return robustSum(ArrayPairs{a, b}, n, keep); }
 
 }  // namespace derp
