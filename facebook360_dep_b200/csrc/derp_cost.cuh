@@ -543,8 +543,14 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
   if (n < 1) return FLT_MAX;  // kMinOverlappingCams - 1
   const int keep = n - 2 > 1 ? n - 2 : 1;
   float cost;
-  if (n == 1) {
-    cost = 0.0f + ps.sel[0].y;
+  if (n <= 3) {
+    // keep == 1: nth_element(v, v+1, v+n) on <= 3 elements is an insertion sort, v[0] = the smallest pair
+    float2 m = ps.sel[0];
+    for (int i = 1; i < n; ++i) {
+      const float2 t = ps.sel[i * ps.selStride];
+      if (pairLess(t.x, t.y, m.x, m.y)) m = t;
+    }
+    cost = 0.0f + m.y;
   } else if (n <= kSelSlots) {
     cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);
   } else {  // rare: gather everything into local arrays

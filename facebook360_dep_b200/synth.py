@@ -49,6 +49,25 @@ def ring_rig(num_cams, width, height, kind="FTHETA", radius=0.218, hfov_deg=None
     return {"cameras": cams}
 
 
+def wall_rig(num_cams, width, height, kind="RECTILINEAR", spacing=0.06, hfov_deg=90.0):
+    """Planar array: all cameras look along +x from positions spread along y (and a little z), so every scene
+    point is seen by every other camera — exercises cost evaluations with many (> 8) contributing sources."""
+    cams = []
+    for i in range(num_cams):
+        fwd, up = [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]
+        right = [fwd[1] * up[2] - fwd[2] * up[1], fwd[2] * up[0] - fwd[0] * up[2], fwd[0] * up[1] - fwd[1] * up[0]]
+        cam = {"version": 1, "type": kind, "origin": [0.0, spacing * (i - (num_cams - 1) / 2.0), 0.02 * ((i * 7) % 3 - 1)],
+               "forward": fwd, "up": up, "right": right, "resolution": [width, height], "id": "cam%d" % i}
+        if kind == "RECTILINEAR":
+            f = (width / 2.0) / math.tan(math.radians(hfov_deg) / 2.0)
+        else:
+            f = width / math.pi
+            cam["fov"] = 1.5707963
+        cam["focal"] = [f, -f]
+        cams.append(cam)
+    return {"cameras": cams}
+
+
 # ---- minimal camera unprojection (pixel -> unit ray in rig space), fp64 torch -------------------
 def _undistort(y, d):
     if not any(d):

@@ -319,3 +319,22 @@ def test_dst_subset_and_edge_sizes(cuda, oracle):
         ctxs[0].level_begin(2, 2)
     with pytest.raises(capi.DerpError):
         ctxs[0].brute_force(0)  # stage before reproject of that dst -> DERP_ESTATE
+
+
+def test_many_overlapping_sources(cuda, oracle):
+    """12-camera planar array: up to 11 sources contribute to one cost (more than the 8 shared-memory selection
+    slots -> local-memory overflow path, introselect on 9..11 elements)."""
+    W, H = 80, 64
+    rig = synth.wall_rig(12, W, H)
+    colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=7))
+    ctxs = make_pair(cuda, oracle, rig)
+    _begin(ctxs, colors, W, H)
+    for d in (0, 5, 11):
+        both(ctxs, "reproject", d)
+        gi, oi = both(ctxs, "brute_force", d, num_depths=40, min_depth_m=1.0)
+        assert np.array_equal(gi, oi)
+        (gd, gc, gf), (od, oc, of) = both(ctxs, "get_disparity", d)
+        assert same_float_bits(gc, oc).all()
+        ev, hits = ctxs[0].get_counters()
+        assert (ev, hits) == ctxs[1].get_counters()
+    assert hits / ev > 8.5, hits / ev  # the overflow path really ran
