@@ -206,23 +206,28 @@ __global__ void biasKernel(int W, int H, float4* in, float4* __restrict__ out) {
   if (x >= W || y >= H) return;
   float4* img = in + (size_t)s * W * H;
   float sb = 0, sg = 0, sr = 0;
+  float4 centre = make_float4(0.f, 0.f, 0.f, 0.f);
+  float below = 0.f;
 #pragma unroll
   for (int j = -1; j <= 1; ++j) {
     const int yy = reflect101(y + j, H);
 #pragma unroll
     for (int i = -1; i <= 1; ++i) {
       const int xx = reflect101(x + i, W);
-      const float* t = reinterpret_cast<const float*>(img + (size_t)yy * W + xx);
-      sb += t[0];
-      sg += t[1];
-      sr += t[2];
+      const float4 t = img[(size_t)yy * W + xx];
+      sb += t.x;
+      sg += t.y;
+      sr += t.z;
+      if (i == 0 && j == 0) centre = t;
+      if (i == 0 && j == 1) below = (y + 1 < H) ? t.z : 0.f;
     }
   }
   // saturate_cast<ushort>(sum * (1.0/9)) == (sum + 4) / 9 for integer sums (no exact .5 cases)
   const int B = ((int)sb + 4) / 9, G = ((int)sg + 4) / 9, R = ((int)sr + 4) / 9;
   out[(size_t)s * W * H + (size_t)y * W + x] = make_float4((float)B, (float)G, (float)R, 0.f);
-  const float below = (y + 1 < H) ? reinterpret_cast<const float*>(img + (size_t)(y + 1) * W + x)[2] : 0.f;
-  reinterpret_cast<float*>(img + (size_t)y * W + x)[3] = below;
+  // w lane = R of the texel below.  The whole texel is stored (one full 16-byte write instead of a 4-byte write
+  // into every sector); x, y, z are rewritten with the values just read, so concurrent readers are unaffected.
+  img[(size_t)y * W + x] = make_float4(centre.x, centre.y, centre.z, below);
 }
 
 // ---- K5: computeImageVariance (DerpUtil.cpp:214-237) for all S planes ---------------------------

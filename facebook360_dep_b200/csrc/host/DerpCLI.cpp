@@ -155,7 +155,16 @@ struct Shared {
   int numLevels = 0, levelStart = 0, levelEnd = 0, widthFull = 0, heightFull = 0, firstFrame = 0, numFrames = 0;
 };
 
-static void saveLevel(const Shared& sh, DerpCtx* ctx, int level, const std::string& frameName, int W, int H) {
+// one GPU's share of the work: a context and the destination cameras it owns
+struct Worker {
+  DerpCtx* ctx = nullptr;
+  std::vector<int> dst;  // indices into rig
+};
+
+static void saveLevel(const Shared& shAll, const Worker& wk, int level, const std::string& frameName, int W, int H) {
+  DerpCtx* ctx = wk.ctx;
+  Shared sh = shAll;
+  sh.dst = wk.dst;
   // saveResults (Derp.cpp:922-938, PyramidLevel.h:487-529): pfm always; png/exr on request
   std::vector<std::string> formats = {"pfm"};
   std::stringstream ss(FLAGS_output_formats);
@@ -189,7 +198,10 @@ static void saveLevel(const Shared& sh, DerpCtx* ctx, int level, const std::stri
 }
 
 // One (level, frame): DerpCLI.cpp:229-320
-static void processFrame(const Shared& sh, DerpCtx* ctx, int level, int iFrame) {
+static void processFrame(const Shared& shAll, const Worker& wk, int level, int iFrame) {
+  DerpCtx* ctx = wk.ctx;
+  Shared sh = shAll;
+  sh.dst = wk.dst;
   const std::string frameName = io::zeroPad(iFrame + sh.firstFrame);
   const int W = sh.sizes.at(level).first, H = sh.sizes.at(level).second;
   const int S = (int)sh.rig.cams.size(), Sd = (int)sh.dst.size();
@@ -270,7 +282,7 @@ static void processFrame(const Shared& sh, DerpCtx* ctx, int level, int iFrame) 
   o.do_median_filter = FLAGS_do_median_filter ? 1 : 0;
   LOG(INFO) << "Processing " << frameName << " level " << level;
   DERP_CALL(derp_process_level(ctx, &o));
-  saveLevel(sh, ctx, level, frameName, W, H);
+  saveLevel(shAll, wk, level, frameName, W, H);
 }
 
 int main(int argc, char* argv[]) {
@@ -320,14 +332,30 @@ int main(int argc, char* argv[]) {
   sh.widthFull = (int)sh.rig.cams[sh.dst[0]].resolution[0];
   sh.heightFull = (int)sh.rig.cams[sh.dst[0]].resolution[1];
 
-  // one context per GPU; frames are sharded in contiguous blocks
-  const int G = std::max(1, std::min(FLAGS_gpus, sh.numFrames));
-  std::vector<DerpCtx*> ctxs(G, nullptr);
-  std::vector<int32_t> d2s(sh.dst.begin(), sh.dst.end());
-  for (int g = 0; g < G; ++g)
-    DERP_CALL(derp_create(sh.rig.cams.data(), (int)sh.rig.cams.size(), d2s.data(), (int)d2s.size(), FLAGS_gpu + g, &ctxs[g]));
-  LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s), " << sh.numFrames << " frame(s), levels "
-            << sh.levelStart << " -> " << sh.levelEnd;
+  // One context per GPU.  Enough frames: contiguous frame blocks per GPU, every context owns all
+  // destinations.  Fewer frames than GPUs (e.g. one 24-camera 4096^2 frame on 8 GPUs): the DESTINATION cameras
+  // are dealt round-robin to the GPUs instead and every GPU processes every frame for its destinations — all
+  // stages except mismatch handling are independent per destination.
+  const int Gmax = std::max(1, FLAGS_gpus);
+  const bool shardCameras = sh.numFrames < Gmax && (int)sh.dst.size() > 1;
+  const int G = shardCameras ? std::min(Gmax, (int)sh.dst.size()) : std::max(1, std::min(Gmax, sh.numFrames));
+  if (shardCameras)
+    CHECK(FLAGS_mismatches_start_level < 0) << "mismatch handling needs all destination cameras on one GPU: use --gpus <= "
+                                              "number of frames";
+  std::vector<Worker> workers(G);
+  for (int g = 0; g < G; ++g) {
+    if (shardCameras) {
+      for (size_t i = g; i < sh.dst.size(); i += G) workers[g].dst.push_back(sh.dst[i]);
+    } else {
+      workers[g].dst = sh.dst;
+    }
+    std::vector<int32_t> d2s(workers[g].dst.begin(), workers[g].dst.end());
+    DERP_CALL(derp_create(sh.rig.cams.data(), (int)sh.rig.cams.size(), d2s.data(), (int)d2s.size(), FLAGS_gpu + g,
+                          &workers[g].ctx));
+  }
+  LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s), " << sh.numFrames << " frame(s), "
+            << (shardCameras ? "destination cameras" : "frames") << " sharded, levels " << sh.levelStart << " -> "
+            << sh.levelEnd;
 
   for (int level = sh.levelStart; level >= sh.levelEnd; --level) {
     CHECK(sh.sizes.count(level)) << "no images for level " << level;
@@ -337,17 +365,21 @@ int main(int argc, char* argv[]) {
         for (const char* t : {io::kDisparityLevels, io::kCost, io::kConfidence, io::kMismatches})
           fs::create_directories(fs::path(io::levelDir(FLAGS_output_root + "/" + t, level)) / sh.rig.ids[d]);
     }
-    std::vector<std::thread> workers;
+    std::vector<std::thread> threads;
     const int per = (sh.numFrames + G - 1) / G;
     for (int g = 0; g < G; ++g)
-      workers.emplace_back([&, g] {
-        for (int i = g * per; i < std::min(sh.numFrames, (g + 1) * per); ++i) processFrame(sh, ctxs[g], level, i);
+      threads.emplace_back([&, g] {
+        if (shardCameras) {
+          for (int i = 0; i < sh.numFrames; ++i) processFrame(sh, workers[g], level, i);
+        } else {
+          for (int i = g * per; i < std::min(sh.numFrames, (g + 1) * per); ++i) processFrame(sh, workers[g], level, i);
+        }
       });
-    for (auto& w : workers) w.join();  // per-level barrier, like the render pipeline (pipeline.py:364-380)
+    for (auto& w : threads) w.join();  // per-level barrier, like the render pipeline (pipeline.py:364-380)
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     LOG(INFO) << "-- Elapsed time: " << el << "s wall";
   }
-  for (auto* c : ctxs) derp_destroy(c);
+  for (auto& w : workers) derp_destroy(w.ctx);
   const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   LOG(INFO) << "-- TOTAL: " << el << "s wall";
   return EXIT_SUCCESS;

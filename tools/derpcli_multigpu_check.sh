@@ -14,5 +14,8 @@ PY
 B=facebook360_dep_b200/bin/DerpCLI
 $B --input_root=$T/in --output_root=$T/out1 --first=000000 --last=000003 --partial_coverage --num_depths=32 --gpus=1 2>/dev/null
 $B --input_root=$T/in --output_root=$T/out2 --first=000000 --last=000003 --partial_coverage --num_depths=32 --gpus=2 2>/dev/null
+# one frame on two GPUs: destination cameras are sharded instead
+$B --input_root=$T/in --output_root=$T/out3 --first=000001 --last=000001 --partial_coverage --num_depths=32 --gpus=2 2>/dev/null
+for f in $(cd $T/out3 && find . -name "*.pfm"); do cmp $T/out3/$f $T/out1/$f; done && echo "camera-sharded frame identical: $(find $T/out3 -name "*.pfm" | wc -l) PFMs"
 diff -r $T/out1 $T/out2 && echo "DerpCLI --gpus=2 == --gpus=1 : $(find $T/out2 -name '*.pfm' | wc -l) PFMs identical"
 rm -rf $T
