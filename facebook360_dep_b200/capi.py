@@ -132,6 +132,11 @@ _SIGS = {
     "derp_mask_fov": (C.c_int, [C.c_void_p, C.c_int]),
     "derp_upsample_from": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "derp_process_level": (C.c_int, [C.c_void_p, _p(ProcessOpts)]),
+    "derp_level_estimate": (C.c_int, [C.c_void_p, _p(ProcessOpts)]),
+    "derp_level_filter": (C.c_int, [C.c_void_p, _p(ProcessOpts)]),
+    "derp_disparity_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "derp_gather_disparities": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "derp_mismatches_gathered": (C.c_int, [C.c_void_p]),
     "derp_eval_cost": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "derp_set_disparity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "derp_get_disparity": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -340,16 +345,58 @@ class Context:
         fm = None if fine_mask is None else np.ascontiguousarray(fine_mask, np.uint8)
         self.L.check(self.L.lib.derp_upsample_from(self.h, dst, coarse.ctypes.data, cw, ch, _dp(cm), _dp(fm)))
 
-    def process_level(self, num_depths=150, min_depth_m=0.5, max_depth_m=1e4, partial_coverage=True,
-                      random_proposals=2, ping_pong_iterations=1, mismatches_start_level=-1,
-                      do_bilateral_filter=True, do_median_filter=True):
+    @staticmethod
+    def _opts(num_depths=150, min_depth_m=0.5, max_depth_m=1e4, partial_coverage=True,
+              random_proposals=2, ping_pong_iterations=1, mismatches_start_level=-1,
+              do_bilateral_filter=True, do_median_filter=True):
         o = ProcessOpts()
         o.num_depths, o.min_depth_m, o.max_depth_m = num_depths, min_depth_m, max_depth_m
         o.partial_coverage = int(partial_coverage)
         o.random_proposals, o.ping_pong_iterations = random_proposals, ping_pong_iterations
         o.mismatches_start_level = mismatches_start_level
         o.do_bilateral_filter, o.do_median_filter = int(do_bilateral_filter), int(do_median_filter)
+        return o
+
+    def process_level(self, **kw):
+        o = self._opts(**kw)
         self.L.check(self.L.lib.derp_process_level(self.h, C.byref(o)))
+
+    def level_estimate(self, **kw):
+        """First half of process_level (everything before mismatch handling)."""
+        o = self._opts(**kw)
+        self.L.check(self.L.lib.derp_level_estimate(self.h, C.byref(o)))
+
+    def level_filter(self, **kw):
+        """Second half of process_level (bilateral, median, maskFov)."""
+        o = self._opts(**kw)
+        self.L.check(self.L.lib.derp_level_filter(self.h, C.byref(o)))
+
+    def disparity_ptr(self, dst):
+        """Address of the context's own disparity plane (device memory on the CUDA library)."""
+        p = self.L.lib.derp_disparity_device_ptr(self.h, dst)
+        if not p:
+            raise DerpError(-1, self.L.lib.derp_last_error().decode())
+        return p
+
+    def gather_disparities(self, planes):
+        """planes: one entry per rig camera — int address (host / this device / peer device), a float32
+        numpy array (H, W), or None for a camera this context owns as a destination."""
+        keep, arr = [], (C.c_void_p * self.S)()
+        assert len(planes) == self.S
+        for s, pl in enumerate(planes):
+            if pl is None:
+                arr[s] = None
+            elif isinstance(pl, int):
+                arr[s] = pl
+            else:
+                a = np.ascontiguousarray(pl, np.float32)
+                assert a.shape == (self.H, self.W)
+                keep.append(a)
+                arr[s] = a.ctypes.data
+        self.L.check(self.L.lib.derp_gather_disparities(self.h, arr))
+
+    def mismatches_gathered(self):
+        self.L.check(self.L.lib.derp_mismatches_gathered(self.h))
 
     def eval_cost(self, dst, disparity):
         d = np.ascontiguousarray(disparity, np.float32)

@@ -147,7 +147,7 @@ struct DerpCtx {
   DevBuf<DevCamera> dCams, dCamsPx;
   DevBuf<float> dWtab;
   // level
-  bool levelOpen = false, haveColors = false, haveFg = false, haveBg = false;
+  bool levelOpen = false, haveColors = false, haveFg = false, haveBg = false, haveGathered = false;
   DerpLevelParams lp{};
   int W = 0, H = 0;
   size_t plane = 0;
@@ -165,7 +165,7 @@ struct DerpCtx {
   std::map<std::pair<int, int>, std::unique_ptr<GeomCache>> geomCaches;
   GeomCache* geom = nullptr;  // cache of the current level size, or null (maps go to the scratch buffers)
   bool geomCached = false;
-  DevBuf<float> dVariance, dBg, dDisp, dCost, dConf, dScratchA, dScratchB, dScratchC, dDisparities;
+  DevBuf<float> dVariance, dBg, dDisp, dCost, dConf, dScratchA, dScratchB, dScratchC, dDisparities, dGathered;
   DevBuf<uint8_t> dFg, dFov, dMismatch, dChangedA, dChangedB, dStage;
   DevBuf<unsigned long long> dBest, dCounters;
   DevBuf<unsigned> dUncovered;
@@ -466,7 +466,7 @@ int derp_level_begin(DerpCtx* c, const DerpLevelParams* p) {
     LAUNCHED("fovMaskKernel");
   }
   c->projDst = -1;
-  c->haveColors = c->haveFg = c->haveBg = false;
+  c->haveColors = c->haveFg = c->haveBg = c->haveGathered = false;
   c->levelOpen = true;
   return DERP_OK;
 }
@@ -731,28 +731,23 @@ int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
   return DERP_OK;
 }
 
-int derp_mismatches(DerpCtx* c) {
-  if (!c) return fail(DERP_EINVAL, "null ctx");
-  if (!c->levelOpen) return fail(DERP_ESTATE, "derp_mismatches: no level");
-  if (c->Sd != c->S) return fail(DERP_EINVAL, "Mismatches only valid when considering all cameras");
-  for (int d = 0; d < c->Sd; ++d)
-    if (c->dst2src[d] != d) return fail(DERP_EINVAL, "derp_mismatches: dst list must equal camera list");
-  int rc = useDevice(c);
-  if (rc) return rc;
+// K9 for this context's destinations; dispAll = [S] planes indexed by rig camera (pre-update values of every camera).
+static int launchMismatches(DerpCtx* c, const float* dispAll) {
   const size_t n = c->plane;
   DevBuf<float> dNew;
   CU(dNew.ensure(n * c->Sd));
   for (int d = 0; d < c->Sd; ++d) {
+    const int self = c->dst2src[d];
     MismatchArgs a;
     a.W = c->W;
     a.H = c->H;
     a.S = c->S;
-    a.self = d;
+    a.self = self;
     a.cams = c->dCams.p;
-    a.dispAll = c->dDisp.p;
-    a.variance = c->dVariance.p + (size_t)d * n;
+    a.dispAll = dispAll;
+    a.variance = c->dVariance.p + (size_t)self * n;
     a.fov = c->dFov.p + (size_t)d * n;
-    a.fg = (c->lp.use_foreground_masks && c->haveFg) ? c->fgOf(d) : nullptr;
+    a.fg = (c->lp.use_foreground_masks && c->haveFg) ? c->fgOf(self) : nullptr;
     a.varNoiseFloor = c->varNoiseFloor;
     a.varHighThresh = c->lp.var_high_thresh;
     a.dispNew = dNew.p + (size_t)d * n;
@@ -763,6 +758,72 @@ int derp_mismatches(DerpCtx* c) {
   CU(cudaMemcpyAsync(c->dDisp.p, dNew.p, n * c->Sd * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));  // dNew is freed on return
   return DERP_OK;
+}
+
+int derp_mismatches(DerpCtx* c) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  if (!c->levelOpen) return fail(DERP_ESTATE, "derp_mismatches: no level");
+  if (c->Sd != c->S) return fail(DERP_EINVAL, "Mismatches only valid when considering all cameras");
+  for (int d = 0; d < c->Sd; ++d)
+    if (c->dst2src[d] != d) return fail(DERP_EINVAL, "derp_mismatches: dst list must equal camera list");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  return launchMismatches(c, c->dDisp.p);
+}
+
+// ---- destination cameras dealt to several contexts: all-gather of disparities, then K9 per shard ---------
+const float* derp_disparity_device_ptr(DerpCtx* c, int dst) {
+  if (checkDst(c, dst, "derp_disparity_device_ptr", false)) return nullptr;
+  return c->dDisp.p + (size_t)dst * c->plane;
+}
+
+int derp_gather_disparities(DerpCtx* c, const float* const* planes) {
+  if (!c || !planes) return fail(DERP_EINVAL, "derp_gather_disparities: bad arguments");
+  if (!c->levelOpen) return fail(DERP_ESTATE, "derp_gather_disparities: no level");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  const size_t n = c->plane, b = n * sizeof(float);
+  CU(c->dGathered.ensure(n * c->S));
+  std::vector<int> ownDst(c->S, -1);
+  for (int d = 0; d < c->Sd; ++d) ownDst[c->dst2src[d]] = d;
+  for (int s = 0; s < c->S; ++s) {
+    float* to = c->dGathered.p + (size_t)s * n;
+    const float* from = planes[s];
+    if (!from) {
+      if (ownDst[s] < 0) return fail(DERP_EINVAL, "derp_gather_disparities: no plane for a camera this context does not own");
+      CU(cudaMemcpyAsync(to, c->dDisp.p + (size_t)ownDst[s] * n, b, cudaMemcpyDeviceToDevice, c->stream));
+      continue;
+    }
+    cudaPointerAttributes at{};
+    CU(cudaPointerGetAttributes(&at, from));
+    if (at.type == cudaMemoryTypeDevice && at.device != c->device) {
+      // a peer context's plane: device-to-device over NVLink (the runtime stages through the host if the two
+      // devices have no peer path)
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, c->device, at.device));
+      if (can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        (void)cudaGetLastError();
+      }
+      CU(cudaMemcpyPeerAsync(to, c->device, from, at.device, b, c->stream));
+    } else {
+      CU(cudaMemcpyAsync(to, from, b, cudaMemcpyDefault, c->stream));
+    }
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->haveGathered = true;
+  return DERP_OK;
+}
+
+int derp_mismatches_gathered(DerpCtx* c) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  if (!c->levelOpen) return fail(DERP_ESTATE, "derp_mismatches_gathered: no level");
+  if (!c->haveGathered) return fail(DERP_ESTATE, "derp_mismatches_gathered: derp_gather_disparities not called for this level");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  c->haveGathered = false;  // one exchange per stage
+  return launchMismatches(c, c->dGathered.p);
 }
 
 int derp_bilateral(DerpCtx* c, int dst) {
@@ -950,9 +1011,9 @@ int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* 
   return DERP_OK;
 }
 
-int derp_process_level(DerpCtx* c, const DerpProcessOpts* o) {
-  if (!c || !o) return fail(DERP_EINVAL, "derp_process_level: bad arguments");
-  if (!c->levelOpen || !c->haveColors) return fail(DERP_ESTATE, "derp_process_level: level/colours not set");
+int derp_level_estimate(DerpCtx* c, const DerpProcessOpts* o) {
+  if (!c || !o) return fail(DERP_EINVAL, "derp_level_estimate: bad arguments");
+  if (!c->levelOpen || !c->haveColors) return fail(DERP_ESTATE, "derp_level_estimate: level/colours not set");
   const bool coarsest = c->lp.level == c->lp.num_levels - 1;
   uint64_t evals = 0, hits = 0;
   int rc;
@@ -977,15 +1038,35 @@ int derp_process_level(DerpCtx* c, const DerpProcessOpts* o) {
       hits += c->lastHits;
     }
   }
-  if (!(c->lp.level > o->mismatches_start_level || coarsest)) {  // Derp.cpp:726-728
-    if ((rc = derp_mismatches(c))) return rc;
-  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->lastEvals = evals;
+  c->lastHits = hits;
+  c->countersOnDevice = false;
+  return DERP_OK;
+}
+
+int derp_level_filter(DerpCtx* c, const DerpProcessOpts* o) {
+  if (!c || !o) return fail(DERP_EINVAL, "derp_level_filter: bad arguments");
+  if (!c->levelOpen || !c->haveColors) return fail(DERP_ESTATE, "derp_level_filter: level/colours not set");
+  int rc;
   for (int d = 0; d < c->Sd; ++d) {
     if (o->do_bilateral_filter && (rc = derp_bilateral(c, d))) return rc;
     if (o->do_median_filter && (rc = derp_median(c, d))) return rc;
     if ((rc = derp_mask_fov(c, d))) return rc;
   }
   CU(cudaStreamSynchronize(c->stream));
+  return DERP_OK;
+}
+
+int derp_process_level(DerpCtx* c, const DerpProcessOpts* o) {
+  int rc = derp_level_estimate(c, o);
+  if (rc) return rc;
+  const bool coarsest = c->lp.level == c->lp.num_levels - 1;
+  if (!(c->lp.level > o->mismatches_start_level || coarsest)) {  // Derp.cpp:726-728
+    if ((rc = derp_mismatches(c))) return rc;
+  }
+  const uint64_t evals = c->lastEvals, hits = c->lastHits;
+  if ((rc = derp_level_filter(c, o))) return rc;
   c->lastEvals = evals;
   c->lastHits = hits;
   c->countersOnDevice = false;
@@ -997,9 +1078,9 @@ int derp_set_disparity(DerpCtx* c, int dst, const float* disparity, const float*
   int rc = checkDst(c, dst, "derp_set_disparity", false);
   if (rc) return rc;
   const size_t n = c->plane, b = n * sizeof(float);
-  if (disparity) CU(cudaMemcpyAsync(c->dDisp.p + (size_t)dst * n, disparity, b, cudaMemcpyHostToDevice, c->stream));
-  if (cost) CU(cudaMemcpyAsync(c->dCost.p + (size_t)dst * n, cost, b, cudaMemcpyHostToDevice, c->stream));
-  if (confidence) CU(cudaMemcpyAsync(c->dConf.p + (size_t)dst * n, confidence, b, cudaMemcpyHostToDevice, c->stream));
+  if (disparity) CU(cudaMemcpyAsync(c->dDisp.p + (size_t)dst * n, disparity, b, cudaMemcpyDefault, c->stream));
+  if (cost) CU(cudaMemcpyAsync(c->dCost.p + (size_t)dst * n, cost, b, cudaMemcpyDefault, c->stream));
+  if (confidence) CU(cudaMemcpyAsync(c->dConf.p + (size_t)dst * n, confidence, b, cudaMemcpyDefault, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return DERP_OK;
 }
@@ -1008,9 +1089,9 @@ int derp_get_disparity(DerpCtx* c, int dst, float* disparity, float* cost, float
   int rc = checkDst(c, dst, "derp_get_disparity", false);
   if (rc) return rc;
   const size_t n = c->plane, b = n * sizeof(float);
-  if (disparity) CU(cudaMemcpyAsync(disparity, c->dDisp.p + (size_t)dst * n, b, cudaMemcpyDeviceToHost, c->stream));
-  if (cost) CU(cudaMemcpyAsync(cost, c->dCost.p + (size_t)dst * n, b, cudaMemcpyDeviceToHost, c->stream));
-  if (confidence) CU(cudaMemcpyAsync(confidence, c->dConf.p + (size_t)dst * n, b, cudaMemcpyDeviceToHost, c->stream));
+  if (disparity) CU(cudaMemcpyAsync(disparity, c->dDisp.p + (size_t)dst * n, b, cudaMemcpyDefault, c->stream));
+  if (cost) CU(cudaMemcpyAsync(cost, c->dCost.p + (size_t)dst * n, b, cudaMemcpyDefault, c->stream));
+  if (confidence) CU(cudaMemcpyAsync(confidence, c->dConf.p + (size_t)dst * n, b, cudaMemcpyDefault, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return DERP_OK;
 }

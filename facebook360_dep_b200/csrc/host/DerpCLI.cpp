@@ -6,6 +6,8 @@
 // DerpCLI.cpp:229-320).  There is no CPU fallback: without a CUDA device the process aborts.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "io.h"
@@ -161,6 +163,29 @@ struct Worker {
   std::vector<int> dst;  // indices into rig
 };
 
+// Rendezvous of the GPU worker threads when the destination cameras of a frame are dealt to several GPUs and
+// the level handles mismatches: the stage reads EVERY camera's disparity (Derp.cpp:734-747), so the workers
+// publish the device addresses of their planes, meet, copy the peers' planes GPU-to-GPU, meet again, update.
+struct Exchange {
+  explicit Exchange(int parties, int numCams) : parties(parties), planes(numCams, nullptr) {}
+  void arriveAndWait() {
+    std::unique_lock<std::mutex> lock(m);
+    const int gen = generation;
+    if (++waiting == parties) {
+      waiting = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lock, [&] { return gen != generation; });
+    }
+  }
+  const int parties;
+  std::vector<const float*> planes;  // per rig camera: address of its disparity plane on the owning GPU
+  std::mutex m;
+  std::condition_variable cv;
+  int waiting = 0, generation = 0;
+};
+
 static void saveLevel(const Shared& shAll, const Worker& wk, int level, const std::string& frameName, int W, int H) {
   DerpCtx* ctx = wk.ctx;
   Shared sh = shAll;
@@ -198,7 +223,7 @@ static void saveLevel(const Shared& shAll, const Worker& wk, int level, const st
 }
 
 // One (level, frame): DerpCLI.cpp:229-320
-static void processFrame(const Shared& shAll, const Worker& wk, int level, int iFrame) {
+static void processFrame(const Shared& shAll, const Worker& wk, int level, int iFrame, Exchange* ex) {
   DerpCtx* ctx = wk.ctx;
   Shared sh = shAll;
   sh.dst = wk.dst;
@@ -281,7 +306,18 @@ static void processFrame(const Shared& shAll, const Worker& wk, int level, int i
   o.do_bilateral_filter = FLAGS_do_bilateral_filter ? 1 : 0;
   o.do_median_filter = FLAGS_do_median_filter ? 1 : 0;
   LOG(INFO) << "Processing " << frameName << " level " << level;
-  DERP_CALL(derp_process_level(ctx, &o));
+  const bool mismatchLevel = !(level > FLAGS_mismatches_start_level || level == sh.numLevels - 1);  // Derp.cpp:726-728
+  if (ex && mismatchLevel) {
+    DERP_CALL(derp_level_estimate(ctx, &o));
+    for (int d = 0; d < Sd; ++d) ex->planes[sh.dst[d]] = derp_disparity_device_ptr(ctx, d);
+    ex->arriveAndWait();  // every plane estimated and published
+    DERP_CALL(derp_gather_disparities(ctx, ex->planes.data()));
+    ex->arriveAndWait();  // every GPU holds its copy: planes may change now
+    DERP_CALL(derp_mismatches_gathered(ctx));
+    DERP_CALL(derp_level_filter(ctx, &o));
+  } else {
+    DERP_CALL(derp_process_level(ctx, &o));
+  }
   saveLevel(shAll, wk, level, frameName, W, H);
 }
 
@@ -335,13 +371,13 @@ int main(int argc, char* argv[]) {
   // One context per GPU.  Enough frames: contiguous frame blocks per GPU, every context owns all
   // destinations.  Fewer frames than GPUs (e.g. one 24-camera 4096^2 frame on 8 GPUs): the DESTINATION cameras
   // are dealt round-robin to the GPUs instead and every GPU processes every frame for its destinations — all
-  // stages except mismatch handling are independent per destination.
+  // stages except mismatch handling are independent per destination; that one stage exchanges the disparity
+  // planes between the GPUs (struct Exchange).
   const int Gmax = std::max(1, FLAGS_gpus);
   const bool shardCameras = sh.numFrames < Gmax && (int)sh.dst.size() > 1;
   const int G = shardCameras ? std::min(Gmax, (int)sh.dst.size()) : std::max(1, std::min(Gmax, sh.numFrames));
-  if (shardCameras)
-    CHECK(FLAGS_mismatches_start_level < 0) << "mismatch handling needs all destination cameras on one GPU: use --gpus <= "
-                                              "number of frames";
+  if (shardCameras && FLAGS_mismatches_start_level >= 0)
+    CHECK_EQ(sh.dst.size(), sh.rig.cams.size()) << "Mismatches only valid when considering all cameras";  // Derp.cpp:689
   std::vector<Worker> workers(G);
   for (int g = 0; g < G; ++g) {
     if (shardCameras) {
@@ -367,12 +403,14 @@ int main(int argc, char* argv[]) {
     }
     std::vector<std::thread> threads;
     const int per = (sh.numFrames + G - 1) / G;
+    Exchange exchange(G, (int)sh.rig.cams.size());
     for (int g = 0; g < G; ++g)
       threads.emplace_back([&, g] {
-        if (shardCameras) {
-          for (int i = 0; i < sh.numFrames; ++i) processFrame(sh, workers[g], level, i);
+        if (shardCameras) {  // all GPUs walk the frames in step; they meet inside processFrame on mismatch levels
+          for (int i = 0; i < sh.numFrames; ++i) processFrame(sh, workers[g], level, i, G > 1 ? &exchange : nullptr);
         } else {
-          for (int i = g * per; i < std::min(sh.numFrames, (g + 1) * per); ++i) processFrame(sh, workers[g], level, i);
+          for (int i = g * per; i < std::min(sh.numFrames, (g + 1) * per); ++i)
+            processFrame(sh, workers[g], level, i, nullptr);
         }
       });
     for (auto& w : threads) w.join();  // per-level barrier, like the render pipeline (pipeline.py:364-380)

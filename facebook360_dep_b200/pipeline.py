@@ -98,3 +98,34 @@ def temporal_filter_block(lib, local_frames, num_frames, time_radius=2, sigma=0.
                                            weight_b, device=gpu))
         out[f] = res
     return out
+
+
+def sharded_mismatches(ctx, num_cams, device=None):
+    """Mismatch handling (handleDisparityMismatches, Derp.cpp:685-748) when the destination cameras of a frame are
+    dealt round-robin to the ranks (shard.camera_shard): the Jacobi update reads every camera's pre-update
+    disparity, so the stage is ONE all-gather of the per-camera planes followed by the kernel on the rank's own
+    destinations.  `ctx` is the rank's context, created with dst list
+    shard.camera_shard(num_cams, world, rank), after level_estimate.  NCCL when `device` is a CUDA device (the
+    planes are copied device-to-device into the collective's buffers), gloo on CPU with the oracle in tests."""
+    device = device or torch.device("cpu")
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    own = shard.camera_shard(num_cams, world, rank)
+    assert ctx.Sd == len(own)
+    per = (num_cams + world - 1) // world
+    send = torch.zeros((per, ctx.H, ctx.W), dtype=torch.float32, device=device)
+    for i in range(len(own)):
+        ctx.L.check(ctx.L.lib.derp_get_disparity(ctx.h, i, send[i].data_ptr(), None, None))
+    if world > 1:
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+    else:
+        recv = [send]
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    planes = [None] * num_cams
+    for r in range(world):
+        for i, cam in enumerate(shard.camera_shard(num_cams, world, r)):
+            planes[cam] = recv[r][i].data_ptr()
+    ctx.gather_disparities(planes)
+    ctx.mismatches_gathered()

@@ -26,6 +26,12 @@ def halo_frames(num_frames, world_size, rank, time_radius):
     return left, right
 
 
+def camera_shard(num_cams, world_size, rank):
+    """Destination cameras of rank `rank` when ONE frame is spread over the GPUs (fewer
+    frames than GPUs, or latency): round-robin, like DerpCLI --gpus with a single frame."""
+    return list(range(rank, num_cams, world_size))
+
+
 def reduce_step(ms_local, units_local, device):
     """Bench contract: time = MAX over ranks, work = SUM over ranks. Returns (ms_max, units_sum)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

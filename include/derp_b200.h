@@ -155,6 +155,20 @@ int derp_random_proposals(DerpCtx* ctx, int dst, int num_proposals, float min_de
 int derp_ping_pong(DerpCtx* ctx, int dst, int iterations);
 /* handleDisparityMismatches body for all destinations (Derp.cpp:685-748); needs num_dsts == num_cams. */
 int derp_mismatches(DerpCtx* ctx);
+/* The same stage when the destination cameras of one frame are dealt to several contexts (one per GPU,
+ * SURVEY.md 8(e)(i)): the Jacobi update of handleDisparityMismatches (Derp.cpp:734-747) reads the
+ * pre-update disparity of EVERY camera, so one all-gather per level is the only exchange.
+ *   derp_disparity_device_ptr  address of this context's disparity plane of `dst` (device memory on the
+ *                              CUDA library, host memory on the oracle) for a zero-copy exchange;
+ *   derp_gather_disparities    planes[s] = disparity of camera s (num_cams entries): host memory, memory
+ *                              of this device or of a peer device (NVLink copy), or NULL for a camera
+ *                              this context owns as a destination.  Copies into a context-owned
+ *                              all-camera buffer and returns when the copies are complete;
+ *   derp_mismatches_gathered   the stage for this context's destinations against the gathered planes.
+ * Callers put a barrier between the last two calls so that no peer still reads a plane being updated. */
+const float* derp_disparity_device_ptr(DerpCtx* ctx, int dst);
+int derp_gather_disparities(DerpCtx* ctx, const float* const* planes);
+int derp_mismatches_gathered(DerpCtx* ctx);
 /* bilateralFilter (Derp.cpp:875-902) / medianFilter (Derp.cpp:904-920) / maskFov (Derp.cpp:940-951) */
 int derp_bilateral(DerpCtx* ctx, int dst);
 int derp_median(DerpCtx* ctx, int dst);
@@ -168,12 +182,20 @@ int derp_upsample_from(DerpCtx* ctx, int dst, const float* coarse, int coarse_w,
 
 /* processLevel minus file output (Derp.cpp:1005-1034) for all destinations. */
 int derp_process_level(DerpCtx* ctx, const DerpProcessOpts* opts);
+/* The two halves of derp_process_level around the mismatch stage, for callers that exchange
+ * disparities between contexts there: estimate = reprojection + brute force | proposals + ping-pong
+ * (Derp.cpp:1024-1027), filter = bilateral + median + maskFov (Derp.cpp:1029-1035).
+ * derp_process_level == estimate; derp_mismatches when the level asks for it; filter. */
+int derp_level_estimate(DerpCtx* ctx, const DerpProcessOpts* opts);
+int derp_level_filter(DerpCtx* ctx, const DerpProcessOpts* opts);
 
 /* Cost of one hypothesis per pixel: out_cost/out_conf[y][x] = computeCost(dst, disparity[y][x], x, y)
  * (Derp.cpp:104-226) on interior pixels, NaN on the 1-px border.  Test/diagnostic entry. */
 int derp_eval_cost(DerpCtx* ctx, int dst, const float* disparity, float* out_cost, float* out_conf);
 
-/* Host <-> context state. NULL pointers are skipped. */
+/* Caller <-> context state. NULL pointers are skipped.  The disparity / cost / confidence planes of
+ * derp_set_disparity and derp_get_disparity may live in host memory or in device memory (unified
+ * addressing: the copy kind is inferred), so an exchange buffer of a collective can be filled directly. */
 int derp_set_disparity(DerpCtx* ctx, int dst, const float* disparity, const float* cost,
                        const float* confidence);
 int derp_get_disparity(DerpCtx* ctx, int dst, float* disparity, float* cost, float* confidence);

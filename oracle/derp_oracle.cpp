@@ -143,6 +143,8 @@ struct Ctx {
   std::vector<std::vector<float>> bgDisp;      // [Sd] (empty unless use_foreground_masks)
   std::vector<std::vector<uint8_t>> fovMask;   // [Sd]
   std::vector<std::vector<float>> disp, cost, conf;  // [Sd]
+  std::vector<std::vector<float>> gathered;          // [S] all-camera disparities of a sharded mismatch stage
+  bool haveGathered = false;
   std::vector<std::vector<uint8_t>> mismatch;  // [Sd]
   bool haveColors = false;
   // tables of the current destination
@@ -741,18 +743,13 @@ int derp_ping_pong(DerpCtx* ctx, int dst, int iterations) {
 }
 
 // getSrcMismatches / updateDstDisparityAndMismatchMask / handleDisparityMismatch(es) (Derp.cpp:553-748)
-int derp_mismatches(DerpCtx* ctx) {
-  if (!ctx) return fail(DERP_EINVAL, "null ctx");
-  Ctx& c = ctx->c;
-  if (!c.levelOpen) return fail(DERP_ESTATE, "derp_mismatches: no level");
-  if (c.Sd != c.S) return fail(DERP_EINVAL, "Mismatches only valid when considering all cameras");
-  for (int d = 0; d < c.Sd; ++d)
-    if (c.dst2src[d] != d) return fail(DERP_EINVAL, "derp_mismatches: dst list must equal camera list");
+// allDisp[s] = pre-update disparity of rig camera s (every camera); updates this context's destinations.
+static int mismatchesImpl(Ctx& c, const std::vector<const float*>& allDisp) {
   const int W = c.W, H = c.H;
   const size_t n = (size_t)W * H;
   std::vector<std::vector<float>> newDisp(c.Sd);
   for (int dstIdx = 0; dstIdx < c.Sd; ++dstIdx) {
-    const std::vector<float>& dstDisp = c.disp[dstIdx];
+    const float* dstDisp = allDisp[c.dst2src[dstIdx]];
     std::vector<uint8_t>& dstMask = c.mismatch[dstIdx];
     std::vector<float>& dstDispNew = newDisp[dstIdx];
     dstDispNew.assign(n, std::numeric_limits<float>::quiet_NaN());
@@ -775,7 +772,7 @@ int derp_mismatches(DerpCtx* ctx) {
               if (srcIdx == c.dst2src[dstIdx]) continue;
               double ptSrc[2];
               if (!worldToSrcPoint(ptSrc, ptWorld, c.cams[srcIdx], W, H)) continue;
-              const float dSrc = bilinearF32(c.disp[srcIdx].data(), W, H, (float)ptSrc[0], (float)ptSrc[1]);
+              const float dSrc = bilinearF32(allDisp[srcIdx], W, H, (float)ptSrc[0], (float)ptSrc[1]);
               static const float kFractionChange = 0.1f;
               const float dDstMin = (1.0f - kFractionChange) * dstDisp[p];
               const float dDstMax = (1.0f + kFractionChange) * dstDisp[p];
@@ -808,6 +805,55 @@ int derp_mismatches(DerpCtx* ctx) {
   }
   for (int d = 0; d < c.Sd; ++d) c.disp[d] = newDisp[d];
   return DERP_OK;
+}
+
+int derp_mismatches(DerpCtx* ctx) {
+  if (!ctx) return fail(DERP_EINVAL, "null ctx");
+  Ctx& c = ctx->c;
+  if (!c.levelOpen) return fail(DERP_ESTATE, "derp_mismatches: no level");
+  if (c.Sd != c.S) return fail(DERP_EINVAL, "Mismatches only valid when considering all cameras");
+  for (int d = 0; d < c.Sd; ++d)
+    if (c.dst2src[d] != d) return fail(DERP_EINVAL, "derp_mismatches: dst list must equal camera list");
+  std::vector<const float*> all(c.S);
+  for (int s = 0; s < c.S; ++s) all[s] = c.disp[s].data();
+  return mismatchesImpl(c, all);
+}
+
+// Destination cameras dealt to several contexts (include/derp_b200.h): same Jacobi update, the other
+// cameras' pre-update planes come from the caller's all-gather.
+const float* derp_disparity_device_ptr(DerpCtx* ctx, int dst) {
+  if (!ctx) return nullptr;
+  Ctx& c = ctx->c;
+  if (checkDst(c, dst, "derp_disparity_device_ptr", false)) return nullptr;
+  return c.disp[dst].data();
+}
+
+int derp_gather_disparities(DerpCtx* ctx, const float* const* planes) {
+  if (!ctx || !planes) return fail(DERP_EINVAL, "derp_gather_disparities: bad arguments");
+  Ctx& c = ctx->c;
+  if (!c.levelOpen) return fail(DERP_ESTATE, "derp_gather_disparities: no level");
+  const size_t n = (size_t)c.W * c.H;
+  std::vector<int> ownDst(c.S, -1);
+  for (int d = 0; d < c.Sd; ++d) ownDst[c.dst2src[d]] = d;
+  c.gathered.assign(c.S, std::vector<float>());
+  for (int s = 0; s < c.S; ++s) {
+    if (planes[s]) c.gathered[s].assign(planes[s], planes[s] + n);
+    else if (ownDst[s] >= 0) c.gathered[s] = c.disp[ownDst[s]];
+    else return fail(DERP_EINVAL, "derp_gather_disparities: no plane for a camera this context does not own");
+  }
+  c.haveGathered = true;
+  return DERP_OK;
+}
+
+int derp_mismatches_gathered(DerpCtx* ctx) {
+  if (!ctx) return fail(DERP_EINVAL, "null ctx");
+  Ctx& c = ctx->c;
+  if (!c.levelOpen) return fail(DERP_ESTATE, "derp_mismatches_gathered: no level");
+  if (!c.haveGathered) return fail(DERP_ESTATE, "derp_mismatches_gathered: derp_gather_disparities not called for this level");
+  c.haveGathered = false;
+  std::vector<const float*> all(c.S);
+  for (int s = 0; s < c.S; ++s) all[s] = c.gathered[s].data();
+  return mismatchesImpl(c, all);
 }
 
 // generalizedJointBilateralFilter (TemporalBilateralFilter.h:39-124).  guideScale = 1/maxPixelValue.
@@ -1057,11 +1103,11 @@ int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* 
                      use_foreground_masks ? mu.data() : nullptr, out_w, out_h, use_foreground_masks != 0, out);
 }
 
-// processLevel (Derp.cpp:1005-1034) minus saveResults
-int derp_process_level(DerpCtx* ctx, const DerpProcessOpts* o) {
-  if (!ctx || !o) return fail(DERP_EINVAL, "derp_process_level: bad arguments");
+// processLevel (Derp.cpp:1004-1035) minus saveResults, in the two halves include/derp_b200.h declares
+int derp_level_estimate(DerpCtx* ctx, const DerpProcessOpts* o) {
+  if (!ctx || !o) return fail(DERP_EINVAL, "derp_level_estimate: bad arguments");
   Ctx& c = ctx->c;
-  if (!c.levelOpen || !c.haveColors) return fail(DERP_ESTATE, "derp_process_level: level/colours not set");
+  if (!c.levelOpen || !c.haveColors) return fail(DERP_ESTATE, "derp_level_estimate: level/colours not set");
   const bool coarsest = c.lp.level == c.lp.num_levels - 1;
   uint64_t evals = 0, hits = 0;
   for (int d = 0; d < c.Sd; ++d) {
@@ -1086,19 +1132,33 @@ int derp_process_level(DerpCtx* ctx, const DerpProcessOpts* o) {
       hits += c.srcHits;
     }
   }
-  if (!(c.lp.level > o->mismatches_start_level || coarsest)) {  // Derp.cpp:726-728
-    int rc = derp_mismatches(ctx);
-    if (rc) return rc;
-  }
+  c.costEvals = evals;
+  c.srcHits = hits;
+  return DERP_OK;
+}
+
+int derp_level_filter(DerpCtx* ctx, const DerpProcessOpts* o) {
+  if (!ctx || !o) return fail(DERP_EINVAL, "derp_level_filter: bad arguments");
+  Ctx& c = ctx->c;
+  if (!c.levelOpen || !c.haveColors) return fail(DERP_ESTATE, "derp_level_filter: level/colours not set");
   for (int d = 0; d < c.Sd; ++d) {
     int rc;
     if (o->do_bilateral_filter && (rc = derp_bilateral(ctx, d))) return rc;
     if (o->do_median_filter && (rc = derp_median(ctx, d))) return rc;
     if ((rc = derp_mask_fov(ctx, d))) return rc;
   }
-  c.costEvals = evals;
-  c.srcHits = hits;
   return DERP_OK;
+}
+
+int derp_process_level(DerpCtx* ctx, const DerpProcessOpts* o) {
+  int rc = derp_level_estimate(ctx, o);
+  if (rc) return rc;
+  Ctx& c = ctx->c;
+  const bool coarsest = c.lp.level == c.lp.num_levels - 1;
+  if (!(c.lp.level > o->mismatches_start_level || coarsest)) {  // Derp.cpp:726-728
+    if ((rc = derp_mismatches(ctx))) return rc;
+  }
+  return derp_level_filter(ctx, o);
 }
 
 // ---- state access ------------------------------------------------------------------------------

@@ -338,3 +338,54 @@ def test_many_overlapping_sources(cuda, oracle):
         ev, hits = ctxs[0].get_counters()
         assert (ev, hits) == ctxs[1].get_counters()
     assert hits / ev > 8.5, hits / ev  # the overflow path really ran
+
+
+def test_camera_sharded_mismatches(cuda, oracle):
+    """Destination cameras of one frame dealt to two contexts (what DerpCLI --gpus does with a single frame, here both
+    on cuda:0): estimate per shard, exchange the disparity planes device-to-device by address, mismatch handling per
+    shard.  Must equal the all-camera context of the same library bit for bit, and the oracle run of the sharded
+    protocol within the float bar."""
+    from tests.test_shard import _MM, _mm_inputs, _mm_run
+    rig, colors, init = _mm_inputs()
+    S = _MM["S"]
+    descs = capi.rig_descs(rig)
+    shards = [[0, 2], [1, 3]]
+
+    def run_sharded(lib):
+        ctxs = [capi.Context(lib, descs, own) for own in shards]
+        res = {}
+        W, H = _MM["W"], _MM["H"]
+        kw = dict(random_proposals=1, ping_pong_iterations=1, mismatches_start_level=0)
+        for ctx, own in zip(ctxs, shards):
+            ctx.level_begin(W, H, level=0, num_levels=2, full_width=W, full_height=H, var_noise_floor=0.0,
+                            var_high_thresh=1e9)
+            ctx.set_colors(colors)
+            for i, cam in enumerate(own):
+                ctx.set_disparity(i, init[cam])
+            ctx.level_estimate(**kw)
+        planes = [None] * S
+        for ctx, own in zip(ctxs, shards):
+            for i, cam in enumerate(own):
+                planes[cam] = ctx.disparity_ptr(i)
+        for ctx in ctxs:  # every shard copies BEFORE any shard updates (the barrier of the multi-GPU protocol)
+            ctx.gather_disparities(planes)
+        for ctx, own in zip(ctxs, shards):
+            ctx.mismatches_gathered()
+            ctx.level_filter(**kw)
+            for i, cam in enumerate(own):
+                res[cam] = (ctx.get_disparity(i, want_cost=False), ctx.get_mismatch_mask(i))
+        return res
+
+    got = run_sharded(cuda)
+    whole = capi.Context(cuda, descs)
+    ref = _mm_run(whole, list(range(S)), colors, init, 1, lambda c: c.mismatches())
+    for cam in range(S):
+        assert np.array_equal(got[cam][1], ref[cam][1])
+        assert same_float_bits(got[cam][0], ref[cam][0]).all()
+    orc = run_sharded(oracle)
+    for cam in range(S):
+        assert (got[cam][1] != orc[cam][1]).mean() <= 1e-3
+        fin = np.isfinite(orc[cam][0])
+        assert np.array_equal(np.isfinite(got[cam][0]), fin)
+        close = np.abs(got[cam][0] - orc[cam][0])[fin] <= 1e-3 * np.abs(orc[cam][0])[fin]
+        assert close.mean() >= 1 - 1e-3

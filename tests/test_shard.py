@@ -124,3 +124,99 @@ def test_temporal_halo_exchange_gloo(tmp_path, oracle):
     for f in range(F):
         got = np.load(tmp_path / ("tf%d.npy" % f))
         assert np.array_equal(got.view(np.uint32), np.stack(ref[f]).view(np.uint32)), f
+
+
+# ---- destination cameras of ONE frame dealt to the ranks: all-gather of disparities before mismatch handling ----
+_MM = dict(S=4, W=40, H=40)
+
+
+def _mm_inputs():
+    from facebook360_dep_b200 import synth
+    S, W, H = _MM["S"], _MM["W"], _MM["H"]
+    rig = synth.ring_rig(S, W, H, kind="FTHETA")
+    colors, true_disp = synth.render_rig(rig, W, H, scene=synth.Scene(seed=5))
+    init = []
+    for s in range(S):
+        d = true_disp[s].copy()
+        d[8:24, 10 + 3 * s:26 + 3 * s] *= 1.6  # a wrong patch per camera: the other cameras disagree with it
+        init.append(d)
+    return rig, colors, init
+
+
+def _mm_run(ctx, own, colors, init, variant, mismatch_stage):
+    """One fine level (level 0 of 2) on the cameras `own`; mismatch_stage(ctx) runs between the two halves."""
+    W, H = _MM["W"], _MM["H"]
+    kw = dict(random_proposals=variant, ping_pong_iterations=variant, mismatches_start_level=0)
+    ctx.level_begin(W, H, level=0, num_levels=2, full_width=W, full_height=H, var_noise_floor=0.0, var_high_thresh=1e9)
+    ctx.set_colors(colors)
+    for i, cam in enumerate(own):
+        ctx.set_disparity(i, init[cam])
+    ctx.level_estimate(**kw)
+    mismatch_stage(ctx)
+    ctx.level_filter(**kw)
+    return [(ctx.get_disparity(i, want_cost=False), ctx.get_mismatch_mask(i)) for i in range(len(own))]
+
+
+def _mm_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from facebook360_dep_b200 import capi, pipeline
+    oracle = capi.load_oracle()
+    oracle.set_threads(2)
+    rig, colors, init = _mm_inputs()
+    own = shard.camera_shard(_MM["S"], world, rank)
+    ctx = capi.Context(oracle, capi.rig_descs(rig), own)
+    for variant in (0, 1):
+        res = _mm_run(ctx, own, colors, init, variant, lambda c: pipeline.sharded_mismatches(c, _MM["S"]))
+        for cam, (d, m) in zip(own, res):
+            np.save(os.path.join(out_dir, "mm%d_cam%d_disp.npy" % (variant, cam)), d)
+            np.save(os.path.join(out_dir, "mm%d_cam%d_mask.npy" % (variant, cam)), m)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_camera_shards():
+    for S in (1, 3, 16, 24):
+        for G in (1, 2, 8):
+            seen = sorted(c for r in range(G) for c in shard.camera_shard(S, G, r))
+            assert seen == list(range(S))
+
+
+def test_camera_sharded_mismatches_gloo(tmp_path, oracle):
+    """4 cameras over 2 ranks: estimate per shard, all-gather the disparity planes (gloo), mismatch handling per
+    shard — must equal the single-context run of derp_process_level bit for bit, and the stage must have fired."""
+    from facebook360_dep_b200 import capi
+    world = 2
+    port = 29700 + (os.getpid() % 1000)
+    mp.spawn(_mm_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rig, colors, init = _mm_inputs()
+    S = _MM["S"]
+    ctx = capi.Context(oracle, capi.rig_descs(rig))
+    for variant in (0, 1):
+        ref = _mm_run(ctx, list(range(S)), colors, init, variant, lambda c: c.mismatches())
+        fired = 0
+        for cam in range(S):
+            d = np.load(tmp_path / ("mm%d_cam%d_disp.npy" % (variant, cam)))
+            m = np.load(tmp_path / ("mm%d_cam%d_mask.npy" % (variant, cam)))
+            assert np.array_equal(m, ref[cam][1]), (variant, cam)
+            same = (d.view(np.uint32) == ref[cam][0].view(np.uint32)) | (np.isnan(d) & np.isnan(ref[cam][0]))
+            assert same.all(), (variant, cam)
+            fired += int(m.sum())
+        if variant == 0:
+            assert fired > 50, "mismatch stage did not fire on the planted patches"
+
+
+def test_sharded_mismatch_state_errors(oracle):
+    from facebook360_dep_b200 import capi
+    rig, colors, init = _mm_inputs()
+    ctx = capi.Context(oracle, capi.rig_descs(rig), [0, 2])
+    ctx.level_begin(_MM["W"], _MM["H"], level=0, num_levels=2)
+    ctx.set_colors(colors)
+    import pytest
+    with pytest.raises(capi.DerpError):  # no gather yet
+        ctx.mismatches_gathered()
+    with pytest.raises(capi.DerpError):  # cameras 1 and 3 are not ours and no plane was given
+        ctx.gather_disparities([None] * 4)
+    with pytest.raises(capi.DerpError):  # the unsharded stage needs every camera as a destination (Derp.cpp:689)
+        ctx.mismatches()

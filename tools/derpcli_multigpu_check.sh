@@ -17,5 +17,10 @@ $B --input_root=$T/in --output_root=$T/out2 --first=000000 --last=000003 --parti
 # one frame on two GPUs: destination cameras are sharded instead
 $B --input_root=$T/in --output_root=$T/out3 --first=000001 --last=000001 --partial_coverage --num_depths=32 --gpus=2 2>/dev/null
 for f in $(cd $T/out3 && find . -name "*.pfm"); do cmp $T/out3/$f $T/out1/$f; done && echo "camera-sharded frame identical: $(find $T/out3 -name "*.pfm" | wc -l) PFMs"
+# the same with mismatch handling on the fine level: the GPUs exchange their disparity planes before the stage
+$B --input_root=$T/in --output_root=$T/out4 --first=000001 --last=000001 --partial_coverage --num_depths=32 --mismatches_start_level=0 --gpus=1 2>/dev/null
+$B --input_root=$T/in --output_root=$T/out5 --first=000001 --last=000001 --partial_coverage --num_depths=32 --mismatches_start_level=0 --gpus=2 2>/dev/null
+diff -r $T/out4 $T/out5 && echo "camera-sharded frame with mismatch handling identical: $(find $T/out5 -name '*.pfm' | wc -l) PFMs"
+if diff -rq $T/out4/disparity_levels/level_0 $T/out1/disparity_levels/level_0 >/dev/null 2>&1; then echo "note: mismatch handling changed nothing on this data"; fi
 diff -r $T/out1 $T/out2 && echo "DerpCLI --gpus=2 == --gpus=1 : $(find $T/out2 -name '*.pfm' | wc -l) PFMs identical"
 rm -rf $T
