@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Run under torchrun with N ranks (one per GPU): frame-sharded temporal filtering with the CUDA library and
-NCCL point-to-point halo exchange, checked on rank 0 against the single-process CPU oracle."""
+NCCL point-to-point halo exchange, checked on rank 0 against the single-process CPU oracle; then camera-sharded
+mismatch handling (NCCL all-gather of the disparity planes) against the single-context run."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -45,5 +46,28 @@ if rank == 0:
     assert worst <= 2e-6, worst
     print("multigpu temporal halo exchange ok: %d ranks, %d frames, worst rel diff %.2e (NCCL %s)" % (
         world, F, worst, ".".join(map(str, torch.cuda.nccl.version()))))
+
+# ---- destination cameras of one frame dealt to the ranks: NCCL all-gather of disparities + mismatch handling -------
+from tests.test_shard import _MM, _mm_inputs, _mm_run
+rig, colors, init = _mm_inputs()
+Sm = _MM["S"]
+own = shard.camera_shard(Sm, world, rank)
+ctx = capi.Context(cuda, capi.rig_descs(rig), own, device=lr)
+res = _mm_run(ctx, own, colors, init, 1, lambda c: pipeline.sharded_mismatches(c, Sm, device=dev))
+planes = torch.zeros((Sm, _MM["H"], _MM["W"]), dtype=torch.float32, device=dev)
+masks = torch.zeros((Sm, _MM["H"], _MM["W"]), dtype=torch.int32, device=dev)
+for cam, (d, m) in zip(own, res):
+    planes[cam] = torch.from_numpy(np.nan_to_num(d, nan=-1.0)).to(dev)
+    masks[cam] = torch.from_numpy(m.astype(np.int32)).to(dev)
+dist.all_reduce(planes, op=dist.ReduceOp.SUM)
+dist.all_reduce(masks, op=dist.ReduceOp.SUM)
+if rank == 0:
+    whole = capi.Context(cuda, capi.rig_descs(rig), device=lr)
+    ref = _mm_run(whole, list(range(Sm)), colors, init, 1, lambda c: c.mismatches())
+    for cam in range(Sm):
+        assert np.array_equal(planes[cam].cpu().numpy(), np.nan_to_num(ref[cam][0], nan=-1.0)), cam
+        assert np.array_equal(masks[cam].cpu().numpy(), ref[cam][1].astype(np.int32)), cam
+    print("multigpu camera-sharded mismatch handling ok: %d ranks, %d cameras, bit-identical to one context (%d masked px)" % (
+        world, Sm, int(masks.sum().item())))
 dist.barrier()
 dist.destroy_process_group()
