@@ -114,6 +114,8 @@ def sharded_mismatches(ctx, num_cams, device=None):
     assert ctx.Sd == len(own)
     per = (num_cams + world - 1) // world
     send = torch.zeros((per, ctx.H, ctx.W), dtype=torch.float32, device=device)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)  # the library copies on its own stream: the fill must have landed
     for i in range(len(own)):
         ctx.L.check(ctx.L.lib.derp_get_disparity(ctx.h, i, send[i].data_ptr(), None, None))
     if world > 1:
