@@ -58,6 +58,10 @@ struct DevBuf {
 
 inline dim3 grid2(int W, int H, int z = 1) { return dim3((W + kBlockX - 1) / kBlockX, (H + kBlockY - 1) / kBlockY, z); }
 inline dim3 block2() { return dim3(kBlockX, kBlockY, 1); }
+inline size_t bilateralSmem(int radius) {  // float4 tile + mask bytes of bilateralKernel
+  const size_t cells = (size_t)(kBlockX + 2 * radius) * (kBlockY + 2 * radius);
+  return cells * sizeof(float4) + ((cells + 15) / 16) * 16;
+}
 inline unsigned grid1(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 // OpenCV's float bicubic table (imgwarp.cpp: interpolateCubic A=-0.75, initInterTab2D, INTER_TAB_SIZE 32)
@@ -837,9 +841,13 @@ int derp_bilateral(DerpCtx* c, int dst) {
   const int spaceRadius = (int)std::max(std::ceil(5 * scale), float(1));
   const uint8_t* fg = (c->lp.use_foreground_masks && c->haveFg) ? c->fgOf(self) : nullptr;
   float* disp = c->dDisp.p + (size_t)dst * n;
-  bilateralKernel<<<grid2(c->W, c->H), block2(), 0, c->stream>>>(c->W, c->H, disp, c->dColor.p + (size_t)self * n,
-                                                                c->dFov.p + (size_t)dst * n, fg, spaceRadius, 0.005f, 0.5f,
-                                                                1.0f, 1.0f, c->dScratchA.p);
+  const float sigma = 0.005f;
+  DivConst three, denom;
+  CU(makeDivConst(3.0f, c->stream, &three));
+  CU(makeDivConst(2.0f * (sigma * sigma), c->stream, &denom));
+  bilateralKernel<GuideU16><<<grid2(c->W, c->H), block2(), bilateralSmem(spaceRadius), c->stream>>>(
+      c->W, c->H, disp, GuideU16{c->dColor.p + (size_t)self * n}, c->dFov.p + (size_t)dst * n, fg, spaceRadius, three, denom,
+      0.5f, 1.0f, 1.0f, c->dScratchA.p);
   LAUNCHED("bilateralKernel");
   CU(cudaMemcpyAsync(disp, c->dScratchA.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
   return DERP_OK;
@@ -1216,7 +1224,8 @@ int derp_temporal_filter(int device, int width, int height, int num_frames, cons
   a.guides = dG.p;
   a.disps = dD.p;
   a.masks = dM.p;
-  a.sigma = sigma;
+  CU(makeDivConst(65535.0f, 0, &a.maxPix));
+  CU(makeDivConst(sigma * sigma, 0, &a.sig2));
   a.w0 = weight0;
   a.w1 = weight1;
   a.w2 = weight2;
@@ -1243,8 +1252,15 @@ int derp_joint_bilateral_f32(int device, int width, int height, const float* ima
   CU(cudaMemcpy(dI.p, image, n * sizeof(float), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(dG.p, guide_bgr, n * 3 * sizeof(float), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(dM.p, mask, n, cudaMemcpyHostToDevice));
-  bilateralF32Kernel<<<grid2(width, height), block2()>>>(width, height, dI.p, dG.p, dM.p, radius, sigma, weight0, weight1,
-                                                        weight2, dO.p);
+  DivConst three, denom;
+  CU(makeDivConst(3.0f, 0, &three));
+  CU(makeDivConst(2.0f * (sigma * sigma), 0, &denom));
+  if (bilateralSmem(radius) <= kBilMaxSmem)
+    bilateralKernel<GuideF32><<<grid2(width, height), block2(), bilateralSmem(radius)>>>(
+        width, height, dI.p, GuideF32{dG.p}, dM.p, nullptr, radius, three, denom, weight0, weight1, weight2, dO.p);
+  else
+    bilateralWideKernel<GuideF32><<<grid2(width, height), block2()>>>(width, height, dI.p, GuideF32{dG.p}, dM.p, nullptr, radius,
+                                                                    three, denom, weight0, weight1, weight2, dO.p);
   CU(cudaGetLastError());
   CU(cudaMemcpy(out, dO.p, n * sizeof(float), cudaMemcpyDeviceToHost));
   return DERP_OK;
@@ -1256,6 +1272,15 @@ int derp_joint_bilateral_f32(int device, int width, int height, const float* ima
 // The selection, RNG and camera code is __host__ __device__; these entry points run the HOST
 // instantiation so that CPU-only tests (-m "not gpu") can check it against libstdc++ / the oracle.
 extern "C" {
+
+// 1 if the three-instruction constant division (derp_divconst.cuh) was validated exact for divisor c on `device`
+// (every dividend mantissa against __fdiv_rn), 0 if it failed and the kernels use the plain division, < 0 on error.
+int derp_test_div_const(int device, float c) {
+  if (cudaSetDevice(device) != cudaSuccess) return DERP_ECUDA;
+  DivConst k;
+  if (makeDivConst(c, 0, &k) != cudaSuccess) return DERP_ECUDA;
+  return k.fast;
+}
 
 float derp_test_robust_sum(const float* first, const float* second, int n, int keep) {
   float a[64], b[64];

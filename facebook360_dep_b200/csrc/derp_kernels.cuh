@@ -7,6 +7,7 @@
 #include <cstdint>
 
 #include "derp_cost.cuh"
+#include "derp_divconst.cuh"
 #include "derp_rng.cuh"
 
 namespace derp {
@@ -763,67 +764,99 @@ __global__ void __launch_bounds__(kBlockX* kBlockY) mismatchKernel(const Mismatc
 
 // ---- K10: generalizedJointBilateralFilter<float, Vec3w> (TemporalBilateralFilter.h:39-124) ----------
 // mask = fov & fg; output copied only onto foreground pixels (Derp.cpp:900).
-__global__ void bilateralKernel(int W, int H, const float* __restrict__ image, const uint2* __restrict__ guide,
-                                const uint8_t* __restrict__ fov, const uint8_t* __restrict__ fg, int radius,
-                                float sigma, float w0, float w1, float w2, float* __restrict__ out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+// One CTA filters a 32 x 8 block from a shared-memory tile with a `radius` halo: an entry holds the guide
+// already scaled to [0,1] (the per-tap `colour * guideFactor` of the reference, hoisted: same fp32 product) and
+// the image value, so a tap is one 16-byte shared load instead of three global loads + unpack + 3 multiplies.
+// The two per-tap divisions by constants use divBy (derp_divconst.cuh).  The tap loop keeps the reference's
+// order (v outer, u inner) and its left-to-right sums.
+constexpr size_t kBilMaxSmem = 48 * 1024;  // tiles up to radius 17; wider filters take bilateralWideKernel
+struct GuideU16 {  // packed u16 BGR texels, factor 1/65535
+  const uint2* g;
+  __device__ __forceinline__ float3 load(size_t q) const {
+    const float f = 1 / 65535.0f;
+    const Texel t = unpack(__ldg(g + q));
+    return make_float3(t.b * f, t.g * f, t.r * f);
+  }
+};
+struct GuideF32 {  // float BGR in [0,1], factor 1/1.0f (UpsampleDisparity.cpp: PixelType = Vec3f)
+  const float* g;
+  __device__ __forceinline__ float3 load(size_t q) const {
+    const float f = 1 / 1.0f;
+    return make_float3(g[q * 3] * f, g[q * 3 + 1] * f, g[q * 3 + 2] * f);
+  }
+};
+
+template <class Guide>
+__global__ void __launch_bounds__(kBlockX* kBlockY)
+    bilateralKernel(int W, int H, const float* __restrict__ image, const Guide guide, const uint8_t* __restrict__ mask0,
+                    const uint8_t* __restrict__ mask1, int radius, DivConst three, DivConst denom, float w0, float w1,
+                    float w2, float* __restrict__ out) {
+  extern __shared__ float4 bilTile[];
+  const int TW = kBlockX + 2 * radius, TH = kBlockY + 2 * radius;
+  uint8_t* tmask = reinterpret_cast<uint8_t*>(bilTile + TW * TH);
+  const int bx = blockIdx.x * kBlockX - radius, by = blockIdx.y * kBlockY - radius;
+  const int tid = threadIdx.y * kBlockX + threadIdx.x;
+  for (int i = tid; i < TW * TH; i += kBlockX * kBlockY) {
+    const int ty = i / TW, tx = i - ty * TW;
+    const size_t q = (size_t)clampIdx(by + ty, H - 1) * W + clampIdx(bx + tx, W - 1);
+    const float3 g = guide.load(q);
+    bilTile[i] = make_float4(g.x, g.y, g.z, __ldg(image + q));
+    tmask[i] = (mask0[q] && (!mask1 || mask1[q])) ? 1 : 0;
+  }
+  __syncthreads();
+  const int x = blockIdx.x * kBlockX + threadIdx.x, y = blockIdx.y * kBlockY + threadIdx.y;
   if (x >= W || y >= H) return;
   const size_t p = (size_t)y * W + x;
-  const float self = image[p];
-  const bool fgp = !fg || fg[p];
-  if (!(fov[p] && fgp)) {
-    out[p] = self;  // dest = image where unmasked; non-fg pixels keep their value anyway
+  const int ci = (threadIdx.y + radius) * TW + threadIdx.x + radius;
+  const float4 c = bilTile[ci];
+  if (!tmask[ci]) {
+    out[p] = c.w;  // dest = image where unmasked; non-fg pixels keep their value anyway
     return;
   }
-  const float f = 1 / 65535.0f;
-  const Texel gc = unpack(__ldg(guide + p));
-  const float g0 = gc.b * f, g1 = gc.g * f, g2 = gc.r * f;
-  const float denom = 2.0f * (sigma * sigma);
   float sumWeight = 0.0f, weightedAvg = 0.0f;
   for (int v = -radius; v <= radius; ++v) {
-    const int sy = clampIdx(y + v, H - 1);
+    const int row = ci + v * TW;
+#pragma unroll 4
     for (int u = -radius; u <= radius; ++u) {
-      const int sx = clampIdx(x + u, W - 1);
-      const size_t q = (size_t)sy * W + sx;
-      if (!(fov[q] && (!fg || fg[q]))) continue;
-      const Texel n = unpack(__ldg(guide + q));
-      const float d0 = g0 - n.b * f, d1 = g1 - n.g * f, d2 = g2 - n.r * f;
+      if (!tmask[row + u]) continue;
+      const float4 n = bilTile[row + u];
+      const float d0 = c.x - n.x, d1 = c.y - n.y, d2 = c.z - n.z;
       const float colorDiffSq = w0 * (d0 * d0) + w1 * (d1 * d1) + w2 * (d2 * d2);
-      const float weight = expf((-colorDiffSq / 3.0f) / denom);
+      const float weight = expf(divBy(divBy(-colorDiffSq, three), denom));
       sumWeight += weight;
-      weightedAvg += weight * __ldg(image + q);
+      weightedAvg += weight * n.w;
     }
   }
-  out[p] = (sumWeight != 0.0f) ? weightedAvg / sumWeight : self;
+  out[p] = (sumWeight != 0.0f) ? weightedAvg / sumWeight : c.w;
 }
 
-// float-guide variant used by UpsampleDisparity (guide already in [0,1], factor 1/1.0f)
-__global__ void bilateralF32Kernel(int W, int H, const float* __restrict__ image, const float* __restrict__ guide,
-                                   const uint8_t* __restrict__ mask, int radius, float sigma, float w0, float w1,
-                                   float w2, float* __restrict__ out) {
+// Same filter without the tile, for radii whose halo does not fit shared memory (UpsampleDisparity at 8x:
+// radius = scale^2 + 1 = 65, UpsampleDisparityLib.cpp:93-96).
+template <class Guide>
+__global__ void bilateralWideKernel(int W, int H, const float* __restrict__ image, const Guide guide,
+                                    const uint8_t* __restrict__ mask0, const uint8_t* __restrict__ mask1, int radius,
+                                    DivConst three, DivConst denom, float w0, float w1, float w2, float* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
   const size_t p = (size_t)y * W + x;
   const float self = image[p];
-  if (!mask[p]) {
+  if (!(mask0[p] && (!mask1 || mask1[p]))) {
     out[p] = self;
     return;
   }
-  const float f = 1 / 1.0f;
-  const float g0 = guide[p * 3] * f, g1 = guide[p * 3 + 1] * f, g2 = guide[p * 3 + 2] * f;
-  const float denom = 2.0f * (sigma * sigma);
+  const float3 c = guide.load(p);
   float sumWeight = 0.0f, weightedAvg = 0.0f;
   for (int v = -radius; v <= radius; ++v) {
     const int sy = clampIdx(y + v, H - 1);
     for (int u = -radius; u <= radius; ++u) {
-      const int sx = clampIdx(x + u, W - 1);
-      const size_t q = (size_t)sy * W + sx;
-      if (!mask[q]) continue;
-      const float d0 = g0 - guide[q * 3] * f, d1 = g1 - guide[q * 3 + 1] * f, d2 = g2 - guide[q * 3 + 2] * f;
+      const size_t q = (size_t)sy * W + clampIdx(x + u, W - 1);
+      if (!(mask0[q] && (!mask1 || mask1[q]))) continue;
+      const float3 n = guide.load(q);
+      const float d0 = c.x - n.x, d1 = c.y - n.y, d2 = c.z - n.z;
       const float colorDiffSq = w0 * (d0 * d0) + w1 * (d1 * d1) + w2 * (d2 * d2);
-      const float weight = expf((-colorDiffSq / 3.0f) / denom);
+      const float weight = expf(divBy(divBy(-colorDiffSq, three), denom));
       sumWeight += weight;
-      weightedAvg += weight * image[q];
+      weightedAvg += weight * __ldg(image + q);
     }
   }
   out[p] = (sumWeight != 0.0f) ? weightedAvg / sumWeight : self;
@@ -956,7 +989,8 @@ struct TemporalArgs {
   const uint2* guides;    // [T][H][W] texels
   const float* disps;     // [T][H][W]
   const uint8_t* masks;   // [T][H][W]
-  float sigma, w0, w1, w2;
+  float w0, w1, w2;
+  DivConst maxPix, sig2;  // 65535.0f and sigma^2 (TemporalBilateralFilter.h:176-185)
   float* out;
 };
 __global__ void temporalKernel(const TemporalArgs a) {
@@ -970,7 +1004,6 @@ __global__ void temporalKernel(const TemporalArgs a) {
   }
   const uint2 rt = __ldg(a.guides + a.frameOffset * plane + p);
   const int r0 = (int)(rt.x & 0xffffu), r1 = (int)(rt.x >> 16), r2 = (int)(rt.y & 0xffffu);
-  const float sig2 = a.sigma * a.sigma;
   float weightedSumPix = 0.0f, sumWeight = 0.0f;
   for (int t = 0; t < a.T; ++t) {
     const float dt = a.disps[t * plane + p];  // centre pixel of frame t (TemporalBilateralFilter.h:165)
@@ -982,11 +1015,11 @@ __global__ void temporalKernel(const TemporalArgs a) {
         if (!a.masks[t * plane + q]) continue;
         const uint2 st = __ldg(a.guides + t * plane + q);
         // (ushort - ushort) is exact in int; int -> float conversion rounds to nearest like the CPU
-        const float e0 = (float)(r0 - (int)(st.x & 0xffffu)) / 65535.0f;
-        const float e1 = (float)(r1 - (int)(st.x >> 16)) / 65535.0f;
-        const float e2 = (float)(r2 - (int)(st.y & 0xffffu)) / 65535.0f;
+        const float e0 = divBy((float)(r0 - (int)(st.x & 0xffffu)), a.maxPix);
+        const float e1 = divBy((float)(r1 - (int)(st.x >> 16)), a.maxPix);
+        const float e2 = divBy((float)(r2 - (int)(st.y & 0xffffu)), a.maxPix);
         const float weightedDiff = a.w0 * (e0 * e0) + a.w1 * (e1 * e1) + a.w2 * (e2 * e2);
-        const float weight = expf(-weightedDiff / sig2);
+        const float weight = expf(divBy(-weightedDiff, a.sig2));
         weightedSumPix += dt * weight;
         sumWeight += weight;
       }

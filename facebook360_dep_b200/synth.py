@@ -68,6 +68,40 @@ def wall_rig(num_cams, width, height, kind="RECTILINEAR", spacing=0.06, hfov_deg
     return {"cameras": cams}
 
 
+def sphere_rig(num_cams, width, height, radius=0.33, seed=3, fov=1.57079632679):
+    """Cameras on a sphere looking outward, like the reference's 16-camera test rig (res/test/rigs/rig.json: FTHETA,
+    3360 x 2160, fov pi/2, shared distortion, individually calibrated focal / principal / roll): Fibonacci-sphere
+    positions, random roll about the optical axis, focal and principal jittered per camera, non-square sensor.
+    Exercises what the ring rigs do not: arbitrary orientations, off-centre principals, per-camera intrinsics."""
+    rng = np.random.RandomState(seed)
+    cams = []
+    golden = math.pi * (3.0 - math.sqrt(5.0))
+    for i in range(num_cams):
+        z = 1.0 - 2.0 * (i + 0.5) / num_cams
+        r = math.sqrt(max(0.0, 1.0 - z * z))
+        th = golden * i
+        fwd = np.array([r * math.cos(th), r * math.sin(th), z])
+        helper = np.array([0.0, 0.0, 1.0]) if abs(z) < 0.9 else np.array([1.0, 0.0, 0.0])
+        right0 = np.cross(fwd, helper)
+        right0 /= np.linalg.norm(right0)
+        up0 = np.cross(right0, fwd)
+        roll = rng.uniform(0, 2 * math.pi)
+        up = math.cos(roll) * up0 + math.sin(roll) * right0
+        right = np.cross(fwd, up)  # right = forward x up (Camera.cpp:89-91)
+        f = (width / 3.0) * (1.0 + 0.004 * rng.standard_normal())
+        cams.append({
+            "version": 1, "type": "FTHETA", "id": "cam%d" % i, "fov": fov,
+            "origin": list(radius * fwd * (1.0 + 0.02 * rng.standard_normal())),
+            "forward": list(fwd), "up": list(up), "right": list(right),
+            "resolution": [width, height],
+            "focal": [f, -f],
+            "principal": [width / 2.0 + 0.01 * width * rng.standard_normal(),
+                          height / 2.0 + 0.01 * height * rng.standard_normal()],
+            "distortion": [-0.03413328161902581, 0.0004374554953464843, -0.0018843963208481174],
+        })
+    return {"cameras": cams}
+
+
 # ---- minimal camera unprojection (pixel -> unit ray in rig space), fp64 torch -------------------
 def _undistort(y, d):
     if not any(d):

@@ -9,7 +9,10 @@ from facebook360_dep_b200 import capi, synth
 @functools.lru_cache(maxsize=16)
 def scene_inputs(num_cams, width, height, kind, hfov_deg=None, distorted=False, noise=True, seed=42):
     dist = (-0.03413328161902581, 0.0004374554953464843, -0.0018843963208481174) if distorted else None
-    rig = synth.ring_rig(num_cams, width, height, kind=kind, hfov_deg=hfov_deg, distortion=dist)
+    if kind == "SPHERE":  # the reference's test-rig layout (synth.sphere_rig)
+        rig = synth.sphere_rig(num_cams, width, height)
+    else:
+        rig = synth.ring_rig(num_cams, width, height, kind=kind, hfov_deg=hfov_deg, distortion=dist)
     colors, true_disp = synth.render_rig(rig, width, height, scene=synth.Scene(seed=seed), noise=noise)
     return rig, colors, true_disp
 

@@ -18,6 +18,8 @@ RIGS = [
     ("rect4", dict(num_cams=4, width=96, height=80, kind="RECTILINEAR", hfov_deg=120.0)),
     ("ftheta8d", dict(num_cams=8, width=112, height=96, kind="FTHETA", distorted=True)),
     ("ftheta5", dict(num_cams=5, width=72, height=72, kind="FTHETA")),
+    # layout of the reference's own 16-camera test rig: cameras on a sphere, rolled, per-camera intrinsics, 14:9 sensor
+    ("sphere16", dict(num_cams=16, width=112, height=72, kind="SPHERE")),
 ]
 
 
@@ -107,6 +109,26 @@ def test_brute_force_cfg1_full_size(cuda, oracle):
         # candidates the sweep still lands within two candidate steps on a good share of covered pixels
         cov = oi >= 0
         assert (np.abs(od - true_disp[d])[cov] < 2 * 2.0 / 31).mean() > 0.3
+
+
+def test_max_size_cfg4_one_destination(cuda, oracle):
+    """BASELINE.json configs[3] (the largest): 24 cameras at 4096 x 4096.  One destination, a handful of candidates:
+    the size is what is tested (16.8 M-pixel planes, 24-plane pair tables of 6.4 GB, 64-bit offsets)."""
+    import torch
+    W = H = 4096
+    rig = synth.ring_rig(24, W, H, kind="FTHETA")
+    colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=9), device="cuda")
+    torch.cuda.empty_cache()
+    ctxs = make_pair(cuda, oracle, rig, dst_to_src=[5])
+    _begin(ctxs, colors, W, H)
+    both(ctxs, "reproject", 0)
+    gi, oi = both(ctxs, "brute_force", 0, num_depths=6)
+    assert (oi >= 0).mean() > 0.5
+    assert np.array_equal(gi, oi)
+    (gd, gc, gf), (od, oc, of) = both(ctxs, "get_disparity", 0)
+    assert same_float_bits(gd, od).all()
+    assert mismatch_fraction(gc, oc) <= 1e-5
+    assert ctxs[0].get_counters() == ctxs[1].get_counters()
 
 
 def test_coverage_check_matches_reference_abort(cuda, oracle):
@@ -275,9 +297,24 @@ def test_temporal_and_joint_bilateral(cuda, oracle):
         assert (np.abs(g - o)[fin] <= 2e-6 * np.abs(o)[fin]).all()
     img = disps[0]
     guide = guides[0].astype(np.float32) * (np.float32(1.0) / np.float32(65535.0))  # loadImage<Vec3f>
-    g = cuda.joint_bilateral_f32(img, guide, masks[0], 3, 0.05, 0.5, 0.5, 1.0)
-    o = oracle.joint_bilateral_f32(img, guide, masks[0], 3, 0.05, 0.5, 0.5, 1.0)
-    assert (np.abs(g - o) <= 2e-6 * np.abs(o)).all()
+    # radius 3 and 17 (= scale^2 + 1 of a 4x UpsampleDisparity) run from the shared-memory tile, 20 from global memory
+    for radius in (3, 17, 20):
+        g = cuda.joint_bilateral_f32(img, guide, masks[0], radius, 0.05, 0.5, 0.5, 1.0)
+        o = oracle.joint_bilateral_f32(img, guide, masks[0], radius, 0.05, 0.5, 0.5, 1.0)
+        assert (np.abs(g - o) <= 2e-6 * np.abs(o)).all(), radius
+
+
+def test_constant_division_is_exact(cuda):
+    """The filters divide per tap by loop-invariant constants with a 3-instruction sequence that the library
+    validates exhaustively against IEEE division per constant; the constants the path uses must all qualify
+    (otherwise the kernels silently take the slow division and the timing claims would not hold)."""
+    import ctypes as C
+    f = cuda.lib.derp_test_div_const
+    f.restype, f.argtypes = C.c_int, [C.c_int, C.c_float]
+    s1, s2 = np.float32(0.005), np.float32(0.01)
+    for c in (3.0, 65535.0, float(np.float32(2.0) * (s1 * s1)), float(s2 * s2), float(np.float32(2.0) * np.float32(0.05) ** 2)):
+        assert f(0, c) == 1, c
+    assert f(0, 0.0) == 0  # degenerate divisors never take the fast path
 
 
 def test_standalone_upsample(cuda, oracle):
