@@ -597,12 +597,12 @@ int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, flo
   static const int sweepBYenv = [] {
     const char* e = getenv("DERP_SWEEP_BY");
     const int v = e ? atoi(e) : 0;
-    return (v == 8 || v == 16 || v == 24) ? v : 0;
+    return (v >= 1 && v <= DERP_SWEEP_MAXBY) ? v : 0;
   }();
-  const int sweepBY = sweepBYenv ? sweepBYenv : (H >= 1024 ? 24 : 8);
+  const int sweepBY = sweepBYenv ? sweepBYenv : (H >= 1024 ? DERP_SWEEP_MAXBY : 8);
   const dim3 g = grid2(W, H);
   const dim3 gs((W + kBlockX - 1) / kBlockX, (H + sweepBY - 1) / sweepBY, 1);
-  const long ctas = (long)gs.x * gs.y * (sweepBY / 8);
+  const long ctas = (long)gs.x * gs.y * std::max(1, sweepBY / 8);
   int chunks = (int)std::min<long>(num_depths, std::max<long>(1, (148L * 8 * 4 + ctas - 1) / ctas));
   const int chunk = (num_depths + chunks - 1) / chunks;
   chunks = (num_depths + chunk - 1) / chunk;

@@ -186,7 +186,10 @@ __device__ __forceinline__ f32x2 bilerp2(f32x2 p00, f32x2 p01, f32x2 p10, f32x2 
 // Two float2 planes so that the packed arithmetic gets its operands with 64-bit shared loads:
 //   bg[row][col] = (B, G),   rr[row][col] = (R(row), R(row+1))   (vertical pair: see the R channel below)
 constexpr int kTileW = 32 + 2;
-constexpr int kMaxTileH = 24 + 2;  // tallest CTA the sweep is launched with (32 x 24 threads)
+#ifndef DERP_SWEEP_MAXBY
+#define DERP_SWEEP_MAXBY 24  // tallest CTA the sweep is launched with (32 x 24 threads)
+#endif
+constexpr int kMaxTileH = DERP_SWEEP_MAXBY + 2;
 constexpr int kTileFloats = 2 * kMaxTileH * kTileW * 2;
 
 __device__ __forceinline__ void loadDstTile(float* tile, const CostView& v, int x0, int y0) {

@@ -319,7 +319,10 @@ struct SweepArgs {
 
 // Launched with 32 x BY threads, BY in {8, 16, 24}: 85 registers allow 768 threads per SM either way; a taller
 // CTA shares more texel rows between its warps (per-warp footprint (BY+3)/BY rows instead of 11/8).
-__global__ void __launch_bounds__(768, 1) sweepKernel(const SweepArgs a) {
+#ifndef DERP_SWEEP_CTAS
+#define DERP_SWEEP_CTAS 1
+#endif
+__global__ void __launch_bounds__(32 * DERP_SWEEP_MAXBY, DERP_SWEEP_CTAS) sweepKernel(const SweepArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
   float* tile = reinterpret_cast<float*>(cams + a.v.S);
