@@ -58,6 +58,13 @@ struct DevBuf {
 
 inline dim3 grid2(int W, int H, int z = 1) { return dim3((W + kBlockX - 1) / kBlockX, (H + kBlockY - 1) / kBlockY, z); }
 inline dim3 block2() { return dim3(kBlockX, kBlockY, 1); }
+// Grid of the kernels that walk the active-pixel list: one CTA per kPatchThreads list slots of the largest
+// possible list (its length is only known on the device); CTAs past the end exit before staging anything.  A
+// capped grid with more loop trips per CTA measured slightly slower (ping-pong 6.08 vs 5.93 ms at 2048^2).
+inline unsigned listGrid(int W, int H) {
+  const size_t all = ((size_t)(W - 2) * (H - 2) + kPatchThreads - 1) / kPatchThreads;
+  return (unsigned)std::max<size_t>(1, all);
+}
 inline size_t bilateralSmem(int radius) {  // float4 tile + mask bytes of bilateralKernel
   const size_t cells = (size_t)(kBlockX + 2 * radius) * (kBlockY + 2 * radius);
   return cells * sizeof(float4) + ((cells + 15) / 16) * 16;
@@ -684,7 +691,7 @@ int derp_random_proposals(DerpCtx* c, int dst, int num_proposals, float min_dept
     backgroundFillKernel<<<grid2(W, H), block2(), 0, c->stream>>>(W, H, a.fov, a.fg, a.bg, a.disp);
     LAUNCHED("backgroundFillKernel");
   }
-  proposalKernel<<<grid1((size_t)(W - 2) * (H - 2), kPatchThreads), kPatchThreads, c->patchSmem(), c->stream>>>(a);
+  proposalKernel<<<listGrid(W, H), kPatchThreads, c->patchSmem(), c->stream>>>(a);
   LAUNCHED("proposalKernel");
   return DERP_OK;
 }
@@ -725,7 +732,7 @@ int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
     a.list = c->dList.p;
     a.listCount = listCountPtr(c);
     a.counters = c->dCounters.p;
-    pingPongKernel<<<grid1((size_t)(W - 2) * (H - 2), kPatchThreads), kPatchThreads, c->patchSmem(), c->stream>>>(a);
+    pingPongKernel<<<listGrid(W, H), kPatchThreads, c->patchSmem(), c->stream>>>(a);
     LAUNCHED("pingPongKernel");
     // disp <- dispRes, cost <- costsRes (Derp.cpp:527-529); confidence is not written back
     CU(cudaMemcpyAsync(disp, c->dScratchA.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));

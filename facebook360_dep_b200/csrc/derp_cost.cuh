@@ -252,7 +252,16 @@ __device__ __forceinline__ void loadPixelState(const CostView& v, const DevCamer
 
 // Compacted kernels (one thread per ACTIVE pixel, pixels of a CTA are not a rectangle): every thread keeps its
 // own 3x3 patch in shared memory, laid out [row][col][thread] so that a warp reads consecutive words.
-constexpr int kPatchThreads = 256;
+#ifndef DERP_PATCH_THREADS
+#define DERP_PATCH_THREADS 256
+#endif
+#ifndef DERP_PATCH_MINB
+// Resident CTAs per SM the compacted kernels are compiled for (register cap).  2 => 128 registers, no spills,
+// 16 warps/SM: these kernels are L1-bound (scattered 4x4 gathers, profiles/README.md), so spill traffic costs more
+// than the lost warps: at 2048^2 proposals 0.98 -> 0.63 ms, ping-pong 5.93 -> 5.51 ms against 3 CTAs / 80 registers.
+#define DERP_PATCH_MINB 2
+#endif
+constexpr int kPatchThreads = DERP_PATCH_THREADS;
 constexpr int kPatchRP = 3 * kPatchThreads, kPatchCP = kPatchThreads;
 constexpr int kPatchFloats = 2 * 9 * kPatchThreads * 2;
 

@@ -572,19 +572,21 @@ __global__ void backgroundFillKernel(int W, int H, const uint8_t* __restrict__ f
   if (fov[p] && !fg[p]) disp[p] = bg[p];
 }
 
-__global__ void __launch_bounds__(kPatchThreads, DERP_SWEEP_MINB) proposalKernel(const ProposalArgs a) {
+__global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) proposalKernel(const ProposalArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
   float* patches = reinterpret_cast<float*>(cams + a.v.S);
+  const int count = *a.listCount;
+  if (blockIdx.x * kPatchThreads >= count) return;  // whole CTA idle: skip the camera staging too
   stageCameras(cams, a.v.cams, a.v.S);
-  const int i = blockIdx.x * kPatchThreads + threadIdx.x;
-  if (i >= *a.listCount) return;
   const int W = a.v.W;
+  // grid-stride over the active list (the launch covers the longest possible list: normally one trip)
+  unsigned hits = 0, evals = 0;
+  for (int i = blockIdx.x * kPatchThreads + threadIdx.x; i < count; i += gridDim.x * kPatchThreads) {
   const int p = a.list[i];
   const int y = p / W, x = p - y * W;
   PixelState ps;
   loadPixelStateCompact(a.v, cams[a.v.self], patches, x, y, ps);
-  unsigned hits = 0;
   float currDisp = a.disp[p];
   float currCost = evalCost<kPatchRP, kPatchCP>(a.v, cams, ps, currDisp, &hits);
   float currConf = (currCost == FLT_MAX) ? 0.f : ps.conf;
@@ -611,7 +613,9 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_SWEEP_MINB) proposalKernel
   a.disp[p] = currDisp;
   a.cost[p] = currCost;
   a.conf[p] = currConf;
-  addCounters(a.counters, (unsigned)(1 + a.numProposals), hits);
+  evals += (unsigned)(1 + a.numProposals);
+  }
+  addCounters(a.counters, evals, hits);
 }
 
 // ---- K8: pingPongRectangle (Derp.cpp:403-478), one Jacobi iteration ------------------------------------
@@ -647,20 +651,21 @@ __global__ void pingPongInitKernel(int W, int H, const uint8_t* __restrict__ fov
   changedNext[p] = (old != res) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(kPatchThreads, DERP_SWEEP_MINB) pingPongKernel(const PingPongArgs a) {
+__global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) pingPongKernel(const PingPongArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
   float* patches = reinterpret_cast<float*>(cams + a.v.S);
+  const int count = *a.listCount;
+  if (blockIdx.x * kPatchThreads >= count) return;
   stageCameras(cams, a.v.cams, a.v.S);
-  const int i = blockIdx.x * kPatchThreads + threadIdx.x;
-  if (i >= *a.listCount) return;
   const int W = a.v.W, H = a.v.H;
+  unsigned hits = 0, evals = 0;
+  for (int i = blockIdx.x * kPatchThreads + threadIdx.x; i < count; i += gridDim.x * kPatchThreads) {
   const int p = a.list[i];
   const int y = p / W, x = p - y * W;
   PixelState ps;
   loadPixelStateCompact(a.v, cams[a.v.self], patches, x, y, ps);
   const float old = a.disp[p];
-  unsigned hits = 0, evals = 0;
   float bestCost = __int_as_float(0x7f800000);
   float bestDisp = old;
   const float backgroundDisparity = a.bg ? a.bg[p] : 0.f;
@@ -686,6 +691,7 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_SWEEP_MINB) pingPongKernel
   a.dispRes[p] = bestDisp;
   a.costRes[p] = bestCost;
   a.changedNext[p] = (old != bestDisp) ? 1 : 0;
+  }
   addCounters(a.counters, evals, hits);
 }
 
