@@ -165,6 +165,8 @@ struct DerpCtx {
   float varNoiseFloor = 0;
   DevBuf<uint2> dColor;
   DevBuf<float4> dProjColor, dProjBias;  // integer-valued float texels (see derp_cost.cuh)
+  DevBuf<uint2> dProjColor16, dProjBias16;  // the same tables as 4 x u16 for the compacted kernels (built on demand)
+  bool tabF32 = false, tabU16 = false;     // which bias/final tables of projDst are built
   DevBuf<float2> dProjWarp, dWarpInv;  // per-destination scratch when the geometry cache is off
   // geometry cache: projWarp / projWarpInv of every (dst, src) pair depend on the rig and the level size only
   // one cache per level size (all levels of cfg-2 together: 21 GB), so both level-major (DerpCLI) and
@@ -205,6 +207,8 @@ struct DerpCtx {
     v.self = dst2src[dst];
     v.projColor = dProjColor.p;
     v.projBias = dProjBias.p;
+    v.projColor16 = dProjColor16.p;
+    v.projBias16 = dProjBias16.p;
     v.projWarp = warpOf(dst);
     v.variance = dVariance.p + (size_t)v.self * plane;
     v.cams = dCams.p;
@@ -543,9 +547,28 @@ int derp_reproject(DerpCtx* c, int dst) {
   reprojectKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->warpInvOf(dst), c->S, self, c->W, c->H, c->dColor.p,
                                                                        c->dWtab.p, c->dProjColor.p);
   LAUNCHED("reprojectKernel");
+  c->projDst = dst;
+  c->tabF32 = c->tabU16 = false;  // colour bias + final table layout: built by the first stage that needs them
+  return DERP_OK;
+}
+
+// K4 in the table format the calling stage reads: float4 for the dense sweep / evalCost / the getters, 4 x u16 for
+// the compacted fine-level kernels.  A level normally needs exactly one of them per destination.
+static int ensureTablesF32(DerpCtx* c) {
+  if (c->tabF32) return DERP_OK;
   biasKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor.p, c->dProjBias.p);
   LAUNCHED("biasKernel");
-  c->projDst = dst;
+  c->tabF32 = true;
+  return DERP_OK;
+}
+static int ensureTablesU16(DerpCtx* c) {
+  if (c->tabU16) return DERP_OK;
+  CU(c->dProjColor16.ensure(c->plane * c->S));
+  CU(c->dProjBias16.ensure(c->plane * c->S));
+  bias16Kernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor.p, c->dProjColor16.p,
+                                                                    c->dProjBias16.p);
+  LAUNCHED("bias16Kernel");
+  c->tabU16 = true;
   return DERP_OK;
 }
 
@@ -557,6 +580,7 @@ int derp_eval_cost(DerpCtx* c, int dst, const float* disparity, float* out_cost,
   CU(c->dScratchC.ensure(n));
   CU(cudaMemcpyAsync(c->dScratchA.p, disparity, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   if ((rc = resetCounters(c))) return rc;
+  if ((rc = ensureTablesF32(c))) return rc;
   evalCostKernel<<<grid2(c->W, c->H), block2(), c->camSmem(), c->stream>>>(c->view(dst), c->dScratchA.p, c->dScratchB.p,
                                                                           c->dScratchC.p, c->dCounters.p);
   LAUNCHED("evalCostKernel");
@@ -593,6 +617,10 @@ int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, flo
     c->tableMin = min_depth_m;
     c->tableMax = max_depth_m;
   }
+  if ((rc = ensureTablesF32(c))) return rc;
+#ifdef DERP_SWEEP_U16
+  if ((rc = ensureTablesU16(c))) return rc;
+#endif
   fillKernel<unsigned long long><<<grid1(n), 256, 0, c->stream>>>(n, c->dBest.p, 0x7f7fffffffffffffull);
   LAUNCHED("fillKernel");
   if ((rc = resetCounters(c))) return rc;
@@ -686,6 +714,8 @@ int derp_random_proposals(DerpCtx* c, int dst, int num_proposals, float min_dept
   a.list = c->dList.p;
   a.listCount = listCountPtr(c);
   if ((rc = resetCounters(c))) return rc;
+  if ((rc = ensureTablesU16(c))) return rc;
+  a.v = c->view(dst);  // the u16 tables may just have been allocated
   if ((rc = buildActiveList(c, a.fov, a.fg, a.v.variance, varThresh))) return rc;
   if (useFg) {
     backgroundFillKernel<<<grid2(W, H), block2(), 0, c->stream>>>(W, H, a.fov, a.fg, a.bg, a.disp);
@@ -710,6 +740,7 @@ int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
   const uint8_t* fg = useFg ? c->fgOf(self) : nullptr;
   const float* bg = useFg ? c->bgOf(dst) : nullptr;
   if ((rc = resetCounters(c))) return rc;
+  if ((rc = ensureTablesU16(c))) return rc;
   // active pixels: interior, in FOV, foreground, variance >= noise floor (Derp.cpp:420-437)
   if ((rc = buildActiveList(c, fov, fg, c->view(dst).variance, c->varNoiseFloor))) return rc;
   fillKernel<uint8_t><<<grid1(n), 256, 0, c->stream>>>(n, c->dChangedA.p, (uint8_t)1);
@@ -1176,6 +1207,7 @@ int derp_get_proj_color(DerpCtx* c, int src, uint16_t* bgr) {
   if (!bgr) return fail(DERP_EINVAL, "bad arguments");
   int rc = checkProj(c, src, "derp_get_proj_color");
   if (rc) return rc;
+  if ((rc = ensureTablesF32(c))) return rc;
   return getTexels(c, c->dProjColor.p + (size_t)src * c->plane, bgr);
 }
 
@@ -1183,6 +1215,7 @@ int derp_get_proj_bias(DerpCtx* c, int src, uint16_t* bgr) {
   if (!bgr) return fail(DERP_EINVAL, "bad arguments");
   int rc = checkProj(c, src, "derp_get_proj_bias");
   if (rc) return rc;
+  if ((rc = ensureTablesF32(c))) return rc;
   return getTexels(c, c->dProjBias.p + (size_t)src * c->plane, bgr);
 }
 

@@ -31,6 +31,11 @@ struct CostView {
   int W, H, S, self;
   const float4* projColor;  // [S][H][W] texels (self slot = the destination's own colour)
   const float4* projBias;   // [S][H][W]
+  // The same two tables as 4 x u16 (B,G,R,R of the texel below) = 8 B per texel, for the compacted fine-level
+  // kernels: their gathers are scattered (list entries of one warp span several image rows) and L1-tag bound, and
+  // half-size texels halve the cache lines a request touches; the conversion costs 4 instructions per texel.
+  const uint2* projColor16;
+  const uint2* projBias16;
   const float2* projWarp;   // [S][H][W]  src px -> dst px at infinity (self slot unused)
   const float* variance;    // destination's own variance [H][W]
   const DevCamera* cams;    // [S] normalised cameras (global memory; staged to smem by kernels)
@@ -69,19 +74,39 @@ __device__ __forceinline__ float bilerp1(float p00, float p01, float p10, float 
 
 __device__ __forceinline__ Texel texelOf(float4 t) { return Texel{t.x, t.y, t.z}; }
 
+// One table texel as float4 (B, G, R, R-below), from either table format.  u16 -> f32 is exact.
+__device__ __forceinline__ float4 ldTexel(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ float4 ldTexel(const uint2* p) {
+  const uint2 t = __ldg(p);
+  return make_float4((float)(t.x & 0xffffu), (float)(t.x >> 16), (float)(t.y & 0xffffu), (float)(t.y >> 16));
+}
+template <class TX>
+struct TablesOf;
+template <>
+struct TablesOf<float4> {
+  static __device__ __forceinline__ const float4* color(const CostView& v) { return v.projColor; }
+  static __device__ __forceinline__ const float4* bias(const CostView& v) { return v.projBias; }
+};
+template <>
+struct TablesOf<uint2> {
+  static __device__ __forceinline__ const uint2* color(const CostView& v) { return v.projColor16; }
+  static __device__ __forceinline__ const uint2* bias(const CostView& v) { return v.projBias16; }
+};
+
 // getPixelBilinear on a Vec3w image: per-channel truncated result (CvUtil.h:90-120), biased by 2^23.
 // Generic path: per-tap clamp-to-edge.
-__device__ __forceinline__ Texel sampleTexelTruncBiased(const float4* __restrict__ img, int W, int H, float x, float y) {
+template <class TX>
+__device__ __forceinline__ Texel sampleTexelTruncBiased(const TX* __restrict__ img, int W, int H, float x, float y) {
   const float xf = roundf(x), yf = roundf(y);
   const int xi = (int)xf, yi = (int)yf;
   const int x0 = clampIdx(xi - 1, W - 1), x1 = clampIdx(xi, W - 1);
   const int y0 = clampIdx(yi - 1, H - 1), y1 = clampIdx(yi, H - 1);
   const float xw = x - xf + 0.5f, yw = y - yf + 0.5f;
   const float w00 = (1 - xw) * (1 - yw), w01 = xw * (1 - yw), w10 = (1 - xw) * yw, w11 = xw * yw;
-  const Texel p00 = texelOf(__ldg(img + (size_t)y0 * W + x0));
-  const Texel p01 = texelOf(__ldg(img + (size_t)y0 * W + x1));
-  const Texel p10 = texelOf(__ldg(img + (size_t)y1 * W + x0));
-  const Texel p11 = texelOf(__ldg(img + (size_t)y1 * W + x1));
+  const Texel p00 = texelOf(ldTexel(img + (size_t)y0 * W + x0));
+  const Texel p01 = texelOf(ldTexel(img + (size_t)y0 * W + x1));
+  const Texel p10 = texelOf(ldTexel(img + (size_t)y1 * W + x0));
+  const Texel p11 = texelOf(ldTexel(img + (size_t)y1 * W + x1));
   Texel o;
   o.b = truncBiased(bilerp1(p00.b, p01.b, p10.b, p11.b, w00, w01, w10, w11));
   o.g = truncBiased(bilerp1(p00.g, p01.g, p10.g, p11.g, w00, w01, w10, w11));
@@ -288,7 +313,7 @@ __device__ __forceinline__ void loadPixelStateCompact(const CostView& v, const D
   ps.rr = rr;
   ps.selStride = kPatchThreads;
   ps.sel = reinterpret_cast<float2*>(patches + kPatchFloats) + tid;
-  const float4 tb = __ldg(v.projBias + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
+  const float4 tb = ldTexel(v.projBias16 + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
   ps.dBias[0] = tb.x + kBias23;
   ps.dBias[1] = tb.y + kBias23;
   ps.dBias[2] = tb.z + kBias23;
@@ -335,7 +360,8 @@ __device__ __forceinline__ SrcPoint projectToSource(const DevCamera& c, double w
 
 // Generic (border / inconsistent-rounding / invalid) path of one source: returns false if the source
 // contributes no SSD (warp entry NaN).  Kept out of line: it runs for a few pixels per image.
-__device__ __noinline__ bool ssdSlowPath(const float4* __restrict__ srcColor, const float4* __restrict__ srcBiasImg,
+template <class TX>
+__device__ __noinline__ bool ssdSlowPath(const TX* __restrict__ srcColor, const TX* __restrict__ srcBiasImg,
                                          int W, int H, const float2* bg, const float2* rr, int rowPitch, int colPitch,
                                          float dBias0, float dBias1, float dBias2, float xDstSrc, float yDstSrc,
                                          float* ssdB, float* ssdU) {
@@ -378,7 +404,8 @@ __device__ __forceinline__ f32x2 roundBiased2(f32x2 p, f32x2 half2, f32x2 b23) {
 // the reference, so the result is bit-identical to the generic per-tap path.
 // RP / CP: row and column pitch (in float2) of the thread's 3x3 destination patch in shared memory —
 // (kTileW, 1) for the dense CTA tile, (3*256, 256) for the per-thread patches of the compacted kernels.
-template <int RP, int CP>
+// TX: table texel type (float4 for the dense sweep, uint2 = 4 x u16 for the compacted kernels).
+template <int RP, int CP, class TX = float4>
 __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __restrict__ cams,
                                           const PixelState& ps, float disparity, unsigned* hits) {
   const double depth = (double)(1.0f / disparity);
@@ -447,29 +474,29 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
       // the RZ rounding needs 0 <= p < 2^22; NaN fails every comparison -> slow path, which rejects it
       const bool fast = (xDstSrc >= 1.5f) & (yDstSrc >= 1.5f) & (xDstSrc < 4.0e6f) & (yDstSrc < 4.0e6f) &
           (xi1 == xi0 + 1) & (xi2 == xi0 + 2) & (yi1 == yi0 + 1) & (yi2 == yi0 + 2) & (X0 + 3 <= W - 1) & (Y0 + 3 <= H - 1);
-      const float4* srcColor = v.projColor + s * plane;
-      const float4* srcBiasImg = v.projBias + s * plane;
+      const TX* srcColor = TablesOf<TX>::color(v) + s * plane;
+      const TX* srcBiasImg = TablesOf<TX>::bias(v) + s * plane;
       SrcPoint nxt;
       if (cur.ok) {
         if (fast) {
           // ---- main block: 20 gathers + fp32 SSD of source s, fp64 projection of source sNext --------------
           const size_t off = (size_t)Y0 * W + X0;
-          const float4* r0 = srcColor + off;
-          const float4* r1 = r0 + W;
-          const float4* r2 = r1 + W;
-          const float4* r3 = r2 + W;
-          const float4* b1 = srcBiasImg + off + W + 1;  // bias sample = centre sample's 2x2 footprint
+          const TX* r0 = srcColor + off;
+          const TX* r1 = r0 + W;
+          const TX* r2 = r1 + W;
+          const TX* r3 = r2 + W;
+          const TX* b1 = srcBiasImg + off + W + 1;  // bias sample = centre sample's 2x2 footprint
 #ifdef DERP_EXPERIMENT_NOBIAS  // measurement-only variant (breaks parity): upper bound of not reading the bias table
           const float4 q00 = make_float4(1.f, 2.f, 3.f, 0.f), q01 = q00, q10 = q00, q11 = q00;
           (void)b1;
 #else
-          const float4 q00 = __ldg(b1), q01 = __ldg(b1 + 1), q10 = __ldg(b1 + W), q11 = __ldg(b1 + W + 1);
+          const float4 q00 = ldTexel(b1), q01 = ldTexel(b1 + 1), q10 = ldTexel(b1 + W), q11 = ldTexel(b1 + W + 1);
 #endif
           float4 colA[4], colB[4];
-          colA[0] = __ldg(r0);
-          colA[1] = __ldg(r1);
-          colA[2] = __ldg(r2);
-          colA[3] = __ldg(r3);
+          colA[0] = ldTexel(r0);
+          colA[1] = ldTexel(r1);
+          colA[2] = ldTexel(r2);
+          colA[3] = ldTexel(r3);
           nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
           // y weights: per sample row r (dy = r-1): yw, 1-yw; rows 0,1 also as a packed pair for channel R
           const float yw0 = hi2(W0), yw1 = hi2(W1), yw2 = hi2(W2);
@@ -491,10 +518,10 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           float sB = 0.0f, sU = 0.0f;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {  // dx = c-1: texel columns c and c+1
-            colB[0] = __ldg(r0 + c + 1);
-            colB[1] = __ldg(r1 + c + 1);
-            colB[2] = __ldg(r2 + c + 1);
-            colB[3] = __ldg(r3 + c + 1);
+            colB[0] = ldTexel(r0 + c + 1);
+            colB[1] = ldTexel(r1 + c + 1);
+            colB[2] = ldTexel(r2 + c + 1);
+            colB[3] = ldTexel(r3 + c + 1);
             const float xwc = xwv[c], xwm = 1 - xwc;
             const f32x2 xwc2 = pk(xwc, xwc), xwm2 = pk(xwm, xwm);
             // weights of samples dy=-1,0 as pairs (lane = sample), dy=+1 scalar: w00=(1-xw)(1-yw) ...

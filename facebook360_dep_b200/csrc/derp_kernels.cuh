@@ -231,6 +231,37 @@ __global__ void biasKernel(int W, int H, float4* in, float4* __restrict__ out) {
   img[(size_t)y * W + x] = make_float4(centre.x, centre.y, centre.z, below);
 }
 
+// K4 for the compacted fine-level kernels: same box filter, outputs as 4 x u16 texels (projColor16 = B,G,R,R-below;
+// projBias16 = B,G,R,0) read from the float4 reprojection (x,y,z lanes only), which is left untouched.
+__global__ void bias16Kernel(int W, int H, const float4* __restrict__ in, uint2* __restrict__ color16,
+                             uint2* __restrict__ bias16) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const float4* img = in + (size_t)s * W * H;
+  float sb = 0, sg = 0, sr = 0;
+  float4 centre = make_float4(0.f, 0.f, 0.f, 0.f);
+  float below = 0.f;
+#pragma unroll
+  for (int j = -1; j <= 1; ++j) {
+    const int yy = reflect101(y + j, H);
+#pragma unroll
+    for (int i = -1; i <= 1; ++i) {
+      const int xx = reflect101(x + i, W);
+      const float4 t = __ldg(img + (size_t)yy * W + xx);
+      sb += t.x;
+      sg += t.y;
+      sr += t.z;
+      if (i == 0 && j == 0) centre = t;
+      if (i == 0 && j == 1) below = (y + 1 < H) ? t.z : 0.f;
+    }
+  }
+  const unsigned B = ((unsigned)sb + 4) / 9, G = ((unsigned)sg + 4) / 9, R = ((unsigned)sr + 4) / 9;
+  const size_t o = (size_t)s * W * H + (size_t)y * W + x;
+  bias16[o] = make_uint2(B | (G << 16), R);
+  color16[o] = make_uint2((unsigned)centre.x | ((unsigned)centre.y << 16), (unsigned)centre.z | ((unsigned)below << 16));
+}
+
 // ---- K5: computeImageVariance (DerpUtil.cpp:214-237) for all S planes ---------------------------
 __global__ void varianceKernel(int W, int H, const uint2* __restrict__ in, float* __restrict__ out) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -345,7 +376,11 @@ __global__ void __launch_bounds__(32 * DERP_SWEEP_MAXBY, DERP_SWEEP_CTAS) sweepK
       for (int c = c0; c < c1; ++c) {
         const float d = __ldg(a.disparities + c);
         if (a.bg && !(bgd < d)) continue;  // closerMask (Derp.cpp:240-243)
+#ifdef DERP_SWEEP_U16  // measurement variant: the dense sweep on the 8-byte u16 tables
+        const float cost = evalCost<kTileW, 1, uint2>(a.v, cams, ps, d, &hits);
+#else
         const float cost = evalCost<kTileW, 1>(a.v, cams, ps, d, &hits);
+#endif
         ++evals;
         if (cost < bestCost) {
           bestCost = cost;
@@ -588,7 +623,7 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) proposalKernel
   PixelState ps;
   loadPixelStateCompact(a.v, cams[a.v.self], patches, x, y, ps);
   float currDisp = a.disp[p];
-  float currCost = evalCost<kPatchRP, kPatchCP>(a.v, cams, ps, currDisp, &hits);
+  float currCost = evalCost<kPatchRP, kPatchCP, uint2>(a.v, cams, ps, currDisp, &hits);
   float currConf = (currCost == FLT_MAX) ? 0.f : ps.conf;
   const float costThresh = fminf(0.5f * currCost, 5.0f);
   const float minDisp = a.bg ? a.bg[p] : a.minDispGlobal;
@@ -602,7 +637,7 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) proposalKernel
     const float lo = fmaxf(minDisp, currDisp - amplitude);
     const float hi = fminf(maxDisp, currDisp + amplitude);
     const float propDisp = rng.uniform(lo, hi);
-    const float propCost = evalCost<kPatchRP, kPatchCP>(a.v, cams, ps, propDisp, &hits);
+    const float propCost = evalCost<kPatchRP, kPatchCP, uint2>(a.v, cams, ps, propDisp, &hits);
     if (propCost < currCost && propCost < costThresh) {
       currCost = propCost;
       currDisp = propDisp;
@@ -680,7 +715,7 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) pingPongKernel
     if (!a.fov[q]) continue;
     const float d = a.disp[q];
     if (d >= backgroundDisparity && a.changed[q]) {
-      const float cost = evalCost<kPatchRP, kPatchCP>(a.v, cams, ps, d, &hits);
+      const float cost = evalCost<kPatchRP, kPatchCP, uint2>(a.v, cams, ps, d, &hits);
       ++evals;
       if (cost < bestCost) {
         bestCost = cost;
