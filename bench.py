@@ -119,17 +119,35 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch(workload):
-    """dram bytes per sweepKernel launch from the committed ncu capture, if one exists for this workload."""
+def ncu_capture(workload):
+    """Per-launch counters of sweepKernel from the committed ncu capture (profiles/sweep_traffic.json), if one exists
+    for this workload: dram bytes and executed warp instructions."""
     p = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(p):
         try:
             j = json.load(open(p))
             if j.get("workload") == workload:
-                return j.get("dram_bytes_per_launch")
+                return j
         except Exception:
             pass
-    return None
+    return {}
+
+
+def ncu_traffic_per_launch(workload):
+    return ncu_capture(workload).get("dram_bytes_per_launch")
+
+
+def issue_roof(workload, ms_per_launch, sm_mhz, sms=148):
+    """The roof that actually binds the sweep: warp-instruction issue.  Instructions per launch come from the
+    committed ncu capture of the same workload (a static property of kernel + inputs), time from this run's CUDA
+    events, peak = SMs x 4 schedulers x 1 instruction/clk at the SM clock sampled during this run."""
+    n = ncu_capture(workload).get("warp_instructions_per_launch")
+    if not n or not ms_per_launch or not sm_mhz:
+        return None
+    achieved = n / (ms_per_launch / 1e3) / 1e9
+    peak = sms * 4 * sm_mhz * 1e6 / 1e9
+    return {"warp_instructions_per_launch": n, "achieved": achieved, "peak": peak, "unit": "G warp-instr/s",
+            "frac": achieved / peak}
 
 
 def cpu_sample(workload, rig, colors, steps=1, warmup=0):
@@ -395,7 +413,8 @@ def main():
             "kernel_share_of_step": (sweep_ms / ms) if ms else None,
             "note": "B_stream = 20 B x (pixel,cand,source) triples + 30 B x pixels (SURVEY.md 8(d)); the kernel is "
                     "FP32/FP64-issue bound, not HBM bound - see DESIGN.md",
-            "triples_per_s": hits_step / S / (sweep_ms_launch / 1e3) if sweep_n else None},
+            "triples_per_s": hits_step / S / (sweep_ms_launch / 1e3) if sweep_n else None,
+            "issue": issue_roof(args.workload, sweep_ms_launch if sweep_n else None, (clocks or {}).get("sm_mhz"))},
     }
     if world == 1 and args.workload == "bf128_l0" and not args.no_c2f:
         line["coarse_to_fine_5level"] = coarse_to_fine(ctx, colors, S, W, H, D, stream)
