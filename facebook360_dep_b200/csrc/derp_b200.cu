@@ -159,6 +159,7 @@ struct DerpCtx {
   DevBuf<float> dWtab;
   // level
   bool levelOpen = false, haveColors = false, haveFg = false, haveBg = false, haveGathered = false;
+  bool accumulateCounters = false;
   DerpLevelParams lp{};
   int W = 0, H = 0;
   size_t plane = 0;
@@ -256,6 +257,7 @@ int launchCheck(DerpCtx* c, const char* what) {
   } while (0)
 
 int resetCounters(DerpCtx* c) {
+  if (c->accumulateCounters) return DERP_OK;  // derp_level_estimate: one reset / one read-back for all stages
   CU(cudaMemsetAsync(c->dCounters.p, 0, 2 * sizeof(unsigned long long), c->stream));
   c->countersOnDevice = true;
   return DERP_OK;
@@ -1061,32 +1063,24 @@ int derp_level_estimate(DerpCtx* c, const DerpProcessOpts* o) {
   if (!c || !o) return fail(DERP_EINVAL, "derp_level_estimate: bad arguments");
   if (!c->levelOpen || !c->haveColors) return fail(DERP_ESTATE, "derp_level_estimate: level/colours not set");
   const bool coarsest = c->lp.level == c->lp.num_levels - 1;
-  uint64_t evals = 0, hits = 0;
-  int rc;
-  for (int d = 0; d < c->Sd; ++d) {
-    if ((rc = derp_reproject(c, d))) return rc;
-    if (coarsest) {  // preprocessLevel (Derp.cpp:826-842)
-      if ((rc = derp_brute_force(c, d, o->num_depths, o->min_depth_m, o->max_depth_m, o->partial_coverage, nullptr))) return rc;
-      if ((rc = readCounters(c))) return rc;
-      evals += c->lastEvals;
-      hits += c->lastHits;
-    }
-    if (o->random_proposals > 0 && !coarsest) {  // Derp.cpp:851-853
-      if ((rc = derp_random_proposals(c, d, o->random_proposals, o->min_depth_m, o->max_depth_m))) return rc;
-      if ((rc = readCounters(c))) return rc;
-      evals += c->lastEvals;
-      hits += c->lastHits;
-    }
-    if (!coarsest) {  // Derp.cpp:545-547
-      if ((rc = derp_ping_pong(c, d, o->ping_pong_iterations))) return rc;
-      if ((rc = readCounters(c))) return rc;
-      evals += c->lastEvals;
-      hits += c->lastHits;
-    }
+  // The work counters accumulate on the device across all stages and destinations and are read back once: a
+  // read-back per stage would drain the stream ~3 times per destination, which dominates the small levels.
+  int rc = useDevice(c);
+  if (rc) return rc;
+  if ((rc = resetCounters(c))) return rc;
+  c->accumulateCounters = true;
+  for (int d = 0; d < c->Sd && !rc; ++d) {
+    if ((rc = derp_reproject(c, d))) break;
+    if (coarsest)  // preprocessLevel (Derp.cpp:826-842)
+      rc = derp_brute_force(c, d, o->num_depths, o->min_depth_m, o->max_depth_m, o->partial_coverage, nullptr);
+    if (!rc && o->random_proposals > 0 && !coarsest)  // Derp.cpp:851-853
+      rc = derp_random_proposals(c, d, o->random_proposals, o->min_depth_m, o->max_depth_m);
+    if (!rc && !coarsest)  // Derp.cpp:545-547
+      rc = derp_ping_pong(c, d, o->ping_pong_iterations);
   }
-  CU(cudaStreamSynchronize(c->stream));
-  c->lastEvals = evals;
-  c->lastHits = hits;
+  c->accumulateCounters = false;
+  if (rc) return rc;
+  if ((rc = readCounters(c))) return rc;  // synchronises the stream
   c->countersOnDevice = false;
   return DERP_OK;
 }
