@@ -4,6 +4,8 @@
 // the temporalKernel of libderp_b200.so (derp_temporal_filter).
 // Reproduced verbatim (parity > elegance): weights are passed as (weight_b, weight_g, weight_b) and
 // --weight_r is ignored (TemporalBilateralFilter.cpp:176-178).
+#include <thread>
+
 #include "io.h"
 
 static const int kTemporalSpaceRadiusMin = 1;
@@ -41,7 +43,8 @@ DEFINE_bool(use_foreground_masks, false, "use pre-computed foreground masks");
 DEFINE_double(weight_b, 0.5, "Blue channel weight");
 DEFINE_double(weight_g, 1.0, "Green channel weight");
 DEFINE_double(weight_r, 1.0, "Red channel weight");
-DEFINE_int32(gpu, 0, "CUDA device to use");
+DEFINE_int32(gpu, 0, "first CUDA device to use");
+DEFINE_int32(gpus, 1, "number of GPUs of this box to shard frames across");
 
 #define DERP_CALL(expr)                                                 \
   do {                                                                  \
@@ -65,10 +68,11 @@ static void populateMinMaxFrame(const std::string& dir, int level, const std::st
 }
 
 // FOV mask of one destination at the level size, through the library (generateFovMasks)
-static std::vector<std::vector<uint8_t>> fovMasks(const io::Rig& rig, const std::vector<int>& dst, int W, int H) {
+static std::vector<std::vector<uint8_t>> fovMasks(const io::Rig& rig, const std::vector<int>& dst, int W, int H,
+                                                  int device) {
   std::vector<int32_t> d2s(dst.begin(), dst.end());
   DerpCtx* ctx = nullptr;
-  DERP_CALL(derp_create(rig.cams.data(), (int)rig.cams.size(), d2s.data(), (int)d2s.size(), FLAGS_gpu, &ctx));
+  DERP_CALL(derp_create(rig.cams.data(), (int)rig.cams.size(), d2s.data(), (int)d2s.size(), device, &ctx));
   DerpLevelParams lp{};
   lp.width = W;
   lp.height = H;
@@ -82,7 +86,13 @@ static std::vector<std::vector<uint8_t>> fovMasks(const io::Rig& rig, const std:
   return out;
 }
 
-static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst) {  // :121-184
+// One GPU worker: its device and the FOV masks (level size only: computed once per worker, not per frame)
+struct Worker {
+  int device = 0;
+  std::vector<std::vector<uint8_t>> fov;
+};
+
+static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst, Worker& wk) {  // :121-184
   int first = 0, last = INT32_MAX;
   const std::string& ref = rig.ids[dst[0]];
   populateMinMaxFrame(FLAGS_color, FLAGS_level, ref, cur, first, last);
@@ -94,7 +104,7 @@ static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst
   const int spaceRadius = FLAGS_space_radius == -1
       ? (int)std::max(std::ceil(kTemporalSpaceRadiusMax * scale), float(kTemporalSpaceRadiusMin))
       : FLAGS_space_radius;
-  std::vector<std::vector<uint8_t>> fov;
+  std::vector<std::vector<uint8_t>>& fov = wk.fov;
   for (size_t ci = 0; ci < dst.size(); ++ci) {
     const std::string& id = rig.ids[dst[ci]];
     std::vector<std::vector<uint16_t>> colors(T);
@@ -109,7 +119,7 @@ static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst
       H = h;
       disps[t] = io::loadFloat(io::imagePath(io::levelDir(FLAGS_disparity, FLAGS_level), id, frame), &w, &h);
       CHECK(w == W && h == H) << "colour / disparity size mismatch";
-      if (fov.empty()) fov = fovMasks(rig, dst, W, H);
+      if (fov.empty()) fov = fovMasks(rig, dst, W, H, wk.device);
       if (FLAGS_use_foreground_masks) {
         masks[t] = io::loadMask(io::imagePath(io::levelDir(FLAGS_foreground_masks, FLAGS_level), id, frame), &w, &h);
         CHECK(w == W && h == H) << "mask size mismatch";
@@ -127,7 +137,7 @@ static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst
       mp[t] = masks[t].data();
     }
     std::vector<float> out((size_t)W * H);
-    DERP_CALL(derp_temporal_filter(FLAGS_gpu, W, H, T, g.data(), dp.data(), mp.data(), cur - first, (float)FLAGS_sigma,
+    DERP_CALL(derp_temporal_filter(wk.device, W, H, T, g.data(), dp.data(), mp.data(), cur - first, (float)FLAGS_sigma,
                                    spaceRadius, (float)FLAGS_weight_b, (float)FLAGS_weight_g, (float)FLAGS_weight_b,
                                    out.data()));
     // saveDisparity (:61-94): pfm always
@@ -153,10 +163,23 @@ int main(int argc, char** argv) {
   const io::Rig rig = io::loadRig(FLAGS_rig);
   const std::vector<int> dst = io::filterDestinations(rig, FLAGS_cameras);
   CHECK_GT(dst.size(), 0u) << "no destination cameras!";
-  LOG(INFO) << "backend " << derp_backend();
-  for (int f = std::stoi(FLAGS_first); f <= std::stoi(FLAGS_last); ++f) {
-    LOG(INFO) << "Filtering images... frame " << io::zeroPad(f);
-    filterFrame(f, rig, dst);
-  }
+  // Frames are independent (every frame reads its +-time_radius neighbours from disk, like the reference): contiguous
+  // frame blocks per GPU, one worker thread per GPU.
+  const int firstFrame = std::stoi(FLAGS_first), numFrames = std::stoi(FLAGS_last) - firstFrame + 1;
+  CHECK_GT(numFrames, 0);
+  const int G = std::max(1, std::min(FLAGS_gpus, numFrames));
+  LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s)";
+  const int per = (numFrames + G - 1) / G;
+  std::vector<std::thread> threads;
+  for (int g = 0; g < G; ++g)
+    threads.emplace_back([&, g] {
+      Worker wk;
+      wk.device = FLAGS_gpu + g;
+      for (int i = g * per; i < std::min(numFrames, (g + 1) * per); ++i) {
+        LOG(INFO) << "Filtering images... frame " << io::zeroPad(firstFrame + i);
+        filterFrame(firstFrame + i, rig, dst, wk);
+      }
+    });
+  for (auto& t : threads) t.join();
   return EXIT_SUCCESS;
 }
