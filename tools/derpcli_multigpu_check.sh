@@ -22,5 +22,12 @@ $B --input_root=$T/in --output_root=$T/out4 --first=000001 --last=000001 --parti
 $B --input_root=$T/in --output_root=$T/out5 --first=000001 --last=000001 --partial_coverage --num_depths=32 --mismatches_start_level=0 --gpus=2 2>/dev/null
 diff -r $T/out4 $T/out5 && echo "camera-sharded frame with mismatch handling identical: $(find $T/out5 -name '*.pfm' | wc -l) PFMs"
 if diff -rq $T/out4/disparity_levels/level_0 $T/out1/disparity_levels/level_0 >/dev/null 2>&1; then echo "note: mismatch handling changed nothing on this data"; fi
+# temporal filter over the 4 frames of out1's level-0 disparities: frame blocks on two GPUs vs one
+TB=facebook360_dep_b200/bin/TemporalBilateralFilter
+cp -r $T/out1 $T/out1b
+$TB --input_root=$T/in --output_root=$T/out1 --rig=$T/in/rigs/rig_calibrated.json --first=000000 --last=000003 --level=0 --gpus=1 2>/dev/null
+$TB --input_root=$T/in --output_root=$T/out1b --rig=$T/in/rigs/rig_calibrated.json --first=000000 --last=000003 --level=0 --gpus=2 2>/dev/null
+diff -r $T/out1/disparity_time_filtered_levels $T/out1b/disparity_time_filtered_levels && echo "TemporalBilateralFilter --gpus=2 == --gpus=1 : $(find $T/out1b/disparity_time_filtered_levels -name '*.pfm' | wc -l) PFMs identical"
+rm -rf $T/out1/disparity_time_filtered_levels
 diff -r $T/out1 $T/out2 && echo "DerpCLI --gpus=2 == --gpus=1 : $(find $T/out2 -name '*.pfm' | wc -l) PFMs identical"
 rm -rf $T
