@@ -3,6 +3,8 @@
 // colour-guided joint bilateral filter run in libderp_b200.so.
 // Deviation, stated: the colour images must already have the output size (the reference would
 // cv::resize(INTER_AREA) them otherwise, UpsampleDisparity.cpp:117); a mismatch is a fatal error here.
+#include <thread>
+
 #include "io.h"
 
 const std::string kUsage = R"(
@@ -38,7 +40,8 @@ DEFINE_int32(threads, -1, "number of threads (-1 = auto, 0 = none)");
 DEFINE_double(weight_b, 0.5, "bilateral filter blue channel weight");
 DEFINE_double(weight_g, 0.5, "bilateral filter green channel weight");
 DEFINE_double(weight_r, 1.0, "bilateral filter red channel weight");
-DEFINE_int32(gpu, 0, "CUDA device to use");
+DEFINE_int32(gpu, 0, "first CUDA device to use");
+DEFINE_int32(gpus, 1, "number of GPUs of this box to shard frames across");
 
 #define DERP_CALL(expr)                                                 \
   do {                                                                  \
@@ -62,7 +65,7 @@ static std::vector<float> loadColorF32(const fs::path& p, int* w, int* h) {
   return out;
 }
 
-static void upsampleFrame(const io::Rig& rig, const std::vector<int>& dst, const std::string& frame) {  // :65-144
+static void upsampleFrame(const io::Rig& rig, const std::vector<int>& dst, const std::string& frame, int device) {  // :65-144
   const std::string exts = FLAGS_output_formats.empty() ? "pfm" : FLAGS_output_formats;
   int height;
   const DerpCameraDesc& c0 = rig.cams[dst[0]];
@@ -93,7 +96,7 @@ static void upsampleFrame(const io::Rig& rig, const std::vector<int>& dst, const
       CHECK(w == W && h == H) << "Desired resolution does not match mask resolution";
     }
     std::vector<float> up((size_t)W * H);
-    DERP_CALL(derp_upsample_disparity(FLAGS_gpu, &rig.cams[dst[i]], disp.data(), cw, ch, bg.empty() ? nullptr : bg.data(),
+    DERP_CALL(derp_upsample_disparity(device, &rig.cams[dst[i]], disp.data(), cw, ch, bg.empty() ? nullptr : bg.data(),
                                       maskIn.data(), maskUp.data(), W, H, useFg ? 1 : 0, up.data()));
     if (!FLAGS_color.empty()) {
       const float scale = float(W) / float(cw);  // getRadius (UpsampleDisparityLib.cpp:93-96)
@@ -102,7 +105,7 @@ static void upsampleFrame(const io::Rig& rig, const std::vector<int>& dst, const
       const std::vector<float> color = loadColorF32(io::imagePath(FLAGS_color, id, frame), &w, &h);
       CHECK(w == W && h == H) << "colour images must have the output resolution (" << W << "x" << H << ")";
       std::vector<float> filtered((size_t)W * H);
-      DERP_CALL(derp_joint_bilateral_f32(FLAGS_gpu, W, H, up.data(), color.data(), maskUp.data(), radius, (float)FLAGS_sigma,
+      DERP_CALL(derp_joint_bilateral_f32(device, W, H, up.data(), color.data(), maskUp.data(), radius, (float)FLAGS_sigma,
                                          (float)FLAGS_weight_b, (float)FLAGS_weight_g, (float)FLAGS_weight_r,
                                          filtered.data()));
       up.swap(filtered);
@@ -134,7 +137,18 @@ int main(int argc, char** argv) {
     if (first.empty()) first = files.front().stem().string();
     if (last.empty()) last = files.back().stem().string();
   }
-  LOG(INFO) << "backend " << derp_backend();
-  for (int f = std::stoi(first); f <= std::stoi(last); ++f) upsampleFrame(rig, dst, io::zeroPad(f));
+  // frames are independent: contiguous frame blocks per GPU, one worker thread per GPU
+  const int firstFrame = std::stoi(first), numFrames = std::stoi(last) - firstFrame + 1;
+  CHECK_GT(numFrames, 0);
+  const int G = std::max(1, std::min(FLAGS_gpus, numFrames));
+  LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s)";
+  const int per = (numFrames + G - 1) / G;
+  std::vector<std::thread> threads;
+  for (int g = 0; g < G; ++g)
+    threads.emplace_back([&, g] {
+      for (int i = g * per; i < std::min(numFrames, (g + 1) * per); ++i)
+        upsampleFrame(rig, dst, io::zeroPad(firstFrame + i), FLAGS_gpu + g);
+    });
+  for (auto& t : threads) t.join();
   return EXIT_SUCCESS;
 }
