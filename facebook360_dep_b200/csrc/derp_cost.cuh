@@ -431,29 +431,51 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     else overflow[n - kSelSlots] = make_float2(b, u);
     ++n;
   };
+  // The four warp-table taps of a projected point (getPixelBilinear on the Vec2f table, CvUtil.h:107-120) and its
+  // bilinear weights.  A point inside the sensor has coordinates >= 0, so the RZ rounding applies; for a point
+  // outside (!ok) the clamped, harmless fetch result is discarded by the caller.
+  struct WarpTaps {
+    float2 p00, p01, p10, p11;
+    float xw, yw;
+  };
+  auto fetchWarp = [&](int s, const SrcPoint& sp) {
+    const f32x2 P = pk(sp.x, sp.y);
+    const f32x2 T = roundBiased2(P, half2, b232);
+    const f32x2 Wt = add2(sub2(P, sub2(T, b232)), half2);  // (xw, yw) = p - round(p) + 0.5
+    const int wxi = __float_as_int(lo2(T)) - 0x4B000000, wyi = __float_as_int(hi2(T)) - 0x4B000000;
+    const float2* wt = v.projWarp + s * plane;
+    const int x0 = clampIdx(wxi - 1, W - 1), x1 = clampIdx(wxi, W - 1);
+    const int y0 = clampIdx(wyi - 1, H - 1), y1 = clampIdx(wyi, H - 1);
+    WarpTaps t;
+    t.p00 = __ldg(wt + (size_t)y0 * W + x0);
+    t.p01 = __ldg(wt + (size_t)y0 * W + x1);
+    t.p10 = __ldg(wt + (size_t)y1 * W + x0);
+    t.p11 = __ldg(wt + (size_t)y1 * W + x1);
+    t.xw = lo2(Wt);
+    t.yw = hi2(Wt);
+    return t;
+  };
   if (mask) {
     int s = __ffs(mask) - 1;
     mask &= mask - 1;
     SrcPoint cur = projectToSource(cams[s], wx, wy, wz, W, H);
+#ifdef DERP_WARP_PREFETCH
+    WarpTaps taps = fetchWarp(s, cur), tapsNext;
+#endif
     while (true) {
       const int sNext = mask ? __ffs(mask) - 1 : s;  // tail: harmless re-projection of the same source
       const bool more = mask != 0;
       mask &= mask - 1;
-      // ---- current source: warp entry (getPixelBilinear on the Vec2f table, CvUtil.h:107-120) ---------
-      // cur is inside the sensor when cur.ok, so its coordinates are >= 0 and the RZ rounding applies; when
-      // !cur.ok the (clamped, harmless) fetch result is discarded below.
-      f32x2 P = pk(cur.x, cur.y);
-      f32x2 T = roundBiased2(P, half2, b232);
-      f32x2 Wt = add2(sub2(P, sub2(T, b232)), half2);  // (xw, yw) = p - round(p) + 0.5
-      const int wxi = __float_as_int(lo2(T)) - 0x4B000000, wyi = __float_as_int(hi2(T)) - 0x4B000000;
+      // ---- current source: warp entry ---------------------------------------------------------------------
       float2 pd;
       {
-        const float2* wt = v.projWarp + s * plane;
-        const int x0 = clampIdx(wxi - 1, W - 1), x1 = clampIdx(wxi, W - 1);
-        const int y0 = clampIdx(wyi - 1, H - 1), y1 = clampIdx(wyi, H - 1);
-        const float2 p00 = __ldg(wt + (size_t)y0 * W + x0), p01 = __ldg(wt + (size_t)y0 * W + x1);
-        const float2 p10 = __ldg(wt + (size_t)y1 * W + x0), p11 = __ldg(wt + (size_t)y1 * W + x1);
-        const float xw = lo2(Wt), yw = hi2(Wt);
+#ifdef DERP_WARP_PREFETCH  // taps were requested right after the projection, one iteration ago
+        const WarpTaps tp = taps;
+#else
+        const WarpTaps tp = fetchWarp(s, cur);
+#endif
+        const float2 p00 = tp.p00, p01 = tp.p01, p10 = tp.p10, p11 = tp.p11;
+        const float xw = tp.xw, yw = tp.yw;
         const float xm = 1 - xw, ym = 1 - yw;
         const f32x2 r = bilerp2(pk(p00.x, p00.y), pk(p01.x, p01.y), pk(p10.x, p10.y), pk(p11.x, p11.y),
                                 pk(xm * ym, xm * ym), pk(xw * ym, xw * ym), pk(xm * yw, xm * yw), pk(xw * yw, xw * yw), one2);
@@ -498,6 +520,9 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           colA[2] = ldTexel(r2);
           colA[3] = ldTexel(r3);
           nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+#ifdef DERP_WARP_PREFETCH
+          tapsNext = fetchWarp(sNext, nxt);
+#endif
           // y weights: per sample row r (dy = r-1): yw, 1-yw; rows 0,1 also as a packed pair for channel R
           const float yw0 = hi2(W0), yw1 = hi2(W1), yw2 = hi2(W2);
           const float ym0 = 1 - yw0, ym1 = 1 - yw1, ym2 = 1 - yw2;
@@ -565,6 +590,9 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           pushPair(sB * scaleFactor, sU * scaleFactor);
         } else {
           nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+#ifdef DERP_WARP_PREFETCH
+          tapsNext = fetchWarp(sNext, nxt);
+#endif
           float slowB, slowU;
           if (ssdSlowPath(srcColor, srcBiasImg, W, H, ps.bg, ps.rr, RP, CP, ps.dBias[0], ps.dBias[1], ps.dBias[2], xDstSrc,
                           yDstSrc, &slowB, &slowU))
@@ -572,10 +600,16 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
         }
       } else {
         nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+#ifdef DERP_WARP_PREFETCH
+          tapsNext = fetchWarp(sNext, nxt);
+#endif
       }
       if (!more) break;
       cur = nxt;
       s = sNext;
+#ifdef DERP_WARP_PREFETCH
+      taps = tapsNext;
+#endif
     }
   }
   *hits += n;
