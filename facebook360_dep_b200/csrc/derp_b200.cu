@@ -628,15 +628,15 @@ int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, flo
   if ((rc = resetCounters(c))) return rc;
   CU(cudaMemsetAsync(c->dUncovered.p, 0, sizeof(unsigned), c->stream));
   // candidate chunks: enough CTAs to fill 148 SMs x 8 resident CTAs even on the coarse levels
-  // CTA height of the sweep: 24 rows (one 768-thread CTA per SM) on large levels — its warps share more texel
-  // rows: 23.2 vs 22.7 G triples/s at 2048^2 — and 8 rows (three CTAs per SM) on small ones, where CTA count
-  // matters more.  DERP_SWEEP_BY overrides for tuning runs.
+  // CTA height of the sweep: DERP_SWEEP_MAXBY rows (one 640-thread CTA per SM, 96 registers) on large levels —
+  // its warps share more texel rows — and half of that (two CTAs per SM, same 20 warps) on small ones, where CTA count matters
+  // more.  DERP_SWEEP_BY overrides for tuning runs.
   static const int sweepBYenv = [] {
     const char* e = getenv("DERP_SWEEP_BY");
     const int v = e ? atoi(e) : 0;
     return (v >= 1 && v <= DERP_SWEEP_MAXBY) ? v : 0;
   }();
-  const int sweepBY = sweepBYenv ? sweepBYenv : (H >= 1024 ? DERP_SWEEP_MAXBY : 8);
+  const int sweepBY = sweepBYenv ? sweepBYenv : (H >= 1024 ? DERP_SWEEP_MAXBY : DERP_SWEEP_MAXBY / 2);
   const dim3 g = grid2(W, H);
   const dim3 gs((W + kBlockX - 1) / kBlockX, (H + sweepBY - 1) / sweepBY, 1);
   const long ctas = (long)gs.x * gs.y * std::max(1, sweepBY / 8);

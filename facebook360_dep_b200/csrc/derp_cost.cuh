@@ -212,7 +212,7 @@ __device__ __forceinline__ f32x2 bilerp2(f32x2 p00, f32x2 p01, f32x2 p10, f32x2 
 //   bg[row][col] = (B, G),   rr[row][col] = (R(row), R(row+1))   (vertical pair: see the R channel below)
 constexpr int kTileW = 32 + 2;
 #ifndef DERP_SWEEP_MAXBY
-#define DERP_SWEEP_MAXBY 24  // tallest CTA the sweep is launched with (32 x 24 threads)
+#define DERP_SWEEP_MAXBY 20  // tallest CTA the sweep is launched with (32 x 20 threads => 96 registers, 20 warps/SM)
 #endif
 constexpr int kMaxTileH = DERP_SWEEP_MAXBY + 2;
 constexpr int kTileFloats = 2 * kMaxTileH * kTileW * 2;
@@ -459,9 +459,6 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     int s = __ffs(mask) - 1;
     mask &= mask - 1;
     SrcPoint cur = projectToSource(cams[s], wx, wy, wz, W, H);
-#ifdef DERP_WARP_PREFETCH
-    WarpTaps taps = fetchWarp(s, cur), tapsNext;
-#endif
     while (true) {
       const int sNext = mask ? __ffs(mask) - 1 : s;  // tail: harmless re-projection of the same source
       const bool more = mask != 0;
@@ -469,11 +466,7 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
       // ---- current source: warp entry ---------------------------------------------------------------------
       float2 pd;
       {
-#ifdef DERP_WARP_PREFETCH  // taps were requested right after the projection, one iteration ago
-        const WarpTaps tp = taps;
-#else
         const WarpTaps tp = fetchWarp(s, cur);
-#endif
         const float2 p00 = tp.p00, p01 = tp.p01, p10 = tp.p10, p11 = tp.p11;
         const float xw = tp.xw, yw = tp.yw;
         const float xm = 1 - xw, ym = 1 - yw;
@@ -520,9 +513,6 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           colA[2] = ldTexel(r2);
           colA[3] = ldTexel(r3);
           nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
-#ifdef DERP_WARP_PREFETCH
-          tapsNext = fetchWarp(sNext, nxt);
-#endif
           // y weights: per sample row r (dy = r-1): yw, 1-yw; rows 0,1 also as a packed pair for channel R
           const float yw0 = hi2(W0), yw1 = hi2(W1), yw2 = hi2(W2);
           const float ym0 = 1 - yw0, ym1 = 1 - yw1, ym2 = 1 - yw2;
@@ -590,9 +580,6 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           pushPair(sB * scaleFactor, sU * scaleFactor);
         } else {
           nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
-#ifdef DERP_WARP_PREFETCH
-          tapsNext = fetchWarp(sNext, nxt);
-#endif
           float slowB, slowU;
           if (ssdSlowPath(srcColor, srcBiasImg, W, H, ps.bg, ps.rr, RP, CP, ps.dBias[0], ps.dBias[1], ps.dBias[2], xDstSrc,
                           yDstSrc, &slowB, &slowU))
@@ -600,16 +587,10 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
         }
       } else {
         nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
-#ifdef DERP_WARP_PREFETCH
-          tapsNext = fetchWarp(sNext, nxt);
-#endif
       }
       if (!more) break;
       cur = nxt;
       s = sNext;
-#ifdef DERP_WARP_PREFETCH
-      taps = tapsNext;
-#endif
     }
   }
   *hits += n;

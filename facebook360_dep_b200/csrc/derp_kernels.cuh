@@ -348,8 +348,10 @@ struct SweepArgs {
   unsigned long long* counters;  // [0] cost evaluations, [1] source hits
 };
 
-// Launched with 32 x BY threads, BY in {8, 16, 24}: 85 registers allow 768 threads per SM either way; a taller
-// CTA shares more texel rows between its warps (per-warp footprint (BY+3)/BY rows instead of 11/8).
+// Launched with 32 x BY threads: BY = DERP_SWEEP_MAXBY (20 => one 640-thread CTA per SM at 96 registers, 44 B of
+// spills) on levels of >= 1024 rows, 8 on smaller ones.  Measured at 2048^2 on one box: 32x20/96 regs 25.7, 32x24/80
+// regs 24.9-25.3, 32x28/72 regs 22.3, 32x16/128 regs 24.0 G triples/s (profiles/README.md); a taller CTA also
+// shares more texel rows between its warps (per-warp footprint (BY+3)/BY rows instead of 11/8).
 #ifndef DERP_SWEEP_CTAS
 #define DERP_SWEEP_CTAS 1
 #endif
