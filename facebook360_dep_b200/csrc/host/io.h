@@ -426,6 +426,31 @@ inline void pngChunk(std::ofstream& f, const char* type, const std::vector<uint8
   f.write(reinterpret_cast<char*>(c), 4);
 }
 
+// 8-bit single-channel PNG (what cv::imwrite produces for a CV_32F matrix: convertTo(CV_8U), modules/imgcodecs loadsave)
+inline void writePng8Gray(const fs::path& path, const uint8_t* data, int w, int h) {
+  std::ofstream f(path, std::ios::binary);
+  CHECK(f.good()) << "failed to save image: " << path.string();
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  f.write(reinterpret_cast<const char*>(sig), 8);
+  std::vector<uint8_t> ihdr(13);
+  ihdr[0] = w >> 24; ihdr[1] = w >> 16; ihdr[2] = w >> 8; ihdr[3] = w;
+  ihdr[4] = h >> 24; ihdr[5] = h >> 16; ihdr[6] = h >> 8; ihdr[7] = h;
+  ihdr[8] = 8;
+  ihdr[9] = 0;
+  pngChunk(f, "IHDR", ihdr);
+  std::vector<uint8_t> raw(((size_t)w + 1) * h);
+  for (int y = 0; y < h; ++y) {
+    raw[(size_t)y * (w + 1)] = 0;
+    std::memcpy(&raw[(size_t)y * (w + 1) + 1], data + (size_t)y * w, (size_t)w);
+  }
+  uLongf clen = compressBound((uLong)raw.size());
+  std::vector<uint8_t> comp(clen);
+  CHECK(compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 3) == Z_OK) << "PNG deflate failed";
+  comp.resize(clen);
+  pngChunk(f, "IDAT", comp);
+  pngChunk(f, "IEND", {});
+}
+
 // 16-bit PNG, `channels` = 1 (gray) or 3 (BGR input, written as RGB)
 inline void writePng16(const fs::path& path, const uint16_t* data, int w, int h, int channels) {
   std::ofstream f(path, std::ios::binary);

@@ -53,6 +53,11 @@ REF_FLAGS = {
         "use_foreground_masks": ("bool", "false"), "weight_b": ("double", "0.5"), "weight_g": ("double", "1.0"),
         "weight_r": ("double", "1.0"),
     },
+    "LayerDisparities": {  # LayerDisparities.cpp:36-44
+        "background_disp": ("string", ""), "background_frame": ("string", "000000"), "cameras": ("string", ""),
+        "first": ("string", "000000"), "foreground_disp": ("string", ""), "last": ("string", "000000"),
+        "output": ("string", ""), "rig": ("string", ""), "threads": ("int32", "-1"),
+    },
     "UpsampleDisparity": {
         "background_disp": ("string", ""), "background_frame": ("string", "000000"), "cameras": ("string", ""),
         "color": ("string", ""), "disparity": ("string", ""), "first": ("string", "000000"),
@@ -162,6 +167,50 @@ def read_pfm(path):
         w, h = map(int, f.readline().split())
         f.readline()
         return np.frombuffer(f.read(), np.float32).reshape(h, w)
+
+
+def write_pfm(path, a):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    a = np.ascontiguousarray(a, np.float32)
+    with open(path, "wb") as f:
+        f.write(b"Pf\n%d %d\n-1.0\n" % (a.shape[1], a.shape[0]))
+        f.write(a.tobytes())
+
+
+def test_layer_disparities_matches_opencv(tmp_path):
+    """LayerDisparities is host code only (file IO + one select per pixel); its output must equal what the reference's
+    OpenCV expression writes: threshold(fg, 0, 1, BINARY) mask, fg.mul(mask) + bg.mul(1 - mask), imwrite(x * 255) of a
+    float matrix (= convertTo 8U).  Pinned with cv2 itself, including NaN / negative / > 1 / half-way values."""
+    rig = synth.ring_rig(3, 40, 24)
+    os.makedirs(tmp_path / "rigs")
+    json.dump(rig, open(tmp_path / "rigs" / "rig.json", "w"))
+    rng = np.random.RandomState(4)
+    H, W = 24, 40
+    want = {}
+    for cam in ("cam0", "cam2"):
+        bg = rng.uniform(0, 1.2, (H, W)).astype(np.float32)
+        bg[3, 5] = np.nan
+        write_pfm(str(tmp_path / "bg" / cam / "000000.pfm"), bg)
+        for f in (7, 8):
+            fg = rng.uniform(-0.2, 1.1, (H, W)).astype(np.float32)
+            fg[rng.uniform(size=(H, W)) < 0.3] = np.nan
+            fg[0, :8] = np.array([0.0, -0.0, 0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 1.0, 300.0], np.float32)
+            fg[1, 0] = np.inf
+            write_pfm(str(tmp_path / "fg" / cam / ("%06d.pfm" % f)), fg)
+            with np.errstate(invalid="ignore"):
+                mask = cv2.threshold(fg, 0.0, 1.0, cv2.THRESH_BINARY)[1]
+                layer = fg * mask + bg * (1 - mask)
+                ref_path = str(tmp_path / ("ref_%s_%d.png" % (cam, f)))
+                assert cv2.imwrite(ref_path, layer * 255)
+            want[(cam, f)] = cv2.imread(ref_path, cv2.IMREAD_UNCHANGED)
+    run("LayerDisparities", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--background_disp=" + str(tmp_path / "bg"),
+        "--foreground_disp=" + str(tmp_path / "fg"), "--output=" + str(tmp_path / "out"), "--first=000007", "--last=000008",
+        "--cameras=cam0,cam2")
+    for (cam, f), ref in want.items():
+        got = cv2.imread(str(tmp_path / "out" / "disparity" / cam / ("%06d.png" % f)), cv2.IMREAD_UNCHANGED)
+        assert got is not None and got.dtype == np.uint8 and got.shape == (H, W)
+        assert np.array_equal(got, ref), (cam, f, np.argwhere(got != ref)[:5])
+    assert not os.path.exists(tmp_path / "out" / "disparity" / "cam1")
 
 
 def test_derpcli_aborts_without_gpu(tmp_path):
