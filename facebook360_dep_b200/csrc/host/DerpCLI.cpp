@@ -6,10 +6,9 @@
 // DerpCLI.cpp:229-320).  There is no CPU fallback: without a CUDA device the process aborts.
 #include <atomic>
 #include <chrono>
-#include <condition_variable>
-#include <mutex>
 #include <thread>
 
+#include "exchange.h"
 #include "io.h"
 
 const std::string kUsageMessage = R"(
@@ -161,29 +160,6 @@ struct Shared {
 struct Worker {
   DerpCtx* ctx = nullptr;
   std::vector<int> dst;  // indices into rig
-};
-
-// Rendezvous of the GPU worker threads when the destination cameras of a frame are dealt to several GPUs and
-// the level handles mismatches: the stage reads EVERY camera's disparity (Derp.cpp:734-747), so the workers
-// publish the device addresses of their planes, meet, copy the peers' planes GPU-to-GPU, meet again, update.
-struct Exchange {
-  explicit Exchange(int parties, int numCams) : parties(parties), planes(numCams, nullptr) {}
-  void arriveAndWait() {
-    std::unique_lock<std::mutex> lock(m);
-    const int gen = generation;
-    if (++waiting == parties) {
-      waiting = 0;
-      ++generation;
-      cv.notify_all();
-    } else {
-      cv.wait(lock, [&] { return gen != generation; });
-    }
-  }
-  const int parties;
-  std::vector<const float*> planes;  // per rig camera: address of its disparity plane on the owning GPU
-  std::mutex m;
-  std::condition_variable cv;
-  int waiting = 0, generation = 0;
 };
 
 static void saveLevel(const Shared& shAll, const Worker& wk, int level, const std::string& frameName, int W, int H) {

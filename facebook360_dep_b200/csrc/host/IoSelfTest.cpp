@@ -1,9 +1,13 @@
 // Test helper (not a reference app): loads an image with the apps' loaders and dumps the converted
 // samples, so tests can compare the PNG/PFM readers and writers with cv2.
+#include <atomic>
+#include <thread>
+
+#include "exchange.h"
 #include "io.h"
 
 DEFINE_string(in, "", "input image");
-DEFINE_string(mode, "color", "color | float | mask | rig");
+DEFINE_string(mode, "color", "color | float | mask | rig | exchange");
 DEFINE_string(out, "", "output file (raw samples, or .png/.pfm for mode=float)");
 
 int main(int argc, char** argv) {
@@ -35,6 +39,28 @@ int main(int argc, char** argv) {
     o.open(FLAGS_out, std::ios::binary);
     o.write(reinterpret_cast<const char*>(rig.cams.data()), (std::streamsize)(rig.cams.size() * sizeof(DerpCameraDesc)));
     for (const auto& id : rig.ids) std::printf("%s\n", id.c_str());
+  } else if (FLAGS_mode == "exchange") {
+    // 5 threads x 200 rounds through the workers' rendezvous: between two barriers every thread must observe the
+    // values all threads published before the first one (the protocol of DerpCLI's camera-sharded mismatch levels)
+    const int parties = 5, rounds = 200;
+    Exchange ex(parties, parties);
+    std::vector<float> slots(parties, 0.f);
+    std::atomic<int> bad{0};
+    std::vector<std::thread> th;
+    for (int g = 0; g < parties; ++g)
+      th.emplace_back([&, g] {
+        for (int r = 1; r <= rounds; ++r) {
+          slots[g] = (float)(r * 100 + g);
+          ex.planes[g] = &slots[g];
+          ex.arriveAndWait();  // everything published
+          for (int k = 0; k < parties; ++k)
+            if (ex.planes[k] != &slots[k] || *ex.planes[k] != (float)(r * 100 + k)) bad++;
+          ex.arriveAndWait();  // everybody has read: values may change
+        }
+      });
+    for (auto& t : th) t.join();
+    std::printf("exchange %s\n", bad.load() == 0 ? "ok" : "FAILED");
+    return bad.load() == 0 ? 0 : 1;
   } else {
     LOG(FATAL) << "bad mode";
   }

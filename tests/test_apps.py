@@ -169,6 +169,14 @@ def read_pfm(path):
         return np.frombuffer(f.read(), np.float32).reshape(h, w)
 
 
+def test_gpu_worker_rendezvous():
+    """The barrier + published-address table DerpCLI's per-GPU worker threads use around camera-sharded mismatch
+    handling (exchange.h), hammered on CPU threads: 5 parties x 200 rounds, every party must see all values of the
+    round between the two barriers."""
+    r = run("IoSelfTest", "--mode=exchange")
+    assert "exchange ok" in r.stdout
+
+
 def write_pfm(path, a):
     os.makedirs(os.path.dirname(path), exist_ok=True)
     a = np.ascontiguousarray(a, np.float32)
