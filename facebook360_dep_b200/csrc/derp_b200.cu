@@ -166,6 +166,9 @@ struct DerpCtx {
   float varNoiseFloor = 0;
   DevBuf<uint2> dColor;
   DevBuf<float4> dProjColor, dProjBias;  // integer-valued float texels (see derp_cost.cuh)
+#ifdef DERP_SELECT_TABLE
+  DevBuf<unsigned> dSelTab;
+#endif
   DevBuf<uint2> dProjColor16, dProjBias16;  // the same tables as 4 x u16 for the compacted kernels (built on demand)
   bool tabF32 = false, tabU16 = false;     // which bias/final tables of projDst are built
   DevBuf<float2> dProjWarp, dWarpInv;  // per-destination scratch when the geometry cache is off
@@ -210,6 +213,9 @@ struct DerpCtx {
     v.projBias = dProjBias.p;
     v.projColor16 = dProjColor16.p;
     v.projBias16 = dProjBias16.p;
+#ifdef DERP_SELECT_TABLE
+    v.selTab = dSelTab.p;
+#endif
     v.projWarp = warpOf(dst);
     v.variance = dVariance.p + (size_t)v.self * plane;
     v.cams = dCams.p;
@@ -338,6 +344,14 @@ int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_
   CU(cudaMemcpy(c->dWtab.p, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
   CU(c->dCounters.ensure(2));
   CU(c->dUncovered.ensure(1));
+#ifdef DERP_SELECT_TABLE
+  {
+    std::vector<unsigned> selTab(kSelTabSize);
+    buildSelectTable(selTab.data());
+    CU(c->dSelTab.ensure(selTab.size()));
+    CU(cudaMemcpy(c->dSelTab.p, selTab.data(), selTab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
+#endif
   // the cost kernels keep cameras, the destination patch tile / per-thread patches and the selection slots in
   // dynamic shared memory: up to ~70 KB per CTA, above the 48 KB default
   CU(cudaFuncSetAttribute(sweepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1314,6 +1328,23 @@ int derp_test_div_const(int device, float c) {
   DivConst k;
   if (makeDivConst(c, 0, &k) != cudaSuccess) return DERP_ECUDA;
   return k.fast;
+}
+
+// Host instantiation of the table-driven selection (derp_select.cuh): returns 1 and the sum when the table path
+// applies (4 <= n <= 8, distinct non-NaN first keys), 0 when the caller must run the general algorithm.
+int derp_test_select_table(const float* first, const float* second, int n, int keep, float* out) {
+  static const std::vector<unsigned> tab = [] {
+    std::vector<unsigned> t(derp::kSelTabSize);
+    derp::buildSelectTable(t.data());
+    return t;
+  }();
+  if (n < derp::kSelTabMinN || n > derp::kSelTabMaxN) return 0;
+  float a[8], b[8];
+  for (int i = 0; i < n; ++i) {
+    a[i] = first[i];
+    b[i] = second[i];
+  }
+  return derp::robustSumTable(derp::ArrayPairs{a, b}, n, keep, tab.data(), out) ? 1 : 0;
 }
 
 float derp_test_robust_sum(const float* first, const float* second, int n, int keep) {

@@ -36,6 +36,9 @@ struct CostView {
   // half-size texels halve the cache lines a request touches; the conversion costs 4 instructions per texel.
   const uint2* projColor16;
   const uint2* projBias16;
+#ifdef DERP_SELECT_TABLE
+  const unsigned* selTab;  // robustSumTable's permutation table (derp_select.cuh)
+#endif
   const float2* projWarp;   // [S][H][W]  src px -> dst px at infinity (self slot unused)
   const float* variance;    // destination's own variance [H][W]
   const DevCamera* cams;    // [S] normalised cameras (global memory; staged to smem by kernels)
@@ -606,7 +609,10 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     }
     cost = 0.0f + m.y;
   } else if (n <= kSelSlots) {
-    cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);
+#ifdef DERP_SELECT_TABLE  // round-2 candidate: host-validated (tests/test_host_units.py), not yet measured on the GPU
+    if (!robustSumTable(SmemPairs{ps.sel, ps.selStride}, n, keep, v.selTab, &cost))
+#endif
+      cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);
   } else {  // rare: gather everything into local arrays
     float la[kMaxCams], lb[kMaxCams];
     for (int i = 0; i < n; ++i) {

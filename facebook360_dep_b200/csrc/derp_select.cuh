@@ -9,6 +9,8 @@
 // tests/test_select.py checks it on the host against std::nth_element itself.
 #pragma once
 
+#include <limits>
+
 #if defined(__CUDACC__)
 #define DERP_SEL_HD __host__ __device__ __forceinline__
 #else
@@ -179,5 +181,106 @@ DERP_SEL_HD float robustSum(const V& v, int n, int keep) {
 }
 
 DERP_SEL_HD float robustSum(float* a, float* b, int n, int keep) { return robustSum(ArrayPairs{a, b}, n, keep); }
+
+// ---- table-driven selection for 4 <= n <= 8 -----------------------------------------------------------
+// nth_element's sequence of swaps depends only on the outcomes of its comparisons.  When the first keys are pairwise
+// distinct, pairLess never looks at the second key and every outcome is determined by the relative order of the keys
+// BY POSITION, i.e. by the permutation that sorts them.  So for small n the final arrangement can be looked up
+// instead of executed: index = the permutation's inversion vector R_j = #{i < j : a_i > a_j} in the mixed radix
+// sum_j R_j * j! (radix j+1 at digit j, independent of n, so slots >= n padded with +inf contribute 0), entry = the
+// positions of the first `keep` elements after nth_element, in order, 3 bits each.  The table (46 224 entries for
+// n = 4..8) is produced on the host by running nthElement above on every permutation.  The evaluation is
+// branch-free: 28 compares, 7 multiply-adds, one table load, `keep` adds — against a few hundred data-dependent,
+// divergent instructions for the general algorithm (13 % of the sweep's instructions, profiles/README.md).
+// Ties or NaNs among the first keys (where the second key or the comparison order matters) return false and the
+// caller runs the general algorithm.
+constexpr int kSelTabMinN = 4, kSelTabMaxN = 8;
+constexpr int kSelTabSize = 24 + 120 + 720 + 5040 + 40320;
+DERP_SEL_HD int selTabOffset(int n) { return n == 4 ? 0 : (n == 5 ? 24 : (n == 6 ? 144 : (n == 7 ? 864 : 5904))); }
+
+template <class V>
+DERP_SEL_HD bool robustSumTable(const V& v, int n, int keep, const unsigned* __restrict__ tab, float* out) {
+#if defined(__CUDA_ARCH__)
+  const float inf = __int_as_float(0x7f800000);
+#else
+  const float inf = std::numeric_limits<float>::infinity();
+#endif
+  float a[kSelTabMaxN];
+#pragma unroll
+  for (int i = 0; i < kSelTabMaxN; ++i) a[i] = i < n ? v.get(i).a : inf;
+  bool bad = false;
+  int idx = 0, fact = 1;
+#pragma unroll
+  for (int j = 1; j < kSelTabMaxN; ++j) {
+    fact *= j;  // j!
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < j; ++i) {
+      r += (a[j] < a[i]) ? 1 : 0;
+      bad |= (a[i] == a[j]) && (j < n);
+    }
+    bad |= !(a[j] == a[j]);
+    idx += r * fact;
+  }
+  bad |= !(a[0] == a[0]);
+  if (bad) return false;
+#if defined(__CUDA_ARCH__)
+  const unsigned entry = __ldg(tab + selTabOffset(n) + idx);
+#else
+  const unsigned entry = tab[selTabOffset(n) + idx];
+#endif
+  float cost = 0;
+  for (int k = 0; k < keep; ++k) cost += v.get((int)((entry >> (3 * k)) & 7u)).b;
+  *out = cost;
+  return true;
+}
+
+// Host: the table robustSumTable reads.  Every permutation of n distinct keys (by inversion-vector index) goes
+// through nthElement; the second key carries the original position so the arrangement can be read back.
+inline void buildSelectTable(unsigned* tab /* kSelTabSize entries */) {
+  for (int n = kSelTabMinN; n <= kSelTabMaxN; ++n) {
+    const int keep = n - 2;
+    int nfact = 1;
+    for (int j = 2; j <= n; ++j) nfact *= j;
+    for (int idx = 0; idx < nfact; ++idx) {
+      // decode R_j, then place element j so that exactly R_j of the earlier ones are greater
+      double key[kSelTabMaxN];
+      for (int j = 0; j < n; ++j) {
+        const int radix = j + 1;
+        int fj = 1;
+        for (int t = 2; t <= j; ++t) fj *= t;
+        const int r = (idx / fj) % radix;
+        // earlier keys sorted ascending; the new key goes above (j - r) of them
+        double sorted[kSelTabMaxN];
+        for (int i = 0; i < j; ++i) sorted[i] = key[i];
+        for (int x = 1; x < j; ++x) {
+          const double t = sorted[x];
+          int y = x - 1;
+          while (y >= 0 && sorted[y] > t) {
+            sorted[y + 1] = sorted[y];
+            --y;
+          }
+          sorted[y + 1] = t;
+        }
+        const int below = j - r;
+        const double lo = below == 0 ? (j == 0 ? 0.0 : sorted[0] - 1.0) : sorted[below - 1];
+        const double hi = below == j ? (j == 0 ? 1.0 : sorted[j - 1] + 1.0) : sorted[below];
+        key[j] = below == 0 ? lo : (below == j ? hi : 0.5 * (lo + hi));
+      }
+      // ranks as exactly representable floats
+      float a[kSelTabMaxN], b[kSelTabMaxN];
+      for (int i = 0; i < n; ++i) {
+        int rank = 0;
+        for (int k = 0; k < n; ++k) rank += key[k] < key[i];
+        a[i] = (float)rank;
+        b[i] = (float)i;
+      }
+      nthElement(ArrayPairs{a, b}, keep, n);
+      unsigned entry = 0;
+      for (int k = 0; k < keep; ++k) entry |= (unsigned)(int)b[k] << (3 * k);
+      tab[selTabOffset(n) + idx] = entry;
+    }
+  }
+}
 
 }  // namespace derp

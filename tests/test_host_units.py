@@ -160,3 +160,47 @@ def test_product_camera_matches_oracle_bitwise(prod, oracle, kind):
     prod.check(f(C.byref(d), rot.ctypes.data, C.byref(dm), C.byref(cf)))
     orot, odm, ocf = oh.camera_info(oracle, d)
     assert np.array_equal(rot.reshape(3, 3), orot) and dm.value == odm and cf.value == ocf
+
+
+def _table(prod, a, b, keep):
+    f = prod.lib.derp_test_select_table
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    out = np.zeros(1, np.float32)
+    ok = f(a.ctypes.data, b.ctypes.data, len(a), keep, out.ctypes.data)
+    return ok, out[0]
+
+
+def test_table_driven_selection_equals_general_algorithm(prod):
+    """derp_select.cuh's permutation-table path (a round-2 candidate for the cost kernels, compiled in with
+    -DDERP_SELECT_TABLE) against the general libstdc++-order algorithm that the kernels run today: every permutation
+    for n = 4..7, random ones for n = 8, bit-identical fp32 sums; ties / NaNs in the first key must be declined."""
+    import itertools
+    rng = np.random.RandomState(11)
+    checked = 0
+    for n in range(4, 9):
+        keep = n - 2
+        perms = itertools.permutations(range(n)) if n <= 7 else (rng.permutation(n) for _ in range(6000))
+        for perm in perms:
+            a = (np.array(perm, np.float32) + 1) * np.float32(0.37) + rng.uniform(0, 0.1)
+            b = rng.uniform(0, 3, n).astype(np.float32)  # sums of these depend on the order in the last bit
+            ok, got = _table(prod, a, b, keep)
+            assert ok == 1
+            want = _robust(prod, a, b, keep)
+            assert np.float32(got).view(np.uint32) == np.float32(want).view(np.uint32), (n, perm)
+            checked += 1
+    assert checked > 11000
+    # declined inputs: equal first keys, NaN, sizes outside 4..8
+    a = np.array([0.3, 0.1, 0.3, 0.7, 0.2], np.float32)
+    assert _table(prod, a, a, 3)[0] == 0
+    a2 = a.copy()
+    a2[2] = np.nan
+    assert _table(prod, a2, a, 3)[0] == 0
+    assert _table(prod, a[:3], a[:3], 1)[0] == 0
+    # equal keys are fine when they are not among the first keys
+    a3 = np.array([0.5, 0.1, 0.3, 0.7, 0.2], np.float32)
+    b3 = np.array([1.0, 1.0, 1.0, 2.0, 2.0], np.float32)
+    ok, got = _table(prod, a3, b3, 3)
+    assert ok == 1 and np.float32(got) == np.float32(_robust(prod, a3, b3, 3))
