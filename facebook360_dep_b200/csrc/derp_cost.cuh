@@ -610,6 +610,7 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     cost = 0.0f + m.y;
   } else if (n <= kSelSlots) {
 #ifdef DERP_SELECT_TABLE  // round-2 candidate: host-validated (tests/test_host_units.py), not yet measured on the GPU
+    static_assert(kSelSlots <= kSelTabMaxN, "the table path covers every evaluation that fits the shared-memory slots");
     if (!robustSumTable(SmemPairs{ps.sel, ps.selStride}, n, keep, v.selTab, &cost))
 #endif
       cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);

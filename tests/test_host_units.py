@@ -176,13 +176,13 @@ def _table(prod, a, b, keep):
 def test_table_driven_selection_equals_general_algorithm(prod):
     """derp_select.cuh's permutation-table path (a round-2 candidate for the cost kernels, compiled in with
     -DDERP_SELECT_TABLE) against the general libstdc++-order algorithm that the kernels run today: every permutation
-    for n = 4..7, random ones for n = 8, bit-identical fp32 sums; ties / NaNs in the first key must be declined."""
+    for n = 4..8, bit-identical fp32 sums; ties / NaNs in the first key must be declined."""
     import itertools
     rng = np.random.RandomState(11)
     checked = 0
     for n in range(4, 9):
         keep = n - 2
-        perms = itertools.permutations(range(n)) if n <= 7 else (rng.permutation(n) for _ in range(6000))
+        perms = itertools.permutations(range(n))  # exhaustive, n = 8 included (40 320 arrangements)
         for perm in perms:
             a = (np.array(perm, np.float32) + 1) * np.float32(0.37) + rng.uniform(0, 0.1)
             b = rng.uniform(0, 3, n).astype(np.float32)  # sums of these depend on the order in the last bit
@@ -191,7 +191,7 @@ def test_table_driven_selection_equals_general_algorithm(prod):
             want = _robust(prod, a, b, keep)
             assert np.float32(got).view(np.uint32) == np.float32(want).view(np.uint32), (n, perm)
             checked += 1
-    assert checked > 11000
+    assert checked == 24 + 120 + 720 + 5040 + 40320
     # declined inputs: equal first keys, NaN, sizes outside 4..8
     a = np.array([0.3, 0.1, 0.3, 0.7, 0.2], np.float32)
     assert _table(prod, a, a, 3)[0] == 0
