@@ -611,7 +611,11 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
   } else if (n <= kSelSlots) {
 #ifdef DERP_SELECT_TABLE  // round-2 candidate: host-validated (tests/test_host_units.py), not yet measured on the GPU
     static_assert(kSelSlots <= kSelTabMaxN, "the table path covers every evaluation that fits the shared-memory slots");
-    if (!robustSumTable(SmemPairs{ps.sel, ps.selStride}, n, keep, v.selTab, &cost))
+    // the 15-compare instance when no lane of the warp that got here holds more than 6 pairs
+    const bool small = __reduce_max_sync(__activemask(), (unsigned)n) <= 6u;
+    const bool done = small ? robustSumTable<6>(SmemPairs{ps.sel, ps.selStride}, n, keep, v.selTab, &cost)
+                            : robustSumTable<8>(SmemPairs{ps.sel, ps.selStride}, n, keep, v.selTab, &cost);
+    if (!done)
 #endif
       cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);
   } else {  // rare: gather everything into local arrays

@@ -198,20 +198,23 @@ constexpr int kSelTabMinN = 4, kSelTabMaxN = 8;
 constexpr int kSelTabSize = 24 + 120 + 720 + 5040 + 40320;
 DERP_SEL_HD int selTabOffset(int n) { return n == 4 ? 0 : (n == 5 ? 24 : (n == 6 ? 144 : (n == 7 ? 864 : 5904))); }
 
-template <class V>
+// K = number of slots examined (n <= K <= 8): the index weights j! do not depend on n and padded slots contribute
+// nothing, so a warp whose lanes all have n <= 6 can run the 15-compare K = 6 instance instead of the 28-compare one.
+template <int K, class V>
 DERP_SEL_HD bool robustSumTable(const V& v, int n, int keep, const unsigned* __restrict__ tab, float* out) {
 #if defined(__CUDA_ARCH__)
   const float inf = __int_as_float(0x7f800000);
 #else
   const float inf = std::numeric_limits<float>::infinity();
 #endif
-  float a[kSelTabMaxN];
+  static_assert(K >= kSelTabMinN && K <= kSelTabMaxN, "slot count");
+  float a[K];
 #pragma unroll
-  for (int i = 0; i < kSelTabMaxN; ++i) a[i] = i < n ? v.get(i).a : inf;
+  for (int i = 0; i < K; ++i) a[i] = i < n ? v.get(i).a : inf;
   bool bad = false;
   int idx = 0, fact = 1;
 #pragma unroll
-  for (int j = 1; j < kSelTabMaxN; ++j) {
+  for (int j = 1; j < K; ++j) {
     fact *= j;  // j!
     int r = 0;
 #pragma unroll
@@ -233,6 +236,11 @@ DERP_SEL_HD bool robustSumTable(const V& v, int n, int keep, const unsigned* __r
   for (int k = 0; k < keep; ++k) cost += v.get((int)((entry >> (3 * k)) & 7u)).b;
   *out = cost;
   return true;
+}
+
+template <class V>
+DERP_SEL_HD bool robustSumTable(const V& v, int n, int keep, const unsigned* __restrict__ tab, float* out) {
+  return robustSumTable<kSelTabMaxN>(v, n, keep, tab, out);
 }
 
 // Host: the table robustSumTable reads.  Every permutation of n distinct keys (by inversion-vector index) goes
