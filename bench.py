@@ -162,47 +162,177 @@ def issue_roof(workload, ms_per_launch, sm_mhz, sms=148):
             "frac": achieved / peak}
 
 
-def cpu_sample(workload, rig, colors, steps=1, warmup=0):
-    """Oracle (port of the reference CPU path) on a bounded sample: 1 dst camera x 8 evenly spaced candidates
-    x full frame, all host threads.  Returns (evals_per_s list, cores, sample description, vbar)."""
-    from facebook360_dep_b200 import capi
-    S, W, H, D, kind = WORKLOADS[workload]
-    oracle = capi.load_oracle()  # bench.py's cpu_baseline / --impl reference legs only
-    ncpu = os.cpu_count() or 1
-    oracle.set_threads(ncpu)
-    ctx = capi.Context(oracle, capi.rig_descs(rig))
-    ctx.level_begin(W, H)
-    ctx.set_colors(colors)
-    ctx.reproject(0)
-    rates = []
-    vbar = None
-    ncand = 8 if W >= 1024 else D
-    # all the host threads it can use: SMT siblings can hurt this fp-heavy loop, so calibrate on 2 candidates
-    cores, best = ncpu, 0.0
-    for t in sorted({ncpu, max(1, ncpu // 2)}, reverse=True):
-        oracle.set_threads(t)
+def host_threads():
+    """Threads this process may really use: the scheduler affinity mask, capped by the cgroup CPU quota (os.cpu_count()
+    ignores both), and the number of distinct physical cores among them."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = list(range(os.cpu_count() or 1))
+    n = len(cpus)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    phys = set()
+    try:
+        cur = {}
+        for line in open("/proc/cpuinfo"):
+            if ":" in line:
+                k, v = [x.strip() for x in line.split(":", 1)]
+                cur[k] = v
+            elif not line.strip():
+                if "processor" in cur and int(cur["processor"]) in cpus:
+                    phys.add((cur.get("physical id", "0"), cur.get("core id", cur["processor"])))
+                cur = {}
+    except Exception:
+        pass
+    return n, (len(phys) or None)
+
+
+def candidate_table(D):
+    """probeDisparity (ImageUtil.cpp:100-107) as Derp.cpp:279-285 calls it: fp32 ends, fp64 mix, fp32 result."""
+    dmin = np.float32(1.0) / np.float32(MAX_DEPTH)
+    dmax = np.float32(1.0) / np.float32(MIN_DEPTH)
+    f = np.arange(D, dtype=np.float64) / float(D - 1)
+    return (f * float(dmin) + (1.0 - f) * float(dmax)).astype(np.float32)
+
+
+class CpuArm:
+    """The reference's CPU implementation of the hot path on this box's host cores, on bounded samples.
+
+    kind "reference": oracle/_ref/libderp_ref.so = the reference's own Derp.cpp / DerpUtil.cpp / Camera.cpp / CvUtil.h ...
+    compiled against stand-in headers (oracle/ref_bridge.cpp); one sample = `threads` candidate slices of destination 0
+    over a band of rows, ONE thread per candidate slice — the reference's own task structure (Derp.cpp:288-304 spawns
+    one ThreadPool task per candidate and joins a batch of `threads` tasks at a time).
+    kind "port": the same through the oracle restatement when oracle/_ref is not there (row-parallel, brute force)."""
+
+    def __init__(self, workload, rig, colors):
+        from facebook360_dep_b200 import capi
+        from tests import oracle_libs  # the checker: cpu_baseline / --impl reference legs only
+        self.S, self.W, self.H, self.D, self.kind_cam = WORKLOADS[workload]
+        self.threads, self.physical = host_threads()
+        self.lib = oracle_libs.load_ref()
+        self.kind = "reference" if self.lib is not None else "port"
+        if self.lib is None:
+            self.lib = oracle_libs.load_oracle()
+        self.lib.set_threads(self.threads)
+        self.table = candidate_table(self.D)
         t0 = time.perf_counter()
-        ctx.brute_force(0, num_depths=2, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True,
-                        want_index=False)
-        r = ctx.get_counters()[0] / (time.perf_counter() - t0)
-        if r > best:
-            best, cores = r, t
-    oracle.set_threads(cores)
-    log("[bench] cpu baseline uses %d of %d host threads" % (cores, ncpu))
-    for i in range(warmup + steps):
+        self.ctx = capi.Context(self.lib, capi.rig_descs(rig), dst_to_src=[0])
+        self.ctx.level_begin(self.W, self.H)
+        self.ctx.set_colors(colors)
+        self.ctx.reproject(0)
+        self.fov = self.ctx.get_fov_mask(0)
+        log("[bench] cpu arm (%s): %d threads (%s physical cores), tables of destination 0 built in %.1fs" % (
+            self.kind, self.threads, self.physical, time.perf_counter() - t0))
+        n = min(self.threads, self.D)
+        self.slices = np.unique(np.round(np.linspace(0, self.D - 1, n)).astype(int))
+        self.rows = None
+        self.vbar = None
+
+    def _band(self, rows):
+        y0 = max(1, (self.H - rows) // 2)
+        return y0, min(self.H - 1, y0 + rows)
+
+    def _run(self, y0, y1, want_costs=False):
+        import ctypes as C
+        n = len(self.slices)
+        disp = np.ascontiguousarray(self.table[self.slices])
+        active = int(self.fov[y0:y1, 1:self.W - 1].astype(bool).sum())
+        if self.kind == "reference":
+            f = self.lib.lib.derp_ref_cost_slices
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            costs = np.empty((n, y1 - y0, self.W), np.float32) if want_costs else None
+            t0 = time.perf_counter()
+            self.lib.check(f(self.ctx.h, 0, disp.ctypes.data, n, y0, y1, None if costs is None else costs.ctypes.data, None))
+            dt = time.perf_counter() - t0
+            return active * n, dt, costs
+        # port: one eval_cost per slice on a full constant-disparity map (row-parallel inside the oracle)
+        costs = np.empty((n, y1 - y0, self.W), np.float32) if want_costs else None
         t0 = time.perf_counter()
-        ctx.brute_force(0, num_depths=ncand, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True,
-                        want_index=False)
+        for k, d in enumerate(disp):
+            c, _ = self.ctx.eval_cost(0, np.full((self.H, self.W), d, np.float32))
+            if costs is not None:
+                costs[k] = np.where(self.fov[y0:y1].astype(bool), c[y0:y1], np.nan)
         dt = time.perf_counter() - t0
-        evals, hits = ctx.get_counters()
-        vbar = hits / max(evals, 1)
-        if i >= warmup:
-            rates.append(evals / dt)
-        log("[bench] cpu sample step %d: %.2fs, %.3f Mpix·cand/s, vbar %.2f" % (i, dt, evals / dt / 1e6, vbar))
-    ctx.close()
-    sample = "1 dst camera x %d evenly spaced candidates x full %dx%d frame (%d-cam rig), brute force only" % (
-        ncand, W, H, S)
-    return rates, cores, sample, vbar
+        full_active = int(self.fov[1:self.H - 1, 1:self.W - 1].astype(bool).sum())
+        return full_active * n, dt, costs
+
+    def calibrate(self, target_s=2.5):
+        """Choose the band height so that one step is about target_s of CPU work (outside every timed region)."""
+        rows = max(8, self.H // 64)
+        y0, y1 = self._band(rows)
+        evals, dt, _ = self._run(y0, y1)
+        per_row = dt / max(1, y1 - y0)
+        self.rows = int(min(self.H - 2, max(8, target_s / max(per_row, 1e-9))))
+        if self.kind == "port":
+            self.rows = self.H - 2
+        log("[bench] cpu arm: calibration %d rows in %.2fs -> %d rows per step" % (y1 - y0, dt, self.rows))
+
+    def sample(self, steps, warmup, want_costs=False):
+        if self.rows is None:
+            self.calibrate()
+        y0, y1 = self._band(self.rows)
+        rates, times, costs = [], [], None
+        for i in range(warmup + steps):
+            last = i == warmup + steps - 1
+            evals, dt, c = self._run(y0, y1, want_costs and last)
+            if c is not None:
+                costs = c
+            if i >= warmup:
+                rates.append(evals / dt)
+                times.append(dt)
+            log("[bench] cpu arm step %d%s: %.2fs, %.3f Mpix·cand/s" % (i, " (warm-up)" if i < warmup else "", dt, evals / dt / 1e6))
+        desc = ("destination 0 of the %d-camera rig, %d candidate slices (one host thread each, the reference's task "
+                "structure) x rows %d..%d of the %dx%d frame" % (self.S, len(self.slices), y0, y1 - 1, self.W, self.H))
+        return {"rates": rates, "times": times, "sample": desc, "band": (y0, y1), "costs": costs}
+
+    def baseline_object(self, res):
+        return {"value": statistics.mean(res["rates"]) / 1e6, "unit": "Mpix·cand/s", "cores": self.threads,
+                "physical_cores": self.physical, "kind": self.kind, "sample": res["sample"],
+                "steps": len(res["rates"]), "seconds_per_step": statistics.mean(res["times"])}
+
+    def close(self):
+        self.ctx.close()
+
+
+def parity_vs_cpu(arm, res, gpu_ctx):
+    """The CPU sample's cost maps against the CUDA library's computeCost of the SAME candidates on the SAME frame
+    (derp_eval_cost on constant-disparity maps, destination 0): mismatching cost fraction and winner-index flips."""
+    y0, y1 = res["band"]
+    cpu = res["costs"]
+    if cpu is None:
+        return None
+    gpu_ctx.reproject(0)
+    n = len(arm.slices)
+    gpu = np.empty_like(cpu)
+    for k in range(n):
+        c, _ = gpu_ctx.eval_cost(0, np.full((arm.H, arm.W), arm.table[arm.slices[k]], np.float32))
+        gpu[k] = c[y0:y1]
+    valid = ~np.isnan(cpu)
+    same = (cpu.view(np.uint32) == gpu.view(np.uint32)) & valid
+    pixels = int(valid.sum())
+    # winner over the sampled slices, first strict minimum in index order (Derp.cpp:323-333); NaN never wins
+    def wta(v):
+        w = np.where(np.isnan(v), np.float32(np.inf), v)
+        return np.argmin(w, axis=0)
+    col = valid.any(axis=0)
+    flips = int((wta(cpu) != wta(np.where(valid, gpu, np.nan)))[col].sum())
+    return {"against": arm.kind, "slices": n, "rows": [int(y0), int(y1)], "pixel_candidates": pixels,
+            "cost_bit_mismatches": int(pixels - same.sum()), "cost_mismatch_frac": float(1.0 - same.sum() / max(1, pixels)),
+            "index_mismatches": flips, "pixels": int(col.sum())}
 
 
 def coarse_to_fine(ctx, colors, S, W, H, D, stream, levels=5):
@@ -239,9 +369,19 @@ def coarse_to_fine(ctx, colors, S, W, H, D, stream, levels=5):
     return out
 
 
+def static_config(workload):
+    """The workload description both arms print verbatim (the driver compares the two `config` objects)."""
+    S, W, H, D, kind = WORKLOADS[workload]
+    return {"workload": workload, "cameras": S, "width": W, "height": H, "candidates": D, "camera_model": kind,
+            "min_depth_m": MIN_DEPTH, "max_depth_m": MAX_DEPTH, "frames_per_step_per_gpu": 1,
+            "l2": "inputs larger than L2 (per destination %.0f MB of pair tables vs 126 MB L2)" % (
+                (S - 1) * W * H * 24 / 1e6)}
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path.  The reference cannot be compiled in this
-    image (OpenCV C++/Eigen/Boost/gflags/glog/folly absent), so this is the oracle port, all host threads."""
+    """Reference arm: the reference's own CPU code of the path (oracle/_ref, see CpuArm) on this box's host cores.
+    Each step is a bounded sample of the workload (a band of rows x `threads` candidate slices of destination 0);
+    --warmup / --steps are honoured like in the GPU arm (at least one warm-up step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -254,25 +394,87 @@ def run_reference(args):
         torch.set_num_threads(os.cpu_count() or 1)
         gen_dev = "cpu"
     rig, colors = make_inputs(args.workload, gen_dev)
-    t0 = time.perf_counter()
-    rates, cores, sample, vbar = cpu_sample(args.workload, rig, colors, steps=args.steps, warmup=min(args.warmup, 1))
-    total = time.perf_counter() - t0
-    value = statistics.mean(rates) / 1e6
-    S, W, H, D, kind = WORKLOADS[args.workload]
+    arm = CpuArm(args.workload, rig, [np.ascontiguousarray(c) for c in colors])
+    warm = max(1, args.warmup)
+    arm.calibrate(target_s=max(0.5, min(2.5, 150.0 / (args.steps + warm))))  # the whole run stays within a few minutes
+    res = arm.sample(args.steps, warm)
+    base = arm.baseline_object(res)
+    value = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix·cand/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": 1e3 * total / max(1, args.steps + min(args.warmup, 1)), "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+        "ms_per_step": 1e3 * statistics.mean(res["times"]), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 cost, f64 projection, u16 texels", "data": "synthetic",
-        "config": {"workload": args.workload, "cameras": S, "width": W, "height": H, "candidates": D,
-                   "camera_model": kind, "note": "each step = bounded sample of the workload"},
-        "cpu_baseline": {"value": value, "unit": "Mpix·cand/s", "cores": cores, "kind": "port", "sample": sample,
-                         "vbar": vbar},
+        "config": static_config(args.workload),
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": "Mpix·cand/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    arm.close()
     print(json.dumps(line), flush=True)
     return 0
+
+
+def cfg1_full(cuda, device):
+    """BASELINE.json configs[0] in full on both sides: 4-camera rectilinear rig, 512x512, 32 candidates, one level.
+    CPU: every candidate slice of every destination through the reference's own code (winner = first strict minimum
+    over the slices, Derp.cpp:323-333); GPU: derp_brute_force.  Reports both rates and the winner-index comparison."""
+    import ctypes as C
+    import torch
+    from facebook360_dep_b200 import capi
+    from tests import oracle_libs
+    S, W, H, D, kind = WORKLOADS["bf32_cfg1"]
+    rig, colors = make_inputs("bf32_cfg1", device)
+    colors = [np.ascontiguousarray(c) for c in colors]
+    table = candidate_table(D)
+    lib = oracle_libs.load_ref()
+    kind_cpu = "reference" if lib is not None else "port"
+    if lib is None:
+        lib = oracle_libs.load_oracle()
+    threads, physical = host_threads()
+    lib.set_threads(threads)
+    cctx = capi.Context(lib, capi.rig_descs(rig))
+    cctx.level_begin(W, H)
+    cctx.set_colors(colors)
+    gctx = capi.Context(cuda, capi.rig_descs(rig), device=device.index or 0)
+    gctx.level_begin(W, H)
+    gctx.set_colors(colors)
+    cpu_s = gpu_s = 0.0
+    evals = flips = pixels = 0
+    for d in range(S):
+        cctx.reproject(d)
+        if kind_cpu == "reference":
+            f = lib.lib.derp_ref_cost_slices
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            costs = np.empty((D, H - 2, W), np.float32)
+            t0 = time.perf_counter()
+            lib.check(f(cctx.h, d, table.ctypes.data, D, 1, H - 1, costs.ctypes.data, None))
+            cpu_s += time.perf_counter() - t0
+            w = np.where(np.isnan(costs), np.float32(np.inf), costs)
+            cpu_idx = np.where(np.isinf(w).all(axis=0) | (w.min(axis=0) >= np.float32(3.4028235e38)), -1, np.argmin(w, axis=0))[:, 1:W - 1]
+        else:
+            t0 = time.perf_counter()
+            cpu_idx = cctx.brute_force(d, num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH)[1:H - 1, 1:W - 1]
+            cpu_s += time.perf_counter() - t0
+        gctx.reproject(d)
+        gctx.brute_force(d, num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH)  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gi = gctx.brute_force(d, num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, want_index=False)
+        gctx.sync()
+        gpu_s += time.perf_counter() - t0
+        gi = gctx.brute_force(d, num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH)[1:H - 1, 1:W - 1]
+        evals += gctx.get_counters()[0]
+        fov = cctx.get_fov_mask(d)[1:H - 1, 1:W - 1].astype(bool)
+        flips += int((gi != cpu_idx)[fov].sum())
+        pixels += int(fov.sum())
+    cctx.close()
+    gctx.close()
+    return {"workload": "bf32_cfg1", "pixel_candidates": int(evals), "cpu": {"value": evals / cpu_s / 1e6, "unit": "Mpix·cand/s",
+            "kind": kind_cpu, "cores": threads, "seconds": cpu_s}, "gpu": {"value": evals / gpu_s / 1e6, "unit": "Mpix·cand/s",
+            "seconds": gpu_s, "note": "reprojection excluded, wall clock around derp_brute_force"},
+            "parity": {"pixels": pixels, "index_mismatches": flips}}
 
 
 def main():
@@ -285,6 +487,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c2f", action="store_true")
+    ap.add_argument("--no-cfg1", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -407,11 +610,8 @@ def main():
         "metric": METRIC, "value": value, "unit": "Mpix·cand/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 cost, f64 projection, u16 texels", "data": "synthetic",
-        "config": {"workload": args.workload, "cameras": S, "width": W, "height": H, "candidates": D,
-                   "camera_model": kind, "frames_per_step_per_gpu": 1, "vbar": round(vbar, 3),
-                   "pixel_cand_per_step_per_gpu": evals_step,
-                   "l2": "inputs larger than L2 (per destination %.0f MB of pair tables vs 126 MB L2)" % (
-                       (S - 1) * W * H * 24 / 1e6)},
+        "config": static_config(args.workload),
+        "work": {"vbar": round(vbar, 3), "pixel_cand_per_step_per_gpu": evals_step, "triples_per_step_per_gpu": hits_step},
         "clocks": clocks,
         "e2e": None if e2e_ms is None else {
             "value": evals_all * args.steps / (e2e_max / 1e3) / 1e6, "unit": "Mpix·cand/s",
@@ -431,10 +631,17 @@ def main():
     if world == 1 and args.workload == "bf128_l0" and not args.no_c2f:
         line["coarse_to_fine_5level"] = coarse_to_fine(ctx, colors, S, W, H, D, stream)
     if world == 1 and not args.no_cpu_baseline:
-        cpu_colors = [np.ascontiguousarray(c) for c in colors]
-        rates, cores, sample, cvbar = cpu_sample(args.workload, rig, cpu_colors, steps=1, warmup=0)
-        line["cpu_baseline"] = {"value": statistics.mean(rates) / 1e6, "unit": "Mpix·cand/s", "cores": cores,
-                                "kind": "port", "sample": sample, "vbar": cvbar}
+        arm = CpuArm(args.workload, rig, [np.ascontiguousarray(c) for c in colors])
+        arm.calibrate(target_s=2.5)
+        res = arm.sample(steps=3, warmup=1, want_costs=True)
+        line["cpu_baseline"] = arm.baseline_object(res)
+        # parity at the benched size, inside the run that benches it: same frame, same candidates, CPU vs CUDA
+        ctx.level_begin(W, H)
+        ctx.set_colors(pin_np)
+        line["parity"] = parity_vs_cpu(arm, res, ctx)
+        arm.close()
+        if args.workload == "bf128_l0" and not args.no_cfg1:
+            line["cfg1_full"] = cfg1_full(cuda, dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1,12 +1,9 @@
 """ctypes binding of include/derp_b200.h.
 
-The same binding drives both shared libraries that export the ABI:
-  * ``load_cuda()``   -> facebook360_dep_b200/libderp_b200.so (the product, sm_100a CUDA)
-  * ``load_oracle()`` -> oracle/libderp_oracle.so (TEST INFRASTRUCTURE: only tests/, smoke() and
-    bench.py's cpu_baseline may call it)
-
-There is deliberately no fallback between them: ``load_cuda()`` raises if the CUDA library is
-missing or reports a different backend.
+``load_cuda()`` -> facebook360_dep_b200/libderp_b200.so, the product (sm_100a CUDA).  It raises if the library is
+missing or reports a different backend: there is no CPU fallback.  The checker libraries that export the same ABI
+(the oracle, the compiled reference) are loaded by tests/oracle_libs.py — test infrastructure lives outside
+this package; ``Library`` below is just the generic ctypes binding of the header.
 """
 import ctypes as C
 import os
@@ -17,7 +14,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 # DERP_B200_LIB: kernel-tuning experiments load an alternative build of the SAME CUDA library
 CUDA_LIB = os.environ.get("DERP_B200_LIB") or os.path.join(_HERE, "libderp_b200.so")
-ORACLE_LIB = os.path.join(ROOT, "oracle", "libderp_oracle.so")
 
 CAM_FTHETA, CAM_RECTILINEAR, CAM_EQUISOLID, CAM_ORTHOGRAPHIC = 0, 1, 2, 3
 CAM_TYPES = {"FTHETA": 0, "RECTILINEAR": 1, "EQUISOLID": 2, "ORTHOGRAPHIC": 3}
@@ -468,13 +464,3 @@ def load_cuda():
             raise RuntimeError("%s reports backend %r, expected the CUDA library" % (CUDA_LIB, lib.backend))
         _cache["cuda"] = lib
     return _cache["cuda"]
-
-
-def load_oracle():
-    """TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py cpu_baseline)."""
-    if "oracle" not in _cache:
-        lib = Library(ORACLE_LIB)
-        if lib.backend != "oracle-cpu":
-            raise RuntimeError("unexpected oracle backend %r" % lib.backend)
-        _cache["oracle"] = lib
-    return _cache["oracle"]

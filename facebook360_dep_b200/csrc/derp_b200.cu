@@ -224,13 +224,14 @@ struct DerpCtx {
     return v;
   }
   // dynamic smem of the cost kernels: S cameras + the destination patch tile
-  // + kSelSlots (ssdB, ssdU) pairs per thread for the robust camera mean
+  // + S - 1 (ssdB, ssdU) pairs per thread for the robust camera mean (one slot per possible source)
+  int selSlots() const { return S > 1 ? S - 1 : 1; }
   size_t camSmem(int threads = kBlockX * kBlockY) const {
-    return (size_t)S * sizeof(DevCamera) + kTileFloats * sizeof(float) + (size_t)kSelSlots * threads * sizeof(float2);
+    return (size_t)S * sizeof(DevCamera) + kTileFloats * sizeof(float) + (size_t)selSlots() * threads * sizeof(float2);
   }
   // compacted kernels: S cameras + one 3x3 patch per thread + the selection slots
   size_t patchSmem() const {
-    return (size_t)S * sizeof(DevCamera) + kPatchFloats * sizeof(float) + (size_t)kSelSlots * kPatchThreads * sizeof(float2);
+    return (size_t)S * sizeof(DevCamera) + kPatchFloats * sizeof(float) + (size_t)selSlots() * kPatchThreads * sizeof(float2);
   }
 };
 
@@ -353,11 +354,12 @@ int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_
   }
 #endif
   // the cost kernels keep cameras, the destination patch tile / per-thread patches and the selection slots in
-  // dynamic shared memory: up to ~70 KB per CTA, above the 48 KB default
-  CU(cudaFuncSetAttribute(sweepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CU(cudaFuncSetAttribute(evalCostKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CU(cudaFuncSetAttribute(proposalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  CU(cudaFuncSetAttribute(pingPongKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  // dynamic shared memory: 92 KB for a 640-thread sweep CTA of a 16-camera rig, 177 KB with 32 cameras
+  const int kMaxDynSmem = 227 * 1024;
+  CU(cudaFuncSetAttribute(sweepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU(cudaFuncSetAttribute(evalCostKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU(cudaFuncSetAttribute(proposalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU(cudaFuncSetAttribute(pingPongKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   *out = c.release();
   return DERP_OK;
 }

@@ -18,6 +18,13 @@
 #include <cfloat>
 #include <cstdint>
 
+// Table-driven robust-mean selection (derp_select.cuh::robustSumTable): measured on B200 at 2048^2 x 128 candidates
+// 94.0 -> 87.0 ms per sweep launch (25.7 -> 27.8 G triples/s), all parity tests bit-exact; -DDERP_NO_SELECT_TABLE
+// builds the general introselect emulation only (the A/B baseline).
+#if !defined(DERP_NO_SELECT_TABLE) && !defined(DERP_SELECT_TABLE)
+#define DERP_SELECT_TABLE 1
+#endif
+
 #include "derp_camera.cuh"
 #include "derp_select.cuh"
 
@@ -249,8 +256,9 @@ struct PixelState {
   int selStride;       // = threads per CTA
 };
 
-// The per-source (biased, unbiased) SSD pairs of one cost evaluation live in shared memory, [slot][thread], for
-// the first kSelSlots sources; evaluations with more visible sources overflow into local memory.
+// The per-source (biased, unbiased) SSD pairs of one cost evaluation live in shared memory, [slot][thread]: S - 1
+// slots per thread, sized at launch (16 cameras, 640-thread sweep CTA: 75 KB).  kSelSlots = how many of them the
+// table-driven selection covers.
 constexpr int kSelSlots = 8;
 struct SmemPairs {
   float2* p;
@@ -334,6 +342,31 @@ __device__ __forceinline__ bool insideCone(const DevCamera& c, double wx, double
   const double dot = -camz;
   const double n2 = vx * vx + vy * vy + vz * vz;
   return !(dot * fabs(dot) <= c.cosFov * fabs(c.cosFov) * n2);
+}
+
+// Conservative fp32 version of the same test: 1 = inside, 0 = outside, -1 = too close to call (the caller then runs
+// insideCone in fp64, so the decision is ALWAYS the reference's).  ~14 fp32 instructions against 16 fp64 ones (which
+// issue at half rate) for each of the S - 1 sources of every evaluation; the fp64 fallback runs for the few tests
+// whose point lies within the error band of the cone surface.
+// Error bound (u = 2^-24, |.|_1 the 1-norm, B = |w|_1 + |pos|_1 >= |v|_1 >= |v|_2): every component of
+// v = fl(fl(w) - fl(pos)) is off by at most u(|w_i| + |pos_i| + |v_i|) <= 2uB; the forward axis is a unit vector
+// rounded to fp32, so dot = f.v (three rounded operations) is off by at most |f|_2 |dv|_2 + 4u|v| < 8uB; n2 = v.v by at most
+// 4|v|uB*sqrt(3) + 3u n2 < 10uB^2; hence lhs - rhs = dot|dot| - c2 n2 (|c2| <= 1, c2 rounded: +u) is off by less than
+// 2B*8uB + (8uB)^2 + 10uB^2 + 3uB^2 < 30uB^2.  The margin used is 64uB^2 = 2^-18 B^2 (2^-20 B on dot for the hemisphere
+// case, bound 8uB = 2^-21 B).  NaN / infinite inputs fail both comparisons and fall through to the fp64 test.
+__device__ __forceinline__ int coneClass(const DevCamera& c, float wx, float wy, float wz, float wL1) {
+  if (c.coneMode == 1) return 1;
+  const float vx = wx - c.conePos[0], vy = wy - c.conePos[1], vz = wz - c.conePos[2];
+  const float dot = __fmaf_rn(c.coneFwd[2], vz, __fmaf_rn(c.coneFwd[1], vy, c.coneFwd[0] * vx));
+  const float B = wL1 + c.conePosL1;
+  if (c.coneMode == 2) {  // inside iff !(camz >= 0) iff forward . v > 0
+    const float m = 9.5367431640625e-07f * B;  // 2^-20 B
+    return dot > m ? 1 : (dot < -m ? 0 : -1);
+  }
+  const float n2 = __fmaf_rn(vz, vz, __fmaf_rn(vy, vy, vx * vx));
+  const float d = __fmaf_rn(-c.coneC2, n2, dot * fabsf(dot));  // inside iff !(dot|dot| <= c2 n2) iff d > 0
+  const float m = 3.814697265625e-06f * (B * B);  // 2^-18 B^2
+  return d > m ? 1 : (d < -m ? 0 : -1);
 }
 
 // pixel() + isOutsideSensor + de-normalisation + narrowing (Camera.h:121-128,180-190, DerpUtil.cpp:56-73,
@@ -422,16 +455,27 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
   const f32x2 one2 = pk(one, one), b232 = pk(b23, b23), half2 = pk(0.5f, 0.5f);
 
   unsigned mask = 0;
+  {
+    const float fx = (float)wx, fy = (float)wy, fz = (float)wz;
+    const float wL1 = fabsf(fx) + fabsf(fy) + fabsf(fz);
 #pragma unroll 4
-  for (int s = 0; s < v.S; ++s)
-    if (insideCone(cams[s], wx, wy, wz)) mask |= 1u << s;
+    for (int s = 0; s < v.S; ++s) {
+#ifdef DERP_NO_CONE_F32  // A/B baseline: every cone test in fp64
+      const int cls = -1;
+#else
+      const int cls = coneClass(cams[s], fx, fy, fz, wL1);
+#endif
+      const bool in = cls < 0 ? insideCone(cams[s], wx, wy, wz) : (cls != 0);
+      if (in) mask |= 1u << s;
+    }
+  }
   mask &= ~(1u << v.self);
 
-  float2 overflow[kMaxCams - kSelSlots];  // touched only when more than kSelSlots sources see the point
+  // (biased, unbiased) SSD of every contributing source: this thread's column of the [slot][thread] array in shared
+  // memory, S - 1 slots (sized at launch), so no evaluation ever touches local memory.
   int n = 0;
   auto pushPair = [&](float b, float u) {
-    if (n < kSelSlots) ps.sel[n * ps.selStride] = make_float2(b, u);
-    else overflow[n - kSelSlots] = make_float2(b, u);
+    ps.sel[n * ps.selStride] = make_float2(b, u);
     ++n;
   };
   // The four warp-table taps of a projected point (getPixelBilinear on the Vec2f table, CvUtil.h:107-120) and its
@@ -609,7 +653,7 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     }
     cost = 0.0f + m.y;
   } else if (n <= kSelSlots) {
-#ifdef DERP_SELECT_TABLE  // round-2 candidate: host-validated (tests/test_host_units.py), not yet measured on the GPU
+#ifdef DERP_SELECT_TABLE  // host-validated on every permutation (tests/test_host_units.py), GPU-validated by the parity suite
     static_assert(kSelSlots <= kSelTabMaxN, "the table path covers every evaluation that fits the shared-memory slots");
     // the 15-compare instance when no lane of the warp that got here holds more than 6 pairs
     const bool small = __reduce_max_sync(__activemask(), (unsigned)n) <= 6u;
@@ -618,14 +662,8 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     if (!done)
 #endif
       cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);
-  } else {  // rare: gather everything into local arrays
-    float la[kMaxCams], lb[kMaxCams];
-    for (int i = 0; i < n; ++i) {
-      const float2 t = i < kSelSlots ? ps.sel[i * ps.selStride] : overflow[i - kSelSlots];
-      la[i] = t.x;
-      lb[i] = t.y;
-    }
-    cost = robustSum(la, lb, n, keep);
+  } else {  // more than kSelTabMaxN sources: the general algorithm on the shared-memory slots
+    cost = robustSum(SmemPairs{ps.sel, ps.selStride}, n, keep);
   }
   cost /= (float)keep;
   const float trustCoef = 1.0f / (float)keep;

@@ -2,7 +2,7 @@
 // libstdc++ implements them (bits/random.h, bits/random.tcc: generate_canonical<float,24> draws ONE
 // engine value r and returns float(r - 1) / 2^31, clamped below 1), with O(log n) skip-ahead so that
 // randomProposal's per-row sequential stream (Derp.cpp:757-808) can be evaluated per pixel.
-// tests/test_rng.py checks the stream on the host against libstdc++ itself.
+// tests/test_host_units.py checks the stream on the host against libstdc++ itself.
 #pragma once
 
 #if defined(__CUDACC__)

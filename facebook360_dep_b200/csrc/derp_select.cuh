@@ -6,7 +6,7 @@
 // permutation libstdc++'s introselect produces (median-of-3 pivot to first, unguarded partition,
 // 2*lg(n) depth limit with heap-select fallback, final insertion sort on <=3 elements), operating
 // on (first, second) pairs with std::pair's lexicographic operator<.
-// tests/test_select.py checks it on the host against std::nth_element itself.
+// tests/test_host_units.py checks it on the host against std::nth_element itself.
 #pragma once
 
 #include <limits>

@@ -48,6 +48,8 @@ def exchange_halos(local_frames, num_frames, time_radius, device):
         return {}
     world, rank = dist.get_world_size(), dist.get_rank()
     first, last = shard.frame_block(num_frames, world, rank)
+    if not local_frames:  # more ranks than frames: an idle rank owns nothing, so it neither sends nor receives
+        return {}
     some = next(iter(local_frames.values()))
     num_cams = len(some)
     H, W = some[0][1].shape

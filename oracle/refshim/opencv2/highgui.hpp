@@ -1,0 +1,3 @@
+// ORACLE — test infrastructure only: see core.hpp in this directory.
+#pragma once
+#include "core.hpp"

@@ -15,10 +15,18 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def oracle():
     """The CPU oracle (test infrastructure). Built on demand from oracle/Makefile."""
-    from facebook360_dep_b200 import capi
-    if not os.path.exists(capi.ORACLE_LIB):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
-    return capi.load_oracle()
+    from tests import oracle_libs
+    return oracle_libs.load_oracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference's own sources compiled into oracle/_ref (test infrastructure); skips when it is not built."""
+    from tests import oracle_libs
+    lib = oracle_libs.load_ref()
+    if lib is None:
+        pytest.skip("oracle/_ref/libderp_ref.so not built (needs /root/reference)")
+    return lib
 
 
 @pytest.fixture(scope="session")

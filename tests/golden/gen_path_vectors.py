@@ -17,6 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from facebook360_dep_b200 import capi, synth  # noqa: E402
+from tests import oracle_libs  # noqa: E402
 
 W, H, S, D = 48, 40, 4, 24
 
@@ -52,7 +53,7 @@ def main():
     rig = synth.ring_rig(S, W, H, kind="RECTILINEAR", hfov_deg=120.0)
     fine, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=21))
     coarse = [synth.downscale_area(c, 2) for c in fine]
-    oracle = capi.load_oracle()
+    oracle = oracle_libs.load_oracle()
     out = run(oracle, rig, fine, coarse)
     out["rig_json"] = np.frombuffer(json.dumps(rig).encode(), dtype=np.uint8)
     for s in range(S):

@@ -192,9 +192,12 @@ def test_fine_level_stages(cuda, oracle, name, cfg):
     both(ctxs, "mismatches")
     for d in range(S):
         gd, od = both(ctxs, "get_disparity", d, want_cost=False)
-        assert mismatch_fraction(gd, od) <= 1e-3
+        # same class as the other fp64-limited stages: a source coordinate whose last fp32 bit flips (atan2 ulp) moves the
+        # bilinear read of that camera's disparity by ~1e-7 relative, which only matters within that distance of the
+        # +-10 % agreement thresholds
+        assert mismatch_fraction(gd, od) <= 2e-5
         gm, om = both(ctxs, "get_mismatch_mask", d)
-        assert (gm != om).mean() <= 1e-3
+        assert (gm != om).mean() <= 2e-5
         ctxs[0].set_disparity(d, od)
     for d in range(S):
         both(ctxs, "bilateral", d)
@@ -375,6 +378,31 @@ def test_many_overlapping_sources(cuda, oracle):
         ev, hits = ctxs[0].get_counters()
         assert (ev, hits) == ctxs[1].get_counters()
     assert hits / ev > 8.5, hits / ev  # the overflow path really ran
+
+
+def test_selection_ties_and_mixed_counts(cuda, oracle):
+    """Robust-mean selection by table (derp_select.cuh::robustSumTable): duplicated source cameras produce EQUAL
+    (biased SSD, unbiased SSD) pairs, i.e. ties among the first keys -> the table path must hand over to the general
+    libstdc++-order algorithm; a ring with few cameras next to a many-camera wall gives warps whose lanes hold
+    different source counts (K = 6 and K = 8 instances, n <= 3 shortcut, > 8 general path)."""
+    import copy
+    W, H = 96, 64
+    rig = synth.ring_rig(6, W, H, kind="FTHETA")
+    colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=21), noise=False)
+    for k in (1, 2, 4):  # exact clones: same pose, same image
+        cam = copy.deepcopy(rig["cameras"][k])
+        cam["id"] = "clone%d" % k
+        rig["cameras"].append(cam)
+        colors.append(colors[k].copy())
+    ctxs = make_pair(cuda, oracle, rig)
+    _begin(ctxs, colors, W, H)
+    for d in (0, 3, 7):
+        both(ctxs, "reproject", d)
+        gi, oi = both(ctxs, "brute_force", d, num_depths=48)
+        assert np.array_equal(gi, oi)
+        (gd, gc, gf), (od, oc, of) = both(ctxs, "get_disparity", d)
+        assert same_float_bits(gc, oc).all() and same_float_bits(gd, od).all()
+        assert ctxs[0].get_counters() == ctxs[1].get_counters()
 
 
 def test_camera_sharded_mismatches(cuda, oracle):

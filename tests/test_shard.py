@@ -9,6 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from facebook360_dep_b200 import shard
+from tests import oracle_libs
 
 
 def test_frame_blocks_cover_and_are_contiguous():
@@ -32,7 +33,7 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from facebook360_dep_b200 import capi, synth
-    oracle = capi.load_oracle()
+    oracle = oracle_libs.load_oracle()
     oracle.set_threads(2)
     F, W, H = 3, 40, 40
     rig = synth.ring_rig(4, W, H, kind="FTHETA")
@@ -93,14 +94,14 @@ def _make_sequence(F, S, H, W):
     return frames
 
 
-def _temporal_worker(rank, world, port, out_dir):
+def _temporal_worker(rank, world, port, out_dir, F=7):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from facebook360_dep_b200 import capi, pipeline
-    oracle = capi.load_oracle()
+    oracle = oracle_libs.load_oracle()
     oracle.set_threads(2)
-    F, S, H, W = 7, 2, 24, 28
+    S, H, W = 2, 24, 28
     seq = _make_sequence(F, S, H, W)
     first, last = shard.frame_block(F, world, rank)
     local = {f: seq[f] for f in range(first, last)}
@@ -121,6 +122,19 @@ def test_temporal_halo_exchange_gloo(tmp_path, oracle):
     F = 7
     seq = _make_sequence(F, 2, 24, 28)
     ref = pipeline.temporal_filter_block(oracle, seq, F, time_radius=2)  # world size 1: no exchange
+    for f in range(F):
+        got = np.load(tmp_path / ("tf%d.npy" % f))
+        assert np.array_equal(got.view(np.uint32), np.stack(ref[f]).view(np.uint32)), f
+
+
+def test_more_ranks_than_frames_gloo(tmp_path, oracle):
+    """3 frames on 4 ranks (blocks of 1,1,1,0): the idle rank must neither crash nor take part in the exchange."""
+    from facebook360_dep_b200 import pipeline
+    world, F = 4, 3
+    port = 29700 + (os.getpid() % 1000)
+    mp.spawn(_temporal_worker, args=(world, port, str(tmp_path), F), nprocs=world, join=True)
+    seq = _make_sequence(F, 2, 24, 28)
+    ref = pipeline.temporal_filter_block(oracle, seq, F, time_radius=2)
     for f in range(F):
         got = np.load(tmp_path / ("tf%d.npy" % f))
         assert np.array_equal(got.view(np.uint32), np.stack(ref[f]).view(np.uint32)), f
@@ -162,7 +176,7 @@ def _mm_worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from facebook360_dep_b200 import capi, pipeline
-    oracle = capi.load_oracle()
+    oracle = oracle_libs.load_oracle()
     oracle.set_threads(2)
     rig, colors, init = _mm_inputs()
     own = shard.camera_shard(_MM["S"], world, rank)

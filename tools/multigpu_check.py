@@ -8,6 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from facebook360_dep_b200 import capi, pipeline, shard
+from tests import oracle_libs
 
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
@@ -30,7 +31,7 @@ for f, cams in out.items():
     mine[f] = torch.from_numpy(np.stack(cams)).to(dev)
 dist.all_reduce(mine, op=dist.ReduceOp.SUM)
 if rank == 0:
-    oracle = capi.load_oracle()
+    oracle = oracle_libs.load_oracle()
     ref = pipeline_ref = None
     # single-process reference: no process group involvement (world-size-1 semantics via direct call)
     worst = 0.0
