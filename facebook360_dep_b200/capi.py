@@ -114,6 +114,8 @@ _SIGS = {
     "derp_get_launch_count": (C.c_int, [C.c_void_p, _p(C.c_uint64)]),
     "derp_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "derp_get_profile": (C.c_int, [C.c_void_p, _p(C.c_double), _p(C.c_uint64)]),
+    "derp_set_sweep_mode": (C.c_int, [C.c_void_p, C.c_int]),
+    "derp_get_sweep_stats": (C.c_int, [C.c_void_p, _p(C.c_uint64), _p(C.c_uint64)]),
     "derp_level_begin": (C.c_int, [C.c_void_p, _p(LevelParams)]),
     "derp_set_colors": (C.c_int, [C.c_void_p, _p(C.c_void_p)]),
     "derp_set_foreground_masks": (C.c_int, [C.c_void_p, _p(C.c_void_p)]),
@@ -127,6 +129,8 @@ _SIGS = {
     "derp_median": (C.c_int, [C.c_void_p, C.c_int]),
     "derp_mask_fov": (C.c_int, [C.c_void_p, C.c_int]),
     "derp_upsample_from": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "derp_level_keep": (C.c_int, [C.c_void_p]),
+    "derp_upsample_from_kept": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "derp_process_level": (C.c_int, [C.c_void_p, _p(ProcessOpts)]),
     "derp_level_estimate": (C.c_int, [C.c_void_p, _p(ProcessOpts)]),
     "derp_level_filter": (C.c_int, [C.c_void_p, _p(ProcessOpts)]),
@@ -151,6 +155,7 @@ _SIGS = {
                                            C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "derp_upsample_disparity": (C.c_int, [C.c_int, _p(CameraDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "derp_downscale_area": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
 }
 
 ABI_SYMBOLS = sorted(_SIGS)
@@ -206,6 +211,14 @@ class Library:
         self.check(self.lib.derp_joint_bilateral_f32(device, W, H, image.ctypes.data, guide.ctypes.data,
                                                      mask.ctypes.data, radius, sigma, w0, w1, w2,
                                                      out.ctypes.data))
+        return out
+
+    def downscale_area(self, image, out_w, out_h, device=0):
+        """cv::resize INTER_AREA of a u16 HxWx3 image (shrinking)."""
+        image = np.ascontiguousarray(image, np.uint16)
+        h, w = image.shape[:2]
+        out = np.empty((out_h, out_w, 3), np.uint16)
+        self.check(self.lib.derp_downscale_area(device, image.ctypes.data, w, h, out.ctypes.data, out_w, out_h))
         return out
 
     def upsample_disparity(self, cam_desc, coarse, out_w, out_h, background_up=None, coarse_mask=None,
@@ -275,6 +288,15 @@ class Context:
         self.L.check(self.L.lib.derp_get_profile(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def set_sweep_mode(self, mode):
+        """0 automatic, 1 plain sweep, 2 filtered sweep (derp_b200.h)."""
+        self.L.check(self.L.lib.derp_set_sweep_mode(self.h, int(mode)))
+
+    def sweep_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.L.check(self.L.lib.derp_get_sweep_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def launch_count(self):
         n = C.c_uint64()
         self.L.check(self.L.lib.derp_get_launch_count(self.h, C.byref(n)))
@@ -295,6 +317,12 @@ class Context:
         a = [np.ascontiguousarray(c, np.uint16) for c in colors]
         assert len(a) == self.S and all(x.shape == (self.H, self.W, 3) for x in a)
         self.L.check(self.L.lib.derp_set_colors(self.h, _ptr_array(a)))
+
+    def set_colors_ptr(self, ptrs):
+        """colors as raw addresses (host or device memory), one u16 HxWx3 image per camera."""
+        assert len(ptrs) == self.S
+        pa = (C.c_void_p * self.S)(*[int(p) for p in ptrs])
+        self.L.check(self.L.lib.derp_set_colors(self.h, pa))
 
     def set_foreground_masks(self, masks):
         a = [np.ascontiguousarray(m, np.uint8) for m in masks]
@@ -340,6 +368,15 @@ class Context:
         cm = None if coarse_mask is None else np.ascontiguousarray(coarse_mask, np.uint8)
         fm = None if fine_mask is None else np.ascontiguousarray(fine_mask, np.uint8)
         self.L.check(self.L.lib.derp_upsample_from(self.h, dst, coarse.ctypes.data, cw, ch, _dp(cm), _dp(fm)))
+
+    def level_keep(self):
+        """Snapshot the finished level's disparities inside the context for upsample_from_kept."""
+        self.L.check(self.L.lib.derp_level_keep(self.h))
+
+    def upsample_from_kept(self, dst, coarse_mask=None, fine_mask=None):
+        cm = None if coarse_mask is None else np.ascontiguousarray(coarse_mask, np.uint8)
+        fm = None if fine_mask is None else np.ascontiguousarray(fine_mask, np.uint8)
+        self.L.check(self.L.lib.derp_upsample_from_kept(self.h, dst, _dp(cm), _dp(fm)))
 
     @staticmethod
     def _opts(num_depths=150, min_depth_m=0.5, max_depth_m=1e4, partial_coverage=True,

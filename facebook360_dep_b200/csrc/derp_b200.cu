@@ -17,6 +17,7 @@
 
 #include "../../include/derp_b200.h"
 #include "derp_kernels.cuh"
+#include "derp_refine.cuh"
 
 using namespace derp;
 
@@ -185,6 +186,15 @@ struct DerpCtx {
   DevBuf<float> dVariance, dBg, dDisp, dCost, dConf, dScratchA, dScratchB, dScratchC, dDisparities, dGathered;
   DevBuf<uint8_t> dFg, dFov, dMismatch, dChangedA, dChangedB, dStage;
   DevBuf<unsigned long long> dBest, dCounters;
+  // filtered sweep (derp_refine.cuh): lower bounds of every (candidate, pixel), seeds, refine list
+  DevBuf<float> dLb;
+  DevBuf<unsigned long long> dSeed, dRefList, dRefCount;
+  unsigned long long lastRefined = 0, lastSeeds = 0;  // exact evaluations of the last filtered sweep
+  int sweepMode = 0;                                  // derp_set_sweep_mode
+  // in-memory level hand-off (derp_level_keep / derp_upsample_from_kept): the finished level's disparity planes
+  DevBuf<float> dKept, dUpA, dUpB;
+  DevBuf<uint8_t> dUpMc, dUpMu, dUpFovC;
+  int keptW = 0, keptH = 0, keptSd = 0;
   DevBuf<unsigned> dUncovered;
   DevBuf<int> dPrefix, dIdx, dOfs, dRowCount, dTileCount, dTileOffset, dList;
   DevBuf<float> dTaps;
@@ -360,6 +370,10 @@ int derp_create(const DerpCameraDesc* cams, int num_cams, const int32_t* dst_to_
   CU(cudaFuncSetAttribute(evalCostKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   CU(cudaFuncSetAttribute(proposalKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   CU(cudaFuncSetAttribute(pingPongKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU(cudaFuncSetAttribute(sweepLowerKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU(cudaFuncSetAttribute(sweepSeedKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU(cudaFuncSetAttribute(refineKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  CU(cudaFuncSetAttribute(lowerBoundCheckKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   *out = c.release();
   return DERP_OK;
 }
@@ -513,7 +527,7 @@ int derp_set_colors(DerpCtx* c, const uint16_t* const* colors) {
   for (int s = 0; s < c->S; ++s) {
     if (!colors[s]) return fail(DERP_EINVAL, "derp_set_colors: null image");
     uint8_t* st = c->dStage.p + (size_t)s * n * 6;
-    CU(cudaMemcpyAsync(st, colors[s], n * 6, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(st, colors[s], n * 6, cudaMemcpyDefault, c->stream));  // host or device image
     packColorKernel<<<grid1(n), 256, 0, c->stream>>>(n, reinterpret_cast<const uint16_t*>(st), c->dColor.p + (size_t)s * n);
     LAUNCHED("packColorKernel");
   }
@@ -675,8 +689,94 @@ int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, flo
     CU(cudaEventCreate(&ev1));
     CU(cudaEventRecord(ev0, c->stream));
   }
-  sweepKernel<<<dim3(gs.x, gs.y, chunks), dim3(kBlockX, sweepBY, 1), c->camSmem(kBlockX * sweepBY), c->stream>>>(a);
-  LAUNCHED("sweepKernel");
+  // Filtered sweep (derp_refine.cuh) unless DERP_SWEEP_MODE=exact, the candidate count is tiny or the bound buffer does
+  // not fit: lower bound of every (pixel, candidate), exact cost only where the bound does not exclude the candidate.
+  static const int modeEnv = [] {
+    const char* e = getenv("DERP_SWEEP_MODE");
+    return (e && !strcmp(e, "exact")) ? 1 : ((e && !strcmp(e, "filter")) ? 2 : 0);
+  }();
+  const int mode = c->sweepMode ? c->sweepMode : modeEnv;
+  bool filtered = mode == 2 || (mode == 0 && num_depths >= 8);
+  const unsigned long long capacity = (unsigned long long)n * (unsigned long long)std::max(2, num_depths / 8);
+  if (filtered) {
+    size_t freeB = 0, totalB = 0;
+    cudaMemGetInfo(&freeB, &totalB);
+    const size_t need = (size_t)num_depths * n * sizeof(float) + capacity * sizeof(unsigned long long) + n * 8;
+    if (c->dLb.n < (size_t)num_depths * n && need > freeB / 2) filtered = false;
+  }
+  c->lastRefined = c->lastSeeds = 0;
+  if (filtered) {
+    CU(c->dLb.ensure((size_t)num_depths * n));
+    CU(c->dSeed.ensure(n));
+    CU(c->dRefList.ensure(capacity));
+    CU(c->dRefCount.ensure(1));
+    fillKernel<unsigned long long><<<grid1(n), 256, 0, c->stream>>>(n, c->dSeed.p, 0x7f7fffffffffffffull);
+    LAUNCHED("fillKernel");
+    CU(cudaMemsetAsync(c->dRefCount.p, 0, sizeof(unsigned long long), c->stream));
+    LowerArgs la;
+    la.v = a.v;
+    la.fov = a.fov;
+    la.fg = a.fg;
+    la.bg = a.bg;
+    la.disparities = a.disparities;
+    la.D = num_depths;
+    la.chunk = chunk;
+    la.lb = c->dLb.p;
+    la.seed = c->dSeed.p;
+    la.counters = c->dCounters.p;
+    sweepLowerKernel<<<dim3(gs.x, gs.y, chunks), dim3(kBlockX, sweepBY, 1), c->camSmem(kBlockX * sweepBY), c->stream>>>(la);
+    LAUNCHED("sweepLowerKernel");
+    SeedArgs sa;
+    sa.v = a.v;
+    sa.fov = a.fov;
+    sa.fg = a.fg;
+    sa.disparities = a.disparities;
+    sa.seed = c->dSeed.p;
+    sa.best = c->dBest.p;
+    sweepSeedKernel<<<g, block2(), c->camSmem(), c->stream>>>(sa);
+    LAUNCHED("sweepSeedKernel");
+    ListArgs li;
+    li.W = W;
+    li.H = H;
+    li.D = num_depths;
+    li.fov = a.fov;
+    li.fg = a.fg;
+    li.lb = c->dLb.p;
+    li.seed = c->dSeed.p;
+    li.best = c->dBest.p;
+    li.list = c->dRefList.p;
+    li.capacity = capacity;
+    li.count = c->dRefCount.p;
+    refineListKernel<<<g, block2(), 0, c->stream>>>(li);
+    LAUNCHED("refineListKernel");
+    unsigned long long count = 0;
+    CU(cudaMemcpyAsync(&count, c->dRefCount.p, sizeof(count), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (count > capacity) {
+      // more survivors than the list holds (bounds useless on this input): redo the destination with the plain sweep
+      filtered = false;
+      fillKernel<unsigned long long><<<grid1(n), 256, 0, c->stream>>>(n, c->dBest.p, 0x7f7fffffffffffffull);
+      LAUNCHED("fillKernel");
+      CU(cudaMemsetAsync(c->dCounters.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    } else {
+      c->lastRefined = count;
+      c->lastSeeds = n;
+      if (count > 0) {
+        RefineArgs ra;
+        ra.v = a.v;
+        ra.disparities = a.disparities;
+        ra.list = c->dRefList.p;
+        ra.count = count;
+        ra.best = c->dBest.p;
+        refineKernel<<<(unsigned)((count + kPatchThreads - 1) / kPatchThreads), kPatchThreads, c->patchSmem(), c->stream>>>(ra);
+        LAUNCHED("refineKernel");
+      }
+    }
+  }
+  if (!filtered) {
+    sweepKernel<<<dim3(gs.x, gs.y, chunks), dim3(kBlockX, sweepBY, 1), c->camSmem(kBlockX * sweepBY), c->stream>>>(a);
+    LAUNCHED("sweepKernel");
+  }
   if (c->profiling) {
     CU(cudaEventRecord(ev1, c->stream));
     c->sweepEvents.emplace_back(ev0, ev1);
@@ -1031,6 +1131,114 @@ int derp_upsample_from(DerpCtx* c, int dst, const float* coarse, int coarse_w, i
   return DERP_OK;
 }
 
+int derp_level_keep(DerpCtx* c) {
+  if (!c || !c->levelOpen) return fail(DERP_ESTATE, "derp_level_keep: no level is open");
+  const size_t n = c->plane * (size_t)c->Sd;
+  CU(cudaSetDevice(c->device));
+  CU(c->dKept.ensure(n));
+  CU(cudaMemcpyAsync(c->dKept.p, c->dDisp.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  c->keptW = c->W;
+  c->keptH = c->H;
+  c->keptSd = c->Sd;
+  return DERP_OK;
+}
+
+int derp_upsample_from_kept(DerpCtx* c, int dst, const uint8_t* coarse_mask, const uint8_t* fine_mask) {
+  int rc = checkDst(c, dst, "derp_upsample_from_kept", false);
+  if (rc) return rc;
+  if (c->keptW < 1 || c->keptSd != c->Sd) return fail(DERP_ESTATE, "derp_upsample_from_kept: derp_level_keep has not been called");
+  const bool useFg = c->lp.use_foreground_masks != 0;
+  const int W = c->W, H = c->H, cw = c->keptW, ch = c->keptH;
+  const size_t nc = (size_t)cw * ch, n = c->plane;
+  const float* coarse = c->dKept.p + (size_t)dst * nc;
+  if (useFg) {
+    if (!coarse_mask || !fine_mask) return fail(DERP_EINVAL, "derp_upsample_from_kept: masks required");
+    if (!c->haveBg) return fail(DERP_ESTATE, "derp_upsample_from_kept: background disparity not set");
+    CU(c->dUpMc.ensure(nc));
+    CU(c->dUpMu.ensure(n));
+    CU(c->dUpFovC.ensure(nc));
+    CU(cudaMemcpyAsync(c->dUpMc.p, coarse_mask, nc, cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(c->dUpMu.p, fine_mask, n, cudaMemcpyDefault, c->stream));
+    fovMaskKernel<<<grid2(cw, ch), block2(), 0, c->stream>>>(c->dCams.p + c->dst2src[dst], cw, ch, c->dUpFovC.p);
+    andMaskKernel<<<grid1(nc), 256, 0, c->stream>>>(nc, c->dUpFovC.p, c->dUpMc.p, c->dUpMc.p);
+    andMaskKernel<<<grid1(n), 256, 0, c->stream>>>(n, c->dFov.p + (size_t)dst * n, c->dUpMu.p, c->dUpMu.p);
+    c->launches += 3;
+  }
+  // stream-ordered: the context's own temporaries, no host synchronisation (the level stays in HBM)
+  return upsampleDevice(c, c->stream, coarse, cw, ch, useFg ? c->bgOf(dst) : nullptr, useFg ? c->dUpMc.p : nullptr,
+                        useFg ? c->dUpMu.p : nullptr, W, H, useFg, c->dDisp.p + (size_t)dst * n, c->dUpA, c->dUpB, c->dOfs,
+                        c->dTaps, c->dSpiral);
+}
+
+// computeResizeAreaTab (resize.cpp) as per-destination tap ranges
+static void areaTaps(int ssize, int dsize, std::vector<int>& ofs, std::vector<int>& si, std::vector<float>& alpha) {
+  const double scale = (double)ssize / dsize;
+  ofs.assign(1, 0);
+  si.clear();
+  alpha.clear();
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cellWidth = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) {
+      si.push_back(sx1 - 1);
+      alpha.push_back((float)((sx1 - fsx1) / cellWidth));
+    }
+    for (int sx = sx1; sx < sx2; ++sx) {
+      si.push_back(sx);
+      alpha.push_back(float(1.0 / cellWidth));
+    }
+    if (fsx2 - sx2 > 1e-3) {
+      si.push_back(sx2);
+      alpha.push_back((float)(std::min(std::min(fsx2 - sx2, 1.), cellWidth) / cellWidth));
+    }
+    ofs.push_back((int)si.size());
+  }
+}
+
+int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, uint16_t* dst, int dst_w, int dst_h) {
+  if (!src || !dst || src_w < 1 || src_h < 1 || dst_w < 1 || dst_h < 1 || dst_w > src_w || dst_h > src_h)
+    return fail(DERP_EINVAL, "derp_downscale_area: bad arguments (INTER_AREA is only used to shrink on this path)");
+  CU(cudaSetDevice(device));
+  const size_t ns = (size_t)src_w * src_h * 3, nd = (size_t)dst_w * dst_h * 3;
+  DevBuf<uint16_t> dS, dD;
+  CU(dS.ensure(ns));
+  CU(dD.ensure(nd));
+  CU(cudaMemcpy(dS.p, src, ns * sizeof(uint16_t), cudaMemcpyDefault));  // host or device source
+  const double sx = (double)src_w / dst_w, sy = (double)src_h / dst_h;
+  const int kx = (int)std::floor(sx + 0.5), ky = (int)std::floor(sy + 0.5);
+  const dim3 grid((dst_w * 3 + 255) / 256, dst_h);
+  if (std::fabs(sx - kx) < 2.220446049250313e-16 && std::fabs(sy - ky) < 2.220446049250313e-16) {
+    areaResizeFastKernel<<<grid, 256>>>(dS.p, src_w, dD.p, dst_w, dst_h, kx, ky);
+  } else {
+    std::vector<int> xo, xs, yo, ys;
+    std::vector<float> xa, ya;
+    areaTaps(src_w, dst_w, xo, xs, xa);
+    areaTaps(src_h, dst_h, yo, ys, ya);
+    DevBuf<int> dXo, dXs, dYo, dYs;
+    DevBuf<float> dXa, dYa;
+    CU(dXo.ensure(xo.size()));
+    CU(dXs.ensure(xs.size()));
+    CU(dXa.ensure(xa.size()));
+    CU(dYo.ensure(yo.size()));
+    CU(dYs.ensure(ys.size()));
+    CU(dYa.ensure(ya.size()));
+    CU(cudaMemcpy(dXo.p, xo.data(), xo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dXs.p, xs.data(), xs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dXa.p, xa.data(), xa.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dYo.p, yo.data(), yo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dYs.p, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dYa.p, ya.data(), ya.size() * sizeof(float), cudaMemcpyHostToDevice));
+    areaResizeKernel<<<grid, 256>>>(dS.p, src_w, src_h, dD.p, dst_w, dst_h, dXo.p, dXs.p, dXa.p, dYo.p, dYs.p, dYa.p);
+    CU(cudaDeviceSynchronize());  // tables are freed on return
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(dst, dD.p, nd * sizeof(uint16_t), cudaMemcpyDefault));  // host or device destination
+  return DERP_OK;
+}
+
 int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* coarse, int coarse_w, int coarse_h,
                             const float* background_up, const uint8_t* coarse_mask, const uint8_t* fine_mask, int out_w,
                             int out_h, int use_foreground_masks, float* out) {
@@ -1239,6 +1447,82 @@ int derp_get_counters(DerpCtx* c, uint64_t* cost_evals, uint64_t* src_hits) {
   }
   if (cost_evals) *cost_evals = c->lastEvals;
   if (src_hits) *src_hits = c->lastHits;
+  return DERP_OK;
+}
+
+int derp_set_sweep_mode(DerpCtx* c, int mode) {
+  if (!c || mode < 0 || mode > 2) return fail(DERP_EINVAL, "derp_set_sweep_mode: bad arguments");
+  c->sweepMode = mode;
+  return DERP_OK;
+}
+
+/* Exact evaluations of the last derp_brute_force when it ran as the filtered sweep (derp_refine.cuh): refined list
+ * entries and seeds (one per pixel plane entry launched); both 0 after a plain sweep. */
+int derp_get_sweep_stats(DerpCtx* c, uint64_t* refined, uint64_t* seeds) {
+  if (!c) return fail(DERP_EINVAL, "derp_get_sweep_stats: null context");
+  if (refined) *refined = c->lastRefined;
+  if (seeds) *seeds = c->lastSeeds;
+  return DERP_OK;
+}
+
+/* Test hook: validates the lower bounds of the filtered sweep against the exact cost of EVERY (pixel, candidate) of one
+ * destination.  stats[5]: evaluations compared, violations (bound > exact cost; must be 0), bounds not formed,
+ * bounds within 5 % of the exact cost, candidates a threshold at the true per-pixel minimum keeps. */
+int derp_debug_lower_bound(DerpCtx* c, int dst, int num_depths, float min_depth_m, float max_depth_m, uint64_t* stats) {
+  int rc = checkDst(c, dst, "derp_debug_lower_bound", true);
+  if (rc) return rc;
+  if (num_depths < 2 || !stats) return fail(DERP_EINVAL, "derp_debug_lower_bound: bad arguments");
+  const bool useFg = c->lp.use_foreground_masks != 0;
+  const int W = c->W, H = c->H;
+  const size_t n = c->plane;
+  const int self = c->dst2src[dst];
+  std::vector<float> disparities(num_depths);
+  const float minDisparity = 1.0f / max_depth_m, maxDisparity = 1.0f / min_depth_m;
+  for (int i = 0; i < num_depths; ++i) {
+    const double fraction = double(i) / double(num_depths - 1);
+    disparities[i] = (float)(fraction * (double)minDisparity + (1 - fraction) * (double)maxDisparity);
+  }
+  DevBuf<float> dTab;
+  DevBuf<unsigned long long> dStats;
+  CU(dTab.ensure(num_depths));
+  CU(dStats.ensure(5));
+  CU(cudaMemcpyAsync(dTab.p, disparities.data(), num_depths * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemsetAsync(dStats.p, 0, 5 * sizeof(unsigned long long), c->stream));
+  if ((rc = ensureTablesF32(c))) return rc;
+  CU(c->dLb.ensure((size_t)num_depths * n));
+  CU(c->dSeed.ensure(n));
+  fillKernel<unsigned long long><<<grid1(n), 256, 0, c->stream>>>(n, c->dSeed.p, 0x7f7fffffffffffffull);
+  LAUNCHED("fillKernel");
+  if ((rc = resetCounters(c))) return rc;
+  LowerArgs la;
+  la.v = c->view(dst);
+  la.fov = c->dFov.p + (size_t)dst * n;
+  la.fg = useFg ? c->fgOf(self) : nullptr;
+  la.bg = useFg ? c->bgOf(dst) : nullptr;
+  la.disparities = dTab.p;
+  la.D = num_depths;
+  la.chunk = num_depths;
+  la.lb = c->dLb.p;
+  la.seed = c->dSeed.p;
+  la.counters = c->dCounters.p;
+  const int by = kBlockY;
+  sweepLowerKernel<<<dim3((W + kBlockX - 1) / kBlockX, (H + by - 1) / by, 1), dim3(kBlockX, by, 1), c->camSmem(kBlockX * by), c->stream>>>(la);
+  LAUNCHED("sweepLowerKernel");
+  CheckArgs ca;
+  ca.v = la.v;
+  ca.fov = la.fov;
+  ca.fg = la.fg;
+  ca.bg = la.bg;
+  ca.disparities = dTab.p;
+  ca.D = num_depths;
+  ca.lb = c->dLb.p;
+  ca.stats = dStats.p;
+  lowerBoundCheckKernel<<<grid2(W, H), block2(), c->camSmem(), c->stream>>>(ca);
+  LAUNCHED("lowerBoundCheckKernel");
+  unsigned long long h[5];
+  CU(cudaMemcpyAsync(h, dStats.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 5; ++i) stats[i] = h[i];
   return DERP_OK;
 }
 

@@ -1074,4 +1074,52 @@ __global__ void temporalKernel(const TemporalArgs a) {
   a.out[p] = weightedSumPix / sumWeight;
 }
 
+
+// ---- cv::resize INTER_AREA, u16 x 3, shrinking (scripts/render/resize.py:79; UpsampleDisparity.cpp:117) ----------------
+// General ratio: resize.cpp's ResizeArea_Invoker<ushort, float> — per destination row the horizontal taps accumulate
+// into a float in table order, the rows are combined with the vertical weights in table order, cvRound + saturate at
+// the end; -fmad=false keeps every product and sum separately rounded like the C++ it restates.  Tables (built on the
+// host exactly like computeResizeAreaTab): xs/xa = source column and weight of each horizontal tap, xo[dx]..xo[dx+1]
+// its taps; the same for rows.
+__global__ void areaResizeKernel(const uint16_t* __restrict__ src, int sw, int sh, uint16_t* __restrict__ dst, int dw, int dh,
+                                 const int* __restrict__ xo, const int* __restrict__ xs, const float* __restrict__ xa,
+                                 const int* __restrict__ yo, const int* __restrict__ ys, const float* __restrict__ ya) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;  // element = dx * 3 + channel
+  const int dy = blockIdx.y;
+  if (e >= dw * 3) return;
+  const int dx = e / 3, ch = e - dx * 3;
+  const int k0 = xo[dx], k1 = xo[dx + 1];
+  float sum = 0.f;
+  for (int j = yo[dy]; j < yo[dy + 1]; ++j) {
+    const uint16_t* S = src + (size_t)ys[j] * sw * 3 + ch;
+    float buf = 0.f;
+    for (int k = k0; k < k1; ++k) buf = buf + (float)S[(size_t)xs[k] * 3] * xa[k];
+    const float t = ya[j] * buf;
+    sum = (j == yo[dy]) ? t : sum + t;  // the first row ASSIGNS (resize.cpp: sum[dx] = beta * buf[dx])
+  }
+  int r = __float2int_rn(sum);
+  r = r < 0 ? 0 : (r > 65535 ? 65535 : r);
+  dst[((size_t)dy * dw + dx) * 3 + ch] = (uint16_t)r;
+}
+// Integer ratios (resizeAreaFast_): 2 x 2 is the integer mean with rounding, anything else a float sum times 1/area.
+__global__ void areaResizeFastKernel(const uint16_t* __restrict__ src, int sw, uint16_t* __restrict__ dst, int dw, int dh,
+                                     int kx, int ky) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int dy = blockIdx.y;
+  if (e >= dw * 3) return;
+  const int dx = e / 3, ch = e - dx * 3;
+  const uint16_t* S = src + ((size_t)dy * ky * sw + (size_t)dx * kx) * 3 + ch;
+  unsigned out;
+  if (kx == 2 && ky == 2) {
+    out = ((unsigned)S[0] + S[3] + S[(size_t)sw * 3] + S[(size_t)sw * 3 + 3] + 2u) >> 2;
+  } else {
+    float sum = 0.f;
+    for (int j = 0; j < ky; ++j)
+      for (int i = 0; i < kx; ++i) sum += (float)S[((size_t)j * sw + i) * 3];
+    int r = __float2int_rn(sum * (1.f / (float)(kx * ky)));
+    out = (unsigned)(r < 0 ? 0 : (r > 65535 ? 65535 : r));
+  }
+  dst[((size_t)dy * dw + dx) * 3 + ch] = (uint16_t)out;
+}
+
 }  // namespace derp

@@ -122,12 +122,25 @@ int derp_get_launch_count(DerpCtx* ctx, uint64_t* out);
 int derp_profile(DerpCtx* ctx, int enable);
 int derp_get_profile(DerpCtx* ctx, double* sweep_ms, uint64_t* sweep_launches);
 
+/* How derp_brute_force sweeps (CUDA library; accepted and ignored by the CPU libraries).  Every mode produces the same
+ * bytes; they differ in how much exact arithmetic runs:
+ *   0  automatic: filtered when num_depths >= 8 and the bound buffer (num_depths x W x H floats) fits in memory
+ *   1  plain sweep: the exact cost of every (pixel, candidate) (sweepKernel)
+ *   2  filtered sweep: a proven lower bound of every (pixel, candidate), the exact cost only where the bound does not
+ *      exclude the candidate (derp_refine.cuh)
+ * derp_get_sweep_stats: exact evaluations the last filtered derp_brute_force performed (list entries, seed pixels);
+ * both 0 after a plain sweep.  The work counters of derp_get_counters always count the algorithmic work
+ * (every (pixel, candidate) and its contributing sources), whichever mode ran. */
+int derp_set_sweep_mode(DerpCtx* ctx, int mode);
+int derp_get_sweep_stats(DerpCtx* ctx, uint64_t* refined, uint64_t* seeds);
+
 /* Starts one (frame, level): allocates level buffers, zero-fills disparity/cost/confidence/
  * mismatch mask (PyramidLevel.h:206-230) and builds the dst FOV masks
  * (generateFovMasks, DerpUtil.cpp:259-276).  Invalidates everything from the previous level. */
 int derp_level_begin(DerpCtx* ctx, const DerpLevelParams* p);
 
-/* Source colours of all cameras, colors[s] = uint16_t[H][W][3]; also computes the per-source
+/* Source colours of all cameras, colors[s] = uint16_t[H][W][3] in host OR device memory (e.g. a level that
+ * derp_downscale_area produced on the device); also computes the per-source
  * variance (PyramidLevel::computeVariances PyramidLevel.h:232-247, computeImageVariance
  * DerpUtil.cpp:214-237). */
 int derp_set_colors(DerpCtx* ctx, const uint16_t* const* colors);
@@ -179,6 +192,14 @@ int derp_mask_fov(DerpCtx* ctx, int dst);
  * both sizes (ignored unless use_foreground_masks). */
 int derp_upsample_from(DerpCtx* ctx, int dst, const float* coarse, int coarse_w, int coarse_h,
                        const uint8_t* coarse_mask, const uint8_t* fine_mask);
+
+/* In-memory level hand-off.  The reference writes every level's disparities as PFM files and reads the coarser level
+ * back from disk before it upsamples it (DerpCLI.cpp:276-303, loadImages of getLevelDisparityDir(level + 1)).
+ * derp_level_keep snapshots the finished level's disparity planes inside the context (device memory on the CUDA library,
+ * stream-ordered, no host copy); after derp_level_begin + derp_set_colors of the next finer level,
+ * derp_upsample_from_kept does what derp_upsample_from does, from that snapshot.  Same bytes as the file round trip. */
+int derp_level_keep(DerpCtx* ctx);
+int derp_upsample_from_kept(DerpCtx* ctx, int dst, const uint8_t* coarse_mask, const uint8_t* fine_mask);
 
 /* processLevel minus file output (Derp.cpp:1005-1034) for all destinations. */
 int derp_process_level(DerpCtx* ctx, const DerpProcessOpts* opts);
@@ -233,6 +254,13 @@ int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* 
                             int coarse_h, const float* background_up, const uint8_t* coarse_mask,
                             const uint8_t* fine_mask, int out_w, int out_h,
                             int use_foreground_masks, float* out);
+
+/* cv::resize(..., INTER_AREA) of a 3-channel 16-bit image, shrinking only: the resize scripts/render/resize.py:51-85
+ * builds every pyramid level with (each level from the FULL-SIZE image, widths scripts/render/config.py:46) and the one
+ * cv_util::resizeImage applies to the colour image in UpsampleDisparity.cpp:117.  Bit-identical to OpenCV for integer
+ * ratios (resizeAreaFast_) and general ratios (computeResizeAreaTab / ResizeArea_Invoker<ushort, float>).  src / dst may
+ * be host or device memory. */
+int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, uint16_t* dst, int dst_w, int dst_h);
 
 #ifdef __cplusplus
 }

@@ -279,4 +279,79 @@ inline void resizeNearest(const T* src, int sw, int sh, T* dst, int dw, int dh) 
   }
 }
 
+// ---- cv::resize INTER_AREA, u16 x 3 channels, shrinking (resize.cpp: resizeAreaFast_ for integer ratios,
+// computeResizeAreaTab + ResizeArea_Invoker<ushort, float> otherwise) — scripts/render/resize.py:79 builds every
+// pyramid level from the full-size image with it, UpsampleDisparity.cpp:117 (cv_util::resizeImage) shrinks colour.
+struct AreaTap {
+  int si, di;
+  float alpha;
+};
+inline void resizeAreaTab(int ssize, int dsize, double scale, std::vector<AreaTap>& tab) {
+  tab.clear();
+  for (int dx = 0; dx < dsize; ++dx) {
+    const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+    const double cellWidth = std::min(scale, ssize - fsx1);
+    int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) tab.push_back({sx1 - 1, dx, (float)((sx1 - fsx1) / cellWidth)});
+    for (int sx = sx1; sx < sx2; ++sx) tab.push_back({sx, dx, float(1.0 / cellWidth)});
+    if (fsx2 - sx2 > 1e-3) tab.push_back({sx2, dx, (float)(std::min(std::min(fsx2 - sx2, 1.), cellWidth) / cellWidth)});
+  }
+}
+// true when both ratios are integers (resize.cpp: is_area_fast)
+inline bool areaIsFast(int sw, int sh, int dw, int dh, int* kx, int* ky) {
+  const double sx = (double)sw / dw, sy = (double)sh / dh;
+  *kx = (int)std::floor(sx + 0.5);
+  *ky = (int)std::floor(sy + 0.5);
+  return std::fabs(sx - *kx) < 2.220446049250313e-16 && std::fabs(sy - *ky) < 2.220446049250313e-16;
+}
+inline bool resizeAreaU16C3(const uint16_t* src, int sw, int sh, uint16_t* dst, int dw, int dh) {
+  if (dw > sw || dh > sh) return false;  // INTER_AREA enlarging is a different code path (not on the depth path)
+  const int cn = 3;
+  int kx, ky;
+  if (areaIsFast(sw, sh, dw, dh, &kx, &ky)) {
+    const int area = kx * ky;
+    const float scale = 1.f / area;
+    for (int y = 0; y < dh; ++y)
+      for (int x = 0; x < dw; ++x)
+        for (int c = 0; c < cn; ++c) {
+          const uint16_t* S = src + ((size_t)y * ky * sw + (size_t)x * kx) * cn + c;
+          if (kx == 2 && ky == 2) {  // ResizeAreaFastVec<ushort>: integer mean with rounding
+            dst[((size_t)y * dw + x) * cn + c] = (uint16_t)((S[0] + S[cn] + S[(size_t)sw * cn] + S[(size_t)sw * cn + cn] + 2) >> 2);
+          } else {
+            float sum = 0;
+            for (int j = 0; j < ky; ++j)
+              for (int i = 0; i < kx; ++i) sum += S[((size_t)j * sw + i) * cn];
+            dst[((size_t)y * dw + x) * cn + c] = saturateU16FromInt(cvRoundF(sum * scale));
+          }
+        }
+    return true;
+  }
+  std::vector<AreaTap> xtab, ytab;
+  resizeAreaTab(sw, dw, (double)sw / dw, xtab);
+  resizeAreaTab(sh, dh, (double)sh / dh, ytab);
+  std::vector<float> buf((size_t)dw * cn), sum((size_t)dw * cn, 0.f);
+  int prev_dy = ytab.empty() ? 0 : ytab[0].di;
+  for (size_t j = 0; j < ytab.size(); ++j) {
+    const float beta = ytab[j].alpha;
+    const int dy = ytab[j].di, sy = ytab[j].si;
+    const uint16_t* S = src + (size_t)sy * sw * cn;
+    std::fill(buf.begin(), buf.end(), 0.f);
+    for (const AreaTap& t : xtab)
+      for (int c = 0; c < cn; ++c) buf[(size_t)t.di * cn + c] = buf[(size_t)t.di * cn + c] + S[(size_t)t.si * cn + c] * t.alpha;
+    if (dy != prev_dy) {
+      for (size_t i = 0; i < sum.size(); ++i) {
+        dst[(size_t)prev_dy * dw * cn + i] = saturateU16FromInt(cvRoundF(sum[i]));
+        sum[i] = beta * buf[i];
+      }
+      prev_dy = dy;
+    } else {
+      for (size_t i = 0; i < sum.size(); ++i) sum[i] += beta * buf[i];
+    }
+  }
+  for (size_t i = 0; i < sum.size(); ++i) dst[(size_t)prev_dy * dw * cn + i] = saturateU16FromInt(cvRoundF(sum[i]));
+  return true;
+}
+
 }  // namespace oracle

@@ -142,7 +142,9 @@ struct Ctx {
   std::vector<std::vector<uint8_t>> fgMask;    // [S] (all-pass unless use_foreground_masks)
   std::vector<std::vector<float>> bgDisp;      // [Sd] (empty unless use_foreground_masks)
   std::vector<std::vector<uint8_t>> fovMask;   // [Sd]
-  std::vector<std::vector<float>> disp, cost, conf;  // [Sd]
+  std::vector<std::vector<float>> disp, cost, conf;
+  std::vector<std::vector<float>> kept;  // derp_level_keep
+  int keptW = 0, keptH = 0;  // [Sd]
   std::vector<std::vector<float>> gathered;          // [S] all-camera disparities of a sharded mismatch stage
   bool haveGathered = false;
   std::vector<std::vector<uint8_t>> mismatch;  // [Sd]
@@ -348,6 +350,12 @@ void derp_destroy(DerpCtx* ctx) { delete ctx; }
 int derp_set_stream(DerpCtx*, void*) { return DERP_OK; }
 int derp_sync(DerpCtx*) { return DERP_OK; }
 int derp_profile(DerpCtx*, int) { return DERP_OK; }
+int derp_set_sweep_mode(DerpCtx*, int) { return DERP_OK; }
+int derp_get_sweep_stats(DerpCtx*, uint64_t* a, uint64_t* b) {
+  if (a) *a = 0;
+  if (b) *b = 0;
+  return DERP_OK;
+}
 int derp_get_profile(DerpCtx*, double* ms, uint64_t* n) {
   if (ms) *ms = 0;
   if (n) *n = 0;
@@ -1079,6 +1087,22 @@ int derp_upsample_from(DerpCtx* ctx, int dst, const float* coarse, int coarse_w,
                      c.disp[dst].data());
 }
 
+int derp_level_keep(DerpCtx* ctx) {
+  if (!ctx) return fail(DERP_EINVAL, "derp_level_keep: null context");
+  Ctx& c = ctx->c;
+  if (c.W < 1) return fail(DERP_ESTATE, "derp_level_keep: no level is open");
+  c.kept = c.disp;
+  c.keptW = c.W;
+  c.keptH = c.H;
+  return DERP_OK;
+}
+int derp_upsample_from_kept(DerpCtx* ctx, int dst, const uint8_t* coarse_mask, const uint8_t* fine_mask) {
+  if (!ctx) return fail(DERP_EINVAL, "derp_upsample_from_kept: null context");
+  Ctx& c = ctx->c;
+  if (c.keptW < 1 || dst < 0 || dst >= (int)c.kept.size()) return fail(DERP_ESTATE, "derp_upsample_from_kept: nothing kept");
+  return derp_upsample_from(ctx, dst, c.kept[dst].data(), c.keptW, c.keptH, coarse_mask, fine_mask);
+}
+
 int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* coarse, int coarse_w,
                             int coarse_h, const float* background_up, const uint8_t* coarse_mask,
                             const uint8_t* fine_mask, int out_w, int out_h, int use_foreground_masks,
@@ -1349,6 +1373,13 @@ void oracle_remap_bicubic(const uint16_t* src, int sw, int sh, const float* map,
   remapBicubicU16C3(src, sw, sh, map, dw, dh, dst);
 }
 void oracle_blur3(const uint16_t* src, int w, int h, uint16_t* dst) { blur3x3U16C3(src, w, h, dst); }
+int derp_downscale_area(int /*device*/, const uint16_t* src, int src_w, int src_h, uint16_t* dst, int dst_w, int dst_h) {
+  if (!src || !dst || !resizeAreaU16C3(src, src_w, src_h, dst, dst_w, dst_h)) return DERP_EINVAL;
+  return DERP_OK;
+}
+int oracle_resize_area(const uint16_t* src, int sw, int sh, uint16_t* dst, int dw, int dh) {
+  return resizeAreaU16C3(src, sw, sh, dst, dw, dh) ? 0 : -1;
+}
 void oracle_variance(const uint16_t* src, int w, int h, float* var) { imageVarianceU16C3(src, w, h, var); }
 void oracle_lanczos4(const float* src, int sw, int sh, float* dst, int dw, int dh) {
   resizeLanczos4F32(src, sw, sh, dst, dw, dh);

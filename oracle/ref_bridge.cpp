@@ -87,6 +87,7 @@ struct DerpCtx {
   bool projected = false;
   int currentDst = -1;
   std::string tmpDir;
+  std::vector<cv::Mat_<float>> kept;  // derp_level_keep
   // values the caller set before the level object existed
   std::vector<cv::Mat_<float>> pendDisp, pendCost, pendConf;
 };
@@ -194,6 +195,12 @@ int derp_get_launch_count(DerpCtx*, uint64_t* out) {
   return DERP_OK;
 }
 int derp_profile(DerpCtx*, int) { return DERP_OK; }
+int derp_set_sweep_mode(DerpCtx*, int) { return DERP_OK; }
+int derp_get_sweep_stats(DerpCtx*, uint64_t* a, uint64_t* b) {
+  if (a) *a = 0;
+  if (b) *b = 0;
+  return DERP_OK;
+}
 int derp_get_profile(DerpCtx*, double* ms, uint64_t* n) {
   if (ms) *ms = 0;
   if (n) *n = 0;
@@ -412,6 +419,18 @@ int derp_upsample_from(DerpCtx* c, int dst, const float* coarse, int coarse_w, i
   });
 }
 
+int derp_level_keep(DerpCtx* c) {
+  if (int rc = needLevel(c)) return rc;
+  c->kept.clear();
+  for (size_t d = 0; d < c->rigDst.size(); ++d) c->kept.push_back(c->level->dstDisparity((int)d).clone());
+  return DERP_OK;
+}
+int derp_upsample_from_kept(DerpCtx* c, int dst, const uint8_t* coarse_mask, const uint8_t* fine_mask) {
+  if (!c || dst < 0 || dst >= (int)c->kept.size()) return fail(DERP_ESTATE, "nothing kept");
+  const cv::Mat_<float> k = c->kept[dst];
+  return derp_upsample_from(c, dst, k.ptr<float>(), k.cols, k.rows, coarse_mask, fine_mask);
+}
+
 static int runHalves(DerpCtx* c, const DerpProcessOpts* o, bool estimate, bool mismatch, bool filter, bool save) {
   return guarded([&] {
     if (int rc = needLevel(c)) return rc;
@@ -594,6 +613,13 @@ int derp_upsample_disparity(int /*device*/, const DerpCameraDesc* cam, const flo
   });
   derp_destroy(c);
   return rc;
+}
+
+/* scripts/render/resize.py is Python + cv2, not part of the compiled reference: the stand-in's INTER_AREA
+ * (oracle/cvprims.h, pinned to cv2 4.13) answers for it so that the library exports the whole ABI */
+int derp_downscale_area(int /*device*/, const uint16_t* src, int src_w, int src_h, uint16_t* dst, int dst_w, int dst_h) {
+  if (!src || !dst || !oracle::resizeAreaU16C3(src, src_w, src_h, dst, dst_w, dst_h)) return fail(DERP_EINVAL, "bad arguments");
+  return DERP_OK;
 }
 
 /* bench / test hook (not part of derp_b200.h): candidate slices of the brute-force cost volume the way the reference

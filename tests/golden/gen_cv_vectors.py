@@ -6,6 +6,7 @@ the reference calls (OpenCV itself is not under /root/reference and the referenc
   blur 3x3 u16x3                            (DerpUtil.cpp:208-210 colorBias, CvUtil.h:314-323)
   computeImageVariance                      (DerpUtil.cpp:214-237) via the same cv2 calls
   resize INTER_LANCZOS4 / INTER_NEAREST f32 (UpsampleDisparityLib.cpp:125,145)
+  resize INTER_AREA u16x3, shrinking          (scripts/render/resize.py:79, UpsampleDisparity.cpp:117)
 """
 import os
 
@@ -66,6 +67,12 @@ def main():
     for (W, H) in ((62, 46), (50, 37), (31, 23), (100, 80)):
         out["lanczos_%dx%d" % (W, H)] = cv2.resize(d, (W, H), interpolation=cv2.INTER_LANCZOS4)
         out["nearest_%dx%d" % (W, H)] = cv2.resize(d, (W, H), interpolation=cv2.INTER_NEAREST)
+    # ---- INTER_AREA (pyramid pre-resize): integer ratios (2x2 fast path, 4x4, 3x2) and general ratios, including the
+    # reference rig's 3360 x 2160 -> 2048 x 1318 ratio at a reduced size
+    a = rng.randint(0, 65536, size=(54, 84, 3)).astype(np.uint16)
+    out["area_src"] = a
+    for (W, H) in ((42, 27), (21, 27), (28, 27), (51, 33), (84, 54), (13, 9), (50, 32)):
+        out["area_%dx%d" % (W, H)] = cv2.resize(a, (W, H), interpolation=cv2.INTER_AREA)
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cv_vectors.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, "cv2", cv2.__version__)

@@ -77,6 +77,16 @@ def blur3(oracle, src):
     return dst
 
 
+def resize_area(oracle, src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint16)
+    dst = np.empty((dh, dw, 3), np.uint16)
+    f = _lib(oracle).oracle_resize_area
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    assert f(src.ctypes.data, src.shape[1], src.shape[0], dst.ctypes.data, dw, dh) == 0
+    return dst
+
+
 def variance(oracle, src):
     src = np.ascontiguousarray(src, np.uint16)
     dst = np.empty(src.shape[:2], np.float32)

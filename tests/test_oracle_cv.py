@@ -37,3 +37,11 @@ def test_resize(oracle, size):
     assert np.array_equal(oh.nearest(oracle, src, W, H), G["nearest_%dx%d" % size])
     got = oh.lanczos4(oracle, src, W, H)
     assert np.abs(got - G["lanczos_%dx%d" % size]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("size", [(42, 27), (21, 27), (28, 27), (51, 33), (84, 54), (13, 9), (50, 32)])
+def test_resize_area_bit_exact(oracle, size):
+    """cv::resize INTER_AREA u16x3 (scripts/render/resize.py:79): integer and general ratios, bit for bit vs cv2 4.13."""
+    w, h = size
+    got = oh.resize_area(oracle, G["area_src"], w, h)
+    assert np.array_equal(got, G["area_%dx%d" % (w, h)])
