@@ -51,7 +51,11 @@ WORKLOADS = {
     # name: (num_cams, width, height, num_depths, kind)
     "bf128_l0": (16, 2048, 2048, 128, "FTHETA"),
     "bf32_cfg1": (4, 512, 512, 32, "RECTILINEAR"),  # BASELINE.json configs[0] (parity case; small)
+    # BASELINE.json configs[1] as the reference runs it: 5-level coarse-to-fine frame (see CoarseToFine)
+    "c2f5": (16, 2048, 2048, 128, "FTHETA"),
 }
+C2F_LEVELS = 5
+C2F_CPU_LEVEL = 3  # the level the CPU arm times (256 x 256 at 2048 full size): seconds, not minutes, of reference code
 MIN_DEPTH, MAX_DEPTH = 0.5, 1e4
 
 
@@ -335,38 +339,72 @@ def parity_vs_cpu(arm, res, gpu_ctx):
             "index_mismatches": flips, "pixels": int(col.sum())}
 
 
-def coarse_to_fine(ctx, colors, S, W, H, D, stream, levels=5):
-    """BASELINE.json configs[1] as the reference runs it (DerpCLI defaults): brute force with D candidates at the
-    coarsest of 5 levels, then random proposals (2) + ping-pong (1) + joint bilateral + median on every finer
-    level, levels handed over in HBM->host->HBM like the PFM round trip.  Reported beside the headline; the
-    second of two passes is timed (geometry caches warm, as from the second frame of a sequence on)."""
-    import torch
-    from facebook360_dep_b200 import synth
-    pyr = [colors]
-    for _ in range(1, levels):
-        pyr.append([synth.downscale_area(c, 2) for c in pyr[-1]])
-    out = None
-    for rep in range(2):
-        prev, tot_ms, tot_e = None, 0.0, 0
-        for level in range(levels - 1, -1, -1):
-            w, h = W >> level, H >> level
-            ctx.level_begin(w, h, level=level, num_levels=levels, full_width=W, full_height=H)
-            ctx.set_colors(pyr[level])
-            if prev is not None:
-                for d in range(S):
-                    ctx.upsample_from(d, prev[d])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            ctx.process_level(num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            tot_ms += e0.elapsed_time(e1)
-            tot_e += ctx.get_counters()[0]
-            prev = [ctx.get_disparity(d, want_cost=False) for d in range(S)]
-        out = {"ms_per_frame": tot_ms, "cost_evaluations": tot_e, "value": tot_e / tot_ms / 1e3, "unit": "Mpix·cand/s",
-               "levels": levels, "note": "process_level time only (uploads / level hand-over excluded)"}
-    return out
+class CoarseToFine:
+    """BASELINE.json configs[1] as the reference runs it (DerpCLI defaults): brute force with D candidates at the coarsest
+    of 5 levels, then random proposals (2) + ping-pong (1) + joint bilateral + median on every finer level.
+
+    The pyramid is what scripts/render/resize.py:79 feeds DerpCLI: every level cv::resize(INTER_AREA) of the FULL-SIZE
+    image — built on the device by derp_downscale_area.  Levels are handed over in HBM (derp_level_keep /
+    derp_upsample_from_kept) instead of the reference's PFM round trip (DerpCLI.cpp:287-288).
+      frame(resident=True)  : level images already in HBM; times level_begin .. process_level of the 5 levels
+      frame(resident=False) : end to end — pinned host full-size images -> device, pyramid build, the 5 levels, the 16
+                              level-0 disparity planes back to pinned host memory"""
+
+    def __init__(self, cuda, ctx, pin_colors, S, W, H, D, stream, device, levels=5):
+        import torch
+        self.torch, self.cuda, self.ctx, self.pin = torch, cuda, ctx, pin_colors
+        self.S, self.W, self.H, self.D, self.stream, self.dev, self.levels = S, W, H, D, stream, device, levels
+        self.full = [torch.empty((H, W, 3), dtype=torch.uint16, device=device) for _ in range(S)]
+        self.lvl = [[torch.empty((H >> k, W >> k, 3), dtype=torch.uint16, device=device) for _ in range(S)]
+                    for k in range(1, levels)]
+        self.out = [torch.empty((H, W), dtype=torch.float32).pin_memory() for _ in range(S)]
+        self.evals = self.hits = 0
+        self.level_out = {}
+        self.level_evals = {}
+
+    def upload(self):
+        for s in range(self.S):
+            self.full[s].copy_(self.pin[s], non_blocking=True)
+
+    def build_pyramid(self):
+        for k in range(1, self.levels):
+            w, h = self.W >> k, self.H >> k
+            for s in range(self.S):
+                self.cuda.check(self.cuda.lib.derp_downscale_area(self.dev.index or 0, self.full[s].data_ptr(), self.W, self.H,
+                                                                 self.lvl[k - 1][s].data_ptr(), w, h))
+
+    def levels_pass(self, keep_level=None):
+        ctx = self.ctx
+        self.evals = self.hits = 0
+        for level in range(self.levels - 1, -1, -1):
+            w, h = self.W >> level, self.H >> level
+            ctx.level_begin(w, h, level=level, num_levels=self.levels, full_width=self.W, full_height=self.H)
+            imgs = self.full if level == 0 else self.lvl[level - 1]
+            ctx.set_colors_ptr([t.data_ptr() for t in imgs])
+            if level < self.levels - 1:
+                for d in range(self.S):
+                    ctx.upsample_from_kept(d)
+            ctx.process_level(num_depths=self.D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True)
+            e, h_ = ctx.get_counters()
+            self.evals += e
+            self.hits += h_
+            self.level_evals[level] = e
+            if level > 0:
+                ctx.level_keep()
+            if keep_level is not None and level in keep_level:
+                self.level_out[level] = [ctx.get_disparity(d, want_cost=False) for d in range(self.S)]
+
+    def download(self):
+        for d in range(self.S):
+            self.cuda.check(self.cuda.lib.derp_get_disparity(self.ctx.h, d, self.out[d].numpy().ctypes.data, None, None))
+
+    def frame(self, resident, keep_level=None):
+        if not resident:
+            self.upload()
+            self.build_pyramid()
+        self.levels_pass(keep_level)
+        if not resident:
+            self.download()
 
 
 def static_config(workload):
@@ -394,6 +432,8 @@ def run_reference(args):
         torch.set_num_threads(os.cpu_count() or 1)
         gen_dev = "cpu"
     rig, colors = make_inputs(args.workload, gen_dev)
+    if args.workload == "c2f5":
+        return run_reference_c2f(args, rig, [np.ascontiguousarray(c) for c in colors])
     arm = CpuArm(args.workload, rig, [np.ascontiguousarray(c) for c in colors])
     warm = max(1, args.warmup)
     arm.calibrate(target_s=max(0.5, min(2.5, 150.0 / (args.steps + warm))))  # the whole run stays within a few minutes
@@ -411,6 +451,203 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     arm.close()
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def c2f_cpu_level(lib, rig, level_colors, coarse_disps, threads, steps, warmup):
+    """The reference's processLevel (Derp.cpp:1005-1034) of ONE fine level of the coarse-to-fine frame on the host cores:
+    level C2F_CPU_LEVEL of C2F_LEVELS, all cameras, started from the given coarser-level disparities.  Returns
+    (seconds per step list, disparities of the level)."""
+    from facebook360_dep_b200 import capi
+    S, W, H, D, kind = WORKLOADS["c2f5"]
+    w, h = W >> C2F_CPU_LEVEL, H >> C2F_CPU_LEVEL
+    lib.set_threads(threads)
+    ctx = capi.Context(lib, capi.rig_descs(rig))
+    times, out = [], None
+    for i in range(warmup + steps):
+        ctx.level_begin(w, h, level=C2F_CPU_LEVEL, num_levels=C2F_LEVELS, full_width=W, full_height=H)
+        ctx.set_colors(level_colors)
+        for d in range(S):
+            ctx.upsample_from(d, coarse_disps[d])
+        t0 = time.perf_counter()
+        ctx.process_level(num_depths=150, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        log("[bench] cpu arm (c2f level %d) step %d%s: %.2fs" % (C2F_CPU_LEVEL, i, " (warm-up)" if i < warmup else "", dt))
+        out = [ctx.get_disparity(d, want_cost=False) for d in range(S)]
+    evals = ctx.get_counters()[0]
+    ctx.close()
+    return times, out, evals
+
+
+def run_c2f(args):
+    """Workload c2f5: one 5-level coarse-to-fine frame of the 16-camera 2048^2 rig per step and per GPU."""
+    import torch
+    import torch.distributed as dist
+    from facebook360_dep_b200 import capi, shard
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, W, H, D, kind = WORKLOADS["c2f5"]
+    rig, colors = make_inputs("c2f5", dev, rank)
+    pin = [torch.from_numpy(np.ascontiguousarray(c)).pin_memory() for c in colors]
+    cuda = capi.load_cuda()
+    ctx = capi.Context(cuda, capi.rig_descs(rig), device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    c2f = CoarseToFine(cuda, ctx, pin, S, W, H, D, stream, dev, C2F_LEVELS)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    c2f.upload()
+    c2f.build_pyramid()
+    for _ in range(max(1, args.warmup)):
+        c2f.frame(True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile(True)
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        c2f.frame(True)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    pp_ms, pp_n, pp_evals, pp_hits = ctx.get_profile_ping_pong()
+    ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    evals_step, hits_step = c2f.evals, c2f.hits
+    # end to end: host images in, host disparities out
+    c2f.frame(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        c2f.frame(False)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    ms, evals_all = shard.reduce_step(ms, evals_step, dev)
+    e2e_max, _ = shard.reduce_step(e2e_ms, 0.0, dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = measured_peak_gbs()
+    value = evals_all * args.steps / (ms / 1e3) / 1e6
+    pp_launch_ms = pp_ms / max(1, pp_n)
+    pp_bytes = (20.0 * pp_hits + 30.0 * (pp_evals / 9.0)) / max(1, pp_n)
+    achieved = pp_bytes / (pp_launch_ms / 1e3) / 1e9 if pp_n else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mpix·cand/s", "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 cost, f64 projection, u16 texels", "data": "synthetic", "config": static_config("c2f5"),
+        "work": {"cost_evaluations_per_frame": evals_step, "triples_per_frame": hits_step,
+                 "per_level": {str(k): int(v) for k, v in sorted(c2f.level_evals.items())}},
+        "clocks": clocks,
+        "e2e": {"value": evals_all * args.steps / (e2e_max / 1e3) / 1e6, "unit": "Mpix·cand/s",
+                "h2d_bytes_per_step": S * W * H * 6, "d2h_bytes_per_step": S * W * H * 4, "ms_per_step": e2e_max / args.steps,
+                "includes": "pinned host -> device of the 16 full-size images, INTER_AREA pyramid on the device, 5 levels "
+                            "with in-HBM hand-off, 16 level-0 disparity planes back to pinned host memory"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "pingPongKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": pp_bytes, "ms_per_launch": pp_launch_ms, "launches_timed": int(pp_n),
+                     "kernel_share_of_step": (pp_ms / ms) if ms else None,
+                     "triples_per_s": pp_hits / (pp_ms / 1e3) if pp_ms else None,
+                     "note": "B_stream = 20 B x (pixel,cand,source) triples + 30 B x pixels, pixels taken as evaluations / 9 "
+                             "(<= 9 neighbour candidates per active pixel); the kernel gathers scattered 4x4 texel blocks "
+                             "and is L1 / latency bound, not HBM bound (profiles/README.md)"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_libs
+        lib = oracle_libs.load_ref()
+        kind_cpu = "reference" if lib is not None else "port"
+        if lib is None:
+            lib = oracle_libs.load_oracle()
+        threads, physical = host_threads()
+        c2f.frame(True, keep_level={C2F_CPU_LEVEL + 1, C2F_CPU_LEVEL})
+        lvl_colors = [t.cpu().numpy() for t in c2f.lvl[C2F_CPU_LEVEL - 1]]
+        times, cpu_disp, _ = c2f_cpu_level(lib, rig, lvl_colors, c2f.level_out[C2F_CPU_LEVEL + 1], threads, steps=3, warmup=1)
+        evals_lvl = c2f.level_evals[C2F_CPU_LEVEL]
+        line["cpu_baseline"] = {"value": evals_lvl / statistics.mean(times) / 1e6, "unit": "Mpix·cand/s", "cores": threads,
+                                "physical_cores": physical, "kind": kind_cpu, "steps": len(times),
+                                "seconds_per_step": statistics.mean(times),
+                                "sample": "processLevel of level %d of %d (%dx%d, all %d cameras: random proposals, ping-pong, "
+                                          "joint bilateral, median) started from the CUDA library's level-%d disparities; work = "
+                                          "the %d cost evaluations the CUDA library counts for that level" % (
+                                              C2F_CPU_LEVEL, C2F_LEVELS, W >> C2F_CPU_LEVEL, H >> C2F_CPU_LEVEL, S,
+                                              C2F_CPU_LEVEL + 1, evals_lvl)}
+        good = tot = nanbad = 0
+        for g, o in zip(c2f.level_out[C2F_CPU_LEVEL], cpu_disp):
+            fin = ~np.isnan(o)
+            nanbad += int((np.isnan(g) != np.isnan(o)).sum())
+            good += int((np.abs(g - o)[fin] <= 1e-3 * np.abs(o)[fin]).sum())
+            tot += int(fin.sum())
+        line["parity"] = {"against": kind_cpu, "level": C2F_CPU_LEVEL, "pixels": tot, "within_1e-3_rel": good,
+                          "fraction": good / max(1, tot), "nan_pattern_mismatches": nanbad}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_reference_c2f(args, rig, colors):
+    """Reference arm of workload c2f5, reference code only: the reference's own processLevel of the coarsest level (its
+    compile-time 150 candidates) feeds its own processLevel of level C2F_CPU_LEVEL, which is the timed step.  The work of
+    that step is counted by the oracle restatement (bit-identical to the reference, tests/test_reference_pin.py) run
+    once, untimed, on the same input — the reference keeps no counters."""
+    from facebook360_dep_b200 import capi
+    from tests import oracle_libs
+    S, W, H, D, kind = WORKLOADS["c2f5"]
+    lib = oracle_libs.load_ref()
+    kind_cpu = "reference" if lib is not None else "port"
+    oracle = oracle_libs.load_oracle()
+    if lib is None:
+        lib = oracle
+    threads, physical = host_threads()
+    lib.set_threads(threads)
+    oracle.set_threads(threads)
+    lv = {k: [lib.downscale_area(c, W >> k, H >> k) for c in colors] for k in (C2F_CPU_LEVEL + 1, C2F_CPU_LEVEL)}
+    ctx = capi.Context(lib, capi.rig_descs(rig))
+    k = C2F_CPU_LEVEL + 1
+    ctx.level_begin(W >> k, H >> k, level=k, num_levels=C2F_LEVELS, full_width=W, full_height=H)
+    ctx.set_colors(lv[k])
+    if k < C2F_LEVELS - 1:
+        raise SystemExit("C2F_CPU_LEVEL must be the second coarsest level")
+    ctx.process_level(num_depths=150, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True)
+    coarse = [ctx.get_disparity(d, want_cost=False) for d in range(S)]
+    ctx.close()
+    _, _, evals = c2f_cpu_level(oracle, rig, lv[C2F_CPU_LEVEL], coarse, threads, steps=1, warmup=0)
+    warm = max(1, args.warmup)
+    times, _, _ = c2f_cpu_level(lib, rig, lv[C2F_CPU_LEVEL], coarse, threads, steps=args.steps, warmup=warm)
+    value = evals / statistics.mean(times) / 1e6
+    base = {"value": value, "unit": "Mpix·cand/s", "cores": threads, "physical_cores": physical, "kind": kind_cpu,
+            "steps": len(times), "seconds_per_step": statistics.mean(times),
+            "sample": "processLevel of level %d of %d (%dx%d, all %d cameras) from the reference's own level-%d result; %d cost "
+                      "evaluations per step (counted by the oracle restatement)" % (
+                          C2F_CPU_LEVEL, C2F_LEVELS, W >> C2F_CPU_LEVEL, H >> C2F_CPU_LEVEL, S, C2F_CPU_LEVEL + 1, evals)}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix·cand/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 cost, f64 projection, u16 texels", "data": "synthetic",
+            "config": static_config("c2f5"), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "Mpix·cand/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -491,6 +728,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c2f5":
+        return run_c2f(args)
 
     import torch
     import torch.distributed as dist
@@ -629,7 +868,22 @@ def main():
             "issue": issue_roof(args.workload, sweep_ms_launch if sweep_n else None, (clocks or {}).get("sm_mhz"))},
     }
     if world == 1 and args.workload == "bf128_l0" and not args.no_c2f:
-        line["coarse_to_fine_5level"] = coarse_to_fine(ctx, colors, S, W, H, D, stream)
+        c2f = CoarseToFine(cuda, ctx, pin_colors, S, W, H, D, stream, dev, C2F_LEVELS)
+        c2f.frame(False)  # uploads, pyramid, warm-up
+        c2f.frame(True)
+        t = []
+        for resident in (True, False):
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record(stream)
+            c2f.frame(resident)
+            q1.record(stream)
+            torch.cuda.synchronize()
+            t.append(q0.elapsed_time(q1))
+        line["coarse_to_fine_5level"] = {
+            "ms_per_frame": t[0], "e2e_ms_per_frame": t[1], "cost_evaluations": c2f.evals, "value": c2f.evals / t[0] / 1e3,
+            "unit": "Mpix·cand/s", "levels": C2F_LEVELS,
+            "note": "configs[1] as the reference runs it; full line: python bench.py --workload c2f5"}
     if world == 1 and not args.no_cpu_baseline:
         arm = CpuArm(args.workload, rig, [np.ascontiguousarray(c) for c in colors])
         arm.calibrate(target_s=2.5)

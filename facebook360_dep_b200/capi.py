@@ -114,6 +114,7 @@ _SIGS = {
     "derp_get_launch_count": (C.c_int, [C.c_void_p, _p(C.c_uint64)]),
     "derp_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "derp_get_profile": (C.c_int, [C.c_void_p, _p(C.c_double), _p(C.c_uint64)]),
+    "derp_get_profile_ping_pong": (C.c_int, [C.c_void_p, _p(C.c_double), _p(C.c_uint64), _p(C.c_uint64), _p(C.c_uint64)]),
     "derp_set_sweep_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "derp_get_sweep_stats": (C.c_int, [C.c_void_p, _p(C.c_uint64), _p(C.c_uint64)]),
     "derp_level_begin": (C.c_int, [C.c_void_p, _p(LevelParams)]),
@@ -287,6 +288,11 @@ class Context:
         ms, n = C.c_double(), C.c_uint64()
         self.L.check(self.L.lib.derp_get_profile(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def get_profile_ping_pong(self):
+        ms, n, e, h = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.L.check(self.L.lib.derp_get_profile_ping_pong(self.h, C.byref(ms), C.byref(n), C.byref(e), C.byref(h)))
+        return ms.value, n.value, e.value, h.value
 
     def set_sweep_mode(self, mode):
         """0 automatic, 1 plain sweep, 2 filtered sweep (derp_b200.h)."""

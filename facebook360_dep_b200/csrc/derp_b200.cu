@@ -208,6 +208,8 @@ struct DerpCtx {
   // optional per-kernel timing of the dominant kernel (sweepKernel) with CUDA events on c->stream
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweepEvents;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pingEvents;  // pingPongKernel launches while profiling
+  DevBuf<unsigned long long> dCountersPP;                         // their own (evaluations, source hits)
 
   float2* warpOf(int dst) const { return geomCached ? geom->buf.p + (size_t)dst * 2 * S * plane : dProjWarp.p; }
   float2* warpInvOf(int dst) const { return geomCached ? geom->buf.p + ((size_t)dst * 2 + 1) * S * plane : dWarpInv.p; }
@@ -412,7 +414,36 @@ int derp_profile(DerpCtx* c, int enable) {
     cudaEventDestroy(e.second);
   }
   c->sweepEvents.clear();
+  for (auto& e : c->pingEvents) {
+    cudaEventDestroy(e.first);
+    cudaEventDestroy(e.second);
+  }
+  c->pingEvents.clear();
   c->profiling = enable != 0;
+  if (c->profiling) {
+    CU(c->dCountersPP.ensure(2));
+    CU(cudaMemsetAsync(c->dCountersPP.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  }
+  return DERP_OK;
+}
+
+int derp_get_profile_ping_pong(DerpCtx* c, double* ms, uint64_t* launches, uint64_t* evals, uint64_t* hits) {
+  if (!c) return fail(DERP_EINVAL, "null ctx");
+  int rc = useDevice(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  double total = 0;
+  for (auto& e : c->pingEvents) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, e.first, e.second));
+    total += t;
+  }
+  unsigned long long h[2] = {0, 0};
+  if (c->dCountersPP.p) CU(cudaMemcpy(h, c->dCountersPP.p, sizeof(h), cudaMemcpyDeviceToHost));
+  if (ms) *ms = total;
+  if (launches) *launches = c->pingEvents.size();
+  if (evals) *evals = h[0];
+  if (hits) *hits = h[1];
   return DERP_OK;
 }
 
@@ -881,8 +912,19 @@ int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
     a.list = c->dList.p;
     a.listCount = listCountPtr(c);
     a.counters = c->dCounters.p;
+    a.counters2 = c->profiling ? c->dCountersPP.p : nullptr;
+    cudaEvent_t p0 = nullptr, p1 = nullptr;
+    if (c->profiling) {
+      CU(cudaEventCreate(&p0));
+      CU(cudaEventCreate(&p1));
+      CU(cudaEventRecord(p0, c->stream));
+    }
     pingPongKernel<<<listGrid(W, H), kPatchThreads, c->patchSmem(), c->stream>>>(a);
     LAUNCHED("pingPongKernel");
+    if (c->profiling) {
+      CU(cudaEventRecord(p1, c->stream));
+      c->pingEvents.emplace_back(p0, p1);
+    }
     // disp <- dispRes, cost <- costsRes (Derp.cpp:527-529); confidence is not written back
     CU(cudaMemcpyAsync(disp, c->dScratchA.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(cost, c->dScratchB.p, n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
@@ -1203,15 +1245,33 @@ int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, u
     return fail(DERP_EINVAL, "derp_downscale_area: bad arguments (INTER_AREA is only used to shrink on this path)");
   CU(cudaSetDevice(device));
   const size_t ns = (size_t)src_w * src_h * 3, nd = (size_t)dst_w * dst_h * 3;
+  // device-resident images are used in place; host images are staged
+  auto onDevice = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  };
+  const bool srcDev = onDevice(src), dstDev = onDevice(dst);
   DevBuf<uint16_t> dS, dD;
-  CU(dS.ensure(ns));
-  CU(dD.ensure(nd));
-  CU(cudaMemcpy(dS.p, src, ns * sizeof(uint16_t), cudaMemcpyDefault));  // host or device source
+  const uint16_t* sp = src;
+  uint16_t* dp = dst;
+  if (!srcDev) {
+    CU(dS.ensure(ns));
+    CU(cudaMemcpy(dS.p, src, ns * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    sp = dS.p;
+  }
+  if (!dstDev) {
+    CU(dD.ensure(nd));
+    dp = dD.p;
+  }
   const double sx = (double)src_w / dst_w, sy = (double)src_h / dst_h;
   const int kx = (int)std::floor(sx + 0.5), ky = (int)std::floor(sy + 0.5);
   const dim3 grid((dst_w * 3 + 255) / 256, dst_h);
   if (std::fabs(sx - kx) < 2.220446049250313e-16 && std::fabs(sy - ky) < 2.220446049250313e-16) {
-    areaResizeFastKernel<<<grid, 256>>>(dS.p, src_w, dD.p, dst_w, dst_h, kx, ky);
+    areaResizeFastKernel<<<grid, 256>>>(sp, src_w, dp, dst_w, dst_h, kx, ky);
   } else {
     std::vector<int> xo, xs, yo, ys;
     std::vector<float> xa, ya;
@@ -1231,11 +1291,12 @@ int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, u
     CU(cudaMemcpy(dYo.p, yo.data(), yo.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dYs.p, ys.data(), ys.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dYa.p, ya.data(), ya.size() * sizeof(float), cudaMemcpyHostToDevice));
-    areaResizeKernel<<<grid, 256>>>(dS.p, src_w, src_h, dD.p, dst_w, dst_h, dXo.p, dXs.p, dXa.p, dYo.p, dYs.p, dYa.p);
+    areaResizeKernel<<<grid, 256>>>(sp, src_w, src_h, dp, dst_w, dst_h, dXo.p, dXs.p, dXa.p, dYo.p, dYs.p, dYa.p);
     CU(cudaDeviceSynchronize());  // tables are freed on return
   }
   CU(cudaGetLastError());
-  CU(cudaMemcpy(dst, dD.p, nd * sizeof(uint16_t), cudaMemcpyDefault));  // host or device destination
+  if (!dstDev) CU(cudaMemcpy(dst, dD.p, nd * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+  else if (!srcDev) CU(cudaDeviceSynchronize());  // the staged source is freed on return
   return DERP_OK;
 }
 

@@ -428,6 +428,34 @@ __device__ __forceinline__ SrcPoint projectToSource(const DevCamera& c, double w
   return o;
 }
 
+#ifdef DERP_EXPERIMENT_PROJ_F32
+// TIMING EXPERIMENT ONLY (results of the lower-bound pass are not valid bounds in this build): the projection of the
+// lower-bound pass in fp32, to measure what an fp32 projection with a position-error analysis could save at most.
+__device__ __forceinline__ SrcPoint projectToSourceF32(const DevCamera& c, float wx, float wy, float wz, int W, int H) {
+  const float vx = wx - c.conePos[0], vy = wy - c.conePos[1], vz = wz - c.conePos[2];
+  const float r0 = (float)c.rot[0], r1 = (float)c.rot[1], r2 = (float)c.rot[2], r3 = (float)c.rot[3], r4 = (float)c.rot[4],
+              r5 = (float)c.rot[5];
+  const float camx = __fmaf_rn(r2, vz, __fmaf_rn(r1, vy, r0 * vx));
+  const float camy = __fmaf_rn(r5, vz, __fmaf_rn(r4, vy, r3 * vx));
+  const float camz = -__fmaf_rn(c.coneFwd[2], vz, __fmaf_rn(c.coneFwd[1], vy, c.coneFwd[0] * vx));
+  const float xy2 = __fmaf_rn(camy, camy, camx * camx);
+  const float inv = rsqrtf(xy2), xy = xy2 * inv;
+  float r = atan2f(xy, -camz);
+  const float dm = (float)c.distMax;
+  r = r < dm ? r : dm;
+  const float q = r * r;
+  const float fac = __fmaf_rn(q, __fmaf_rn(q, __fmaf_rn(q, (float)c.dist[2], (float)c.dist[1]), (float)c.dist[0]), 1.0f);
+  const float f = fac * r * inv;
+  const float px = __fmaf_rn((float)c.focal[0], f * camx, (float)c.principal[0]);
+  const float py = __fmaf_rn((float)c.focal[1], f * camy, (float)c.principal[1]);
+  SrcPoint o;
+  o.ok = !(0 > px || px >= 1.0f || 0 > py || py >= 1.0f);
+  o.x = px * W;
+  o.y = py * H;
+  return o;
+}
+#endif
+
 // Generic (border / inconsistent-rounding / invalid) path of one source: returns false if the source
 // contributes no SSD (warp entry NaN).  Kept out of line: it runs for a few pixels per image.
 template <class TX>
@@ -639,7 +667,13 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     const float wL1 = fabsf(fx) + fabsf(fy) + fabsf(fz);
 #pragma unroll 4
     for (int s = 0; s < v.S; ++s) {
-#ifdef DERP_CONE_F32  // measured on B200 (2048^2 x 128): 89.1 ms per launch with the pre-test, 88.0 without: not kept
+#if defined(DERP_EXPERIMENT_PROJ_F32)
+      int cls = -1;
+      if constexpr (LOWER) {
+        cls = coneClass(cams[s], fx, fy, fz, wL1);
+        cls = cls < 0 ? 1 : cls;
+      }
+#elif defined(DERP_CONE_F32)  // measured on B200 (2048^2 x 128): 89.1 ms per launch with the pre-test, 88.0 without: not kept
       const int cls = coneClass(cams[s], fx, fy, fz, wL1);
 #else
       const int cls = -1;
@@ -682,10 +716,15 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
     t.yw = hi2(Wt);
     return t;
   };
+#ifdef DERP_EXPERIMENT_PROJ_F32
+#define DERP_PROJECT(cam) (LOWER ? projectToSourceF32(cam, (float)wx, (float)wy, (float)wz, W, H) : projectToSource(cam, wx, wy, wz, W, H))
+#else
+#define DERP_PROJECT(cam) projectToSource(cam, wx, wy, wz, W, H)
+#endif
   if (mask) {
     int s = __ffs(mask) - 1;
     mask &= mask - 1;
-    SrcPoint cur = projectToSource(cams[s], wx, wy, wz, W, H);
+    SrcPoint cur = DERP_PROJECT(cams[s]);
     while (true) {
       const int sNext = mask ? __ffs(mask) - 1 : s;  // tail: harmless re-projection of the same source
       const bool more = mask != 0;
@@ -729,7 +768,7 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
           const TX* r3 = r2 + W;
           const TX* b1 = srcBiasImg + off + W + 1;  // bias sample = centre sample's 2x2 footprint
           if constexpr (LOWER) {
-            nxt = projectToSource(cams[sNext], wx, wy, wz, W, H);
+            nxt = DERP_PROJECT(cams[sNext]);
             float sB, sU;
             ssdApprox<RP, CP>(r0, r1, r2, r3, b1, W, ps, W0, W1, W2, &sB, &sU);
             // slot = (sqrt of the biased sum, lower bound of the unbiased sum), see lowerBoundOfCost

@@ -669,6 +669,7 @@ struct PingPongArgs {
   const int* list;
   const int* listCount;
   unsigned long long* counters;
+  unsigned long long* counters2;  // nullable: a second tally of the same work (profiling)
 };
 
 // every pixel: the values a skipped pixel ends up with (Derp.cpp:420-437, 486-487, 525-529)
@@ -730,6 +731,7 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) pingPongKernel
   a.changedNext[p] = (old != bestDisp) ? 1 : 0;
   }
   addCounters(a.counters, evals, hits);
+  if (a.counters2) addCounters(a.counters2, evals, hits);
 }
 
 // ---- K9: handleDisparityMismatch (Derp.cpp:553-720) for one destination ----------------------------------

@@ -173,9 +173,12 @@ static void saveLevel(const Shared& shAll, const Worker& wk, int level, const st
   while (std::getline(ss, f, ','))
     if (!f.empty() && f != "pfm") formats.push_back(f);
   std::vector<float> disp((size_t)W * H), cost, conf;
+  std::vector<uint8_t> mism, fov;
   if (FLAGS_save_debug_images) {
     cost.resize(disp.size());
     conf.resize(disp.size());
+    mism.resize(disp.size());
+    fov.resize(disp.size());
   }
   for (size_t d = 0; d < sh.dst.size(); ++d) {
     DERP_CALL(derp_get_disparity(ctx, (int)d, disp.data(), cost.empty() ? nullptr : cost.data(),
@@ -183,23 +186,46 @@ static void saveLevel(const Shared& shAll, const Worker& wk, int level, const st
     const std::string& id = sh.rig.ids[sh.dst[d]];
     const fs::path stem = fs::path(io::levelDir(FLAGS_output_root + "/" + io::kDisparityLevels, level)) / id / frameName;
     for (const auto& ext : formats) io::saveDisparity(stem, ext, disp.data(), W, H);
-    if (FLAGS_save_debug_images) {  // saveDebugImages (PyramidLevel.h:418-461): scaled 16-bit previews
-      auto scaled = [&](const std::vector<float>& src, float s) {
-        std::vector<float> o(src.size());
-        for (size_t i = 0; i < o.size(); ++i) o[i] = src[i] * s / 65535.0f;  // written as raw u16 of value*scale
-        return o;
-      };
-      const auto c = scaled(cost, 255.0f / 100.0f), q = scaled(conf, 255.0f * 100.0f);
-      io::saveDisparity(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kCost, level)) / id / frameName, "png",
-                        c.data(), W, H);
-      io::saveDisparity(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kConfidence, level)) / id / frameName,
-                        "png", q.data(), W, H);
+    if (FLAGS_save_debug_images) {
+      // saveDebugImages (PyramidLevel.h:418-461).  disparity_levels: convertTo<uint16_t> -> the same 16-bit PNG as the
+      // png output format.  cost / confidence / mismatches: a CV_32F matrix times its plot scale handed to cv::imwrite,
+      // which converts it to 8 bits (saturate_cast<uchar>(cvRound(v)), NaN -> 0) before encoding.
+      io::saveDisparity(stem, "png", disp.data(), W, H);
+      std::vector<uint8_t> g(disp.size());
+      for (size_t i = 0; i < g.size(); ++i) g[i] = io::saturateU8(cost[i] * (255.0f / 100.0f));  // kScaleCostPlot
+      io::writePng8(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kCost, level)) / id / (frameName + ".png"), g.data(), W, H, 1);
+      for (size_t i = 0; i < g.size(); ++i) g[i] = io::saturateU8(conf[i] * (255.0f * 100.0f));  // kScaleConfidencePlot
+      io::writePng8(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kConfidence, level)) / id / (frameName + ".png"), g.data(), W, H, 1);
+      // overlayMismatchedDstDisparityMask (PyramidLevel.h:441-461): BGRA float, NaN outside the FOV, red where the
+      // mismatch mask is set, (d, d, d, 1) elsewhere; times kScaleDisparityPlot = 255
+      DERP_CALL(derp_get_mismatch_mask(ctx, (int)d, mism.data()));
+      DERP_CALL(derp_get_fov_mask(ctx, (int)d, fov.data()));
+      std::vector<uint8_t> bgra(disp.size() * 4);
+      for (size_t i = 0; i < disp.size(); ++i) {
+        float px[4];
+        if (!fov[i]) {
+          px[0] = NAN;  // cv::Mat_<cv::Vec4f>(size, NAN): Vec4f(NAN) sets channel 0 only
+          px[1] = px[2] = px[3] = 0.f;
+        } else if (mism[i]) {
+          px[0] = 0.f;
+          px[1] = 0.f;
+          px[2] = 1.f;
+          px[3] = 1.f;
+        } else {
+          px[0] = px[1] = px[2] = disp[i];
+          px[3] = 1.f;
+        }
+        for (int k = 0; k < 4; ++k) bgra[i * 4 + k] = io::saturateU8(px[k] * 255.0f);
+      }
+      io::writePng8(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kMismatches, level)) / id / (frameName + ".png"), bgra.data(), W, H, 4);
     }
   }
 }
 
 // One (level, frame): DerpCLI.cpp:229-320
-static void processFrame(const Shared& shAll, const Worker& wk, int level, int iFrame, Exchange* ex) {
+// `fromKept`: the coarser level of this frame was processed by this context just before and its disparities are still
+// in device memory (derp_level_keep) — the PFM round trip of DerpCLI.cpp:287-288 is skipped (the files are still written).
+static void processFrame(const Shared& shAll, const Worker& wk, int level, int iFrame, Exchange* ex, bool fromKept) {
   DerpCtx* ctx = wk.ctx;
   Shared sh = shAll;
   sh.dst = wk.dst;
@@ -257,8 +283,9 @@ static void processFrame(const Shared& shAll, const Worker& wk, int level, int i
     const std::string coarseDir = io::levelDir(FLAGS_output_root + "/" + io::kDisparityLevels, level + 1);
     for (int d = 0; d < Sd; ++d) {
       const std::string& id = sh.rig.ids[sh.dst[d]];
-      int cw, ch;
-      const std::vector<float> coarse = io::loadFloat(io::imagePath(coarseDir, id, frameName), &cw, &ch);
+      int cw = sh.sizes.at(level + 1).first, ch = sh.sizes.at(level + 1).second;
+      std::vector<float> coarse;
+      if (!fromKept) coarse = io::loadFloat(io::imagePath(coarseDir, id, frameName), &cw, &ch);
       std::vector<uint8_t> mc;
       const uint8_t* mfine = nullptr;
       if (FLAGS_use_foreground_masks) {
@@ -267,7 +294,10 @@ static void processFrame(const Shared& shAll, const Worker& wk, int level, int i
         CHECK(w == cw && h == ch) << "coarse mask / disparity size mismatch";
         mfine = masks[sh.dst[d]].data();
       }
-      DERP_CALL(derp_upsample_from(ctx, d, coarse.data(), cw, ch, mc.empty() ? nullptr : mc.data(), mfine));
+      if (fromKept)
+        DERP_CALL(derp_upsample_from_kept(ctx, d, mc.empty() ? nullptr : mc.data(), mfine));
+      else
+        DERP_CALL(derp_upsample_from(ctx, d, coarse.data(), cw, ch, mc.empty() ? nullptr : mc.data(), mfine));
     }
   }
 
@@ -294,6 +324,7 @@ static void processFrame(const Shared& shAll, const Worker& wk, int level, int i
   } else {
     DERP_CALL(derp_process_level(ctx, &o));
   }
+  if (level > shAll.levelEnd) DERP_CALL(derp_level_keep(ctx));  // hand the level to the next finer one in device memory
   saveLevel(shAll, wk, level, frameName, W, H);
 }
 
@@ -377,19 +408,22 @@ int main(int argc, char* argv[]) {
         for (const char* t : {io::kDisparityLevels, io::kCost, io::kConfidence, io::kMismatches})
           fs::create_directories(fs::path(io::levelDir(FLAGS_output_root + "/" + t, level)) / sh.rig.ids[d]);
     }
+  }
+  // The reference walks level-outer / frame-inner and re-reads the coarser level's PFMs (DerpCLI.cpp:220-320).  Frames
+  // are independent, so each GPU worker walks ITS frames level by level instead and hands a finished level to the next
+  // one in device memory; every file of the reference's run is still written, with the same bytes.
+  {
     std::vector<std::thread> threads;
     const int per = (sh.numFrames + G - 1) / G;
     Exchange exchange(G, (int)sh.rig.cams.size());
     for (int g = 0; g < G; ++g)
       threads.emplace_back([&, g] {
-        if (shardCameras) {  // all GPUs walk the frames in step; they meet inside processFrame on mismatch levels
-          for (int i = 0; i < sh.numFrames; ++i) processFrame(sh, workers[g], level, i, G > 1 ? &exchange : nullptr);
-        } else {
-          for (int i = g * per; i < std::min(sh.numFrames, (g + 1) * per); ++i)
-            processFrame(sh, workers[g], level, i, nullptr);
-        }
+        const int f0 = shardCameras ? 0 : g * per, f1 = shardCameras ? sh.numFrames : std::min(sh.numFrames, (g + 1) * per);
+        for (int i = f0; i < f1; ++i)  // camera sharding: all GPUs walk the frames in step and meet on mismatch levels
+          for (int level = sh.levelStart; level >= sh.levelEnd; --level)
+            processFrame(sh, workers[g], level, i, (shardCameras && G > 1) ? &exchange : nullptr, level < sh.levelStart);
       });
-    for (auto& w : threads) w.join();  // per-level barrier, like the render pipeline (pipeline.py:364-380)
+    for (auto& w : threads) w.join();
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     LOG(INFO) << "-- Elapsed time: " << el << "s wall";
   }

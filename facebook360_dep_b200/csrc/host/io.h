@@ -426,8 +426,9 @@ inline void pngChunk(std::ofstream& f, const char* type, const std::vector<uint8
   f.write(reinterpret_cast<char*>(c), 4);
 }
 
-// 8-bit single-channel PNG (what cv::imwrite produces for a CV_32F matrix: convertTo(CV_8U), modules/imgcodecs loadsave)
-inline void writePng8Gray(const fs::path& path, const uint8_t* data, int w, int h) {
+// 8-bit PNG, `channels` = 1 (gray) or 4 (BGRA input, written as RGBA) — what cv::imwrite produces for a CV_32F matrix:
+// it converts to CV_8U first (convertTo, i.e. saturate_cast<uchar>(cvRound(v)); modules/imgcodecs loadsave.cpp)
+inline void writePng8(const fs::path& path, const uint8_t* data, int w, int h, int channels) {
   std::ofstream f(path, std::ios::binary);
   CHECK(f.good()) << "failed to save image: " << path.string();
   static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
@@ -436,12 +437,24 @@ inline void writePng8Gray(const fs::path& path, const uint8_t* data, int w, int 
   ihdr[0] = w >> 24; ihdr[1] = w >> 16; ihdr[2] = w >> 8; ihdr[3] = w;
   ihdr[4] = h >> 24; ihdr[5] = h >> 16; ihdr[6] = h >> 8; ihdr[7] = h;
   ihdr[8] = 8;
-  ihdr[9] = 0;
+  ihdr[9] = channels == 1 ? 0 : 6;
   pngChunk(f, "IHDR", ihdr);
-  std::vector<uint8_t> raw(((size_t)w + 1) * h);
+  const size_t stride = (size_t)w * channels;
+  std::vector<uint8_t> raw((stride + 1) * h);
   for (int y = 0; y < h; ++y) {
-    raw[(size_t)y * (w + 1)] = 0;
-    std::memcpy(&raw[(size_t)y * (w + 1) + 1], data + (size_t)y * w, (size_t)w);
+    uint8_t* out = &raw[(size_t)y * (stride + 1)];
+    *out++ = 0;
+    const uint8_t* in = data + (size_t)y * stride;
+    if (channels == 1) {
+      std::memcpy(out, in, stride);
+    } else {
+      for (int x = 0; x < w; ++x, in += 4, out += 4) {
+        out[0] = in[2];
+        out[1] = in[1];
+        out[2] = in[0];
+        out[3] = in[3];
+      }
+    }
   }
   uLongf clen = compressBound((uLong)raw.size());
   std::vector<uint8_t> comp(clen);
@@ -449,6 +462,94 @@ inline void writePng8Gray(const fs::path& path, const uint8_t* data, int w, int 
   comp.resize(clen);
   pngChunk(f, "IDAT", comp);
   pngChunk(f, "IEND", {});
+}
+inline void writePng8Gray(const fs::path& path, const uint8_t* data, int w, int h) { writePng8(path, data, w, h, 1); }
+inline uint8_t saturateU8(float v) {  // saturate_cast<uchar>(float): cvRound then clamp; NaN -> INT_MIN -> 0
+  if (v != v) return 0;
+  const long r = std::lrintf(v);
+  return (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+}
+
+// One-channel 32-bit float OpenEXR file (scan lines, no compression, channel "Y" like OpenCV's grayscale EXR output):
+// the layout of the OpenEXR file-format document — magic, version, attribute list, line offset table, scan lines.
+inline void writeExrFloat(const fs::path& path, const float* data, int w, int h) {
+  std::ofstream f(path, std::ios::binary);
+  CHECK(f.good()) << "failed to save image: " << path.string();
+  std::vector<uint8_t> hd;
+  auto put32 = [&](std::vector<uint8_t>& v, uint32_t x) {
+    for (int i = 0; i < 4; ++i) v.push_back((uint8_t)(x >> (8 * i)));
+  };
+  auto putF = [&](std::vector<uint8_t>& v, float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    put32(v, u);
+  };
+  auto putS = [&](std::vector<uint8_t>& v, const char* s) {
+    while (*s) v.push_back((uint8_t)*s++);
+    v.push_back(0);
+  };
+  auto attr = [&](const char* name, const char* type, const std::vector<uint8_t>& val) {
+    putS(hd, name);
+    putS(hd, type);
+    put32(hd, (uint32_t)val.size());
+    hd.insert(hd.end(), val.begin(), val.end());
+  };
+  put32(hd, 20000630u);  // magic
+  put32(hd, 2u);         // version 2, single-part scan-line file
+  {
+    std::vector<uint8_t> v;
+    putS(v, "Y");
+    put32(v, 2);  // FLOAT
+    put32(v, 0);  // pLinear + reserved
+    put32(v, 1);  // xSampling
+    put32(v, 1);  // ySampling
+    v.push_back(0);
+    attr("channels", "chlist", v);
+  }
+  attr("compression", "compression", {0});
+  {
+    std::vector<uint8_t> v;
+    put32(v, 0);
+    put32(v, 0);
+    put32(v, (uint32_t)(w - 1));
+    put32(v, (uint32_t)(h - 1));
+    attr("dataWindow", "box2i", v);
+    attr("displayWindow", "box2i", v);
+  }
+  attr("lineOrder", "lineOrder", {0});
+  {
+    std::vector<uint8_t> v;
+    putF(v, 1.0f);
+    attr("pixelAspectRatio", "float", v);
+  }
+  {
+    std::vector<uint8_t> v;
+    putF(v, 0.0f);
+    putF(v, 0.0f);
+    attr("screenWindowCenter", "v2f", v);
+  }
+  {
+    std::vector<uint8_t> v;
+    putF(v, 1.0f);
+    attr("screenWindowWidth", "float", v);
+  }
+  hd.push_back(0);  // end of header
+  f.write(reinterpret_cast<const char*>(hd.data()), (std::streamsize)hd.size());
+  const uint64_t lineBytes = 8 + (uint64_t)w * 4;
+  uint64_t ofs = hd.size() + (uint64_t)h * 8;
+  for (int y = 0; y < h; ++y, ofs += lineBytes) {
+    uint8_t b[8];
+    for (int i = 0; i < 8; ++i) b[i] = (uint8_t)(ofs >> (8 * i));
+    f.write(reinterpret_cast<const char*>(b), 8);
+  }
+  for (int y = 0; y < h; ++y) {
+    std::vector<uint8_t> l;
+    put32(l, (uint32_t)y);
+    put32(l, (uint32_t)(w * 4));
+    f.write(reinterpret_cast<const char*>(l.data()), 8);
+    f.write(reinterpret_cast<const char*>(data + (size_t)y * w), (std::streamsize)w * 4);
+  }
+  CHECK(f.good()) << "failed to save image: " << path.string();
 }
 
 // 16-bit PNG, `channels` = 1 (gray) or 3 (BGR input, written as RGB)
@@ -591,7 +692,7 @@ inline void saveDisparity(const fs::path& stem, const std::string& ext, const fl
     const auto v = disparityTo16(d, (size_t)w * h);
     writePng16(stem.string() + ".png", v.data(), w, h, 1);
   } else if (ext == "exr") {
-    LOG(WARNING) << "exr output is not supported by this build; skipping " << stem.string() << ".exr";
+    writeExrFloat(stem.string() + ".exr", d, w, h);
   } else {
     LOG(FATAL) << "Invalid type: " << ext;
   }

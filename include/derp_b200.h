@@ -121,6 +121,9 @@ int derp_get_launch_count(DerpCtx* ctx, uint64_t* out);
  * returns the summed device time and the number of launches since derp_profile(ctx, 1). */
 int derp_profile(DerpCtx* ctx, int enable);
 int derp_get_profile(DerpCtx* ctx, double* sweep_ms, uint64_t* sweep_launches);
+/* The same for the dominant kernel of a fine level (pingPongKernel): summed device time, launches, and the cost
+ * evaluations / contributing sources those launches performed, since derp_profile(ctx, 1). */
+int derp_get_profile_ping_pong(DerpCtx* ctx, double* ms, uint64_t* launches, uint64_t* evals, uint64_t* hits);
 
 /* How derp_brute_force sweeps (CUDA library; accepted and ignored by the CPU libraries).  Every mode produces the same
  * bytes; they differ in how much exact arithmetic runs:

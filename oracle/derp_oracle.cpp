@@ -351,6 +351,13 @@ int derp_set_stream(DerpCtx*, void*) { return DERP_OK; }
 int derp_sync(DerpCtx*) { return DERP_OK; }
 int derp_profile(DerpCtx*, int) { return DERP_OK; }
 int derp_set_sweep_mode(DerpCtx*, int) { return DERP_OK; }
+int derp_get_profile_ping_pong(DerpCtx*, double* ms, uint64_t* n, uint64_t* e, uint64_t* h) {
+  if (ms) *ms = 0;
+  if (n) *n = 0;
+  if (e) *e = 0;
+  if (h) *h = 0;
+  return DERP_OK;
+}
 int derp_get_sweep_stats(DerpCtx*, uint64_t* a, uint64_t* b) {
   if (a) *a = 0;
   if (b) *b = 0;

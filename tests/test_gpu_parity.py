@@ -454,3 +454,57 @@ def test_camera_sharded_mismatches(cuda, oracle):
         assert np.array_equal(np.isfinite(got[cam][0]), fin)
         close = np.abs(got[cam][0] - orc[cam][0])[fin] <= 1e-3 * np.abs(orc[cam][0])[fin]
         assert close.mean() >= 1 - 1e-3
+
+
+def test_downscale_area_pyramid_widths(cuda, oracle):
+    """§8(f) pyramid pre-resize: cv::resize INTER_AREA exactly as scripts/render/resize.py:79 applies it (every level from
+    the full-size image; widths scripts/render/config.py:46), bit for bit vs the oracle restatement, which is pinned to
+    cv2 4.13 (tests/test_oracle_cv.py).  Integer ratios (2 x 2 integer mean, other areas) and general ratios."""
+    rng = np.random.RandomState(4)
+    full = rng.randint(0, 65536, (540, 840, 3)).astype(np.uint16)  # the reference rig's 3360 x 2160 at 1/4
+    for width in (512, 256, 200, 128, 100, 80, 60, 50):  # 2048 .. 50 of the reference at 1/4 + the small levels as they are
+        height = round(540 / 840 * width)
+        height += height % 2
+        g = cuda.downscale_area(full, width, height)
+        o = oracle.downscale_area(full, width, height)
+        assert np.array_equal(g, o), width
+    sq = rng.randint(0, 65536, (512, 512, 3)).astype(np.uint16)
+    for w in (256, 128, 64, 200, 100):
+        assert np.array_equal(cuda.downscale_area(sq, w, w), oracle.downscale_area(sq, w, w)), w
+    assert np.array_equal(cuda.downscale_area(sq, 512, 512), sq)
+    with pytest.raises(capi.DerpError):
+        cuda.downscale_area(sq, 600, 600)  # enlarging is not INTER_AREA's shrinking path
+
+
+def test_level_handoff_in_memory(cuda, oracle):
+    """§8(f) in-memory level hand-off: derp_level_keep + derp_upsample_from_kept must give the bytes of the file round
+    trip they replace (derp_get_disparity -> derp_upsample_from), with and without foreground masks."""
+    cfg = dict(num_cams=5, width=96, height=80, kind="FTHETA")
+    rig, colors, true_disp = scene_inputs(**cfg)
+    W, H = 96, 80
+    coarse_colors = [cuda.downscale_area(c, W // 2, H // 2) for c in colors]
+    for use_fg in (False, True):
+        rng = np.random.RandomState(8)
+        ctx = capi.Context(cuda, capi.rig_descs(rig))
+        ctx.level_begin(W // 2, H // 2, level=1, num_levels=2, full_width=W, full_height=H, use_foreground_masks=use_fg)
+        ctx.set_colors(coarse_colors)
+        coarse = [rng.uniform(0.01, 1.5, (H // 2, W // 2)).astype(np.float32) for _ in range(5)]
+        for d in range(5):
+            coarse[d][rng.uniform(size=coarse[d].shape) < 0.05] = np.nan
+            ctx.set_disparity(d, coarse[d])
+        ctx.level_keep()
+        masks = [(rng.uniform(size=(H, W)) > 0.2).astype(np.uint8) for _ in range(5)]
+        cmasks = [m[::2, ::2].copy() for m in masks]
+        ctx.level_begin(W, H, level=0, num_levels=2, full_width=W, full_height=H, use_foreground_masks=use_fg)
+        ctx.set_colors(colors)
+        if use_fg:
+            ctx.set_foreground_masks(masks)
+            ctx.set_background_disparity([np.full((H, W), 0.02, np.float32)] * 5)
+        got = []
+        for d in range(5):
+            ctx.upsample_from_kept(d, cmasks[d] if use_fg else None, masks[d] if use_fg else None)
+            got.append(ctx.get_disparity(d, want_cost=False))
+        for d in range(5):
+            ctx.upsample_from(d, coarse[d], cmasks[d] if use_fg else None, masks[d] if use_fg else None)
+            assert same_float_bits(got[d], ctx.get_disparity(d, want_cost=False)).all(), (use_fg, d)
+        ctx.close()

@@ -33,6 +33,10 @@ for d in range(a.dsts):
         ctx.brute_force(d, num_depths=a.depths, want_index=False)
     ms, n = ctx.get_profile()
     ctx.profile(False)
+    try:
+        print("dst %d: sweep stats (refined, seeds) %s" % (d, ctx.sweep_stats()))
+    except Exception as ex:
+        print("no sweep stats", ex)
     print("dst %d: sweep %.2f ms/launch  %.2f Gpix·cand/s  %.2f Gtriples/s  vbar %.2f" % (
         d, ms / n, e / (ms / n) / 1e6, hits / (ms / n) / 1e6, hits / e))
 print("idx sha1", h.hexdigest()[:16])
