@@ -157,6 +157,8 @@ _SIGS = {
     "derp_upsample_disparity": (C.c_int, [C.c_int, _p(CameraDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "derp_downscale_area": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "derp_foreground_mask": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                       C.c_void_p]),
 }
 
 ABI_SYMBOLS = sorted(_SIGS)
@@ -220,6 +222,16 @@ class Library:
         h, w = image.shape[:2]
         out = np.empty((out_h, out_w, 3), np.uint16)
         self.check(self.lib.derp_downscale_area(device, image.ctypes.data, w, h, out.ctypes.data, out_w, out_h))
+        return out
+
+    def foreground_mask(self, templ, frame, blur_radius=1, threshold=0.04, morph_closing_size=4, device=0):
+        """generateForegroundMask (BackgroundSubtractionUtil.h:20-59) for one camera; returns a uint8 0/1 mask."""
+        templ = np.ascontiguousarray(templ, np.uint16)
+        frame = np.ascontiguousarray(frame, np.uint16)
+        h, w = templ.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        self.check(self.lib.derp_foreground_mask(device, templ.ctypes.data, frame.ctypes.data, w, h, blur_radius, threshold,
+                                                 morph_closing_size, out.ctypes.data))
         return out
 
     def upsample_disparity(self, cam_desc, coarse, out_w, out_h, background_up=None, coarse_mask=None,

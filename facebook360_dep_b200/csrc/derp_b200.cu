@@ -1300,6 +1300,42 @@ int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, u
   return DERP_OK;
 }
 
+int derp_foreground_mask(int device, const uint16_t* templ, const uint16_t* frame, int width, int height, int blur_radius,
+                         float threshold, int morph_closing_size, uint8_t* mask) {
+  if (!templ || !frame || !mask || width < 1 || height < 1 || morph_closing_size < 0)
+    return fail(DERP_EINVAL, "derp_foreground_mask: bad arguments");
+  if (blur_radius < 0 || blur_radius > 1)
+    return fail(DERP_EINVAL, "derp_foreground_mask: blur_radius 0 or 1 (the app's default 3 x 3 Gaussian)");
+  CU(cudaSetDevice(device));
+  const size_t n = (size_t)width * height;
+  DevBuf<uint16_t> dT, dF, dTb, dFb;
+  DevBuf<uint8_t> dM, dM2;
+  CU(dT.ensure(n * 3));
+  CU(dF.ensure(n * 3));
+  CU(dM.ensure(n));
+  CU(cudaMemcpy(dT.p, templ, n * 6, cudaMemcpyDefault));
+  CU(cudaMemcpy(dF.p, frame, n * 6, cudaMemcpyDefault));
+  const uint16_t *pt = dT.p, *pf = dF.p;
+  if (blur_radius == 1) {
+    CU(dTb.ensure(n * 3));
+    CU(dFb.ensure(n * 3));
+    const dim3 g((width * 3 + 255) / 256, height);
+    gaussian3Kernel<<<g, 256>>>(dT.p, width, height, dTb.p);
+    gaussian3Kernel<<<g, 256>>>(dF.p, width, height, dFb.p);
+    pt = dTb.p;
+    pf = dFb.p;
+  }
+  foregroundDiffKernel<<<grid1(n), 256>>>(n, pt, pf, threshold, dM.p);
+  if (morph_closing_size > 0) {  // MORPH_CLOSE = dilate, then erode
+    CU(dM2.ensure(n));
+    morphRectKernel<<<grid2(width, height), block2()>>>(dM.p, width, height, morph_closing_size, 1, dM2.p);
+    morphRectKernel<<<grid2(width, height), block2()>>>(dM2.p, width, height, morph_closing_size, 0, dM.p);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(mask, dM.p, n, cudaMemcpyDefault));
+  return DERP_OK;
+}
+
 int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* coarse, int coarse_w, int coarse_h,
                             const float* background_up, const uint8_t* coarse_mask, const uint8_t* fine_mask, int out_w,
                             int out_h, int use_foreground_masks, float* out) {

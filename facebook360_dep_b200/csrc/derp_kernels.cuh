@@ -1124,4 +1124,53 @@ __global__ void areaResizeFastKernel(const uint16_t* __restrict__ src, int sw, u
   dst[((size_t)dy * dw + dx) * 3 + ch] = (uint16_t)out;
 }
 
+
+// ---- GenerateForegroundMasks (source/render/BackgroundSubtractionUtil.h:20-59) ---------------------------------------
+// cv::GaussianBlur 3 x 3, sigma 0, u16 x 3: (1 2 1; 2 4 2; 1 2 1) / 16 in fixed point, round half up, REFLECT_101
+__global__ void gaussian3Kernel(const uint16_t* __restrict__ src, int w, int h, uint16_t* __restrict__ dst) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (e >= w * 3) return;
+  const int x = e / 3, c = e - x * 3;
+  const int ys[3] = {reflect101(y - 1, h), y, reflect101(y + 1, h)};
+  const int xs[3] = {reflect101(x - 1, w), x, reflect101(x + 1, w)};
+  unsigned s = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s += (unsigned)((j == 1 ? 2 : 1) * (i == 1 ? 2 : 1)) * src[((size_t)ys[j] * w + xs[i]) * 3 + c];
+  dst[((size_t)y * w + x) * 3 + c] = (uint16_t)((s + 8u) >> 4);
+}
+// mask = || float(template) - float(frame) ||_2 > threshold; cv::norm accumulates the squares in double
+__global__ void foregroundDiffKernel(size_t n, const uint16_t* __restrict__ templ, const uint16_t* __restrict__ frame, float threshold,
+                                     uint8_t* __restrict__ mask) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float alpha = 1.0f / 65535.0f;
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float d = fabsf((float)templ[i * 3 + c] * alpha - (float)frame[i * 3 + c] * alpha);
+    s += (double)d * (double)d;
+  }
+  mask[i] = sqrt(s) > (double)threshold ? 1 : 0;
+}
+// cv::dilate / cv::erode with a k x k rectangle anchored at k / 2; border taps never win
+__global__ void morphRectKernel(const uint8_t* __restrict__ src, int w, int h, int k, int dilate, uint8_t* __restrict__ dst) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const int a = k / 2;
+  unsigned v = dilate ? 0u : 255u;
+  for (int j = -a; j < k - a; ++j) {
+    const int yy = y + j;
+    if (yy < 0 || yy >= h) continue;
+    for (int i = -a; i < k - a; ++i) {
+      const int xx = x + i;
+      if (xx < 0 || xx >= w) continue;
+      const unsigned t = src[(size_t)yy * w + xx];
+      v = dilate ? max(v, t) : min(v, t);
+    }
+  }
+  dst[(size_t)y * w + x] = (uint8_t)v;
+}
+
 }  // namespace derp

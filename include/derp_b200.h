@@ -265,6 +265,14 @@ int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* 
  * be host or device memory. */
 int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, uint16_t* dst, int dst_w, int dst_h);
 
+/* generateForegroundMask<cv::Vec3w, cv::Vec3f> (source/render/BackgroundSubtractionUtil.h:20-59), the per-camera body of
+ * the GenerateForegroundMasks app that produces the masks --use_foreground_masks consumes: Gaussian blur of template
+ * (background) and frame (blur_radius 0 or 1 = the app's default 3 x 3 kernel), conversion to [0, 1] floats,
+ * mask = ||template - frame||_2 > threshold, morphological closing with a morph_closing_size^2 rectangle.
+ * Images u16 HxWx3 (host or device memory), mask uint8 HxW with values 0 / 1. */
+int derp_foreground_mask(int device, const uint16_t* templ, const uint16_t* frame, int width, int height, int blur_radius,
+                         float threshold, int morph_closing_size, uint8_t* mask);
+
 #ifdef __cplusplus
 }
 #endif

@@ -354,4 +354,72 @@ inline bool resizeAreaU16C3(const uint16_t* src, int sw, int sh, uint16_t* dst, 
   return true;
 }
 
+// ---- GenerateForegroundMasks (source/render/BackgroundSubtractionUtil.h:20-59) -------------------------------------
+// cv::GaussianBlur(3 x 3, sigma 0) on u16 x 3: OpenCV's fixed-point path with the table kernel (1/4, 1/2, 1/4), i.e.
+// (sum of (1 2 1; 2 4 2; 1 2 1) weights + 8) >> 4, BORDER_REFLECT_101 (verified against cv2 4.13).
+inline void gaussian3U16C3(const uint16_t* src, int w, int h, uint16_t* dst) {
+  static const int k[3] = {1, 2, 1};
+  for (int y = 0; y < h; ++y) {
+    const int ys[3] = {reflect101(y - 1, h), y, reflect101(y + 1, h)};
+    for (int x = 0; x < w; ++x) {
+      const int xs[3] = {reflect101(x - 1, w), x, reflect101(x + 1, w)};
+      for (int c = 0; c < 3; ++c) {
+        unsigned s = 0;
+        for (int j = 0; j < 3; ++j)
+          for (int i = 0; i < 3; ++i) s += (unsigned)(k[j] * k[i]) * src[((size_t)ys[j] * w + xs[i]) * 3 + c];
+        dst[((size_t)y * w + x) * 3 + c] = (uint16_t)((s + 8u) >> 4);
+      }
+    }
+  }
+}
+// cv::dilate / cv::erode with a k x k rectangle, anchor at its centre (k / 2), constant border that never wins
+inline void morphRectU8(const uint8_t* src, int w, int h, int k, bool dilate, uint8_t* dst) {
+  const int a = k / 2;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      uint8_t v = dilate ? 0 : 255;
+      for (int j = -a; j < k - a; ++j)
+        for (int i = -a; i < k - a; ++i) {
+          const int yy = y + j, xx = x + i;
+          if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+          const uint8_t t = src[(size_t)yy * w + xx];
+          v = dilate ? std::max(v, t) : std::min(v, t);
+        }
+      dst[(size_t)y * w + x] = v;
+    }
+}
+// generateForegroundMask<Vec3w, Vec3f>: blur both images, convert to float in [0, 1], mask = ||template - frame||_2 >
+// threshold (cv::norm accumulates in double), morphological closing with a `closing` x `closing` rectangle.
+inline bool foregroundMaskU16C3(const uint16_t* templ, const uint16_t* frame, int w, int h, int blurRadius, float threshold,
+                                int closing, uint8_t* mask) {
+  if (blurRadius < 0 || blurRadius > 1 || closing < 0) return false;  // radius 1 = the reference's default; larger kernels are not restated
+  const size_t n = (size_t)w * h;
+  std::vector<uint16_t> tb, fb;
+  if (blurRadius == 1) {
+    tb.resize(n * 3);
+    fb.resize(n * 3);
+    gaussian3U16C3(templ, w, h, tb.data());
+    gaussian3U16C3(frame, w, h, fb.data());
+    templ = tb.data();
+    frame = fb.data();
+  }
+  const float alpha = 1.0f / 65535.0f;
+  std::vector<uint8_t> m(n);
+  for (size_t i = 0; i < n; ++i) {
+    double s = 0;
+    for (int c = 0; c < 3; ++c) {
+      const float d = std::fabs(templ[i * 3 + c] * alpha - frame[i * 3 + c] * alpha);
+      s += (double)d * (double)d;
+    }
+    m[i] = std::sqrt(s) > (double)threshold ? 1 : 0;
+  }
+  if (closing > 0) {
+    std::vector<uint8_t> t(n);
+    morphRectU8(m.data(), w, h, closing, true, t.data());
+    morphRectU8(t.data(), w, h, closing, false, m.data());
+  }
+  std::memcpy(mask, m.data(), n);
+  return true;
+}
+
 }  // namespace oracle

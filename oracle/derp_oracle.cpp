@@ -1384,6 +1384,13 @@ int derp_downscale_area(int /*device*/, const uint16_t* src, int src_w, int src_
   if (!src || !dst || !resizeAreaU16C3(src, src_w, src_h, dst, dst_w, dst_h)) return DERP_EINVAL;
   return DERP_OK;
 }
+int derp_foreground_mask(int /*device*/, const uint16_t* templ, const uint16_t* frame, int w, int h, int blur_radius,
+                         float threshold, int morph_closing_size, uint8_t* mask) {
+  if (!templ || !frame || !mask || w < 1 || h < 1 ||
+      !foregroundMaskU16C3(templ, frame, w, h, blur_radius, threshold, morph_closing_size, mask))
+    return DERP_EINVAL;
+  return DERP_OK;
+}
 int oracle_resize_area(const uint16_t* src, int sw, int sh, uint16_t* dst, int dw, int dh) {
   return resizeAreaU16C3(src, sw, sh, dst, dw, dh) ? 0 : -1;
 }

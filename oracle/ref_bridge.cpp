@@ -629,6 +629,15 @@ int derp_downscale_area(int /*device*/, const uint16_t* src, int src_w, int src_
   return DERP_OK;
 }
 
+/* source/render/BackgroundSubtractionUtil.h is outside the sources compiled here (it needs cv::GaussianBlur /
+ * morphologyEx): the stand-in's restatement (oracle/cvprims.h, pinned to cv2 4.13) answers for it */
+int derp_foreground_mask(int /*device*/, const uint16_t* templ, const uint16_t* frame, int w, int h, int blur_radius,
+                         float threshold, int morph_closing_size, uint8_t* mask) {
+  if (!templ || !frame || !mask || !oracle::foregroundMaskU16C3(templ, frame, w, h, blur_radius, threshold, morph_closing_size, mask))
+    return fail(DERP_EINVAL, "bad arguments");
+  return DERP_OK;
+}
+
 /* bench / test hook (not part of derp_b200.h): candidate slices of the brute-force cost volume the way the reference
  * builds them (Derp.cpp:288-304): ONE ThreadPool task per candidate, each writing a full-size cost and confidence map
  * (NaN where ignored).  Rows [y0, y1) only, so that a bench step can be a bounded band of the frame: with the full

@@ -73,6 +73,24 @@ def main():
     out["area_src"] = a
     for (W, H) in ((42, 27), (21, 27), (28, 27), (51, 33), (84, 54), (13, 9), (50, 32)):
         out["area_%dx%d" % (W, H)] = cv2.resize(a, (W, H), interpolation=cv2.INTER_AREA)
+    # ---- generateForegroundMask (BackgroundSubtractionUtil.h:20-59) with the same cv2 calls: GaussianBlur 3x3 sigma 0,
+    # convertTo float, absdiff, per-pixel L2 norm (double) > 0.04, MORPH_CLOSE with a 4x4 rectangle
+    bgimg = np.clip(rng.normal(30000, 9000, size=(40, 52, 3)), 0, 65535).astype(np.uint16)
+    fr = bgimg.copy()
+    fr[8:22, 10:30] = np.clip(fr[8:22, 10:30].astype(np.int64) + rng.randint(-9000, 9000, size=(14, 20, 3)), 0, 65535).astype(np.uint16)
+    fr = np.clip(fr.astype(np.int64) + rng.randint(-600, 600, size=fr.shape), 0, 65535).astype(np.uint16)
+    out["fg_template"] = bgimg
+    out["fg_frame"] = fr
+    out["fg_gauss"] = cv2.GaussianBlur(fr, (3, 3), 0)
+    for tag, blur, close in (("fg_mask_b1_c4", 1, 4), ("fg_mask_b0_c3", 0, 3), ("fg_mask_b1_c0", 1, 0)):
+        tb = cv2.GaussianBlur(bgimg, (3, 3), 0) if blur else bgimg
+        fb = cv2.GaussianBlur(fr, (3, 3), 0) if blur else fr
+        a32 = np.float32(1.0) / np.float32(65535.0)
+        diff = cv2.absdiff(tb.astype(np.float32) * a32, fb.astype(np.float32) * a32)
+        mask = (np.sqrt((diff.astype(np.float64) ** 2).sum(-1)) > np.float64(np.float32(0.04))).astype(np.uint8)
+        if close:
+            mask = cv2.morphologyEx(mask, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (close, close)))
+        out[tag] = mask
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cv_vectors.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, "cv2", cv2.__version__)

@@ -58,6 +58,12 @@ REF_FLAGS = {
         "first": ("string", "000000"), "foreground_disp": ("string", ""), "last": ("string", "000000"),
         "output": ("string", ""), "rig": ("string", ""), "threads": ("int32", "-1"),
     },
+    "GenerateForegroundMasks": {  # source/render/GenerateForegroundMasks.cpp:43-55
+        "background_color": ("string", ""), "background_frame": ("string", "000000"), "blur_radius": ("int32", "1"),
+        "cameras": ("string", ""), "color": ("string", ""), "first": ("string", ""), "foreground_masks": ("string", ""),
+        "last": ("string", ""), "morph_closing_size": ("int32", "4"), "rig": ("string", ""), "threads": ("int32", "-1"),
+        "threshold": ("double", "0.04"), "width": ("int32", "2048"),
+    },
     "UpsampleDisparity": {
         "background_disp": ("string", ""), "background_frame": ("string", "000000"), "cameras": ("string", ""),
         "color": ("string", ""), "disparity": ("string", ""), "first": ("string", "000000"),
@@ -303,3 +309,109 @@ def test_apps_end_to_end(tmp_path, cuda, oracle):
     assert not os.path.exists(os.path.join(out, "disparity_upsample", "cam0"))
     # Lanczos ringing next to the NaN->1e-4 fill gives values near zero: absolute floor on the tolerance
     assert (np.abs(up - ref) <= 2e-6 * np.abs(ref) + 2e-7).all()
+
+
+def _read_exr_y(path):
+    """Minimal reader of the single-channel float scan-line EXR io.h writes (OpenEXR file layout)."""
+    import struct
+    b = open(path, "rb").read()
+    assert struct.unpack("<I", b[:4])[0] == 20000630 and struct.unpack("<I", b[4:8])[0] == 2
+    pos, attrs = 8, {}
+    while b[pos] != 0:
+        e = b.index(b"\0", pos)
+        name = b[pos:e].decode()
+        pos = e + 1
+        e = b.index(b"\0", pos)
+        typ = b[pos:e].decode()
+        pos = e + 1
+        size = struct.unpack("<I", b[pos:pos + 4])[0]
+        attrs[name] = (typ, b[pos + 4:pos + 4 + size])
+        pos += 4 + size
+    pos += 1
+    assert attrs["compression"][1] == b"\0" and attrs["channels"][1][:2] == b"Y\0"
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    offs = struct.unpack("<%dQ" % h, b[pos:pos + 8 * h])
+    out = np.empty((h, w), np.float32)
+    for y in range(h):
+        yy, nbytes = struct.unpack("<iI", b[offs[y]:offs[y] + 8])
+        assert yy == y and nbytes == w * 4
+        out[y] = np.frombuffer(b[offs[y] + 8:offs[y] + 8 + nbytes], np.float32)
+    return out
+
+
+@pytest.mark.gpu
+def test_debug_images_exr_and_foreground_masks(tmp_path, cuda):
+    """a20: --save_debug_images writes what PyramidLevel::saveDebugImages writes (8-bit cost / confidence PNGs, the red
+    mismatch overlay, the 16-bit disparity preview), --output_formats=exr writes a readable EXR; §8(f): the
+    GenerateForegroundMasks app against the same sequence of cv2 calls the reference's code makes."""
+    W = H = 64
+    S = 4
+    rig = synth.ring_rig(S, W, H, kind="FTHETA")
+    colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=3))
+    inp, out = str(tmp_path / "in"), str(tmp_path / "out")
+    write_dataset(inp, rig, [colors], 2)
+    run("DerpCLI", "--input_root=" + inp, "--output_root=" + out, "--partial_coverage=true", "--num_depths=32",
+        "--output_formats=png,exr", "--save_debug_images=true", "--mismatches_start_level=0")
+    disp = read_pfm(os.path.join(out, "disparity_levels", "level_0", "cam1", "000000.pfm"))
+    exr = _read_exr_y(os.path.join(out, "disparity_levels", "level_0", "cam1", "000000.exr"))
+    assert np.array_equal(exr.view(np.uint32), disp.view(np.uint32))
+    # the same level through the binding, for cost / confidence / mismatch mask
+    ctx = capi.Context(cuda, capi.rig_descs(rig))
+    ctx.level_begin(W // 2, H // 2, level=1, num_levels=2, full_width=W, full_height=H)
+    ctx.set_colors([synth.downscale_area(c, 2) for c in colors])
+    ctx.process_level(num_depths=32, mismatches_start_level=0)
+    c1 = [ctx.get_disparity(d, want_cost=False) for d in range(S)]
+    ctx.level_begin(W, H, level=0, num_levels=2, full_width=W, full_height=H)
+    ctx.set_colors(colors)
+    for d in range(S):
+        ctx.upsample_from(d, c1[d])
+    ctx.process_level(num_depths=32, mismatches_start_level=0)
+    d1, cost, conf = ctx.get_disparity(1)
+    assert np.array_equal(d1.view(np.uint32), disp.view(np.uint32))
+
+    def u8(v):
+        with np.errstate(invalid="ignore"):
+            r = np.where(np.isnan(v), 0, np.clip(np.rint(np.nan_to_num(v, nan=0.0, posinf=1e9, neginf=-1e9)), 0, 255))
+        return r.astype(np.uint8)
+
+    png = cv2.imread(os.path.join(out, "cost", "level_0", "cam1", "000000.png"), cv2.IMREAD_UNCHANGED)
+    assert png.dtype == np.uint8 and png.shape == (H, W)
+    assert np.array_equal(png, u8(cost * np.float32(255.0 / 100.0)))
+    png = cv2.imread(os.path.join(out, "confidence", "level_0", "cam1", "000000.png"), cv2.IMREAD_UNCHANGED)
+    assert np.array_equal(png, u8(conf * np.float32(255.0 * 100.0)))
+    ov = cv2.imread(os.path.join(out, "mismatches", "level_0", "cam1", "000000.png"), cv2.IMREAD_UNCHANGED)
+    assert ov.dtype == np.uint8 and ov.shape == (H, W, 4)
+    mm, fov = ctx.get_mismatch_mask(1).astype(bool), ctx.get_fov_mask(1).astype(bool)
+    assert (ov[fov & mm] == np.array([0, 0, 255, 255], np.uint8)).all()
+    assert (ov[~fov] == 0).all()
+    keep = fov & ~mm
+    assert np.array_equal(ov[keep][:, 0], u8(d1 * np.float32(255.0))[keep]) and (ov[keep][:, 3] == 255).all()
+    prev = cv2.imread(os.path.join(out, "disparity_levels", "level_0", "cam1", "000000.png"), cv2.IMREAD_UNCHANGED)
+    assert prev.dtype == np.uint16
+    ctx.close()
+
+    # ---- GenerateForegroundMasks
+    rng = np.random.RandomState(2)
+    bgdir, fgdir, mdir = str(tmp_path / "bg"), str(tmp_path / "fg"), str(tmp_path / "masks")
+    Wf, Hf = 120, 90
+    for s in range(S):
+        bgimg = np.clip(rng.normal(30000, 9000, (Hf, Wf, 3)), 0, 65535).astype(np.uint16)
+        fr = bgimg.copy()
+        fr[20:60, 30 + 5 * s:80] = rng.randint(0, 65536, (40, 50 - 5 * s, 3)).astype(np.uint16)
+        os.makedirs(os.path.join(bgdir, "cam%d" % s))
+        os.makedirs(os.path.join(fgdir, "cam%d" % s))
+        cv2.imwrite(os.path.join(bgdir, "cam%d" % s, "000000.png"), bgimg)
+        cv2.imwrite(os.path.join(fgdir, "cam%d" % s, "000007.png"), fr)
+    run("GenerateForegroundMasks", "--rig=" + inp + "/rigs/rig_calibrated.json", "--color=" + fgdir, "--background_color=" + bgdir,
+        "--foreground_masks=" + mdir, "--first=000007", "--last=000007", "--width=80")
+    Wo, Ho = 80, int(np.rint(80 * Hf / np.float32(Wf)))
+    a32 = np.float32(1.0) / np.float32(65535.0)
+    for s in range(S):
+        b = cv2.resize(cv2.imread(os.path.join(bgdir, "cam%d" % s, "000000.png"), cv2.IMREAD_UNCHANGED), (Wo, Ho), interpolation=cv2.INTER_AREA)
+        f = cv2.resize(cv2.imread(os.path.join(fgdir, "cam%d" % s, "000007.png"), cv2.IMREAD_UNCHANGED), (Wo, Ho), interpolation=cv2.INTER_AREA)
+        diff = cv2.absdiff(cv2.GaussianBlur(b, (3, 3), 0).astype(np.float32) * a32, cv2.GaussianBlur(f, (3, 3), 0).astype(np.float32) * a32)
+        m = (np.sqrt((diff.astype(np.float64) ** 2).sum(-1)) > np.float64(np.float32(0.04))).astype(np.uint8)
+        m = cv2.morphologyEx(m, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (4, 4)))
+        got = cv2.imread(os.path.join(mdir, "cam%d" % s, "000007.png"), cv2.IMREAD_UNCHANGED)
+        assert got.dtype == np.uint8 and np.array_equal(got, m * 255), s

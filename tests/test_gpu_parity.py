@@ -508,3 +508,20 @@ def test_level_handoff_in_memory(cuda, oracle):
             ctx.upsample_from(d, coarse[d], cmasks[d] if use_fg else None, masks[d] if use_fg else None)
             assert same_float_bits(got[d], ctx.get_disparity(d, want_cost=False)).all(), (use_fg, d)
         ctx.close()
+
+
+def test_foreground_mask(cuda, oracle):
+    """§8(f) GenerateForegroundMasks body (BackgroundSubtractionUtil.h:20-59): CUDA vs the oracle restatement (itself
+    pinned to the cv2 call sequence, tests/test_oracle_cv.py), bit for bit."""
+    rng = np.random.RandomState(6)
+    H, W = 150, 211
+    bg = np.clip(rng.normal(30000, 9000, (H, W, 3)), 0, 65535).astype(np.uint16)
+    fr = np.clip(bg.astype(np.int64) + rng.randint(-1500, 1500, bg.shape), 0, 65535).astype(np.uint16)
+    fr[40:100, 60:150] = rng.randint(0, 65536, (60, 90, 3)).astype(np.uint16)
+    for blur, close, thr in ((1, 4, 0.04), (0, 3, 0.04), (1, 0, 0.02), (1, 7, 0.06)):
+        g = cuda.foreground_mask(bg, fr, blur, thr, close)
+        o = oracle.foreground_mask(bg, fr, blur, thr, close)
+        assert np.array_equal(g, o), (blur, close, thr)
+        assert 0.05 < g.mean() < 0.95
+    with pytest.raises(capi.DerpError):
+        cuda.foreground_mask(bg, fr, 2, 0.04, 4)

@@ -45,3 +45,11 @@ def test_resize_area_bit_exact(oracle, size):
     w, h = size
     got = oh.resize_area(oracle, G["area_src"], w, h)
     assert np.array_equal(got, G["area_%dx%d" % (w, h)])
+
+
+@pytest.mark.parametrize("tag,blur,close", [("fg_mask_b1_c4", 1, 4), ("fg_mask_b0_c3", 0, 3), ("fg_mask_b1_c0", 1, 0)])
+def test_foreground_mask_bit_exact(oracle, tag, blur, close):
+    """generateForegroundMask (BackgroundSubtractionUtil.h:20-59) against the same sequence of cv2 4.13 calls."""
+    got = oracle.foreground_mask(G["fg_template"], G["fg_frame"], blur, 0.04, close)
+    assert np.array_equal(got, G[tag])
+    assert 0 < got.mean() < 1
