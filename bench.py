@@ -53,7 +53,14 @@ WORKLOADS = {
     "bf32_cfg1": (4, 512, 512, 32, "RECTILINEAR"),  # BASELINE.json configs[0] (parity case; small)
     # BASELINE.json configs[1] as the reference runs it: 5-level coarse-to-fine frame (see CoarseToFine)
     "c2f5": (16, 2048, 2048, 128, "FTHETA"),
+    # BASELINE.json configs[3]: ONE 24-camera 4096^2 frame, 256 candidates + bilateral, destination cameras dealt to the GPUs
+    # (strong scaling); two levels so that the mismatch stage and its all-gather of disparity planes are on the path
+    "cfg4": (24, 4096, 4096, 256, "FTHETA"),
+    # BASELINE.json configs[4]: 16 cameras x 30 frames, 5-level coarse-to-fine per frame with the temporal filter after every
+    # level (scripts/render/pipeline.py:364-408), contiguous frame blocks per GPU, halo frames exchanged over NVLink
+    "cfg5": (16, 2048, 2048, 128, "FTHETA"),
 }
+CFG5_FRAMES = 30
 C2F_LEVELS = 5
 C2F_CPU_LEVEL = 3  # the level the CPU arm times (256 x 256 at 2048 full size): seconds, not minutes, of reference code
 MIN_DEPTH, MAX_DEPTH = 0.5, 1e4
@@ -652,6 +659,244 @@ def run_reference_c2f(args, rig, colors):
     return 0
 
 
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return torch, dist, world, rank, local_rank, dev
+
+
+def run_cfg4(args):
+    """Workload cfg4 (BASELINE.json configs[3]): one 24-camera 4096^2 frame per step, STRONG scaling — the destination
+    cameras are dealt round-robin to the GPUs (shard.camera_shard).  Level 1 (2048^2): brute force with 256 candidates;
+    level 0 (4096^2): proposals, ping-pong, mismatch handling, joint bilateral (radius 5), median.  Every stage is
+    independent per destination except mismatch handling, which reads every camera's pre-update disparity: ONE NCCL
+    all-gather of the per-camera planes per mismatch level, inside the timed region."""
+    torch, dist, world, rank, local_rank, dev = _dist_setup()
+    from facebook360_dep_b200 import capi, pipeline, shard, synth
+    S, W, H, D, kind = WORKLOADS["cfg4"]
+    rig = synth.ring_rig(S, W, H, kind=kind)
+    t0 = time.time()
+    colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=42), device=dev)
+    log("[bench] rank %d rendered %d x %dx%d frames in %.1fs" % (rank, S, W, H, time.time() - t0))
+    cuda = capi.load_cuda()
+    own = shard.camera_shard(S, world, rank)
+    ctx = capi.Context(cuda, capi.rig_descs(rig), own, device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    full = [torch.from_numpy(np.ascontiguousarray(c)).to(dev) for c in colors]
+    half = [torch.empty((H // 2, W // 2, 3), dtype=torch.uint16, device=dev) for _ in range(S)]
+    for s in range(S):
+        cuda.check(cuda.lib.derp_downscale_area(local_rank, full[s].data_ptr(), W, H, half[s].data_ptr(), W // 2, H // 2))
+    del colors
+    kw = dict(num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True, mismatches_start_level=0)
+    stats = {"evals": 0, "gather_bytes": 0, "gather_ms": 0.0}
+
+    def frame():
+        stats["evals"] = 0
+        stats["gather_bytes"] = 0
+        stats["gather_ms"] = 0.0
+        for level, imgs, (w, h) in ((1, half, (W // 2, H // 2)), (0, full, (W, H))):
+            ctx.level_begin(w, h, level=level, num_levels=2, full_width=W, full_height=H)
+            ctx.set_colors_ptr([t.data_ptr() for t in imgs])
+            if level == 0:
+                for d in range(len(own)):
+                    ctx.upsample_from_kept(d)
+            ctx.level_estimate(**kw)
+            stats["evals"] += ctx.get_counters()[0]
+            if level == 0:  # Derp.cpp:726-728: mismatch handling on levels <= mismatches_start_level, not the coarsest
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                stats["gather_bytes"] += pipeline.all_gather_disparities_device(ctx, S, dev)
+                g1.record(stream)
+                torch.cuda.synchronize()
+                stats["gather_ms"] += g0.elapsed_time(g1)
+                if world > 1:
+                    dist.barrier()  # every rank holds its copy before any rank updates its planes
+                ctx.mismatches_gathered()
+            ctx.level_filter(**kw)
+            if level == 1:
+                ctx.level_keep()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        frame()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile(True)
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        frame()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    sweep_ms, sweep_n = ctx.get_profile()
+    ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms, evals_all = shard.reduce_step(ms, stats["evals"], dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = measured_peak_gbs()
+    line = {
+        "metric": METRIC, "value": evals_all * args.steps / (ms / 1e3) / 1e6, "unit": "Mpix·cand/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 cost, f64 projection, u16 texels", "data": "synthetic",
+        "config": dict(static_config("cfg4"), parallelism="destination cameras round-robin over %d GPU(s)" % world, levels=2,
+                       frames_per_step=1),
+        "work": {"cost_evaluations_per_frame": evals_all},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "exchange": {"collective": "NCCL all-gather of the per-camera disparity planes before mismatch handling (level 0)",
+                     "bytes_received_per_rank_per_frame": stats["gather_bytes"], "ms_per_frame_rank0": stats["gather_ms"],
+                     "GBps_rank0": (stats["gather_bytes"] / 1e9) / (stats["gather_ms"] / 1e3) if stats["gather_ms"] else None},
+        "roofline": {"bound": "hbm", "kernel": "sweep (rank 0's destinations, level 1)", "peak": peak, "unit": "GB/s",
+                     "peak_source": peak_src, "ms_per_launch": sweep_ms / max(1, sweep_n), "launches_timed": int(sweep_n),
+                     "kernel_share_of_step": sweep_ms / ms if ms else None, "achieved": None, "frac": None, "traffic": None,
+                     "note": "see workload bf128_l0 for the sweep's roofline; here the share of the step and the exchange are "
+                             "what is measured"},
+        "e2e": None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_cfg5(args):
+    """Workload cfg5 (BASELINE.json configs[4]): a 30-frame sequence of the 16-camera rig, contiguous frame blocks per
+    GPU.  Like scripts/render/pipeline.py:364-408, every pyramid level is estimated for all frames (processLevel), then
+    temporally filtered (TemporalBilateralFilter, time_radius 2), and the FILTERED level feeds the next finer one.  The
+    filter needs the colour and disparity of the +-2 neighbouring frames: the boundary frames travel rank to rank over
+    NVLink (NCCL send/recv of device tensors) inside the timed region."""
+    torch, dist, world, rank, local_rank, dev = _dist_setup()
+    from facebook360_dep_b200 import capi, pipeline, shard, synth
+    S, W, H, D, kind = WORKLOADS["cfg5"]
+    F = CFG5_FRAMES if not args.frames else args.frames
+    rig = synth.ring_rig(S, W, H, kind=kind)
+    cuda = capi.load_cuda()
+    ctx = capi.Context(cuda, capi.rig_descs(rig), device=local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    first, last = shard.frame_block(F, world, rank)
+    levels = C2F_LEVELS
+    pyr = {}  # frame -> level -> uint16 [S,h,w,3] on the device
+    t0 = time.time()
+    for f in range(first, last):
+        colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=42, shift=(0.01 * f, 0, 0)), device=dev)
+        lv = {0: torch.stack([torch.from_numpy(np.ascontiguousarray(c)).to(dev) for c in colors])}
+        for k in range(1, levels):
+            lv[k] = torch.empty((S, H >> k, W >> k, 3), dtype=torch.uint16, device=dev)
+            for s in range(S):
+                cuda.check(cuda.lib.derp_downscale_area(local_rank, lv[0][s].data_ptr(), W, H, lv[k][s].data_ptr(), W >> k, H >> k))
+        pyr[f] = lv
+    log("[bench] rank %d: frames %d..%d rendered and resized in %.1fs" % (rank, first, last - 1, time.time() - t0))
+    fov = {}
+    for k in range(levels):
+        ctx.level_begin(W >> k, H >> k, level=k, num_levels=levels, full_width=W, full_height=H)
+        fov[k] = torch.stack([torch.from_numpy(ctx.get_fov_mask(d)).to(dev) for d in range(S)])
+    kw = dict(num_depths=D, min_depth_m=MIN_DEPTH, max_depth_m=MAX_DEPTH, partial_coverage=True)
+    stats = {"evals": 0, "halo_bytes": 0, "halo_ms": 0.0}
+
+    def sequence():
+        stats["evals"] = 0
+        stats["halo_bytes"] = 0
+        filtered = {}  # frame -> f32 [S,h,w] of the level just finished
+        for k in range(levels - 1, -1, -1):
+            w, h = W >> k, H >> k
+            est = {}
+            for f in range(first, last):
+                ctx.level_begin(w, h, level=k, num_levels=levels, full_width=W, full_height=H)
+                ctx.set_colors_ptr([pyr[f][k][s].data_ptr() for s in range(S)])
+                if k < levels - 1:
+                    for d in range(S):
+                        cuda.check(cuda.lib.derp_upsample_from(ctx.h, d, filtered[f][d].data_ptr(), W >> (k + 1), H >> (k + 1), None, None))
+                ctx.process_level(**kw)
+                stats["evals"] += ctx.get_counters()[0]
+                out = torch.empty((S, h, w), dtype=torch.float32, device=dev)
+                for d in range(S):
+                    cuda.check(cuda.lib.derp_get_disparity(ctx.h, d, out[d].data_ptr(), None, None))
+                est[f] = out
+            ctx.sync()
+            local = {f: (pyr[f][k], est[f]) for f in range(first, last)}
+            filtered, nbytes = pipeline.temporal_filter_block_device(cuda, local, F, fov[k], time_radius=2, gpu=local_rank)
+            stats["halo_bytes"] += nbytes
+        return filtered
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup)):
+        sequence()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        sequence()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # the exchange alone, for its bandwidth: level-0 boundary frames
+    local0 = {f: (pyr[f][0], torch.zeros((S, H, W), dtype=torch.float32, device=dev)) for f in range(first, last)}
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record(stream)
+    _, halo0 = pipeline.exchange_halos_device(local0, F, 2)
+    h1.record(stream)
+    barrier()
+    halo_ms = h0.elapsed_time(h1)
+    ms, evals_all = shard.reduce_step(ms, stats["evals"], dev)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    line = {
+        "metric": METRIC, "value": evals_all * args.steps / (ms / 1e3) / 1e6, "unit": "Mpix·cand/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 cost, f64 projection, u16 texels", "data": "synthetic",
+        "config": dict(static_config("cfg5"), frames=F, levels=levels, time_radius=2,
+                       parallelism="contiguous frame blocks over %d GPU(s), +-2-frame halo over NCCL" % world),
+        "work": {"cost_evaluations_per_sequence": evals_all, "frames_per_s": F * args.steps / (ms / 1e3)},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "exchange": {"collective": "NCCL send/recv of the +-2 boundary frames (colour + disparity) after every level",
+                     "bytes_received_rank0_per_sequence": stats["halo_bytes"],
+                     "level0_bytes_received_rank0": halo0, "level0_ms": halo_ms,
+                     "level0_GBps_rank0": (halo0 / 1e9) / (halo_ms / 1e3) if halo_ms and halo0 else None},
+        "roofline": None, "e2e": None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def cfg1_full(cuda, device):
     """BASELINE.json configs[0] in full on both sides: 4-camera rectilinear rig, 512x512, 32 candidates, one level.
     CPU: every candidate slice of every destination through the reference's own code (winner = first strict minimum
@@ -725,11 +970,16 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-c2f", action="store_true")
     ap.add_argument("--no-cfg1", action="store_true")
+    ap.add_argument("--frames", type=int, default=0, help="cfg5: sequence length (default 30)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "c2f5":
         return run_c2f(args)
+    if args.workload == "cfg4":
+        return run_cfg4(args)
+    if args.workload == "cfg5":
+        return run_cfg5(args)
 
     import torch
     import torch.distributed as dist

@@ -156,6 +156,9 @@ _SIGS = {
                                            C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "derp_upsample_disparity": (C.c_int, [C.c_int, _p(CameraDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "derp_device_alloc": (C.c_int, [C.c_int, C.c_size_t, _p(C.c_void_p)]),
+    "derp_device_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "derp_device_copy": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "derp_downscale_area": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "derp_foreground_mask": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                        C.c_void_p]),

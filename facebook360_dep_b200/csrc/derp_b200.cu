@@ -1151,7 +1151,7 @@ int derp_upsample_from(DerpCtx* c, int dst, const float* coarse, int coarse_w, i
   DevBuf<float> dCoarse, tA, tB;
   DevBuf<uint8_t> dMc, dMu, dFovC;
   CU(dCoarse.ensure(nc));
-  CU(cudaMemcpyAsync(dCoarse.p, coarse, nc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(dCoarse.p, coarse, nc * sizeof(float), cudaMemcpyDefault, c->stream));  // host or device plane
   if (useFg) {
     if (!coarse_mask || !fine_mask) return fail(DERP_EINVAL, "derp_upsample_from: masks required");
     if (!c->haveBg) return fail(DERP_ESTATE, "derp_upsample_from: background disparity not set");
@@ -1297,6 +1297,37 @@ int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, u
   CU(cudaGetLastError());
   if (!dstDev) CU(cudaMemcpy(dst, dD.p, nd * sizeof(uint16_t), cudaMemcpyDeviceToHost));
   else if (!srcDev) CU(cudaDeviceSynchronize());  // the staged source is freed on return
+  return DERP_OK;
+}
+
+int derp_device_alloc(int device, size_t bytes, void** out) {
+  if (!out) return fail(DERP_EINVAL, "derp_device_alloc: null out");
+  CU(cudaSetDevice(device));
+  CU(cudaMalloc(out, bytes ? bytes : 1));
+  return DERP_OK;
+}
+int derp_device_free(int device, void* p) {
+  if (!p) return DERP_OK;
+  CU(cudaSetDevice(device));
+  CU(cudaFree(p));
+  return DERP_OK;
+}
+int derp_device_copy(int device, void* dst, const void* src, size_t bytes) {
+  if (!dst || !src) return fail(DERP_EINVAL, "derp_device_copy: null pointer");
+  CU(cudaSetDevice(device));
+  // a source (or destination) on another GPU: make sure the direct NVLink path is enabled
+  for (const void* p : {src, (const void*)dst}) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice && a.device != device) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, device, a.device) == cudaSuccess && can) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(DERP_ECUDA, cudaGetErrorString(e));
+      }
+    }
+    cudaGetLastError();
+  }
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
   return DERP_OK;
 }
 
@@ -1632,19 +1663,40 @@ int derp_temporal_filter(int device, int width, int height, int num_frames, cons
     return fail(DERP_EINVAL, "derp_temporal_filter: bad arguments");
   CU(cudaSetDevice(device));
   const size_t n = (size_t)width * height;
-  DevBuf<uint2> dG;
-  DevBuf<float> dD, dOut;
-  DevBuf<uint8_t> dM, dStage;
+  // grow-only scratch per host thread (one thread drives one GPU): a sequence filters thousands of (frame, camera)
+  // windows of the same size, cudaMalloc per call would dominate the 0.8 ms kernel
+  struct Scratch {
+    DevBuf<uint2> dG;
+    DevBuf<float> dD, dOut;
+    DevBuf<uint8_t> dM, dStage;
+    int device = -1;
+  };
+  static thread_local Scratch sc;
+  if (sc.device != device) {  // the thread moved to another GPU: the old buffers belong to the old device
+    if (sc.device >= 0) {
+      cudaSetDevice(sc.device);
+      sc.dG.release();
+      sc.dD.release();
+      sc.dOut.release();
+      sc.dM.release();
+      sc.dStage.release();
+      CU(cudaSetDevice(device));
+    }
+    sc.device = device;
+  }
+  DevBuf<uint2>& dG = sc.dG;
+  DevBuf<float>&dD = sc.dD, &dOut = sc.dOut;
+  DevBuf<uint8_t>&dM = sc.dM, &dStage = sc.dStage;
   CU(dG.ensure(n * num_frames));
   CU(dD.ensure(n * num_frames));
   CU(dM.ensure(n * num_frames));
   CU(dOut.ensure(n));
   CU(dStage.ensure(n * 6));
-  for (int t = 0; t < num_frames; ++t) {
-    CU(cudaMemcpy(dStage.p, guides[t], n * 6, cudaMemcpyHostToDevice));
+  for (int t = 0; t < num_frames; ++t) {  // frames may live in host or device memory (e.g. halo frames received over NVLink)
+    CU(cudaMemcpy(dStage.p, guides[t], n * 6, cudaMemcpyDefault));
     packColorKernel<<<grid1(n), 256>>>(n, reinterpret_cast<const uint16_t*>(dStage.p), dG.p + (size_t)t * n);
-    CU(cudaMemcpy(dD.p + (size_t)t * n, disps[t], n * sizeof(float), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dM.p + (size_t)t * n, masks[t], n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dD.p + (size_t)t * n, disps[t], n * sizeof(float), cudaMemcpyDefault));
+    CU(cudaMemcpy(dM.p + (size_t)t * n, masks[t], n, cudaMemcpyDefault));
   }
   TemporalArgs a;
   a.W = width;
@@ -1663,7 +1715,7 @@ int derp_temporal_filter(int device, int width, int height, int num_frames, cons
   a.out = dOut.p;
   temporalKernel<<<grid2(width, height), block2()>>>(a);
   CU(cudaGetLastError());
-  CU(cudaMemcpy(out, dOut.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, dOut.p, n * sizeof(float), cudaMemcpyDefault));
   return DERP_OK;
 }
 

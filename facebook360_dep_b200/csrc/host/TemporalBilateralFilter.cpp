@@ -4,8 +4,15 @@
 // the temporalKernel of libderp_b200.so (derp_temporal_filter).
 // Reproduced verbatim (parity > elegance): weights are passed as (weight_b, weight_g, weight_b) and
 // --weight_r is ignored (TemporalBilateralFilter.cpp:176-178).
+//
+// Frames live in DEVICE memory between filter calls: every frame of a GPU's block is decoded and uploaded once (the
+// reference re-reads the +-time_radius window from disk for every frame, TemporalBilateralFilter.cpp:139-160), and with
+// --gpus > 1 the halo frames of a block are copied from the neighbouring GPU's store over NVLink (derp_device_copy)
+// after a rendezvous of the worker threads instead of being decoded a second time.
+#include <map>
 #include <thread>
 
+#include "exchange.h"
 #include "io.h"
 
 static const int kTemporalSpaceRadiusMin = 1;
@@ -86,11 +93,95 @@ static std::vector<std::vector<uint8_t>> fovMasks(const io::Rig& rig, const std:
   return out;
 }
 
-// One GPU worker: its device and the FOV masks (level size only: computed once per worker, not per frame)
+// One frame of the level on a GPU: per destination camera colour (u16 x 3), disparity (f32) and mask (u8) planes
+struct DevFrame {
+  int device = 0, W = 0, H = 0;
+  std::vector<void*> color, disp, mask;
+  bool valid = false;
+};
+
+// One GPU worker: its device, the FOV masks (level size only: computed once per worker) and its resident frames
 struct Worker {
   int device = 0;
   std::vector<std::vector<uint8_t>> fov;
+  std::map<int, DevFrame> frames;
 };
+
+static void freeFrame(DevFrame& f) {
+  for (auto* v : {&f.color, &f.disp, &f.mask})
+    for (void* p : *v) derp_device_free(f.device, p);
+  f = DevFrame();
+}
+
+static bool frameOnDisk(int frame, const io::Rig& rig, const std::vector<int>& dst) {
+  const std::string& ref = rig.ids[dst[0]];
+  auto has = [&](const std::string& dir) {
+    const std::string levelDir = io::levelDir(dir, FLAGS_level) + "/" + ref;
+    return fs::exists(fs::path(levelDir) / (io::zeroPad(frame) + io::firstExtension(levelDir)));
+  };
+  return frame >= 0 && has(FLAGS_color) && has(FLAGS_disparity) && (!FLAGS_use_foreground_masks || has(FLAGS_foreground_masks));
+}
+
+// decode one frame of the level (all destination cameras) and upload it
+static void loadFrame(int frame, const io::Rig& rig, const std::vector<int>& dst, Worker& wk) {
+  DevFrame df;
+  df.device = wk.device;
+  const std::string name = io::zeroPad(frame);
+  for (size_t ci = 0; ci < dst.size(); ++ci) {
+    const std::string& id = rig.ids[dst[ci]];
+    int w, h, W, H;
+    const std::vector<uint16_t> color = io::loadColor16(io::imagePath(io::levelDir(FLAGS_color, FLAGS_level), id, name), &W, &H);
+    const std::vector<float> disp = io::loadFloat(io::imagePath(io::levelDir(FLAGS_disparity, FLAGS_level), id, name), &w, &h);
+    CHECK(w == W && h == H) << "colour / disparity size mismatch";
+    if (wk.fov.empty()) wk.fov = fovMasks(rig, dst, W, H, wk.device);
+    std::vector<uint8_t> mask;
+    if (FLAGS_use_foreground_masks) {
+      mask = io::loadMask(io::imagePath(io::levelDir(FLAGS_foreground_masks, FLAGS_level), id, name), &w, &h);
+      CHECK(w == W && h == H) << "mask size mismatch";
+      for (size_t i = 0; i < mask.size(); ++i) mask[i] = mask[i] & wk.fov[ci][i];
+    } else {
+      mask = wk.fov[ci];
+    }
+    df.W = W;
+    df.H = H;
+    const size_t n = (size_t)W * H;
+    void *pc, *pd, *pm;
+    DERP_CALL(derp_device_alloc(wk.device, n * 6, &pc));
+    DERP_CALL(derp_device_alloc(wk.device, n * 4, &pd));
+    DERP_CALL(derp_device_alloc(wk.device, n, &pm));
+    DERP_CALL(derp_device_copy(wk.device, pc, color.data(), n * 6));
+    DERP_CALL(derp_device_copy(wk.device, pd, disp.data(), n * 4));
+    DERP_CALL(derp_device_copy(wk.device, pm, mask.data(), n));
+    df.color.push_back(pc);
+    df.disp.push_back(pd);
+    df.mask.push_back(pm);
+  }
+  df.valid = true;
+  wk.frames[frame] = df;
+}
+
+// copy a frame that is resident on a peer GPU (NVLink) instead of decoding it again
+static void fetchFrame(int frame, const DevFrame& src, Worker& wk) {
+  DevFrame df;
+  df.device = wk.device;
+  df.W = src.W;
+  df.H = src.H;
+  const size_t n = (size_t)src.W * src.H;
+  for (size_t ci = 0; ci < src.color.size(); ++ci) {
+    void *pc, *pd, *pm;
+    DERP_CALL(derp_device_alloc(wk.device, n * 6, &pc));
+    DERP_CALL(derp_device_alloc(wk.device, n * 4, &pd));
+    DERP_CALL(derp_device_alloc(wk.device, n, &pm));
+    DERP_CALL(derp_device_copy(wk.device, pc, src.color[ci], n * 6));
+    DERP_CALL(derp_device_copy(wk.device, pd, src.disp[ci], n * 4));
+    DERP_CALL(derp_device_copy(wk.device, pm, src.mask[ci], n));
+    df.color.push_back(pc);
+    df.disp.push_back(pd);
+    df.mask.push_back(pm);
+  }
+  df.valid = true;
+  wk.frames[frame] = df;
+}
 
 static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst, Worker& wk) {  // :121-184
   int first = 0, last = INT32_MAX;
@@ -104,37 +195,20 @@ static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst
   const int spaceRadius = FLAGS_space_radius == -1
       ? (int)std::max(std::ceil(kTemporalSpaceRadiusMax * scale), float(kTemporalSpaceRadiusMin))
       : FLAGS_space_radius;
-  std::vector<std::vector<uint8_t>>& fov = wk.fov;
+  for (int f = first; f <= last; ++f)
+    if (!wk.frames.count(f)) loadFrame(f, rig, dst, wk);  // not resident (first use, or beyond what the peers hold)
+  const int W = wk.frames[cur].W, H = wk.frames[cur].H;
   for (size_t ci = 0; ci < dst.size(); ++ci) {
     const std::string& id = rig.ids[dst[ci]];
-    std::vector<std::vector<uint16_t>> colors(T);
-    std::vector<std::vector<float>> disps(T);
-    std::vector<std::vector<uint8_t>> masks(T);
-    int W = 0, H = 0;
-    for (int t = 0; t < T; ++t) {
-      const std::string frame = io::zeroPad(first + t);
-      int w, h;
-      colors[t] = io::loadColor16(io::imagePath(io::levelDir(FLAGS_color, FLAGS_level), id, frame), &w, &h);
-      W = w;
-      H = h;
-      disps[t] = io::loadFloat(io::imagePath(io::levelDir(FLAGS_disparity, FLAGS_level), id, frame), &w, &h);
-      CHECK(w == W && h == H) << "colour / disparity size mismatch";
-      if (fov.empty()) fov = fovMasks(rig, dst, W, H, wk.device);
-      if (FLAGS_use_foreground_masks) {
-        masks[t] = io::loadMask(io::imagePath(io::levelDir(FLAGS_foreground_masks, FLAGS_level), id, frame), &w, &h);
-        CHECK(w == W && h == H) << "mask size mismatch";
-        for (size_t i = 0; i < masks[t].size(); ++i) masks[t][i] = masks[t][i] & fov[ci][i];
-      } else {
-        masks[t] = fov[ci];
-      }
-    }
     std::vector<const uint16_t*> g(T);
     std::vector<const float*> dp(T);
     std::vector<const uint8_t*> mp(T);
     for (int t = 0; t < T; ++t) {
-      g[t] = colors[t].data();
-      dp[t] = disps[t].data();
-      mp[t] = masks[t].data();
+      const DevFrame& df = wk.frames[first + t];
+      CHECK(df.W == W && df.H == H) << "frame size mismatch";
+      g[t] = static_cast<const uint16_t*>(df.color[ci]);
+      dp[t] = static_cast<const float*>(df.disp[ci]);
+      mp[t] = static_cast<const uint8_t*>(df.mask[ci]);
     }
     std::vector<float> out((size_t)W * H);
     DERP_CALL(derp_temporal_filter(wk.device, W, H, T, g.data(), dp.data(), mp.data(), cur - first, (float)FLAGS_sigma,
@@ -150,6 +224,14 @@ static void filterFrame(int cur, const io::Rig& rig, const std::vector<int>& dst
         id / io::zeroPad(cur);
     for (const auto& ext : formats) io::saveDisparity(stem, ext, out.data(), W, H);
   }
+  // frames before the next window are never needed again
+  for (auto it = wk.frames.begin(); it != wk.frames.end();)
+    if (it->first < cur + 1 - FLAGS_time_radius) {
+      freeFrame(it->second);
+      it = wk.frames.erase(it);
+    } else {
+      ++it;
+    }
 }
 
 int main(int argc, char** argv) {
@@ -163,22 +245,45 @@ int main(int argc, char** argv) {
   const io::Rig rig = io::loadRig(FLAGS_rig);
   const std::vector<int> dst = io::filterDestinations(rig, FLAGS_cameras);
   CHECK_GT(dst.size(), 0u) << "no destination cameras!";
-  // Frames are independent (every frame reads its +-time_radius neighbours from disk, like the reference): contiguous
-  // frame blocks per GPU, one worker thread per GPU.
+  // Contiguous frame blocks per GPU, one worker thread per GPU.  With several GPUs every worker first
+  // makes its own block resident (as far as kMaxResident frames go), the workers meet, and each copies the halo frames
+  // it needs from the neighbour that holds them; frames nobody holds are decoded from disk on first use.
   const int firstFrame = std::stoi(FLAGS_first), numFrames = std::stoi(FLAGS_last) - firstFrame + 1;
   CHECK_GT(numFrames, 0);
   const int G = std::max(1, std::min(FLAGS_gpus, numFrames));
   LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s)";
   const int per = (numFrames + G - 1) / G;
+  const int kMaxResident = 2 * FLAGS_time_radius + 4;  // what a worker publishes to its neighbours
+  std::vector<Worker> workers(G);
+  Exchange meet(G, 0);
   std::vector<std::thread> threads;
   for (int g = 0; g < G; ++g)
     threads.emplace_back([&, g] {
-      Worker wk;
+      Worker& wk = workers[g];
       wk.device = FLAGS_gpu + g;
-      for (int i = g * per; i < std::min(numFrames, (g + 1) * per); ++i) {
-        LOG(INFO) << "Filtering images... frame " << io::zeroPad(firstFrame + i);
-        filterFrame(firstFrame + i, rig, dst, wk);
+      const int b0 = firstFrame + g * per, b1 = firstFrame + std::min(numFrames, (g + 1) * per);
+      if (G > 1) {
+        // publish: the first and last frames of the block (the ones neighbours need), bounded
+        for (int f = b0; f < b1; ++f)
+          if ((f < b0 + FLAGS_time_radius || f >= b1 - FLAGS_time_radius) && (int)wk.frames.size() < kMaxResident &&
+              frameOnDisk(f, rig, dst))
+            loadFrame(f, rig, dst, wk);
+        meet.arriveAndWait();  // every store is complete and read-only from here
+        for (int f = b0 - FLAGS_time_radius; f < b1 + FLAGS_time_radius; ++f) {
+          if (f >= b0 && f < b1) continue;
+          const int owner = (f - firstFrame) / per;
+          if (f < firstFrame || owner < 0 || owner >= G) continue;
+          const auto it = workers[owner].frames.find(f);
+          if (it != workers[owner].frames.end() && it->second.valid) fetchFrame(f, it->second, wk);
+        }
+        meet.arriveAndWait();  // all peer copies done: stores may evict from here
       }
+      for (int f = b0; f < b1; ++f) {
+        LOG(INFO) << "Filtering images... frame " << io::zeroPad(f);
+        filterFrame(f, rig, dst, wk);
+      }
+      for (auto& kv : wk.frames) freeFrame(kv.second);
+      wk.frames.clear();
     });
   for (auto& t : threads) t.join();
   return EXIT_SUCCESS;

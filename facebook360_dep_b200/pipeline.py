@@ -133,3 +133,85 @@ def sharded_mismatches(ctx, num_cams, device=None):
             planes[cam] = recv[r][i].data_ptr()
     ctx.gather_disparities(planes)
     ctx.mismatches_gathered()
+
+
+# ---- device-resident variants (one process per GPU, NCCL over NVLink): nothing below touches host memory ------------
+def exchange_halos_device(local, num_frames, time_radius):
+    """local: {frame: (color u16 [S,H,W,3], disp f32 [S,H,W])} CUDA tensors of this rank's frame block.  Moves the
+    +-time_radius boundary frames rank to rank with NCCL point-to-point ops straight from / into device memory (the
+    reference moves them as files between workers, scripts/render/pipeline.py:382-408).  Returns the halo frames and
+    the number of bytes this rank received."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1 or not local:
+        return {}, 0
+    world, rank = dist.get_world_size(), dist.get_rank()
+    some = next(iter(local.values()))
+    per = (num_frames + world - 1) // world
+    ops, recv = [], {}
+    for r in range(world):
+        left, right = shard.halo_frames(num_frames, world, r, time_radius)
+        for f in left + right:
+            o = f // per
+            if o == rank and r != rank:
+                for t in local[f]:
+                    ops.append(dist.P2POp(dist.isend, t, r))
+            elif r == rank and o != rank:
+                bufs = tuple(torch.empty_like(t) for t in some)
+                recv[f] = bufs
+                for t in bufs:
+                    ops.append(dist.P2POp(dist.irecv, t, o))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    nbytes = sum(t.numel() * t.element_size() for bufs in recv.values() for t in bufs)
+    return recv, nbytes
+
+
+def temporal_filter_block_device(lib, local, num_frames, fov_masks, time_radius=2, sigma=0.01, space_radius=1,
+                                 weight_b=0.5, weight_g=1.0, gpu=0):
+    """Temporal joint-bilateral filter of this rank's frames, device memory in and out.  local: {frame: (color, disp)}
+    as in exchange_halos_device; fov_masks: uint8 [S,H,W] CUDA tensor (mask of every frame = the camera's FOV mask,
+    TemporalBilateralFilter.cpp:150-160 without foreground masks).  Returns ({frame: filtered f32 [S,H,W]}, halo bytes)."""
+    import ctypes as C
+    halos, nbytes = exchange_halos_device(local, num_frames, time_radius)
+    frames = dict(local)
+    frames.update(halos)
+    out = {}
+    for f in sorted(local):
+        lo, hi = max(0, f - time_radius), min(num_frames - 1, f + time_radius)
+        window = [frames[t] for t in range(lo, hi + 1)]
+        S, H, W = local[f][1].shape
+        T = len(window)
+        res = torch.empty_like(local[f][1])
+        for cam in range(S):
+            guides = (C.c_void_p * T)(*[w[0][cam].data_ptr() for w in window])
+            disps = (C.c_void_p * T)(*[w[1][cam].data_ptr() for w in window])
+            masks = (C.c_void_p * T)(*([fov_masks[cam].data_ptr()] * T))
+            lib.check(lib.lib.derp_temporal_filter(gpu, W, H, T, guides, disps, masks, f - lo, sigma, space_radius,
+                                                   weight_b, weight_g, weight_b, res[cam].data_ptr()))
+        out[f] = res
+    return out, nbytes
+
+
+def all_gather_disparities_device(ctx, num_cams, device):
+    """The exchange step of camera-sharded mismatch handling on its own (what sharded_mismatches does before the kernel),
+    returning the bytes this rank received: one NCCL all-gather of the per-camera disparity planes, device to device."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    own = shard.camera_shard(num_cams, world, rank)
+    per = (num_cams + world - 1) // world
+    send = torch.zeros((per, ctx.H, ctx.W), dtype=torch.float32, device=device)
+    torch.cuda.synchronize(device)
+    for i in range(len(own)):
+        ctx.L.check(ctx.L.lib.derp_get_disparity(ctx.h, i, send[i].data_ptr(), None, None))
+    if world > 1:
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+    else:
+        recv = [send]
+    torch.cuda.synchronize(device)
+    planes = [None] * num_cams
+    for r in range(world):
+        for i, cam in enumerate(shard.camera_shard(num_cams, world, r)):
+            planes[cam] = recv[r][i].data_ptr()
+    ctx.gather_disparities(planes)
+    return (world - 1) * send.numel() * 4

@@ -258,6 +258,14 @@ int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* 
                             const uint8_t* fine_mask, int out_w, int out_h,
                             int use_foreground_masks, float* out);
 
+/* Device memory for callers that keep frames resident between calls (e.g. the temporal filter's sliding window):
+ * derp_device_alloc / derp_device_free on `device`; derp_device_copy copies `bytes` between any two addresses — host,
+ * this device or a PEER device (NVLink copy; peer access is enabled on first use).  The CPU libraries implement the
+ * three with malloc / free / memcpy so that callers need no second code path in tests. */
+int derp_device_alloc(int device, size_t bytes, void** out);
+int derp_device_free(int device, void* p);
+int derp_device_copy(int device, void* dst, const void* src, size_t bytes);
+
 /* cv::resize(..., INTER_AREA) of a 3-channel 16-bit image, shrinking only: the resize scripts/render/resize.py:51-85
  * builds every pyramid level with (each level from the FULL-SIZE image, widths scripts/render/config.py:46) and the one
  * cv_util::resizeImage applies to the colour image in UpsampleDisparity.cpp:117.  Bit-identical to OpenCV for integer

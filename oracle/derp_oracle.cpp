@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -1382,6 +1383,20 @@ void oracle_remap_bicubic(const uint16_t* src, int sw, int sh, const float* map,
 void oracle_blur3(const uint16_t* src, int w, int h, uint16_t* dst) { blur3x3U16C3(src, w, h, dst); }
 int derp_downscale_area(int /*device*/, const uint16_t* src, int src_w, int src_h, uint16_t* dst, int dst_w, int dst_h) {
   if (!src || !dst || !resizeAreaU16C3(src, src_w, src_h, dst, dst_w, dst_h)) return DERP_EINVAL;
+  return DERP_OK;
+}
+int derp_device_alloc(int /*device*/, size_t bytes, void** out) {
+  if (!out) return DERP_EINVAL;
+  *out = std::malloc(bytes ? bytes : 1);
+  return *out ? DERP_OK : DERP_ENOMEM;
+}
+int derp_device_free(int /*device*/, void* p) {
+  std::free(p);
+  return DERP_OK;
+}
+int derp_device_copy(int /*device*/, void* dst, const void* src, size_t bytes) {
+  if (!dst || !src) return DERP_EINVAL;
+  std::memmove(dst, src, bytes);
   return DERP_OK;
 }
 int derp_foreground_mask(int /*device*/, const uint16_t* templ, const uint16_t* frame, int w, int h, int blur_radius,

@@ -24,6 +24,7 @@
 // kNumDepths is a compile-time constant of the reference (Derp.h:33): brute force accepts num_depths == 150 only.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <filesystem>
 #include <memory>
@@ -629,6 +630,20 @@ int derp_downscale_area(int /*device*/, const uint16_t* src, int src_w, int src_
   return DERP_OK;
 }
 
+int derp_device_alloc(int /*device*/, size_t bytes, void** out) {
+  if (!out) return DERP_EINVAL;
+  *out = std::malloc(bytes ? bytes : 1);
+  return *out ? DERP_OK : DERP_ENOMEM;
+}
+int derp_device_free(int /*device*/, void* p) {
+  std::free(p);
+  return DERP_OK;
+}
+int derp_device_copy(int /*device*/, void* dst, const void* src, size_t bytes) {
+  if (!dst || !src) return DERP_EINVAL;
+  std::memmove(dst, src, bytes);
+  return DERP_OK;
+}
 /* source/render/BackgroundSubtractionUtil.h is outside the sources compiled here (it needs cv::GaussianBlur /
  * morphologyEx): the stand-in's restatement (oracle/cvprims.h, pinned to cv2 4.13) answers for it */
 int derp_foreground_mask(int /*device*/, const uint16_t* templ, const uint16_t* frame, int w, int h, int blur_radius,

@@ -127,6 +127,48 @@ def test_temporal_halo_exchange_gloo(tmp_path, oracle):
         assert np.array_equal(got.view(np.uint32), np.stack(ref[f]).view(np.uint32)), f
 
 
+def _temporal_device_worker(rank, world, port, out_dir, F=7):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from facebook360_dep_b200 import pipeline
+    oracle = oracle_libs.load_oracle()
+    oracle.set_threads(2)
+    S, H, W = 2, 24, 28
+    seq = _make_sequence(F, S, H, W)
+    first, last = shard.frame_block(F, world, rank)
+    # the tensor form the GPU pipeline uses (bench.py --workload cfg5), here on CPU tensors over gloo
+    local = {f: (torch.from_numpy(np.stack([c[0] for c in seq[f]])), torch.from_numpy(np.stack([c[1] for c in seq[f]])))
+             for f in range(first, last)}
+    masks = torch.from_numpy(np.stack([c[2] for c in seq[0]]))  # one mask per camera for every frame (FOV mask)
+    out, nbytes = pipeline.temporal_filter_block_device(oracle, local, F, masks, time_radius=2)
+    for f, t in out.items():
+        np.save(os.path.join(out_dir, "tfd%d.npy" % f), t.numpy())
+    np.save(os.path.join(out_dir, "bytes%d.npy" % rank), np.array([nbytes]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_device_resident_halo_exchange_gloo(tmp_path, oracle):
+    """The tensor-to-tensor halo exchange + block filter of the cfg5 workload (pipeline.exchange_halos_device /
+    temporal_filter_block_device), 7 frames over 3 ranks on CPU tensors over gloo, against the single-process result."""
+    world, F = 3, 7
+    port = 29800 + (os.getpid() % 1000)
+    mp.spawn(_temporal_device_worker, args=(world, port, str(tmp_path), F), nprocs=world, join=True)
+    seq = _make_sequence(F, 2, 24, 28)
+    masks = [c[2] for c in seq[0]]
+    for f in range(F):
+        lo, hi = max(0, f - 2), min(F - 1, f + 2)
+        got = np.load(tmp_path / ("tfd%d.npy" % f))
+        for cam in range(2):
+            ref = oracle.temporal_filter([seq[t][cam][0] for t in range(lo, hi + 1)], [seq[t][cam][1] for t in range(lo, hi + 1)],
+                                         [masks[cam]] * (hi - lo + 1), f - lo, 0.01, 1, 0.5, 1.0, 0.5)
+            assert np.array_equal(got[cam].view(np.uint32), ref.view(np.uint32)), (f, cam)
+    per_frame = 2 * 24 * 28 * (6 + 4)
+    # blocks 3,3,1: rank 0 needs frames 3,4; rank 1 needs 1,2 and 6; rank 2 needs 4,5
+    assert [int(np.load(tmp_path / ("bytes%d.npy" % r))[0]) for r in range(3)] == [2 * per_frame, 3 * per_frame, 2 * per_frame]
+
+
 def test_more_ranks_than_frames_gloo(tmp_path, oracle):
     """3 frames on 4 ranks (blocks of 1,1,1,0): the idle rank must neither crash nor take part in the exchange."""
     from facebook360_dep_b200 import pipeline
