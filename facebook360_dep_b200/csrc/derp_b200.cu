@@ -727,7 +727,10 @@ int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, flo
     return (e && !strcmp(e, "exact")) ? 1 : ((e && !strcmp(e, "filter")) ? 2 : 0);
   }();
   const int mode = c->sweepMode ? c->sweepMode : modeEnv;
-  bool filtered = mode == 2 || (mode == 0 && num_depths >= 8);
+  // automatic: the filter pays off when the bound pass amortises its extra launches and the read-back of the list
+  // length: >= 32 M (pixel, candidate) pairs (512^2 x 128); BASELINE.json configs[0] (512^2 x 32) and the coarsest
+  // pyramid levels stay on the plain sweep (measured: 1.3 ms plain vs 19 ms filtered for the four 512^2 x 32 sweeps)
+  bool filtered = mode == 2 || (mode == 0 && num_depths >= 8 && (unsigned long long)n * (unsigned long long)num_depths >= (32ull << 20));
   const unsigned long long capacity = (unsigned long long)n * (unsigned long long)std::max(2, num_depths / 8);
   if (filtered) {
     size_t freeB = 0, totalB = 0;

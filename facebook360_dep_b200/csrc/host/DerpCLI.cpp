@@ -336,6 +336,8 @@ int main(int argc, char* argv[]) {
   Shared sh;
   sh.rig = io::loadRig(FLAGS_rig);
   CHECK_GT(sh.rig.cams.size(), 0u) << "no source cameras!";
+  CHECK_LE(sh.rig.cams.size(), 32u) << "this build handles rigs of up to 32 cameras (source-visibility masks are 32-bit); the "
+                                       "reference has no such limit";
   sh.dst = io::filterDestinations(sh.rig, FLAGS_cameras);
   CHECK_GT(sh.dst.size(), 0u) << "no destination cameras!";
 

@@ -464,8 +464,10 @@ inline void writePng8(const fs::path& path, const uint8_t* data, int w, int h, i
   pngChunk(f, "IEND", {});
 }
 inline void writePng8Gray(const fs::path& path, const uint8_t* data, int w, int h) { writePng8(path, data, w, h, 1); }
-inline uint8_t saturateU8(float v) {  // saturate_cast<uchar>(float): cvRound then clamp; NaN -> INT_MIN -> 0
-  if (v != v) return 0;
+// saturate_cast<uchar>(float) = saturate_cast<uchar>(cvRound(v)): cvRound is cvtss2si, which answers INT_MIN for NaN and for
+// anything outside the int range (e.g. the +inf cost ping-pong leaves on skipped pixels) -> 0 after the clamp
+inline uint8_t saturateU8(float v) {
+  if (!(v > -2147483648.0f && v < 2147483648.0f)) return 0;
   const long r = std::lrintf(v);
   return (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
 }

@@ -127,7 +127,8 @@ int derp_get_profile_ping_pong(DerpCtx* ctx, double* ms, uint64_t* launches, uin
 
 /* How derp_brute_force sweeps (CUDA library; accepted and ignored by the CPU libraries).  Every mode produces the same
  * bytes; they differ in how much exact arithmetic runs:
- *   0  automatic: filtered when num_depths >= 8 and the bound buffer (num_depths x W x H floats) fits in memory
+ *   0  automatic: filtered when the sweep has >= 32 M (pixel, candidate) pairs (e.g. 512^2 x 128) and the bound buffer
+ *      (num_depths x W x H floats) fits in memory; plain otherwise (small sweeps: the filter's extra launches cost more)
  *   1  plain sweep: the exact cost of every (pixel, candidate) (sweepKernel)
  *   2  filtered sweep: a proven lower bound of every (pixel, candidate), the exact cost only where the bound does not
  *      exclude the candidate (derp_refine.cuh)

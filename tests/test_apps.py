@@ -370,9 +370,10 @@ def test_debug_images_exr_and_foreground_masks(tmp_path, cuda):
     d1, cost, conf = ctx.get_disparity(1)
     assert np.array_equal(d1.view(np.uint32), disp.view(np.uint32))
 
-    def u8(v):
-        with np.errstate(invalid="ignore"):
-            r = np.where(np.isnan(v), 0, np.clip(np.rint(np.nan_to_num(v, nan=0.0, posinf=1e9, neginf=-1e9)), 0, 255))
+    def u8(v):  # saturate_cast<uchar>(cvRound(v)); cvRound answers INT_MIN outside the int range (NaN, inf, huge) -> 0
+        with np.errstate(invalid="ignore", over="ignore"):
+            ok = np.isfinite(v) & (np.abs(v) < 2147483648.0)
+            r = np.where(ok, np.clip(np.rint(np.where(ok, v, 0)), 0, 255), 0)
         return r.astype(np.uint8)
 
     png = cv2.imread(os.path.join(out, "cost", "level_0", "cam1", "000000.png"), cv2.IMREAD_UNCHANGED)
