@@ -957,7 +957,7 @@ static int launchMismatches(DerpCtx* c, const float* dispAll) {
     a.varHighThresh = c->lp.var_high_thresh;
     a.dispNew = dNew.p + (size_t)d * n;
     a.mask = c->dMismatch.p + (size_t)d * n;
-    mismatchKernel<<<grid2(c->W, c->H), block2(), c->camSmem(), c->stream>>>(a);
+    mismatchKernel<<<grid2(c->W, c->H), block2(), (size_t)c->S * sizeof(DevCamera), c->stream>>>(a);  // cameras only
     LAUNCHED("mismatchKernel");
   }
   CU(cudaMemcpyAsync(c->dDisp.p, dNew.p, n * c->Sd * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));

@@ -147,18 +147,22 @@ def exchange_halos_device(local, num_frames, time_radius):
     some = next(iter(local.values()))
     per = (num_frames + world - 1) // world
     ops, recv = [], {}
+
+    def raw(t):  # NCCL has no 16-bit unsigned type: the planes travel as bytes
+        return t.view(torch.uint8) if t.dtype == torch.uint16 else t
+
     for r in range(world):
         left, right = shard.halo_frames(num_frames, world, r, time_radius)
         for f in left + right:
             o = f // per
             if o == rank and r != rank:
                 for t in local[f]:
-                    ops.append(dist.P2POp(dist.isend, t, r))
+                    ops.append(dist.P2POp(dist.isend, raw(t), r))
             elif r == rank and o != rank:
                 bufs = tuple(torch.empty_like(t) for t in some)
                 recv[f] = bufs
                 for t in bufs:
-                    ops.append(dist.P2POp(dist.irecv, t, o))
+                    ops.append(dist.P2POp(dist.irecv, raw(t), o))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()

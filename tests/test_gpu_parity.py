@@ -525,3 +525,30 @@ def test_foreground_mask(cuda, oracle):
         assert 0.05 < g.mean() < 0.95
     with pytest.raises(capi.DerpError):
         cuda.foreground_mask(bg, fr, 2, 0.04, 4)
+
+
+def test_24_camera_rig_all_stages(cuda, oracle):
+    """BASELINE.json configs[3]'s camera count (24) at a small size, every stage of a fine level incl. mismatch handling:
+    the shared-memory footprints (S - 1 selection slots per thread, S camera structs) scale with the rig."""
+    W, H, S = 72, 56, 24
+    rig = synth.ring_rig(S, W, H, kind="FTHETA")
+    colors, true_disp = synth.render_rig(rig, W, H, scene=synth.Scene(seed=12))
+    ctxs = make_pair(cuda, oracle, rig)
+    both(ctxs, "level_begin", W, H, level=0, num_levels=2, full_width=W, full_height=H)
+    both(ctxs, "set_colors", colors)
+    rng = np.random.RandomState(3)
+    for d in range(S):
+        start = np.clip(true_disp[d] * rng.uniform(0.85, 1.2, (H, W)).astype(np.float32), 1e-4, 2.0).astype(np.float32)
+        both(ctxs, "set_disparity", d, start, np.zeros_like(start), np.zeros_like(start))
+    both(ctxs, "process_level", num_depths=32, mismatches_start_level=0)
+    good = tot = 0
+    for d in range(S):
+        g, o = both(ctxs, "get_disparity", d, want_cost=False)
+        assert np.array_equal(np.isnan(g), np.isnan(o))
+        fin = ~np.isnan(o)
+        good += int((np.abs(g - o)[fin] <= 1e-3 * np.abs(o)[fin]).sum())
+        tot += int(fin.sum())
+    assert good / tot >= 0.999
+    both(ctxs, "reproject", 7)
+    gi, oi = both(ctxs, "brute_force", 7, num_depths=24)
+    assert np.array_equal(gi, oi)
