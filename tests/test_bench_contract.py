@@ -59,3 +59,23 @@ def test_bench_prints_baseline_metric_verbatim():
     sys.path.insert(0, ROOT)
     import bench
     assert bench.METRIC == json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+
+
+def test_round2_lines_same_config_and_parity():
+    """Round 2: the two arms print the SAME config object (the driver compares them), the CPU arm is the reference's own
+    code with a reproducible thread count, and the GPU line carries the in-run parity object."""
+    g = _line("r2_bench_bf128_l0_n1.json")
+    r = _line("r2_bench_reference_arm_n1.json")
+    assert g["config"] == r["config"] and g["metric"] == r["metric"] and g["unit"] == r["unit"]
+    assert r["impl"] == "reference" and r["cpu_baseline"]["kind"] == "reference" and r["cpu_baseline"]["steps"] >= 3
+    c = g["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] == r["cpu_baseline"]["cores"]
+    assert abs(c["value"] - r["value"]) / r["value"] < 0.10  # reproducible across runs / boxes (round 1: 4.3x apart)
+    p = g["parity"]
+    assert p["against"] == "reference" and p["index_mismatches"] == 0 and p["cost_mismatch_frac"] <= 1e-5
+    assert p["pixel_candidates"] > 1e6
+    assert g["cfg1_full"]["parity"]["index_mismatches"] == 0
+    assert g["e2e"]["value"] > 0 and g["roofline"]["frac"] > 0.08 and g["gpu_launches"] > 0
+    c2f = _line("r2_bench_c2f5_n1.json")
+    assert c2f["config"]["workload"] == "c2f5" and c2f["roofline"]["kernel"] == "pingPongKernel"
+    assert c2f["e2e"]["ms_per_step"] >= c2f["ms_per_step"] and c2f["parity"]["fraction"] >= 0.999
