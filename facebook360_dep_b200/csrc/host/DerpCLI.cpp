@@ -149,6 +149,27 @@ static void verifyImagePaths(const fs::path& dir, const io::Rig& rig, const std:
     }
 }
 
+// --threads like ThreadPool.h:30-45 (-1 = all cores, 0 = inline): host-side image decoding and file writing only — the
+// reference decodes a level's images with one task per camera (ImageUtil.h:65-94)
+static int hostThreads() {
+  return FLAGS_threads < 0 ? (int)std::max(1u, std::thread::hardware_concurrency()) : FLAGS_threads;
+}
+template <class F>
+static void parallelFor(int n, F&& fn) {
+  const int T = std::min(hostThreads(), n);
+  if (T <= 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < T; ++t)
+    pool.emplace_back([&] {
+      for (int i = next++; i < n; i = next++) fn(i);
+    });
+  for (auto& th : pool) th.join();
+}
+
 struct Shared {
   io::Rig rig;
   std::vector<int> dst;  // indices into rig
@@ -160,9 +181,14 @@ struct Shared {
 struct Worker {
   DerpCtx* ctx = nullptr;
   std::vector<int> dst;  // indices into rig
+  std::vector<std::thread> writers;  // file output of finished levels, overlapped with the next level's GPU work
+  void drain() {
+    for (auto& t : writers) t.join();
+    writers.clear();
+  }
 };
 
-static void saveLevel(const Shared& shAll, const Worker& wk, int level, const std::string& frameName, int W, int H) {
+static void saveLevel(const Shared& shAll, Worker& wk, int level, const std::string& frameName, int W, int H) {
   DerpCtx* ctx = wk.ctx;
   Shared sh = shAll;
   sh.dst = wk.dst;
@@ -183,7 +209,15 @@ static void saveLevel(const Shared& shAll, const Worker& wk, int level, const st
   for (size_t d = 0; d < sh.dst.size(); ++d) {
     DERP_CALL(derp_get_disparity(ctx, (int)d, disp.data(), cost.empty() ? nullptr : cost.data(),
                                  conf.empty() ? nullptr : conf.data()));
-    const std::string& id = sh.rig.ids[sh.dst[d]];
+    if (FLAGS_save_debug_images) {
+      DERP_CALL(derp_get_mismatch_mask(ctx, (int)d, mism.data()));
+      DERP_CALL(derp_get_fov_mask(ctx, (int)d, fov.data()));
+    }
+    // the buffers are copied into the writer: encoding + disk IO run while the GPU works on the next level
+    wk.writers.emplace_back([=, &sh0 = shAll, dstIds = sh.dst]() {
+    const Shared& sh = sh0;
+    (void)dstIds;
+    const std::string& id = sh.rig.ids[dstIds[d]];
     const fs::path stem = fs::path(io::levelDir(FLAGS_output_root + "/" + io::kDisparityLevels, level)) / id / frameName;
     for (const auto& ext : formats) io::saveDisparity(stem, ext, disp.data(), W, H);
     if (FLAGS_save_debug_images) {
@@ -198,8 +232,6 @@ static void saveLevel(const Shared& shAll, const Worker& wk, int level, const st
       io::writePng8(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kConfidence, level)) / id / (frameName + ".png"), g.data(), W, H, 1);
       // overlayMismatchedDstDisparityMask (PyramidLevel.h:441-461): BGRA float, NaN outside the FOV, red where the
       // mismatch mask is set, (d, d, d, 1) elsewhere; times kScaleDisparityPlot = 255
-      DERP_CALL(derp_get_mismatch_mask(ctx, (int)d, mism.data()));
-      DERP_CALL(derp_get_fov_mask(ctx, (int)d, fov.data()));
       std::vector<uint8_t> bgra(disp.size() * 4);
       for (size_t i = 0; i < disp.size(); ++i) {
         float px[4];
@@ -219,13 +251,15 @@ static void saveLevel(const Shared& shAll, const Worker& wk, int level, const st
       }
       io::writePng8(fs::path(io::levelDir(FLAGS_output_root + "/" + io::kMismatches, level)) / id / (frameName + ".png"), bgra.data(), W, H, 4);
     }
+    });
+    if ((int)wk.writers.size() >= std::max(1, hostThreads())) wk.drain();  // bound the copies in flight
   }
 }
 
 // One (level, frame): DerpCLI.cpp:229-320
 // `fromKept`: the coarser level of this frame was processed by this context just before and its disparities are still
 // in device memory (derp_level_keep) — the PFM round trip of DerpCLI.cpp:287-288 is skipped (the files are still written).
-static void processFrame(const Shared& shAll, const Worker& wk, int level, int iFrame, Exchange* ex, bool fromKept) {
+static void processFrame(const Shared& shAll, Worker& wk, int level, int iFrame, Exchange* ex, bool fromKept) {
   DerpCtx* ctx = wk.ctx;
   Shared sh = shAll;
   sh.dst = wk.dst;
@@ -247,12 +281,12 @@ static void processFrame(const Shared& shAll, const Worker& wk, int level, int i
   const std::string colorDir = io::levelDir(FLAGS_color, level);
   std::vector<std::vector<uint16_t>> colors(S);
   std::vector<const uint16_t*> cptr(S);
-  for (int s = 0; s < S; ++s) {
+  parallelFor(S, [&](int s) {
     int w, h;
     colors[s] = io::loadColor16(io::imagePath(colorDir, sh.rig.ids[s], frameName), &w, &h);
     CHECK(w == W && h == H) << "unexpected image size for " << sh.rig.ids[s] << " at level " << level;
     cptr[s] = colors[s].data();
-  }
+  });
   DERP_CALL(derp_set_colors(ctx, cptr.data()));
 
   std::vector<std::vector<uint8_t>> masks, masksCoarse;
@@ -424,6 +458,7 @@ int main(int argc, char* argv[]) {
         for (int i = f0; i < f1; ++i)  // camera sharding: all GPUs walk the frames in step and meet on mismatch levels
           for (int level = sh.levelStart; level >= sh.levelEnd; --level)
             processFrame(sh, workers[g], level, i, (shardCameras && G > 1) ? &exchange : nullptr, level < sh.levelStart);
+        workers[g].drain();
       });
     for (auto& w : threads) w.join();
     const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
