@@ -192,7 +192,7 @@ struct DerpCtx {
   unsigned long long lastRefined = 0, lastSeeds = 0;  // exact evaluations of the last filtered sweep
   int sweepMode = 0;                                  // derp_set_sweep_mode
   // in-memory level hand-off (derp_level_keep / derp_upsample_from_kept): the finished level's disparity planes
-  DevBuf<float> dKept, dUpA, dUpB;
+  DevBuf<float> dKept, dUpA, dUpB, dUpCoarse;
   DevBuf<uint8_t> dUpMc, dUpMu, dUpFovC;
   int keptW = 0, keptH = 0, keptSd = 0;
   DevBuf<unsigned> dUncovered;
@@ -1143,37 +1143,51 @@ __global__ void andMaskKernel(size_t n, const uint8_t* a, const uint8_t* b, uint
 
 extern "C" {
 
+// shared body of derp_upsample_from / derp_upsample_from_kept: dCoarse is a device plane; every temporary belongs to the
+// context (no allocation, no host synchronisation per call)
+static int upsampleIntoLevel(DerpCtx* c, int dst, const float* dCoarse, int cw, int ch, const uint8_t* coarse_mask,
+                             const uint8_t* fine_mask, const char* who) {
+  const bool useFg = c->lp.use_foreground_masks != 0;
+  const int W = c->W, H = c->H;
+  const size_t nc = (size_t)cw * ch, n = c->plane;
+  if (useFg) {
+    if (!coarse_mask || !fine_mask) return fail(DERP_EINVAL, std::string(who) + ": masks required");
+    if (!c->haveBg) return fail(DERP_ESTATE, std::string(who) + ": background disparity not set");
+    CU(c->dUpMc.ensure(nc));
+    CU(c->dUpMu.ensure(n));
+    CU(c->dUpFovC.ensure(nc));
+    CU(cudaMemcpyAsync(c->dUpMc.p, coarse_mask, nc, cudaMemcpyDefault, c->stream));
+    CU(cudaMemcpyAsync(c->dUpMu.p, fine_mask, n, cudaMemcpyDefault, c->stream));
+    // FOV masks at both sizes (UpsampleDisparityLib.cpp:163-176)
+    fovMaskKernel<<<grid2(cw, ch), block2(), 0, c->stream>>>(c->dCams.p + c->dst2src[dst], cw, ch, c->dUpFovC.p);
+    andMaskKernel<<<grid1(nc), 256, 0, c->stream>>>(nc, c->dUpFovC.p, c->dUpMc.p, c->dUpMc.p);
+    andMaskKernel<<<grid1(n), 256, 0, c->stream>>>(n, c->dFov.p + (size_t)dst * n, c->dUpMu.p, c->dUpMu.p);
+    c->launches += 3;
+  }
+  return upsampleDevice(c, c->stream, dCoarse, cw, ch, useFg ? c->bgOf(dst) : nullptr, useFg ? c->dUpMc.p : nullptr,
+                        useFg ? c->dUpMu.p : nullptr, W, H, useFg, c->dDisp.p + (size_t)dst * n, c->dUpA, c->dUpB, c->dOfs,
+                        c->dTaps, c->dSpiral);
+}
+
 int derp_upsample_from(DerpCtx* c, int dst, const float* coarse, int coarse_w, int coarse_h, const uint8_t* coarse_mask,
                        const uint8_t* fine_mask) {
   if (!coarse || coarse_w < 1 || coarse_h < 1) return fail(DERP_EINVAL, "derp_upsample_from: bad arguments");
   int rc = checkDst(c, dst, "derp_upsample_from", false);
   if (rc) return rc;
-  const bool useFg = c->lp.use_foreground_masks != 0;
-  const int W = c->W, H = c->H;
-  const size_t nc = (size_t)coarse_w * coarse_h, n = c->plane;
-  DevBuf<float> dCoarse, tA, tB;
-  DevBuf<uint8_t> dMc, dMu, dFovC;
-  CU(dCoarse.ensure(nc));
-  CU(cudaMemcpyAsync(dCoarse.p, coarse, nc * sizeof(float), cudaMemcpyDefault, c->stream));  // host or device plane
-  if (useFg) {
-    if (!coarse_mask || !fine_mask) return fail(DERP_EINVAL, "derp_upsample_from: masks required");
-    if (!c->haveBg) return fail(DERP_ESTATE, "derp_upsample_from: background disparity not set");
-    CU(dMc.ensure(nc));
-    CU(dMu.ensure(n));
-    CU(dFovC.ensure(nc));
-    CU(cudaMemcpyAsync(dMc.p, coarse_mask, nc, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(dMu.p, fine_mask, n, cudaMemcpyHostToDevice, c->stream));
-    // FOV masks at both sizes (UpsampleDisparityLib.cpp:163-176)
-    fovMaskKernel<<<grid2(coarse_w, coarse_h), block2(), 0, c->stream>>>(c->dCams.p + c->dst2src[dst], coarse_w, coarse_h, dFovC.p);
-    andMaskKernel<<<grid1(nc), 256, 0, c->stream>>>(nc, dFovC.p, dMc.p, dMc.p);
-    andMaskKernel<<<grid1(n), 256, 0, c->stream>>>(n, c->dFov.p + (size_t)dst * n, dMu.p, dMu.p);
-    c->launches += 3;
+  const size_t nc = (size_t)coarse_w * coarse_h;
+  cudaPointerAttributes a;
+  const bool onDevice = cudaPointerGetAttributes(&a, coarse) == cudaSuccess &&
+      (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  const float* dCoarse = coarse;
+  if (!onDevice) {  // host plane (the PFM a caller read back): staged once into a context buffer
+    CU(c->dUpCoarse.ensure(nc));
+    CU(cudaMemcpyAsync(c->dUpCoarse.p, coarse, nc * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    dCoarse = c->dUpCoarse.p;
   }
-  rc = upsampleDevice(c, c->stream, dCoarse.p, coarse_w, coarse_h, useFg ? c->bgOf(dst) : nullptr, useFg ? dMc.p : nullptr,
-                      useFg ? dMu.p : nullptr, W, H, useFg, c->dDisp.p + (size_t)dst * n, tA, tB, c->dOfs, c->dTaps, c->dSpiral);
-  if (rc) return rc;
-  CU(cudaStreamSynchronize(c->stream));  // temporaries are freed on return
-  return DERP_OK;
+  rc = upsampleIntoLevel(c, dst, dCoarse, coarse_w, coarse_h, coarse_mask, fine_mask, "derp_upsample_from");
+  if (rc == DERP_OK && !onDevice) CU(cudaStreamSynchronize(c->stream));  // the caller's host plane may be reused on return
+  return rc;
 }
 
 int derp_level_keep(DerpCtx* c) {
@@ -1192,27 +1206,9 @@ int derp_upsample_from_kept(DerpCtx* c, int dst, const uint8_t* coarse_mask, con
   int rc = checkDst(c, dst, "derp_upsample_from_kept", false);
   if (rc) return rc;
   if (c->keptW < 1 || c->keptSd != c->Sd) return fail(DERP_ESTATE, "derp_upsample_from_kept: derp_level_keep has not been called");
-  const bool useFg = c->lp.use_foreground_masks != 0;
-  const int W = c->W, H = c->H, cw = c->keptW, ch = c->keptH;
-  const size_t nc = (size_t)cw * ch, n = c->plane;
-  const float* coarse = c->dKept.p + (size_t)dst * nc;
-  if (useFg) {
-    if (!coarse_mask || !fine_mask) return fail(DERP_EINVAL, "derp_upsample_from_kept: masks required");
-    if (!c->haveBg) return fail(DERP_ESTATE, "derp_upsample_from_kept: background disparity not set");
-    CU(c->dUpMc.ensure(nc));
-    CU(c->dUpMu.ensure(n));
-    CU(c->dUpFovC.ensure(nc));
-    CU(cudaMemcpyAsync(c->dUpMc.p, coarse_mask, nc, cudaMemcpyDefault, c->stream));
-    CU(cudaMemcpyAsync(c->dUpMu.p, fine_mask, n, cudaMemcpyDefault, c->stream));
-    fovMaskKernel<<<grid2(cw, ch), block2(), 0, c->stream>>>(c->dCams.p + c->dst2src[dst], cw, ch, c->dUpFovC.p);
-    andMaskKernel<<<grid1(nc), 256, 0, c->stream>>>(nc, c->dUpFovC.p, c->dUpMc.p, c->dUpMc.p);
-    andMaskKernel<<<grid1(n), 256, 0, c->stream>>>(n, c->dFov.p + (size_t)dst * n, c->dUpMu.p, c->dUpMu.p);
-    c->launches += 3;
-  }
-  // stream-ordered: the context's own temporaries, no host synchronisation (the level stays in HBM)
-  return upsampleDevice(c, c->stream, coarse, cw, ch, useFg ? c->bgOf(dst) : nullptr, useFg ? c->dUpMc.p : nullptr,
-                        useFg ? c->dUpMu.p : nullptr, W, H, useFg, c->dDisp.p + (size_t)dst * n, c->dUpA, c->dUpB, c->dOfs,
-                        c->dTaps, c->dSpiral);
+  const size_t nc = (size_t)c->keptW * c->keptH;
+  return upsampleIntoLevel(c, dst, c->dKept.p + (size_t)dst * nc, c->keptW, c->keptH, coarse_mask, fine_mask,
+                           "derp_upsample_from_kept");
 }
 
 // computeResizeAreaTab (resize.cpp) as per-destination tap ranges
