@@ -163,3 +163,38 @@ def test_temporal_filter_2048(cuda, checker):
     fin = np.isfinite(o)
     assert np.array_equal(np.isfinite(g), fin)
     assert (np.abs(g - o)[fin] <= 2e-6 * np.abs(o)[fin]).all()
+
+
+def test_cfg4_size_band_256_candidates(cuda, checker):
+    """BASELINE.json configs[3]'s size — 24 cameras, 4096 x 4096, 256 candidates — on one destination: a 48-row band x all
+    256 candidates of the reference's own cost code against the winner of the CUDA sweep (filtered, 4.3 GB bound buffer)."""
+    import torch
+    W = H = 4096
+    D = 256
+    rig = synth.ring_rig(24, W, H, kind="FTHETA")
+    colors, _ = synth.render_rig(rig, W, H, scene=synth.Scene(seed=9), device="cuda")
+    colors = [np.ascontiguousarray(c) for c in colors]
+    torch.cuda.empty_cache()
+    descs = capi.rig_descs(rig)
+    g = capi.Context(cuda, descs, dst_to_src=[5])
+    c = capi.Context(checker, descs, dst_to_src=[5])
+    for ctx in (g, c):
+        ctx.level_begin(W, H)
+        ctx.set_colors(colors)
+        ctx.reproject(0)
+    gi = g.brute_force(0, num_depths=D)
+    assert g.sweep_stats()[1] > 0, "the sweep at this size runs filtered"
+    _, gc, _ = g.get_disparity(0)
+    fov = g.get_fov_mask(0).astype(bool)
+    y0 = 2017
+    y1 = y0 + 48
+    costs = cpu_cost_slices(checker, c, 0, candidate_table(D), y0, y1, W, H)
+    w = np.where(np.isnan(costs), np.float32(np.inf), costs)
+    best = np.argmin(w, axis=0)
+    bcost = np.take_along_axis(w, best[None], axis=0)[0]
+    covered = fov[y0:y1, 1:W - 1] & (bcost[:, 1:W - 1] < np.float32(3.4028235e38))
+    assert covered.sum() > 48 * 2000
+    assert int(((gi[y0:y1, 1:W - 1] != best[:, 1:W - 1]) & covered).sum()) == 0
+    assert mismatch_fraction(gc[y0:y1, 1:W - 1][covered], bcost[:, 1:W - 1][covered]) <= 1e-5
+    g.close()
+    c.close()
