@@ -162,6 +162,10 @@ _SIGS = {
     "derp_downscale_area": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "derp_foreground_mask": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                        C.c_void_p]),
+    "derp_camera_mesh_size": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "derp_camera_mesh": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 ABI_SYMBOLS = sorted(_SIGS)
@@ -236,6 +240,25 @@ class Library:
         self.check(self.lib.derp_foreground_mask(device, templ.ctypes.data, frame.ctypes.data, w, h, blur_radius, threshold,
                                                  morph_closing_size, out.ctypes.data))
         return out
+
+    def camera_mesh(self, disparity, resolution, scalar_focal, depth_scale=1.0, tear_ratio=0.95, foreground_mask=None,
+                    device=0):
+        """The camera mesh ConvertToBinary builds from one disparity map before simplification
+        (ConvertToBinary.cpp:150-183, MeshUtil.h): returns (vertexes float32 [nv, 3], faces uint32 [nf, 3])."""
+        disparity = np.ascontiguousarray(disparity, np.float32)
+        h, w = disparity.shape
+        mw, mh = C.c_int(), C.c_int()
+        self.check(self.lib.derp_camera_mesh_size(w, h, depth_scale, C.byref(mw), C.byref(mh)))
+        cells = mw.value * mh.value
+        vtx = np.empty((max(cells, 1), 3), np.float32)
+        idx = np.empty((max(2 * cells, 1), 3), np.uint32)
+        fm = None if foreground_mask is None else np.ascontiguousarray(foreground_mask, np.uint8)
+        nv, nf = C.c_uint64(), C.c_uint64()
+        self.check(self.lib.derp_camera_mesh(
+            device, disparity.ctypes.data, w, h, depth_scale, float(resolution[0]), float(resolution[1]),
+            float(scalar_focal), tear_ratio, _dp(fm), 0 if fm is None else fm.shape[1], 0 if fm is None else fm.shape[0],
+            vtx.ctypes.data, idx.ctypes.data, C.byref(nv), C.byref(nf)))
+        return vtx[:nv.value].copy(), idx[:nf.value].copy()
 
     def upsample_disparity(self, cam_desc, coarse, out_w, out_h, background_up=None, coarse_mask=None,
                            fine_mask=None, use_foreground_masks=False, device=0):

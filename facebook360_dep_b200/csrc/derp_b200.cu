@@ -18,6 +18,7 @@
 #include "../../include/derp_b200.h"
 #include "derp_kernels.cuh"
 #include "derp_refine.cuh"
+#include "derp_mesh.cuh"
 
 using namespace derp;
 
@@ -83,11 +84,10 @@ void buildBicubicTable(std::vector<float>& tab) {
     t1[i][2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
     t1[i][3] = 1.f - t1[i][0] - t1[i][1] - t1[i][2];
   }
-  tab.resize(32 * 32 * 16);
+  // the 2-D table entry (fy, fx)[k1][k2] = t1[fy][k1] * t1[fx][k2] (initInterTab2D) is formed in reprojectKernel
+  tab.resize(32 * 4);
   for (int i = 0; i < 32; ++i)
-    for (int j = 0; j < 32; ++j)
-      for (int k1 = 0; k1 < 4; ++k1)
-        for (int k2 = 0; k2 < 4; ++k2) tab[(i * 32 + j) * 16 + k1 * 4 + k2] = t1[i][k1] * t1[j][k2];
+    for (int k = 0; k < 4; ++k) tab[i * 4 + k] = t1[i][k];
 }
 
 // resize.cpp interpolateLanczos4
@@ -485,8 +485,7 @@ int derp_level_begin(DerpCtx* c, const DerpLevelParams* p) {
   c->varNoiseFloor = std::max(p->var_noise_floor * scaleVar, kMinVarF);
   CU(c->dColor.ensure(n * c->S));
   CU(c->dVariance.ensure(n * c->S));
-  CU(c->dProjColor.ensure(n * c->S));
-  CU(c->dProjBias.ensure(n * c->S));
+  CU(c->dProjColor16.ensure(n * c->S));  // the float4 / u16 bias tables are allocated by the first stage that reads them
   {  // geometry cache of this level size: create it if all pairs' maps fit in (half of the free) HBM
     const auto key = std::make_pair(c->W, c->H);
     auto it = c->geomCaches.find(key);
@@ -608,7 +607,7 @@ int derp_reproject(DerpCtx* c, int dst) {
     if (c->geomCached) c->geom->valid[dst] = 1;
   }
   reprojectKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->warpInvOf(dst), c->S, self, c->W, c->H, c->dColor.p,
-                                                                       c->dWtab.p, c->dProjColor.p);
+                                                                       c->dWtab.p, c->dProjColor16.p);
   LAUNCHED("reprojectKernel");
   c->projDst = dst;
   c->tabF32 = c->tabU16 = false;  // colour bias + final table layout: built by the first stage that needs them
@@ -619,17 +618,18 @@ int derp_reproject(DerpCtx* c, int dst) {
 // the compacted fine-level kernels.  A level normally needs exactly one of them per destination.
 static int ensureTablesF32(DerpCtx* c) {
   if (c->tabF32) return DERP_OK;
-  biasKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor.p, c->dProjBias.p);
+  CU(c->dProjColor.ensure(c->plane * c->S));
+  CU(c->dProjBias.ensure(c->plane * c->S));
+  biasKernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor16.p, c->dProjColor.p,
+                                                                  c->dProjBias.p);
   LAUNCHED("biasKernel");
   c->tabF32 = true;
   return DERP_OK;
 }
 static int ensureTablesU16(DerpCtx* c) {
   if (c->tabU16) return DERP_OK;
-  CU(c->dProjColor16.ensure(c->plane * c->S));
   CU(c->dProjBias16.ensure(c->plane * c->S));
-  bias16Kernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor.p, c->dProjColor16.p,
-                                                                    c->dProjBias16.p);
+  bias16Kernel<<<grid2(c->W, c->H, c->S), block2(), 0, c->stream>>>(c->W, c->H, c->dProjColor16.p, c->dProjBias16.p);
   LAUNCHED("bias16Kernel");
   c->tabU16 = true;
   return DERP_OK;
@@ -1363,6 +1363,125 @@ int derp_foreground_mask(int device, const uint16_t* templ, const uint16_t* fram
   }
   CU(cudaGetLastError());
   CU(cudaMemcpy(mask, dM.p, n, cudaMemcpyDefault));
+  return DERP_OK;
+}
+
+// cv::resize(depth, depth, Size(), s, s, INTER_NEAREST) (ConvertToBinary.cpp:153-156): dsize = cvRound(size * s),
+// source index = min(floor(d * (1 / s)), size - 1) (resize.cpp resizeNN with the caller's scale factors)
+static void meshAxis(int sn, double scale, std::vector<int>& ofs) {
+  if (!(scale < 1)) {
+    ofs.resize(sn);
+    for (int d = 0; d < sn; ++d) ofs[d] = d;
+    return;
+  }
+  const int dn = (int)std::nearbyint(sn * scale);
+  const double ifx = 1. / scale;
+  ofs.resize(std::max(dn, 0));
+  for (int d = 0; d < dn; ++d) ofs[d] = std::min(floorD(d * ifx), sn - 1);
+}
+
+int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_width, int* mesh_height) {
+  if (width < 1 || height < 1 || !(depth_scale > 0) || depth_scale > 1 || !mesh_width || !mesh_height)
+    return fail(DERP_EINVAL, "derp_camera_mesh_size: bad arguments (depth_scale in (0, 1], ConvertToBinary.cpp:348)");
+  *mesh_width = depth_scale < 1 ? (int)std::nearbyint(width * depth_scale) : width;
+  *mesh_height = depth_scale < 1 ? (int)std::nearbyint(height * depth_scale) : height;
+  return DERP_OK;
+}
+
+int derp_camera_mesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                     int mask_width, int mask_height, float* vertexes, uint32_t* faces, uint64_t* num_vertexes,
+                     uint64_t* num_faces) {
+  int W = 0, H = 0;
+  int rc = derp_camera_mesh_size(width, height, depth_scale, &W, &H);
+  if (rc) return rc;
+  if (!disparity || !vertexes || !faces || !num_vertexes || !num_faces || W < 1 || H < 1 ||
+      (foreground_mask && (mask_width < 1 || mask_height < 1)))
+    return fail(DERP_EINVAL, "derp_camera_mesh: bad arguments");
+  CU(cudaSetDevice(device));
+  const size_t n = (size_t)W * H, nsrc = (size_t)width * height;
+  if (n >= (1ull << 31)) return fail(DERP_EINVAL, "derp_camera_mesh: grid too large for 32-bit indexes");
+  std::vector<int> ofs, tmp;
+  meshAxis(width, depth_scale, ofs);
+  meshAxis(height, depth_scale, tmp);
+  ofs.insert(ofs.end(), tmp.begin(), tmp.end());
+  if (foreground_mask) {  // cv::resize(mask, mask, depth.size(), 0, 0, INTER_NEAREST), ConvertToBinary.cpp:171-174
+    nearestAxis(mask_width, W, tmp);
+    ofs.insert(ofs.end(), tmp.begin(), tmp.end());
+    nearestAxis(mask_height, H, tmp);
+    ofs.insert(ofs.end(), tmp.begin(), tmp.end());
+  }
+  DevBuf<float> dDisp, dVtx;
+  DevBuf<int> dOfs;
+  DevBuf<uint8_t> dFg, dQuad, dUsed;
+  DevBuf<unsigned> dTiles, dIndex, dFaces;
+  DevBuf<unsigned long long> dTotals;
+  const float* disp = disparity;
+  const uint8_t* fg = foreground_mask;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, disparity) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    (void)cudaGetLastError();
+    CU(dDisp.ensure(nsrc));
+    CU(cudaMemcpy(dDisp.p, disparity, nsrc * sizeof(float), cudaMemcpyDefault));
+    disp = dDisp.p;
+  }
+  if (fg && (cudaPointerGetAttributes(&at, fg) != cudaSuccess || at.type != cudaMemoryTypeDevice)) {
+    (void)cudaGetLastError();
+    CU(dFg.ensure((size_t)mask_width * mask_height));
+    CU(cudaMemcpy(dFg.p, fg, (size_t)mask_width * mask_height, cudaMemcpyDefault));
+    fg = dFg.p;
+  }
+  const int tiles = (int)((n + kScanTile - 1) / kScanTile);
+  CU(dOfs.ensure(ofs.size()));
+  CU(cudaMemcpy(dOfs.p, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU(dQuad.ensure(n));
+  CU(dUsed.ensure(n));
+  CU(dTiles.ensure(2 * (size_t)tiles));
+  CU(dIndex.ensure(n));
+  CU(dTotals.ensure(2));
+  CU(cudaMemset(dUsed.p, 0, n));
+  MeshGrid g;
+  g.W = W;
+  g.H = H;
+  g.srcW = width;
+  g.disp = disp;
+  g.xofs = dOfs.p;
+  g.yofs = dOfs.p + W;
+  g.fg = fg;
+  g.fgW = mask_width;
+  g.fgx = dOfs.p + W + H;
+  g.fgy = dOfs.p + 2 * (size_t)W + H;
+  g.stepX = resolution_x / W;
+  g.stepY = resolution_y / H;
+  g.scale = scalar_focal * 1.0;  // kRadius = 1 (MeshUtil.h:316)
+  g.tearRatio = tear_ratio;
+  meshQuadKernel<<<grid2(W, H), block2()>>>(g, dQuad.p, dUsed.p);
+  meshTileCountKernel<<<tiles, kScanThreads>>>(n, dQuad.p, dUsed.p, dTiles.p, dTiles.p + tiles);
+  meshTileScanKernel<<<1, kScanThreads>>>(tiles, dTiles.p, dTiles.p + tiles, dTotals.p);
+  CU(cudaGetLastError());
+  unsigned long long totals[2] = {0, 0};
+  CU(cudaMemcpy(totals, dTotals.p, sizeof(totals), cudaMemcpyDeviceToHost));
+  // outputs: written in place when the caller's buffers are device memory, else staged
+  float* vtx = vertexes;
+  uint32_t* fac = faces;
+  if (cudaPointerGetAttributes(&at, vertexes) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    (void)cudaGetLastError();
+    CU(dVtx.ensure(std::max<size_t>(1, totals[1] * 3)));
+    vtx = dVtx.p;
+  }
+  if (cudaPointerGetAttributes(&at, faces) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    (void)cudaGetLastError();
+    CU(dFaces.ensure(std::max<size_t>(1, totals[0] * 3)));
+    fac = dFaces.p;
+  }
+  meshEmitVertexesKernel<<<tiles, kScanThreads>>>(g, dUsed.p, dTiles.p + tiles, dIndex.p, vtx);
+  meshEmitFacesKernel<<<tiles, kScanThreads>>>(W, n, dQuad.p, dTiles.p, dIndex.p, fac);
+  CU(cudaGetLastError());
+  if (vtx != vertexes) CU(cudaMemcpy(vertexes, vtx, totals[1] * 3 * sizeof(float), cudaMemcpyDefault));
+  if (fac != faces) CU(cudaMemcpy(faces, fac, totals[0] * 3 * sizeof(uint32_t), cudaMemcpyDefault));
+  CU(cudaDeviceSynchronize());
+  *num_faces = totals[0];
+  *num_vertexes = totals[1];
   return DERP_OK;
 }
 

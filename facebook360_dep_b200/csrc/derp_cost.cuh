@@ -307,13 +307,13 @@ __device__ __forceinline__ void loadPixelStateCompact(const CostView& v, const D
   const int tid = threadIdx.x;
   float2* bg = reinterpret_cast<float2*>(patches) + tid;
   float2* rr = bg + 9 * kPatchThreads;
-  const float4* col = v.projColor + (size_t)v.self * v.W * v.H;
+  const uint2* col = v.projColor16 + (size_t)v.self * v.W * v.H;  // u16 -> f32 is exact
   float rz[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {  // rows y-1 .. y+1 (interior pixel: always in bounds)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float4 t = __ldg(col + (size_t)(y - 1 + r) * v.W + (x - 1 + c));
+      const float4 t = ldTexel(col + (size_t)(y - 1 + r) * v.W + (x - 1 + c));
       bg[r * kPatchRP + c * kPatchCP] = make_float2(t.x + kBias23, t.y + kBias23);
       // rr[r] = (R(row r), R(row r+1)); the fast path reads rr[0] (both lanes) and rr[2].x, the slow path rr[r].x
       if (r >= 1) rr[(r - 1) * kPatchRP + c * kPatchCP] = make_float2(rz[c] + kBias23, t.z + kBias23);

@@ -117,28 +117,42 @@ __device__ __forceinline__ float roundSatU16(float v) {
   return (float)r;
 }
 
+__device__ __forceinline__ unsigned roundSatU16i(float v) {
+  int r = __float2int_rn(v);  // cvRound, then saturate_cast<ushort>
+  return (unsigned)(r < 0 ? 0 : (r > 65535 ? 65535 : r));
+}
+
+// wtab1 = the 32 x 4 one-dimensional coefficient rows; OpenCV's 2-D table entry (fy, fx)[k1][k2] is the fp32 product
+// wtab1[fy][k1] * wtab1[fx][k2] (initInterTab2D), formed here from two 16-byte shared-memory loads instead of 16
+// scattered table reads.  Output: 4 x u16 texels (B | G << 16, R); the R-below lane is filled by the bias kernels.
 __global__ void reprojectKernel(const float2* __restrict__ warpInv, int S, int self, int W, int H,
-                                const uint2* __restrict__ color, const float* __restrict__ wtab,
-                                float4* __restrict__ projColor) {
+                                const uint2* __restrict__ color, const float* __restrict__ wtab1,
+                                uint2* __restrict__ projColor16) {
+  __shared__ float4 tab[32];
+  {
+    const int t = threadIdx.y * blockDim.x + threadIdx.x;
+    if (t < 32) tab[t] = __ldg(reinterpret_cast<const float4*>(wtab1) + t);
+  }
+  __syncthreads();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   const int s = blockIdx.z;
   if (x >= W || y >= H) return;
   const size_t plane = (size_t)W * H;
   const size_t p = (size_t)y * W + x;
   if (s == self) {  // Derp.cpp:989-991: the destination's own colour
-    const Texel t = unpack(color[s * plane + p]);
-    projColor[s * plane + p] = make_float4(t.b, t.g, t.r, 0.f);
+    const uint2 t = color[s * plane + p];
+    projColor16[s * plane + p] = make_uint2(t.x, t.y & 0xffffu);
     return;
   }
   const float2 m = __ldg(warpInv + s * plane + p);
   const float mx = m.x, my = m.y;
   const int sxq = cvRoundQ5(mx), syq = cvRoundQ5(my);
-  const int fidx = (syq & 31) * 32 + (sxq & 31);
   int ix = sxq >> 5, iy = syq >> 5;
   ix = ix < -32768 ? -32768 : (ix > 32767 ? 32767 : ix);  // saturate_cast<short>
   iy = iy < -32768 ? -32768 : (iy > 32767 ? 32767 : iy);
   const int sx = ix - 1, sy = iy - 1;
-  const float* w = wtab + fidx * 16;
+  const float4 tx = tab[sxq & 31], ty = tab[syq & 31];
+  const float wy[4] = {ty.x, ty.y, ty.z, ty.w};
   const uint2* S0 = color + s * plane;
   float sum0, sum1, sum2;
   if ((unsigned)sx < (unsigned)max(W - 3, 0) && (unsigned)sy < (unsigned)max(H - 3, 0)) {
@@ -149,7 +163,7 @@ __global__ void reprojectKernel(const float2* __restrict__ warpInv, int S, int s
       const uint2* row = S0 + (size_t)(sy + i) * W + sx;
       const Texel a = unpack(__ldg(row)), b = unpack(__ldg(row + 1)), c = unpack(__ldg(row + 2)),
                   d = unpack(__ldg(row + 3));
-      const float w0 = __ldg(w + i * 4), w1 = __ldg(w + i * 4 + 1), w2 = __ldg(w + i * 4 + 2), w3 = __ldg(w + i * 4 + 3);
+      const float w0 = wy[i] * tx.x, w1 = wy[i] * tx.y, w2 = wy[i] * tx.z, w3 = wy[i] * tx.w;
       const float r0 = a.b * w0 + b.b * w1 + c.b * w2 + d.b * w3;
       const float r1 = a.g * w0 + b.g * w1 + c.g * w2 + d.g * w3;
       const float r2 = a.r * w0 + b.r * w1 + c.r * w2 + d.r * w3;
@@ -165,10 +179,11 @@ __global__ void reprojectKernel(const float2* __restrict__ warpInv, int S, int s
     }
   } else {
     if (sx >= W || sx + 4 <= 0 || sy >= H || sy + 4 <= 0) {
-      projColor[s * plane + p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      projColor16[s * plane + p] = make_uint2(0u, 0u);
       return;
     }
     // border: taps outside contribute the constant 0; one sequential sum (imgwarp.cpp)
+    const float wx[4] = {tx.x, tx.y, tx.z, tx.w};
     sum0 = sum1 = sum2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -179,14 +194,14 @@ __global__ void reprojectKernel(const float2* __restrict__ warpInv, int S, int s
         const int xj = sx + j;
         if ((unsigned)xj >= (unsigned)W) continue;
         const Texel t = unpack(__ldg(S0 + (size_t)yi * W + xj));
-        const float ww = __ldg(w + i * 4 + j);
+        const float ww = wy[i] * wx[j];
         sum0 += (t.b - 0.f) * ww;
         sum1 += (t.g - 0.f) * ww;
         sum2 += (t.r - 0.f) * ww;
       }
     }
   }
-  projColor[s * plane + p] = make_float4(roundSatU16(sum0), roundSatU16(sum1), roundSatU16(sum2), 0.f);
+  projColor16[s * plane + p] = make_uint2(roundSatU16i(sum0) | (roundSatU16i(sum1) << 16), roundSatU16i(sum2));
 }
 
 __device__ __forceinline__ int reflect101(int p, int len) {
@@ -196,70 +211,61 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 // ---- K4: colorBias = cv::blur 3x3 on u16x3 (DerpUtil.cpp:208-210) for all S planes -----------------
-// The texels are integer-valued floats (< 2^16), so the 9-term sums are exact in fp32 (< 2^24) and equal
-// OpenCV's integer row/column sums.
-// Also fills the w lane of every projColor texel with R of the texel below, which lets the cost kernel run
-// channel R of two vertically adjacent samples on the two lanes of the packed fp32x2 instructions
-// (derp_cost.cuh).  Only the 4 bytes of w are written, so concurrent readers of x,y,z are unaffected.
-__global__ void biasKernel(int W, int H, float4* in, float4* __restrict__ out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  const int s = blockIdx.z;
-  if (x >= W || y >= H) return;
-  float4* img = in + (size_t)s * W * H;
-  float sb = 0, sg = 0, sr = 0;
-  float4 centre = make_float4(0.f, 0.f, 0.f, 0.f);
-  float below = 0.f;
+// Input: the 4 x u16 reprojection (B | G << 16, R) written by reprojectKernel.  The 9-term sums are plain integer sums,
+// as in OpenCV's row/column filter; saturate_cast<ushort>(sum * (1.0/9)) == (sum + 4) / 9 for integer sums (no exact .5
+// cases).  Two output formats, one per consumer:
+//  * biasKernel: float4 tables for the dense sweep / evalCost / the getters — projColor = (B, G, R, R of the texel
+//    below), projBias = (B, G, R, 0) as integer-valued floats; the w lane lets the cost kernel run channel R of two
+//    vertically adjacent samples on the two lanes of the packed fp32x2 instructions (derp_cost.cuh);
+//  * bias16Kernel: the same two tables as 4 x u16 for the compacted fine-level kernels; projColor16 is the input
+//    itself, completed IN PLACE with the R-below lane (bits 16..31 of .y).  Concurrent readers of a texel being
+//    completed see either version of the 32-bit word and use only its low half, which does not change.
+struct BoxSum {
+  unsigned b, g, r, cx, cy, below;
+};
+__device__ __forceinline__ BoxSum boxSum3(const uint2* img, int W, int H, int x, int y) {
+  BoxSum o{0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
   for (int j = -1; j <= 1; ++j) {
     const int yy = reflect101(y + j, H);
 #pragma unroll
     for (int i = -1; i <= 1; ++i) {
       const int xx = reflect101(x + i, W);
-      const float4 t = img[(size_t)yy * W + xx];
-      sb += t.x;
-      sg += t.y;
-      sr += t.z;
-      if (i == 0 && j == 0) centre = t;
-      if (i == 0 && j == 1) below = (y + 1 < H) ? t.z : 0.f;
+      const uint2 t = img[(size_t)yy * W + xx];
+      o.b += t.x & 0xffffu;
+      o.g += t.x >> 16;
+      o.r += t.y & 0xffffu;
+      if (i == 0 && j == 0) {
+        o.cx = t.x;
+        o.cy = t.y & 0xffffu;
+      }
+      if (i == 0 && j == 1) o.below = (y + 1 < H) ? (t.y & 0xffffu) : 0u;
     }
   }
-  // saturate_cast<ushort>(sum * (1.0/9)) == (sum + 4) / 9 for integer sums (no exact .5 cases)
-  const int B = ((int)sb + 4) / 9, G = ((int)sg + 4) / 9, R = ((int)sr + 4) / 9;
-  out[(size_t)s * W * H + (size_t)y * W + x] = make_float4((float)B, (float)G, (float)R, 0.f);
-  // w lane = R of the texel below.  The whole texel is stored (one full 16-byte write instead of a 4-byte write
-  // into every sector); x, y, z are rewritten with the values just read, so concurrent readers are unaffected.
-  img[(size_t)y * W + x] = make_float4(centre.x, centre.y, centre.z, below);
+  o.b = (o.b + 4) / 9;
+  o.g = (o.g + 4) / 9;
+  o.r = (o.r + 4) / 9;
+  return o;
 }
 
-// K4 for the compacted fine-level kernels: same box filter, outputs as 4 x u16 texels (projColor16 = B,G,R,R-below;
-// projBias16 = B,G,R,0) read from the float4 reprojection (x,y,z lanes only), which is left untouched.
-__global__ void bias16Kernel(int W, int H, const float4* __restrict__ in, uint2* __restrict__ color16,
-                             uint2* __restrict__ bias16) {
+__global__ void biasKernel(int W, int H, const uint2* in, float4* __restrict__ color, float4* __restrict__ bias) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   const int s = blockIdx.z;
   if (x >= W || y >= H) return;
-  const float4* img = in + (size_t)s * W * H;
-  float sb = 0, sg = 0, sr = 0;
-  float4 centre = make_float4(0.f, 0.f, 0.f, 0.f);
-  float below = 0.f;
-#pragma unroll
-  for (int j = -1; j <= 1; ++j) {
-    const int yy = reflect101(y + j, H);
-#pragma unroll
-    for (int i = -1; i <= 1; ++i) {
-      const int xx = reflect101(x + i, W);
-      const float4 t = __ldg(img + (size_t)yy * W + xx);
-      sb += t.x;
-      sg += t.y;
-      sr += t.z;
-      if (i == 0 && j == 0) centre = t;
-      if (i == 0 && j == 1) below = (y + 1 < H) ? t.z : 0.f;
-    }
-  }
-  const unsigned B = ((unsigned)sb + 4) / 9, G = ((unsigned)sg + 4) / 9, R = ((unsigned)sr + 4) / 9;
-  const size_t o = (size_t)s * W * H + (size_t)y * W + x;
-  bias16[o] = make_uint2(B | (G << 16), R);
-  color16[o] = make_uint2((unsigned)centre.x | ((unsigned)centre.y << 16), (unsigned)centre.z | ((unsigned)below << 16));
+  const BoxSum o = boxSum3(in + (size_t)s * W * H, W, H, x, y);
+  const size_t q = (size_t)s * W * H + (size_t)y * W + x;
+  bias[q] = make_float4((float)o.b, (float)o.g, (float)o.r, 0.f);
+  color[q] = make_float4((float)(o.cx & 0xffffu), (float)(o.cx >> 16), (float)o.cy, (float)o.below);
+}
+
+__global__ void bias16Kernel(int W, int H, uint2* color16, uint2* __restrict__ bias16) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int s = blockIdx.z;
+  if (x >= W || y >= H) return;
+  const BoxSum o = boxSum3(color16 + (size_t)s * W * H, W, H, x, y);
+  const size_t q = (size_t)s * W * H + (size_t)y * W + x;
+  bias16[q] = make_uint2(o.b | (o.g << 16), o.r);
+  color16[q] = make_uint2(o.cx, o.cy | (o.below << 16));
 }
 
 // ---- K5: computeImageVariance (DerpUtil.cpp:214-237) for all S planes ---------------------------

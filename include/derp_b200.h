@@ -282,6 +282,23 @@ int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, u
 int derp_foreground_mask(int device, const uint16_t* templ, const uint16_t* frame, int width, int height, int blur_radius,
                          float threshold, int morph_closing_size, uint8_t* mask);
 
+/* Camera mesh of one disparity map, the geometry half of ConvertToBinary's convertDepth BEFORE mesh simplification
+ * (source/mesh_stream/ConvertToBinary.cpp:150-183; SURVEY §8(f) rank 4, first slice): depth = 1 / disparity, optional
+ * INTER_NEAREST shrink by depth_scale (< 1; 1 = none), mesh_util::getVertexesEquiError (source/render/MeshUtil.h:313-338),
+ * mesh_util::getFaces(wrapHorizontally = false, isRigCoordinates = false, tear_ratio) (MeshUtil.h:162-298), vertex mask =
+ * !isnan(depth) [& bit 0 of the foreground mask, resized INTER_NEAREST to the depth grid],
+ * mesh_util::applyMaskToVertexesAndFaces (MeshUtil.h:342-403).  Outputs in the layout mesh_util::writeDepth stores as
+ * .vtx / .idx (MeshUtil.h:74-93): float32 x, y, z per vertex, uint32 x 3 per face, in the reference's order.
+ * resolution_* / scalar_focal: the camera's (possibly rescaled, ConvertToBinary.cpp:322-343) resolution and
+ * Camera::getScalarFocal().  `vertexes` needs room for 3 floats per grid cell, `faces` for 6 uint32 per grid cell
+ * (derp_camera_mesh_size gives the grid); both may be host or device memory, like the inputs.
+ * Not built: MeshSimplifier (--triangles > 0), BC7 colour, fusion. */
+int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_width, int* mesh_height);
+int derp_camera_mesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                     int mask_width, int mask_height, float* vertexes, uint32_t* faces, uint64_t* num_vertexes,
+                     uint64_t* num_faces);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,6 +279,27 @@ inline void resizeNearest(const T* src, int sw, int sh, T* dst, int dw, int dh) 
   }
 }
 
+// cv::resize(src, dst, Size(), fx, fy, INTER_NEAREST): dsize = cvRound(size * f), source index =
+// min(floor(d * (1 / f)), size - 1) — the scale factors the caller gave, not the size ratio (resize.cpp).
+// ConvertToBinary.cpp:153-156 shrinks the depth map with it.
+inline void nearestScaledAxis(int sn, double f, std::vector<int>& ofs) {
+  const int dn = cvRoundD(sn * f);
+  const double ifx = 1. / f;
+  ofs.resize(dn > 0 ? dn : 0);
+  for (int d = 0; d < dn; ++d) ofs[d] = std::min(cvFloorD(d * ifx), sn - 1);
+}
+template <typename T>
+inline void resizeNearestScaled(const T* src, int sw, int sh, double fx, double fy, std::vector<T>& dst, int* dw, int* dh) {
+  std::vector<int> xo, yo;
+  nearestScaledAxis(sw, fx, xo);
+  nearestScaledAxis(sh, fy, yo);
+  *dw = (int)xo.size();
+  *dh = (int)yo.size();
+  dst.resize(xo.size() * yo.size());
+  for (size_t y = 0; y < yo.size(); ++y)
+    for (size_t x = 0; x < xo.size(); ++x) dst[y * xo.size() + x] = src[(size_t)yo[y] * sw + xo[x]];
+}
+
 // ---- cv::resize INTER_AREA, u16 x 3 channels, shrinking (resize.cpp: resizeAreaFast_ for integer ratios,
 // computeResizeAreaTab + ResizeArea_Invoker<ushort, float> otherwise) — scripts/render/resize.py:79 builds every
 // pyramid level from the full-size image with it, UpsampleDisparity.cpp:117 (cv_util::resizeImage) shrinks colour.

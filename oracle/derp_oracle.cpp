@@ -32,6 +32,7 @@
 #include <random>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -1406,6 +1407,117 @@ int derp_foreground_mask(int /*device*/, const uint16_t* templ, const uint16_t* 
     return DERP_EINVAL;
   return DERP_OK;
 }
+// ---- camera mesh (first slice): ConvertToBinary.cpp:150-183 before simplification -----------
+namespace mesh {
+// getTriangleMask, source/render/MeshUtil.h:162-221 (isRigCoordinates = false: z is the distance measure)
+static unsigned triangleMask(const std::vector<double>& z, int base, int width, float tearRatio) {
+  const double tl = z[base], tr = z[base + 1], bl = z[base + width], br = z[base + width + 1];
+  std::vector<std::tuple<double, int>> v = {std::make_tuple(tl, 0), std::make_tuple(tr, 1), std::make_tuple(bl, 2),
+                                            std::make_tuple(br, 3)};
+  std::sort(v.begin(), v.end());  // literal: with NaN depths the order is whatever libstdc++'s insertion sort leaves
+  if (std::get<0>(v.front()) / std::get<0>(v.back()) > tearRatio) {
+    if (std::abs(tl - br) < std::abs(tr - bl)) return 1 << 1 | 1 << 2;
+    return 1 << 0 | 1 << 3;
+  }
+  const double lo = std::get<0>(v.front()) / std::get<0>(v[2]);
+  const double hi = std::get<0>(v[1]) / std::get<0>(v.back());
+  if (lo >= tearRatio && lo > hi) return 1 << (std::get<1>(v.back()) ^ 0x3);
+  if (hi >= tearRatio) return 1 << (std::get<1>(v.front()) ^ 0x3);
+  return 0;
+}
+// addTriangle, MeshUtil.h:224-251
+static void triangle(int which, int base, int width, int* f) {
+  switch (which) {
+    case 0: f[0] = base + width, f[1] = base + 1, f[2] = base; break;
+    case 1: f[0] = base, f[1] = base + width + 1, f[2] = base + 1; break;
+    case 2: f[0] = base + width + 1, f[1] = base, f[2] = base + width; break;
+    default: f[0] = base + 1, f[1] = base + width, f[2] = base + width + 1; break;
+  }
+}
+}  // namespace mesh
+
+int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_width, int* mesh_height) {
+  if (width < 1 || height < 1 || !(depth_scale > 0) || depth_scale > 1 || !mesh_width || !mesh_height) return DERP_EINVAL;
+  *mesh_width = depth_scale < 1 ? cvRoundD(width * depth_scale) : width;
+  *mesh_height = depth_scale < 1 ? cvRoundD(height * depth_scale) : height;
+  return DERP_OK;
+}
+
+int derp_camera_mesh(int /*device*/, const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                     int mask_width, int mask_height, float* vertexes, uint32_t* faces, uint64_t* num_vertexes,
+                     uint64_t* num_faces) {
+  int W = 0, H = 0;
+  if (derp_camera_mesh_size(width, height, depth_scale, &W, &H) || !disparity || !vertexes || !faces || !num_vertexes ||
+      !num_faces || W < 1 || H < 1 || (foreground_mask && (mask_width < 1 || mask_height < 1)))
+    return DERP_EINVAL;
+  // depth = 1.0f / disparity (cv::divide on floats: IEEE since OpenCV 4), ConvertToBinary.cpp:151-152
+  std::vector<float> depth((size_t)width * height);
+  for (size_t i = 0; i < depth.size(); ++i) depth[i] = 1.0f / disparity[i];
+  if (depth_scale < 1) {  // :153-156
+    std::vector<float> small;
+    int w2, h2;
+    resizeNearestScaled<float>(depth.data(), width, height, depth_scale, depth_scale, small, &w2, &h2);
+    depth.swap(small);
+  }
+  const size_t n = (size_t)W * H;
+  // getVertexesEquiError, MeshUtil.h:313-338
+  const double scale = scalar_focal * 1.0;
+  std::vector<double> vx(n), vy(n), vz(n);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const size_t i = (size_t)y * W + x;
+      vx[i] = resolution_x / W * (x + 0.5);
+      vy[i] = resolution_y / H * (y + 0.5);
+      vz[i] = scale / depth[i];
+    }
+  // getFaces(wrapHorizontally = false, isRigCoordinates = false), MeshUtil.h:267-298
+  std::vector<int> fc;
+  fc.reserve(n * 6);
+  for (int y = 0; y < H - 1; ++y)
+    for (int x = 0; x < W - 1; ++x) {
+      const int base = y * W + x;
+      const unsigned m = mesh::triangleMask(vz, base, W, tear_ratio);
+      for (int t = 0; t < 4; ++t)
+        if ((m >> t) & 1) {
+          int f[3];
+          mesh::triangle(t, base, W, f);
+          fc.insert(fc.end(), f, f + 3);
+        }
+    }
+  // vertex mask, ConvertToBinary.cpp:163-176
+  std::vector<uint8_t> vmask(n);
+  for (size_t i = 0; i < n; ++i) vmask[i] = !std::isnan(depth[i]);
+  if (foreground_mask) {
+    std::vector<uint8_t> fm(n);
+    resizeNearest<uint8_t>(foreground_mask, mask_width, mask_height, fm.data(), W, H);
+    for (size_t i = 0; i < n; ++i) vmask[i] = vmask[i] & fm[i];  // Mat_<bool> & Mat_<bool>: bitwise on the bytes
+  }
+  // applyMaskToVertexesAndFaces, MeshUtil.h:342-403
+  std::vector<size_t> keep;
+  for (size_t i = 0; i < fc.size() / 3; ++i)
+    if (vmask[fc[3 * i]] && vmask[fc[3 * i + 1]] && vmask[fc[3 * i + 2]]) keep.push_back(i);
+  std::vector<uint8_t> usedv(n, 0);
+  for (size_t i : keep)
+    for (int j = 0; j < 3; ++j) usedv[fc[3 * i + j]] = 1;
+  std::vector<int> newIndex(n, -1);
+  uint64_t nv = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (usedv[i]) {
+      newIndex[i] = (int)nv;
+      // writeDepth's vertexes.cast<float>(), MeshUtil.h:80-83
+      vertexes[nv * 3 + 0] = (float)vx[i];
+      vertexes[nv * 3 + 1] = (float)vy[i];
+      vertexes[nv * 3 + 2] = (float)vz[i];
+      ++nv;
+    }
+  for (size_t k = 0; k < keep.size(); ++k)
+    for (int j = 0; j < 3; ++j) faces[k * 3 + j] = (uint32_t)newIndex[fc[3 * keep[k] + j]];
+  *num_vertexes = nv;
+  *num_faces = keep.size();
+  return DERP_OK;
+}
+
 int oracle_resize_area(const uint16_t* src, int sw, int sh, uint16_t* dst, int dw, int dh) {
   return resizeAreaU16C3(src, sw, sh, dst, dw, dh) ? 0 : -1;
 }

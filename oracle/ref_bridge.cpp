@@ -37,6 +37,7 @@
 #include "source/depth_estimation/Derp.h"
 #include "source/depth_estimation/TemporalBilateralFilter.h"
 #include "source/depth_estimation/UpsampleDisparityLib.h"
+#include "source/render/MeshUtil.h"
 #include "source/util/Camera.h"
 
 #include "../include/derp_b200.h"
@@ -651,6 +652,54 @@ int derp_foreground_mask(int /*device*/, const uint16_t* templ, const uint16_t* 
   if (!templ || !frame || !mask || !oracle::foregroundMaskU16C3(templ, frame, w, h, blur_radius, threshold, morph_closing_size, mask))
     return fail(DERP_EINVAL, "bad arguments");
   return DERP_OK;
+}
+
+/* Camera mesh: the reference's own mesh_util functions (source/render/MeshUtil.h, compiled unmodified) called in the order
+ * convertDepth calls them (source/mesh_stream/ConvertToBinary.cpp:150-183; that file itself is an executable with BC7 and
+ * MeshSimplifier dependencies, so its dozen lines of glue are restated here), up to the casts of mesh_util::writeDepth. */
+int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_width, int* mesh_height) {
+  if (width < 1 || height < 1 || !(depth_scale > 0) || depth_scale > 1 || !mesh_width || !mesh_height)
+    return fail(DERP_EINVAL, "bad arguments");
+  *mesh_width = depth_scale < 1 ? oracle::cvRoundD(width * depth_scale) : width;
+  *mesh_height = depth_scale < 1 ? oracle::cvRoundD(height * depth_scale) : height;
+  return DERP_OK;
+}
+
+int derp_camera_mesh(int /*device*/, const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                     int mask_width, int mask_height, float* vertexesOut, uint32_t* facesOut, uint64_t* num_vertexes,
+                     uint64_t* num_faces) {
+  int W = 0, H = 0;
+  if (derp_camera_mesh_size(width, height, depth_scale, &W, &H) || !disparity || !vertexesOut || !facesOut ||
+      !num_vertexes || !num_faces || W < 1 || H < 1 || (foreground_mask && (mask_width < 1 || mask_height < 1)))
+    return fail(DERP_EINVAL, "bad arguments");
+  return guarded([&] {
+    cv::Mat_<float> depth(height, width);
+    for (int y = 0; y < height; ++y)
+      for (int x = 0; x < width; ++x) depth(y, x) = 1.0f / disparity[(size_t)y * width + x];  // cv::Mat 1.0f / disparity
+    if (depth_scale < 1) cv::resize(depth, depth, cv::Size(), depth_scale, depth_scale, cv::INTER_NEAREST);
+    const Camera cam(Camera::Type::FTHETA, Camera::Vector2(resolution_x, resolution_y),
+                     Camera::Vector2(scalar_focal, -scalar_focal));
+    Eigen::MatrixXd vertexes = mesh_util::getVertexesEquiError(depth, cam);
+    Eigen::MatrixXi faces = mesh_util::getFaces(vertexes, depth.cols, depth.rows, false, false, tear_ratio);
+    cv::Mat_<bool> vertexMask(depth.size());
+    for (int i = 0; i < depth.rows; ++i)
+      for (int j = 0; j < depth.cols; ++j) vertexMask(i, j) = !std::isnan(depth(i, j));
+    if (foreground_mask) {
+      cv::Mat_<bool> foregroundMask(mask_height, mask_width);
+      std::memcpy(foregroundMask.data, foreground_mask, (size_t)mask_width * mask_height);
+      cv::resize(foregroundMask, foregroundMask, depth.size(), 0, 0, cv::INTER_NEAREST);
+      vertexMask = vertexMask & foregroundMask;
+    }
+    mesh_util::applyMaskToVertexesAndFaces(vertexes, faces, vertexMask);
+    Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> v = vertexes.cast<float>();  // writeDepth
+    Eigen::Matrix<uint32_t, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> f = faces.cast<uint32_t>();
+    std::memcpy(vertexesOut, v.data(), v.size() * sizeof(float));
+    std::memcpy(facesOut, f.data(), f.size() * sizeof(uint32_t));
+    *num_vertexes = (uint64_t)vertexes.rows();
+    *num_faces = (uint64_t)faces.rows();
+    return (int)DERP_OK;
+  });
 }
 
 /* bench / test hook (not part of derp_b200.h): candidate slices of the brute-force cost volume the way the reference

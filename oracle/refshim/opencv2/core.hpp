@@ -665,7 +665,17 @@ inline void blur(const Mat& src, Mat& dst, Size ksize) {
   }
   dst = out;
 }
-inline void resize(const Mat& src, Mat& dst, Size dsize, double /*fx*/, double /*fy*/, int interpolation) {
+inline void resize(const Mat& src, Mat& dst, Size dsize, double fx, double fy, int interpolation) {
+  if (dsize.width == 0 && dsize.height == 0) {  // scale factors instead of a size (ConvertToBinary.cpp:155)
+    if (src.type() != CV_32FC1 || interpolation != INTER_NEAREST) shimUnsupported("resize by factors other than float NEAREST");
+    std::vector<float> small;
+    int dw = 0, dh = 0;
+    oracle::resizeNearestScaled<float>(src.ptr<float>(), src.cols, src.rows, fx, fy, small, &dw, &dh);
+    Mat scaled(dh, dw, src.type());
+    std::memcpy(scaled.data, small.data(), small.size() * sizeof(float));
+    dst = scaled;
+    return;
+  }
   Mat out(dsize.height, dsize.width, src.type());
   if (src.type() == CV_32FC1 && interpolation == INTER_LANCZOS4) {
     oracle::resizeLanczos4F32(src.ptr<float>(), src.cols, src.rows, out.ptr<float>(), dsize.width, dsize.height);

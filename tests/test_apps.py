@@ -64,6 +64,14 @@ REF_FLAGS = {
         "last": ("string", ""), "morph_closing_size": ("int32", "4"), "rig": ("string", ""), "threads": ("int32", "-1"),
         "threshold": ("double", "0.04"), "width": ("int32", "2048"),
     },
+    "ConvertToBinary": {  # source/mesh_stream/ConvertToBinary.cpp:62-87
+        "bin": ("string", "bin"), "cameras": ("string", ""), "color": ("string", ""), "color_scale": ("double", "1"),
+        "depth_scale": ("double", "1"), "disparity": ("string", ""), "first": ("string", ""),
+        "foreground_masks": ("string", ""), "fuse_strip": ("int32", "1"), "fused": ("string", ""),
+        "gamma_correction": ("expr", "2.2 / 1.8"), "last": ("string", ""), "output_formats": ("string", "idx,vtx,bc7"), "rig": ("string", ""),
+        "run_conversion": ("bool", "true"), "tear_ratio": ("double", "0.95"), "threads": ("int32", "-1"),
+        "triangles": ("int32", "150000"),
+    },
     "UpsampleDisparity": {
         "background_disp": ("string", ""), "background_frame": ("string", "000000"), "cameras": ("string", ""),
         "color": ("string", ""), "disparity": ("string", ""), "first": ("string", "000000"),
@@ -82,10 +90,13 @@ def test_flag_surface_matches_reference(app):
     with the reference's types and defaults (extra B200 flags allowed)."""
     src = open(os.path.join(HOST, app + ".cpp")).read()
     found = {}
-    for m in re.finditer(r"DEFINE_(\w+)\(\s*(\w+)\s*,\s*([^,]*?)\s*,\s*\"", src):
+    for m in re.finditer(r'DEFINE_(\w+)\(\s*(\w+)\s*,\s*("[^"]*"|[^,]*?)\s*,\s*"', src):
         found[m.group(2)] = (m.group(1), m.group(3).strip().strip('"'))
     for name, (typ, default) in REF_FLAGS[app].items():
         assert name in found, name
+        if typ == "expr":  # a double whose default is written as an expression
+            assert found[name] == ("double", default), name
+            continue
         assert found[name][0] == typ, name
         if typ == "double":
             assert float(found[name][1]) == float(default), name
@@ -418,3 +429,94 @@ def test_debug_images_exr_and_foreground_masks(tmp_path, cuda):
         m = cv2.morphologyEx(m, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (4, 4)))
         got = cv2.imread(os.path.join(mdir, "cam%d" % s, "000007.png"), cv2.IMREAD_UNCHANGED)
         assert got.dtype == np.uint8 and np.array_equal(got, m * 255), s
+
+
+def _mesh_dataset(tmp_path, W=96, H=80, S=3, F=2):
+    rig = synth.ring_rig(S, W, H, kind="FTHETA")
+    os.makedirs(tmp_path / "rigs", exist_ok=True)
+    json.dump(rig, open(tmp_path / "rigs" / "rig.json", "w"))
+    rng = np.random.RandomState(4)
+    disps = {}
+    for cam in rig["cameras"]:
+        for f in range(F):
+            yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+            d = (0.3 + 0.1 * np.sin(xx / 9.0 + f) * np.cos(yy / 7.0)).astype(np.float32)
+            d[(xx + yy) % 31 < 9] *= 1.5
+            d[rng.uniform(size=d.shape) < 0.03] = np.nan
+            write_pfm(str(tmp_path / "disparity" / cam["id"] / ("%06d.pfm" % f)), d)
+            disps[cam["id"], f] = d
+    return rig, disps
+
+
+def test_convert_to_binary_refuses_unbuilt_parts(tmp_path):
+    """The reference's defaults ask for simplification to 150 k triangles and BC7 colour: neither is built, and the
+    executable says so instead of writing something else (no GPU needed to get that far)."""
+    rig, _ = _mesh_dataset(tmp_path, F=1)
+    base = ["--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
+            "--disparity=" + str(tmp_path / "disparity"), "--bin=" + str(tmp_path / "bin")]
+    p = run("ConvertToBinary", *base, check=False)
+    assert p.returncode != 0 and "--triangles=0" in p.stderr
+    os.makedirs(tmp_path / "color" / rig["cameras"][0]["id"], exist_ok=True)
+    p = run("ConvertToBinary", *base, "--triangles=0", "--color=" + str(tmp_path / "color"), check=False)
+    assert p.returncode != 0 and "bc7" in p.stderr
+
+
+@pytest.mark.gpu
+def test_convert_to_binary_meshes(tmp_path, cuda, oracle):
+    """Files in -> files out: .vtx / .idx equal the checker's mesh of the same PFMs byte for byte (--depth_scale and a
+    foreground mask included), the .obj lists the same mesh, the fused stream holds every file at the catalogued offset
+    with 0x5A padding to the 512 KiB stripe, and the fused rig is written."""
+    from tests import oracle_libs
+    checker = oracle_libs.load_ref() or oracle
+    rig, disps = _mesh_dataset(tmp_path)
+    H, W = next(iter(disps.values())).shape
+    rng = np.random.RandomState(1)
+    masks = {}
+    for cam in rig["cameras"]:
+        for f in range(2):
+            m = (rng.uniform(size=(H // 2, W // 2)) > 0.15).astype(np.uint8)
+            d = tmp_path / "masks" / cam["id"]
+            os.makedirs(d, exist_ok=True)
+            assert cv2.imwrite(str(d / ("%06d.png" % f)), m * 255)
+            masks[cam["id"], f] = m
+    run("ConvertToBinary", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000001",
+        "--disparity=" + str(tmp_path / "disparity"), "--foreground_masks=" + str(tmp_path / "masks"),
+        "--bin=" + str(tmp_path / "bin"), "--fused=" + str(tmp_path / "fused"), "--fuse_strip=2", "--triangles=0",
+        "--depth_scale=0.5", "--output_formats=idx,vtx,obj")
+    catalog = json.load(open(tmp_path / "fused" / "fused.json"))
+    assert catalog["metadata"]["isLittleEndian"] is True
+    disks = [open(tmp_path / "fused" / ("fused_%d.bin" % i), "rb").read() for i in range(2)]
+    stripe = 512 * 1024
+
+    def fused_bytes(offset, size):  # StripedFile.h:96-101
+        out = b""
+        while size:
+            s = offset // stripe
+            local = (s // 2) * stripe + offset % stripe
+            n = min(size, stripe - offset % stripe)
+            out += disks[s % 2][local:local + n]
+            offset += n
+            size -= n
+        return out
+
+    for cam in rig["cameras"]:
+        res, focal = cam["resolution"], cam["focal"][0]
+        for f in range(2):
+            v, i = checker.camera_mesh(disps[cam["id"], f], res, focal, depth_scale=0.5, tear_ratio=0.95,
+                                       foreground_mask=masks[cam["id"], f])
+            stem = tmp_path / "bin" / cam["id"] / ("%06d" % f)
+            assert open(str(stem) + ".vtx", "rb").read() == v.tobytes()
+            assert open(str(stem) + ".idx", "rb").read() == i.tobytes()
+            obj = open(str(stem) + ".obj").read().splitlines()
+            assert sum(l.startswith("v ") for l in obj) == len(v) and sum(l.startswith("f ") for l in obj) == len(i)
+            entry = catalog["frames"]["%06d" % f][cam["id"]]
+            assert entry["offset"] % stripe == 0
+            for ext in (".idx", ".vtx", ".obj"):
+                e = entry[ext]
+                assert fused_bytes(e["offset"], e["size"]) == open(str(stem) + ext, "rb").read()
+            end = entry["offset"] + entry["size"]
+            pad = fused_bytes(end, -end % stripe)
+            assert pad == b"\x5a" * len(pad)
+    fused_rig = json.load(open(tmp_path / "fused" / "rig_fused.json"))
+    assert [c["id"] for c in fused_rig["cameras"]] == [c["id"] for c in rig["cameras"]]
+    assert np.allclose(fused_rig["cameras"][0]["focal"], rig["cameras"][0]["focal"])

@@ -1,0 +1,114 @@
+"""Camera mesh of a disparity map (first slice: the geometry half of ConvertToBinary's convertDepth
+before simplification — ConvertToBinary.cpp:150-183, MeshUtil.h).  CPU: the oracle restatement against the reference's own
+MeshUtil.h (oracle/_ref) and hand-checked small cases.  GPU: the CUDA library against the checker, exactly (index work and
+IEEE fp64 divisions only — no tolerance)."""
+import numpy as np
+import pytest
+
+from tests import oracle_libs
+
+
+def disparity_case(rng, w, h, nan_frac=0.02, zero_frac=0.005, steps=True):
+    """Smooth disparity with depth discontinuities (tears), NaN holes and a few zeros (infinite depth)."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    d = 0.4 + 0.2 * np.sin(xx / 17.0) * np.cos(yy / 11.0)
+    if steps:
+        d[(xx + 2 * yy) % 61 < 20] *= 1.6  # discontinuities well beyond the 0.95 tear ratio
+        d += rng.uniform(-0.012, 0.012, d.shape)  # and many ratios close to it
+    d = d.astype(np.float32)
+    d[rng.uniform(size=d.shape) < nan_frac] = np.nan
+    d[rng.uniform(size=d.shape) < zero_frac] = 0.0
+    return d
+
+
+def check_mesh_invariants(vtx, idx, w, h):
+    assert vtx.dtype == np.float32 and idx.dtype == np.uint32
+    if len(idx):
+        assert idx.max() < len(vtx)
+        # every vertex is referenced (applyMaskToVertexesAndFaces drops the others), in ascending first-use-free order
+        assert np.array_equal(np.unique(idx), np.arange(len(vtx)))
+    assert len(idx) <= 2 * (w - 1) * (h - 1)
+
+
+CASES = [
+    dict(w=37, h=23, scale=1.0, fg=False, tear=0.95),
+    dict(w=64, h=48, scale=1.0, fg=True, tear=0.95),
+    dict(w=96, h=80, scale=0.5, fg=False, tear=0.95),
+    dict(w=101, h=67, scale=0.37, fg=True, tear=0.9),
+    dict(w=40, h=40, scale=1.0, fg=False, tear=0.0),
+    dict(w=2, h=2, scale=1.0, fg=False, tear=0.95),
+    dict(w=1, h=5, scale=1.0, fg=False, tear=0.95),
+]
+
+
+def run_case(lib, case, seed=0):
+    rng = np.random.RandomState(seed)
+    d = disparity_case(rng, case["w"], case["h"])
+    fg = None
+    if case["fg"]:  # a mask at another resolution, values 0 / 1 / 255 / 254 (bit 0 decides, like Mat_<bool> & Mat_<bool>)
+        fg = rng.choice(np.array([0, 1, 255, 254], np.uint8), size=(case["h"] // 2 + 3, case["w"] // 2 + 1), p=[0.1, 0.4, 0.4, 0.1])
+    return lib.camera_mesh(d, (case["w"] * 4.0, case["h"] * 4.0), 317.25, depth_scale=case["scale"],
+                           tear_ratio=case["tear"], foreground_mask=fg)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_equals_reference_mesh_util(oracle, case):
+    ref = oracle_libs.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    for seed in range(3):
+        ov, oi = run_case(oracle, case, seed)
+        rv, ri = run_case(ref, case, seed)
+        assert np.array_equal(oi, ri)
+        assert np.array_equal(ov.view(np.uint32), rv.view(np.uint32))
+        check_mesh_invariants(ov, oi, case["w"], case["h"])
+
+
+def test_flat_quad_by_hand(oracle):
+    """2 x 2 constant disparity: both triangles, split along the tl-br diagonal rule (|tl-br| < |tr-bl| is false ->
+    triangles 0 and 3), vertexes = pixel centres scaled to the camera resolution, z = focal * disparity."""
+    d = np.full((2, 2), 0.5, np.float32)
+    v, f = oracle.camera_mesh(d, (8.0, 8.0), 100.0)
+    assert np.array_equal(f, np.array([[2, 1, 0], [1, 2, 3]], np.uint32))
+    assert np.allclose(v, [[2, 2, 50], [6, 2, 50], [2, 6, 50], [6, 6, 50]])
+    # one NaN corner: only the triangle opposite to it survives the vertex mask, and the vertexes are re-indexed
+    d[0, 0] = np.nan
+    v, f = oracle.camera_mesh(d, (8.0, 8.0), 100.0)
+    assert len(v) == 3 and len(f) <= 1
+    # a tear: one corner much closer -> the triangle that avoids it
+    d = np.array([[0.5, 0.5], [0.5, 5.0]], np.float32)
+    v, f = oracle.camera_mesh(d, (8.0, 8.0), 100.0)
+    assert np.array_equal(f, np.array([[2, 1, 0]], np.uint32)) and len(v) == 3
+
+
+def test_bad_arguments(oracle):
+    with pytest.raises(Exception):
+        oracle.camera_mesh(np.ones((4, 4), np.float32), (4.0, 4.0), 1.0, depth_scale=1.5)  # CHECK_LE(depth_scale, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_gpu_mesh_equals_checker(cuda, oracle, case):
+    ref = oracle_libs.load_ref()
+    checker = ref if ref is not None else oracle
+    for seed in range(3):
+        gv, gi = run_case(cuda, case, seed)
+        cv, ci = run_case(checker, case, seed)
+        assert np.array_equal(gi, ci)
+        assert np.array_equal(gv.view(np.uint32), cv.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_mesh_full_size(cuda, oracle):
+    """2048 x 2048 (level-0 disparity of the headline rig) with holes, tears and a foreground mask: exact against the
+    oracle, and the mesh invariants."""
+    rng = np.random.RandomState(11)
+    w = h = 2048
+    d = disparity_case(rng, w, h)
+    fg = (rng.uniform(size=(h // 4, w // 4)) > 0.2).astype(np.uint8)
+    gv, gi = cuda.camera_mesh(d, (float(w), float(h)), 651.9, foreground_mask=fg)
+    ov, oi = oracle.camera_mesh(d, (float(w), float(h)), 651.9, foreground_mask=fg)
+    assert len(gi) > 1_000_000
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(gv.view(np.uint32), ov.view(np.uint32))
+    check_mesh_invariants(gv, gi, w, h)
