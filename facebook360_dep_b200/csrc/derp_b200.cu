@@ -63,8 +63,8 @@ inline dim3 block2() { return dim3(kBlockX, kBlockY, 1); }
 // Grid of the kernels that walk the active-pixel list: one CTA per kPatchThreads list slots of the largest
 // possible list (its length is only known on the device); CTAs past the end exit before staging anything.  A
 // capped grid with more loop trips per CTA measured slightly slower (ping-pong 6.08 vs 5.93 ms at 2048^2).
-inline unsigned listGrid(int W, int H) {
-  const size_t all = ((size_t)(W - 2) * (H - 2) + kPatchThreads - 1) / kPatchThreads;
+inline unsigned listGrid(int W, int H, int threads = kPatchThreads) {
+  const size_t all = ((size_t)(W - 2) * (H - 2) + threads - 1) / threads;
   return (unsigned)std::max<size_t>(1, all);
 }
 inline size_t bilateralSmem(int radius) {  // float4 tile + mask bytes of bilateralKernel
@@ -242,8 +242,8 @@ struct DerpCtx {
     return (size_t)S * sizeof(DevCamera) + kTileFloats * sizeof(float) + (size_t)selSlots() * threads * sizeof(float2);
   }
   // compacted kernels: S cameras + one 3x3 patch per thread + the selection slots
-  size_t patchSmem() const {
-    return (size_t)S * sizeof(DevCamera) + kPatchFloats * sizeof(float) + (size_t)selSlots() * kPatchThreads * sizeof(float2);
+  size_t patchSmem(int threads = kPatchThreads) const {
+    return (size_t)S * sizeof(DevCamera) + (size_t)2 * 9 * threads * 2 * sizeof(float) + (size_t)selSlots() * threads * sizeof(float2);
   }
 };
 
@@ -922,7 +922,7 @@ int derp_ping_pong(DerpCtx* c, int dst, int iterations) {
       CU(cudaEventCreate(&p1));
       CU(cudaEventRecord(p0, c->stream));
     }
-    pingPongKernel<<<listGrid(W, H), kPatchThreads, c->patchSmem(), c->stream>>>(a);
+    pingPongKernel<<<listGrid(W, H, kPingThreads), kPingThreads, c->patchSmem(kPingThreads), c->stream>>>(a);
     LAUNCHED("pingPongKernel");
     if (c->profiling) {
       CU(cudaEventRecord(p1, c->stream));
@@ -1411,11 +1411,38 @@ int derp_camera_mesh(int device, const float* disparity, int width, int height, 
     nearestAxis(mask_height, H, tmp);
     ofs.insert(ofs.end(), tmp.begin(), tmp.end());
   }
-  DevBuf<float> dDisp, dVtx;
-  DevBuf<int> dOfs;
-  DevBuf<uint8_t> dFg, dQuad, dUsed;
-  DevBuf<unsigned> dTiles, dIndex, dFaces;
-  DevBuf<unsigned long long> dTotals;
+  // grow-only scratch per host thread (the app converts one (frame, camera) after the other on each GPU worker thread)
+  struct MeshScratch {
+    DevBuf<float> dDisp, dVtx;
+    DevBuf<int> dOfs;
+    DevBuf<uint8_t> dFg, dQuad, dUsed;
+    DevBuf<unsigned> dTiles, dIndex, dFaces;
+    DevBuf<unsigned long long> dTotals;
+    int device = -1;
+  };
+  static thread_local MeshScratch sc;
+  if (sc.device != device) {  // the thread moved to another GPU: the old buffers belong to the old device
+    if (sc.device >= 0) {
+      cudaSetDevice(sc.device);
+      sc.dDisp.release();
+      sc.dVtx.release();
+      sc.dOfs.release();
+      sc.dFg.release();
+      sc.dQuad.release();
+      sc.dUsed.release();
+      sc.dTiles.release();
+      sc.dIndex.release();
+      sc.dFaces.release();
+      sc.dTotals.release();
+      CU(cudaSetDevice(device));
+    }
+    sc.device = device;
+  }
+  DevBuf<float>&dDisp = sc.dDisp, &dVtx = sc.dVtx;
+  DevBuf<int>& dOfs = sc.dOfs;
+  DevBuf<uint8_t>&dFg = sc.dFg, &dQuad = sc.dQuad, &dUsed = sc.dUsed;
+  DevBuf<unsigned>&dTiles = sc.dTiles, &dIndex = sc.dIndex, &dFaces = sc.dFaces;
+  DevBuf<unsigned long long>& dTotals = sc.dTotals;
   const float* disp = disparity;
   const uint8_t* fg = foreground_mask;
   cudaPointerAttributes at{};

@@ -293,20 +293,32 @@ __device__ __forceinline__ void loadPixelState(const CostView& v, const DevCamer
 #define DERP_PATCH_THREADS 256
 #endif
 #ifndef DERP_PATCH_MINB
-// Resident CTAs per SM the compacted kernels are compiled for (register cap).  2 => 128 registers, no spills,
-// 16 warps/SM: these kernels are L1-bound (scattered 4x4 gathers, profiles/README.md), so spill traffic costs more
-// than the lost warps: at 2048^2 proposals 0.98 -> 0.63 ms, ping-pong 5.93 -> 5.51 ms against 3 CTAs / 80 registers.
+// Resident CTAs per SM the compacted kernels are compiled for (register cap).  2 => 128 registers (4 - 56 bytes of
+// spills since the table-driven selection), 16 warps/SM: these kernels are L1-bound (scattered 4x4 gathers,
+// profiles/README.md), so spill traffic costs more than the lost warps: at 2048^2 proposals 0.98 -> 0.63 ms,
+// ping-pong 5.93 -> 5.51 ms against 3 CTAs / 80 registers (round 1); 96-register shapes re-measured in round 2
+// (profiles/README.md, "compacted kernels: CTA shape").
 #define DERP_PATCH_MINB 2
 #endif
 constexpr int kPatchThreads = DERP_PATCH_THREADS;
 constexpr int kPatchRP = 3 * kPatchThreads, kPatchCP = kPatchThreads;
 constexpr int kPatchFloats = 2 * 9 * kPatchThreads * 2;
+// pingPongKernel has its own CTA shape: 128 threads x 5 CTAs per SM (96 registers, 20 warps/SM) measured 4.40 ms against
+// 4.65 ms for 256 x 2 at 2048^2, while proposalKernel is faster at 256 x 2 (0.52 vs 0.62 ms: it spills more at 96).
+#ifndef DERP_PING_THREADS
+#define DERP_PING_THREADS 128
+#endif
+#ifndef DERP_PING_MINB
+#define DERP_PING_MINB 5
+#endif
+constexpr int kPingThreads = DERP_PING_THREADS;
 
+template <int T>
 __device__ __forceinline__ void loadPixelStateCompact(const CostView& v, const DevCamera& camDst, float* patches, int x,
                                                       int y, PixelState& ps) {
   const int tid = threadIdx.x;
   float2* bg = reinterpret_cast<float2*>(patches) + tid;
-  float2* rr = bg + 9 * kPatchThreads;
+  float2* rr = bg + 9 * T;
   const uint2* col = v.projColor16 + (size_t)v.self * v.W * v.H;  // u16 -> f32 is exact
   float rz[3];
 #pragma unroll
@@ -314,17 +326,17 @@ __device__ __forceinline__ void loadPixelStateCompact(const CostView& v, const D
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float4 t = ldTexel(col + (size_t)(y - 1 + r) * v.W + (x - 1 + c));
-      bg[r * kPatchRP + c * kPatchCP] = make_float2(t.x + kBias23, t.y + kBias23);
+      bg[r * (3 * T) + c * T] = make_float2(t.x + kBias23, t.y + kBias23);
       // rr[r] = (R(row r), R(row r+1)); the fast path reads rr[0] (both lanes) and rr[2].x, the slow path rr[r].x
-      if (r >= 1) rr[(r - 1) * kPatchRP + c * kPatchCP] = make_float2(rz[c] + kBias23, t.z + kBias23);
-      if (r == 2) rr[2 * kPatchRP + c * kPatchCP] = make_float2(t.z + kBias23, 0.f);
+      if (r >= 1) rr[(r - 1) * (3 * T) + c * T] = make_float2(rz[c] + kBias23, t.z + kBias23);
+      if (r == 2) rr[2 * (3 * T) + c * T] = make_float2(t.z + kBias23, 0.f);
       rz[c] = t.z;
     }
   }
   ps.bg = bg;
   ps.rr = rr;
-  ps.selStride = kPatchThreads;
-  ps.sel = reinterpret_cast<float2*>(patches + kPatchFloats) + tid;
+  ps.selStride = T;
+  ps.sel = reinterpret_cast<float2*>(patches + 2 * 9 * T * 2) + tid;
   const float4 tb = ldTexel(v.projBias16 + (size_t)v.self * v.W * v.H + (size_t)y * v.W + x);
   ps.dBias[0] = tb.x + kBias23;
   ps.dBias[1] = tb.y + kBias23;

@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) proposalKernel
   const int p = a.list[i];
   const int y = p / W, x = p - y * W;
   PixelState ps;
-  loadPixelStateCompact(a.v, cams[a.v.self], patches, x, y, ps);
+  loadPixelStateCompact<kPatchThreads>(a.v, cams[a.v.self], patches, x, y, ps);
   float currDisp = a.disp[p];
   float currCost = evalCost<kPatchRP, kPatchCP, uint2>(a.v, cams, ps, currDisp, &hits);
   float currConf = (currCost == FLT_MAX) ? 0.f : ps.conf;
@@ -695,20 +695,20 @@ __global__ void pingPongInitKernel(int W, int H, const uint8_t* __restrict__ fov
   changedNext[p] = (old != res) ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) pingPongKernel(const PingPongArgs a) {
+__global__ void __launch_bounds__(kPingThreads, DERP_PING_MINB) pingPongKernel(const PingPongArgs a) {
   extern __shared__ double smemRaw[];
   DevCamera* cams = reinterpret_cast<DevCamera*>(smemRaw);
   float* patches = reinterpret_cast<float*>(cams + a.v.S);
   const int count = *a.listCount;
-  if (blockIdx.x * kPatchThreads >= count) return;
+  if (blockIdx.x * kPingThreads >= count) return;
   stageCameras(cams, a.v.cams, a.v.S);
   const int W = a.v.W, H = a.v.H;
   unsigned hits = 0, evals = 0;
-  for (int i = blockIdx.x * kPatchThreads + threadIdx.x; i < count; i += gridDim.x * kPatchThreads) {
+  for (int i = blockIdx.x * kPingThreads + threadIdx.x; i < count; i += gridDim.x * kPingThreads) {
   const int p = a.list[i];
   const int y = p / W, x = p - y * W;
   PixelState ps;
-  loadPixelStateCompact(a.v, cams[a.v.self], patches, x, y, ps);
+  loadPixelStateCompact<kPingThreads>(a.v, cams[a.v.self], patches, x, y, ps);
   const float old = a.disp[p];
   float bestCost = __int_as_float(0x7f800000);
   float bestDisp = old;
@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kPatchThreads, DERP_PATCH_MINB) pingPongKernel
     if (!a.fov[q]) continue;
     const float d = a.disp[q];
     if (d >= backgroundDisparity && a.changed[q]) {
-      const float cost = evalCost<kPatchRP, kPatchCP, uint2>(a.v, cams, ps, d, &hits);
+      const float cost = evalCost<3 * kPingThreads, kPingThreads, uint2>(a.v, cams, ps, d, &hits);
       ++evals;
       if (cost < bestCost) {
         bestCost = cost;
