@@ -654,6 +654,20 @@ int derp_eval_cost(DerpCtx* c, int dst, const float* disparity, float* out_cost,
   return rc;
 }
 
+#ifdef DERP_CONE_PARAMS
+static void fillCone(const DerpCtx* c, ConeCam* cone) {
+  for (int s = 0; s < c->S; ++s) {
+    const DevCamera& d = c->camsNorm[s];
+    for (int k = 0; k < 3; ++k) {
+      cone[s].pos[k] = d.pos[k];
+      cone[s].back[k] = d.rot[6 + k];
+    }
+    cone[s].cosFov = d.cosFov;
+    cone[s].pad = 0;
+  }
+}
+#endif
+
 int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, float max_depth_m, int partial_coverage,
                      int32_t* best_index) {
   if (num_depths < 2) return fail(DERP_EINVAL, "derp_brute_force: bad arguments");
@@ -758,6 +772,9 @@ int derp_brute_force(DerpCtx* c, int dst, int num_depths, float min_depth_m, flo
     la.lb = c->dLb.p;
     la.seed = c->dSeed.p;
     la.counters = c->dCounters.p;
+#ifdef DERP_CONE_PARAMS
+    fillCone(c, la.cone);
+#endif
     sweepLowerKernel<<<dim3(gs.x, gs.y, chunks), dim3(kBlockX, sweepBY, 1), c->camSmem(kBlockX * sweepBY), c->stream>>>(la);
     LAUNCHED("sweepLowerKernel");
     SeedArgs sa;
@@ -1778,6 +1795,9 @@ int derp_debug_lower_bound(DerpCtx* c, int dst, int num_depths, float min_depth_
   la.lb = c->dLb.p;
   la.seed = c->dSeed.p;
   la.counters = c->dCounters.p;
+#ifdef DERP_CONE_PARAMS
+  fillCone(c, la.cone);
+#endif
   const int by = kBlockY;
   sweepLowerKernel<<<dim3((W + kBlockX - 1) / kBlockX, (H + by - 1) / by, 1), dim3(kBlockX, by, 1), c->camSmem(kBlockX * by), c->stream>>>(la);
   LAUNCHED("sweepLowerKernel");

@@ -390,6 +390,26 @@ __device__ __forceinline__ bool insideCone(const DevCamera& c, double wx, double
   return !(dot * fabs(dot) <= c.cosFov * fabs(c.cosFov) * n2);
 }
 
+// The fields of the cone test alone, for kernels that pass them BY VALUE in their parameter block: the candidate loop
+// of the dense sweep tests every source for every candidate with a warp-uniform source index, so reading the seven doubles
+// from the constant bank (uniform loads / constant operands) instead of shared memory takes that traffic off the
+// L1 / shared-memory pipe the sweep is limited by.
+struct ConeCam {
+  double pos[3];
+  double back[3];  // rotation row 2 (= -forward)
+  double cosFov;
+  double pad;
+};
+__device__ __forceinline__ bool insideCone(const ConeCam& c, double wx, double wy, double wz) {
+  if (c.cosFov == -1) return true;
+  const double vx = wx - c.pos[0], vy = wy - c.pos[1], vz = wz - c.pos[2];
+  const double camz = c.back[0] * vx + c.back[1] * vy + c.back[2] * vz;
+  if (c.cosFov == 0) return !(camz >= 0);  // !isBehind
+  const double dot = -camz;
+  const double n2 = vx * vx + vy * vy + vz * vz;
+  return !(dot * fabs(dot) <= c.cosFov * fabs(c.cosFov) * n2);
+}
+
 // Conservative fp32 version of the same test (-DDERP_CONE_F32; built, validated, measured 1.2 % SLOWER than the plain fp64
 // test on B200 — the fp64 pipe is not the binding resource of the sweep — and therefore off by default):
 // 1 = inside, 0 = outside, -1 = too close to call (the caller then runs insideCone in fp64, so the decision is ALWAYS the
@@ -662,7 +682,8 @@ __device__ __forceinline__ float lowerBoundOfCost(const V& slots, int n, int kee
 // error bound, and the return value is a number that is <= the exact cost (0 = "unknown", FLT_MAX = no source).
 template <int RP, int CP, class TX = float4, bool LOWER = false>
 __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __restrict__ cams,
-                                          const PixelState& ps, float disparity, unsigned* hits) {
+                                          const PixelState& ps, float disparity, unsigned* hits,
+                                          const ConeCam* __restrict__ cone = nullptr) {
   const double depth = (double)(1.0f / disparity);
   const DevCamera& cd = cams[v.self];
   const double wx = cd.pos[0] + ps.dir[0] * depth;
@@ -690,7 +711,7 @@ __device__ __forceinline__ float evalCost(const CostView& v, const DevCamera* __
 #else
       const int cls = -1;
 #endif
-      const bool in = cls < 0 ? insideCone(cams[s], wx, wy, wz) : (cls != 0);
+      const bool in = cls < 0 ? (cone ? insideCone(cone[s], wx, wy, wz) : insideCone(cams[s], wx, wy, wz)) : (cls != 0);
       if (in) mask |= 1u << s;
     }
   }

@@ -123,7 +123,7 @@ __global__ void meshQuadKernel(const MeshGrid g, uint8_t* __restrict__ quadBits,
 }
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;  // consecutive grid cells per thread
+constexpr int kScanItems = 8;  // grid cells per thread and tile
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 // exclusive scan of one value per thread over a 256-thread CTA; *total = CTA sum
@@ -200,23 +200,24 @@ __global__ void __launch_bounds__(kScanThreads) meshTileScanKernel(int tiles, un
   }
 }
 
+// The emit passes walk a tile in kScanItems rounds of kScanThreads CONSECUTIVE cells (thread t takes cell round * 256 + t),
+// carrying the running offset from round to round, so that a warp's outputs are contiguous in memory.
+
 // pass 3: vertexes in grid order (MeshUtil.h:373-388), new index of every used vertex, float32 xyz (writeDepth's cast)
 __global__ void __launch_bounds__(kScanThreads) meshEmitVertexesKernel(const MeshGrid g, const uint8_t* __restrict__ used,
                                                                        const unsigned* __restrict__ tileVerts,
                                                                        unsigned* __restrict__ newIndex,
                                                                        float* __restrict__ vertexes) {
   const size_t n = (size_t)g.W * g.H;
-  const size_t i0 = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-  unsigned v = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k)
-    if (i0 + k < n) v += used[i0 + k] ? 1u : 0u;
-  unsigned total;
-  unsigned at = tileVerts[blockIdx.x] + blockExclusive(v, &total);
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const size_t i = i0 + k;
-    if (i >= n || !used[i]) continue;
+  unsigned running = tileVerts[blockIdx.x];
+#pragma unroll 1
+  for (int round = 0; round < kScanItems; ++round) {
+    const size_t i = (size_t)blockIdx.x * kScanTile + (size_t)round * kScanThreads + threadIdx.x;
+    const bool take = i < n && used[i];
+    unsigned total;
+    const unsigned at = running + blockExclusive(take ? 1u : 0u, &total);
+    running += total;
+    if (!take) continue;
     const int y = (int)(i / (size_t)g.W), x = (int)(i - (size_t)y * g.W);
     bool ok;
     const double z = meshZ(g, x, y, &ok);
@@ -224,7 +225,6 @@ __global__ void __launch_bounds__(kScanThreads) meshEmitVertexesKernel(const Mes
     vertexes[(size_t)at * 3 + 0] = (float)(g.stepX * (x + 0.5));
     vertexes[(size_t)at * 3 + 1] = (float)(g.stepY * (y + 0.5));
     vertexes[(size_t)at * 3 + 2] = (float)z;
-    ++at;
   }
 }
 
@@ -233,18 +233,14 @@ __global__ void __launch_bounds__(kScanThreads) meshEmitFacesKernel(int W, size_
                                                                     const unsigned* __restrict__ tileFaces,
                                                                     const unsigned* __restrict__ newIndex,
                                                                     uint32_t* __restrict__ faces) {
-  const size_t i0 = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-  unsigned f = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k)
-    if (i0 + k < n) f += __popc((unsigned)quadBits[i0 + k]);
-  unsigned total;
-  unsigned at = tileFaces[blockIdx.x] + blockExclusive(f, &total);
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const size_t i = i0 + k;
-    if (i >= n) continue;
-    const unsigned bits = quadBits[i];
+  unsigned running = tileFaces[blockIdx.x];
+#pragma unroll 1
+  for (int round = 0; round < kScanItems; ++round) {
+    const size_t i = (size_t)blockIdx.x * kScanTile + (size_t)round * kScanThreads + threadIdx.x;
+    const unsigned bits = i < n ? quadBits[i] : 0u;
+    unsigned total;
+    unsigned at = running + blockExclusive((unsigned)__popc(bits), &total);
+    running += total;
     if (!bits) continue;
     const size_t corner[4] = {i, i + 1, i + (size_t)W, i + (size_t)W + 1};
 #pragma unroll

@@ -31,6 +31,9 @@ struct LowerArgs {
   float* lb;                   // [D][H][W]
   unsigned long long* seed;    // [H][W]  (L bits << 32 | candidate), atomicMin across candidate chunks
   unsigned long long* counters;
+#ifdef DERP_CONE_PARAMS
+  ConeCam cone[kMaxCams];      // cone-test fields of every camera, read from the constant bank (derp_cost.cuh)
+#endif
 };
 
 __global__ void __launch_bounds__(32 * DERP_SWEEP_MAXBY, DERP_SWEEP_CTAS) sweepLowerKernel(const LowerArgs a) {
@@ -58,7 +61,11 @@ __global__ void __launch_bounds__(32 * DERP_SWEEP_MAXBY, DERP_SWEEP_CTAS) sweepL
         const float d = __ldg(a.disparities + c);
         float L = FLT_MAX;
         if (!(a.bg && !(bgd < d))) {  // closerMask (Derp.cpp:240-243)
+#ifdef DERP_CONE_PARAMS
+          L = evalCost<kTileW, 1, float4, true>(a.v, cams, ps, d, &hits, a.cone);
+#else
           L = evalCost<kTileW, 1, float4, true>(a.v, cams, ps, d, &hits);
+#endif
           ++evals;
         }
         a.lb[c * plane + p] = L;

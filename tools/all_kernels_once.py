@@ -30,4 +30,6 @@ guides = [colors[0]] * T
 disps = [true[0]] * T
 masks = [np.ones((W, W), np.uint8)] * T
 L.temporal_filter(guides, disps, masks, 2, 0.01, 1, 0.5, 1.0, 0.5)
+L.camera_mesh(true[0], (float(W), float(W)), 651.9)  # K17: the mesh of one level-0 disparity map
+L.downscale_area(colors[0], W // 2, W // 2)
 print("done")
