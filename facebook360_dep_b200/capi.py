@@ -166,6 +166,9 @@ _SIGS = {
     "derp_camera_mesh": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "derp_camera_mesh_simplified": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                              C.c_double, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 ABI_SYMBOLS = sorted(_SIGS)
@@ -242,7 +245,7 @@ class Library:
         return out
 
     def camera_mesh(self, disparity, resolution, scalar_focal, depth_scale=1.0, tear_ratio=0.95, foreground_mask=None,
-                    device=0):
+                    device=0, triangles=0):
         """The camera mesh ConvertToBinary builds from one disparity map before simplification
         (ConvertToBinary.cpp:150-183, MeshUtil.h): returns (vertexes float32 [nv, 3], faces uint32 [nf, 3])."""
         disparity = np.ascontiguousarray(disparity, np.float32)
@@ -254,10 +257,13 @@ class Library:
         idx = np.empty((max(2 * cells, 1), 3), np.uint32)
         fm = None if foreground_mask is None else np.ascontiguousarray(foreground_mask, np.uint8)
         nv, nf = C.c_uint64(), C.c_uint64()
-        self.check(self.lib.derp_camera_mesh(
-            device, disparity.ctypes.data, w, h, depth_scale, float(resolution[0]), float(resolution[1]),
-            float(scalar_focal), tear_ratio, _dp(fm), 0 if fm is None else fm.shape[1], 0 if fm is None else fm.shape[0],
-            vtx.ctypes.data, idx.ctypes.data, C.byref(nv), C.byref(nf)))
+        head = (device, disparity.ctypes.data, w, h, depth_scale, float(resolution[0]), float(resolution[1]),
+                float(scalar_focal), tear_ratio, _dp(fm), 0 if fm is None else fm.shape[1], 0 if fm is None else fm.shape[0])
+        tail = (vtx.ctypes.data, idx.ctypes.data, C.byref(nv), C.byref(nf))
+        if triangles > 0:  # + MeshSimplifier with convertDepth's constants (ConvertToBinary.cpp:186-203)
+            self.check(self.lib.derp_camera_mesh_simplified(*head, int(triangles), *tail))
+        else:
+            self.check(self.lib.derp_camera_mesh(*head, *tail))
         return vtx[:nv.value].copy(), idx[:nf.value].copy()
 
     def upsample_disparity(self, cam_desc, coarse, out_w, out_h, background_up=None, coarse_mask=None,

@@ -19,6 +19,7 @@
 #include "derp_kernels.cuh"
 #include "derp_refine.cuh"
 #include "derp_mesh.cuh"
+#include "derp_simplify.h"
 
 using namespace derp;
 
@@ -1405,10 +1406,10 @@ int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_w
   return DERP_OK;
 }
 
-int derp_camera_mesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
-                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
-                     int mask_width, int mask_height, float* vertexes, uint32_t* faces, uint64_t* num_vertexes,
-                     uint64_t* num_faces) {
+static int cameraMesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                      double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                      int mask_width, int mask_height, int triangles, float* vertexes, uint32_t* faces,
+                      uint64_t* num_vertexes, uint64_t* num_faces) {
   int W = 0, H = 0;
   int rc = derp_camera_mesh_size(width, height, depth_scale, &W, &H);
   if (rc) return rc;
@@ -1431,6 +1432,7 @@ int derp_camera_mesh(int device, const float* disparity, int width, int height, 
   // grow-only scratch per host thread (the app converts one (frame, camera) after the other on each GPU worker thread)
   struct MeshScratch {
     DevBuf<float> dDisp, dVtx;
+    DevBuf<double> dVtx64;
     DevBuf<int> dOfs;
     DevBuf<uint8_t> dFg, dQuad, dUsed;
     DevBuf<unsigned> dTiles, dIndex, dFaces;
@@ -1443,6 +1445,7 @@ int derp_camera_mesh(int device, const float* disparity, int width, int height, 
       cudaSetDevice(sc.device);
       sc.dDisp.release();
       sc.dVtx.release();
+      sc.dVtx64.release();
       sc.dOfs.release();
       sc.dFg.release();
       sc.dQuad.release();
@@ -1505,6 +1508,37 @@ int derp_camera_mesh(int device, const float* disparity, int width, int height, 
   CU(cudaGetLastError());
   unsigned long long totals[2] = {0, 0};
   CU(cudaMemcpy(totals, dTotals.p, sizeof(totals), cudaMemcpyDeviceToHost));
+  if (triangles > 0 && totals[0] > (unsigned long long)triangles) {
+    // Simplification (ConvertToBinary.cpp:186-203): the mesh in double precision goes to the host, where the strictly
+    // sequential edge-contraction sweeps run (derp_simplify.h), like MeshSimplifier with kThreads = 1 in the reference.
+    DevBuf<double>& dVtx64 = sc.dVtx64;
+    CU(dVtx64.ensure(std::max<size_t>(1, totals[1] * 3)));
+    CU(dFaces.ensure(std::max<size_t>(1, totals[0] * 3)));
+    meshEmitVertexesKernel<double><<<tiles, kScanThreads>>>(g, dUsed.p, dTiles.p + tiles, dIndex.p, dVtx64.p);
+    meshEmitFacesKernel<<<tiles, kScanThreads>>>(W, n, dQuad.p, dTiles.p, dIndex.p, dFaces.p);
+    CU(cudaGetLastError());
+    std::vector<double> hv(totals[1] * 3);
+    std::vector<uint32_t> hf(totals[0] * 3);
+    CU(cudaMemcpy(hv.data(), dVtx64.p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hf.data(), dFaces.p, hf.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    simplify::Mesh mesh(hv.data(), totals[1], hf.data(), totals[0]);
+    mesh.run(triangles, 0.2f, false);  // kStrictness, kRemoveBoundaryEdges (ConvertToBinary.cpp:193-195)
+    std::vector<float> ov(mesh.verts.size() * 3);
+    std::vector<uint32_t> of(mesh.faces.size() * 3);
+    for (size_t i = 0; i < mesh.verts.size(); ++i) {
+      const simplify::V3& p = mesh.verts[i].p;
+      ov[3 * i] = (float)p.x;
+      ov[3 * i + 1] = (float)p.y;
+      ov[3 * i + 2] = (float)(p.z < 0 ? (double)FLT_MIN : p.z);  // ConvertToBinary.cpp:199-203
+    }
+    for (size_t i = 0; i < mesh.faces.size(); ++i)
+      for (int j = 0; j < 3; ++j) of[3 * i + j] = (uint32_t)mesh.faces[i].v[j];
+    CU(cudaMemcpy(vertexes, ov.data(), ov.size() * sizeof(float), cudaMemcpyDefault));
+    CU(cudaMemcpy(faces, of.data(), of.size() * sizeof(uint32_t), cudaMemcpyDefault));
+    *num_vertexes = mesh.verts.size();
+    *num_faces = mesh.faces.size();
+    return DERP_OK;
+  }
   // outputs: written in place when the caller's buffers are device memory, else staged
   float* vtx = vertexes;
   uint32_t* fac = faces;
@@ -1518,7 +1552,7 @@ int derp_camera_mesh(int device, const float* disparity, int width, int height, 
     CU(dFaces.ensure(std::max<size_t>(1, totals[0] * 3)));
     fac = dFaces.p;
   }
-  meshEmitVertexesKernel<<<tiles, kScanThreads>>>(g, dUsed.p, dTiles.p + tiles, dIndex.p, vtx);
+  meshEmitVertexesKernel<float><<<tiles, kScanThreads>>>(g, dUsed.p, dTiles.p + tiles, dIndex.p, vtx);
   meshEmitFacesKernel<<<tiles, kScanThreads>>>(W, n, dQuad.p, dTiles.p, dIndex.p, fac);
   CU(cudaGetLastError());
   if (vtx != vertexes) CU(cudaMemcpy(vertexes, vtx, totals[1] * 3 * sizeof(float), cudaMemcpyDefault));
@@ -1527,6 +1561,22 @@ int derp_camera_mesh(int device, const float* disparity, int width, int height, 
   *num_faces = totals[0];
   *num_vertexes = totals[1];
   return DERP_OK;
+}
+
+int derp_camera_mesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                     int mask_width, int mask_height, float* vertexes, uint32_t* faces, uint64_t* num_vertexes,
+                     uint64_t* num_faces) {
+  return cameraMesh(device, disparity, width, height, depth_scale, resolution_x, resolution_y, scalar_focal, tear_ratio,
+                    foreground_mask, mask_width, mask_height, 0, vertexes, faces, num_vertexes, num_faces);
+}
+
+int derp_camera_mesh_simplified(int device, const float* disparity, int width, int height, double depth_scale,
+                                double resolution_x, double resolution_y, double scalar_focal, float tear_ratio,
+                                const uint8_t* foreground_mask, int mask_width, int mask_height, int triangles,
+                                float* vertexes, uint32_t* faces, uint64_t* num_vertexes, uint64_t* num_faces) {
+  return cameraMesh(device, disparity, width, height, depth_scale, resolution_x, resolution_y, scalar_focal, tear_ratio,
+                    foreground_mask, mask_width, mask_height, triangles, vertexes, faces, num_vertexes, num_faces);
 }
 
 int derp_upsample_disparity(int device, const DerpCameraDesc* cam, const float* coarse, int coarse_w, int coarse_h,
@@ -1951,6 +2001,24 @@ int derp_test_select_table(const float* first, const float* second, int n, int k
     if (ok6 != ok8 || (ok8 && memcmp(&out6, out, 4) != 0)) return -1;
   }
   return ok8 ? 1 : 0;
+}
+
+// host-only hook for tests/test_mesh.py: the simplifier on an arbitrary mesh (double xyz, uint32 indices); outputs sized
+// like the inputs
+int derp_test_simplify(const double* xyz, uint64_t nv, const uint32_t* idx, uint64_t nf, int triangles, float strictness,
+                       int remove_boundary_edges, double* out_xyz, uint32_t* out_idx, uint64_t* out_nv, uint64_t* out_nf) {
+  derp::simplify::Mesh mesh(xyz, nv, idx, nf);
+  mesh.run(triangles, strictness, remove_boundary_edges != 0);
+  for (size_t i = 0; i < mesh.verts.size(); ++i) {
+    out_xyz[3 * i] = mesh.verts[i].p.x;
+    out_xyz[3 * i + 1] = mesh.verts[i].p.y;
+    out_xyz[3 * i + 2] = mesh.verts[i].p.z;
+  }
+  for (size_t i = 0; i < mesh.faces.size(); ++i)
+    for (int j = 0; j < 3; ++j) out_idx[3 * i + j] = (uint32_t)mesh.faces[i].v[j];
+  *out_nv = mesh.verts.size();
+  *out_nf = mesh.faces.size();
+  return 0;
 }
 
 float derp_test_robust_sum(const float* first, const float* second, int n, int keep) {

@@ -204,10 +204,12 @@ __global__ void __launch_bounds__(kScanThreads) meshTileScanKernel(int tiles, un
 // carrying the running offset from round to round, so that a warp's outputs are contiguous in memory.
 
 // pass 3: vertexes in grid order (MeshUtil.h:373-388), new index of every used vertex, float32 xyz (writeDepth's cast)
+// T = float: writeDepth's cast; T = double: the values the mesh simplifier starts from (ConvertToBinary.cpp:190)
+template <typename T>
 __global__ void __launch_bounds__(kScanThreads) meshEmitVertexesKernel(const MeshGrid g, const uint8_t* __restrict__ used,
                                                                        const unsigned* __restrict__ tileVerts,
                                                                        unsigned* __restrict__ newIndex,
-                                                                       float* __restrict__ vertexes) {
+                                                                       T* __restrict__ vertexes) {
   const size_t n = (size_t)g.W * g.H;
   unsigned running = tileVerts[blockIdx.x];
 #pragma unroll 1
@@ -222,9 +224,9 @@ __global__ void __launch_bounds__(kScanThreads) meshEmitVertexesKernel(const Mes
     bool ok;
     const double z = meshZ(g, x, y, &ok);
     newIndex[i] = at;
-    vertexes[(size_t)at * 3 + 0] = (float)(g.stepX * (x + 0.5));
-    vertexes[(size_t)at * 3 + 1] = (float)(g.stepY * (y + 0.5));
-    vertexes[(size_t)at * 3 + 2] = (float)z;
+    vertexes[(size_t)at * 3 + 0] = (T)(g.stepX * (x + 0.5));
+    vertexes[(size_t)at * 3 + 1] = (T)(g.stepY * (y + 0.5));
+    vertexes[(size_t)at * 3 + 2] = (T)z;
   }
 }
 

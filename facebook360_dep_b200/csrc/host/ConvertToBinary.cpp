@@ -1,12 +1,12 @@
-// ConvertToBinary — first slice of the drop-in for source/mesh_stream/ConvertToBinary.cpp on B200.
+// ConvertToBinary — drop-in for the geometry half of source/mesh_stream/ConvertToBinary.cpp on B200.
 //
-// Built: the depth half before simplification — disparity PFM -> camera mesh (.vtx float32 xyz, .idx uint32 x 3, optional
-// .obj) through derp_camera_mesh (libderp_b200.so: mesh_util::getVertexesEquiError / getFaces / applyMaskToVertexesAndFaces
-// on the GPU), the rescaled `<rig>_fused.json`, and the striped fusion of the produced files (BinaryFusionUtil.h).
-// NOT built, and refused loudly instead of silently skipped: mesh simplification (--triangles > 0, MeshSimplifier.cpp),
-// BC7 / RGBA colour (bc7, rgba formats; the ISPC texture compressor) and the rasterised pfm format.  With the
-// reference's default flags (--triangles=150000, --output_formats=idx,vtx,bc7 and a --color directory) this executable
-// therefore stops with a message naming the flag to change: --triangles=0 --output_formats=idx,vtx.
+// Built: disparity PFM -> camera mesh (.vtx float32 xyz, .idx uint32 x 3, optional .obj) through libderp_b200.so
+// (derp_camera_mesh_simplified: mesh_util::getVertexesEquiError / getFaces / applyMaskToVertexesAndFaces on the GPU, then
+// render::MeshSimplifier's contraction sweeps down to --triangles, sequential host code like the reference's), the rescaled
+// `<rig>_fused.json`, and the striped fusion of the produced files (BinaryFusionUtil.h).
+// NOT built, and refused loudly instead of silently skipped: BC7 / RGBA colour (bc7, rgba formats; the vendored ISPC
+// texture compressor) and the rasterised pfm format.  With the reference's default --output_formats=idx,vtx,bc7 AND a
+// --color directory this executable therefore stops with a message naming the flag to change: --output_formats=idx,vtx.
 #include <set>
 #include <thread>
 
@@ -272,8 +272,6 @@ int main(int argc, char** argv) {
   CHECK(!wantColor) << "colour formats (bc7, rgba) are not built in this port: pass --output_formats=idx,vtx[,obj]";
   CHECK(FLAGS_disparity.empty() || !contains(formats, "pfm")) << "the rasterised pfm format is not built in this port";
   const bool wantDepth = !FLAGS_disparity.empty() && (contains(formats, "idx") || contains(formats, "vtx") || contains(formats, "obj"));
-  CHECK(!wantDepth || FLAGS_triangles <= 0)
-      << "mesh simplification (MeshSimplifier) is not built in this port: pass --triangles=0 for the unsimplified mesh";
 
   // resizeRig (ConvertToBinary.cpp:322-343): camera resolutions follow the (scaled) colour images
   if (!FLAGS_color.empty()) {
@@ -338,9 +336,11 @@ int main(int argc, char** argv) {
           std::vector<uint32_t> idx((size_t)gw * gh * 6);
           uint64_t nv = 0, nf = 0;
           const DerpCameraDesc& cam = rig.cams[tasks[t].cam];
-          DERP_CALL(derp_camera_mesh(device, disparity.data(), w, h, FLAGS_depth_scale, cam.resolution[0], cam.resolution[1],
-                                     cam.focal[0], (float)FLAGS_tear_ratio, mask.empty() ? nullptr : mask.data(), mw, mh,
-                                     vtx.data(), idx.data(), &nv, &nf));
+          if (FLAGS_triangles > 0) LOG(INFO) << "Target number of faces: " << FLAGS_triangles;
+          DERP_CALL(derp_camera_mesh_simplified(device, disparity.data(), w, h, FLAGS_depth_scale, cam.resolution[0],
+                                                cam.resolution[1], cam.focal[0], (float)FLAGS_tear_ratio,
+                                                mask.empty() ? nullptr : mask.data(), mw, mh, FLAGS_triangles, vtx.data(),
+                                                idx.data(), &nv, &nf));
           vtx.resize(nv * 3);
           idx.resize(nf * 3);
           LOG(INFO) << "camera " << id << ": " << nv << " vertexes, " << nf << " faces";

@@ -292,12 +292,21 @@ int derp_foreground_mask(int device, const uint16_t* templ, const uint16_t* fram
  * resolution_* / scalar_focal: the camera's (possibly rescaled, ConvertToBinary.cpp:322-343) resolution and
  * Camera::getScalarFocal().  `vertexes` needs room for 3 floats per grid cell, `faces` for 6 uint32 per grid cell
  * (derp_camera_mesh_size gives the grid); both may be host or device memory, like the inputs.
- * Not built: MeshSimplifier (--triangles > 0), BC7 colour, fusion. */
+ * derp_camera_mesh_simplified adds the simplification step (ConvertToBinary.cpp:186-203): render::MeshSimplifier
+ * (source/render/MeshSimplifier.cpp: quadric-error edge contraction, equi-error costs, strictness 0.2, boundary edges kept)
+ * down to `triangles` faces when the mesh has more, then z < 0 -> FLT_MIN.  That stage is a chain of dependent
+ * contractions (one thread in the reference's call): the GPU builds the mesh in double precision, the contraction sweeps
+ * run on the host inside the library.
+ * Not built: BC7 / RGBA colour. */
 int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_width, int* mesh_height);
 int derp_camera_mesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
                      double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
                      int mask_width, int mask_height, float* vertexes, uint32_t* faces, uint64_t* num_vertexes,
                      uint64_t* num_faces);
+int derp_camera_mesh_simplified(int device, const float* disparity, int width, int height, double depth_scale,
+                                double resolution_x, double resolution_y, double scalar_focal, float tear_ratio,
+                                const uint8_t* foreground_mask, int mask_width, int mask_height, int triangles,
+                                float* vertexes, uint32_t* faces, uint64_t* num_vertexes, uint64_t* num_faces);
 
 #ifdef __cplusplus
 }

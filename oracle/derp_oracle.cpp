@@ -1518,6 +1518,13 @@ int derp_camera_mesh(int /*device*/, const float* disparity, int width, int heig
   return DERP_OK;
 }
 
+// The simplifier is checked against the reference's own MeshSimplifier.cpp (oracle/_ref) only: no second restatement here.
+int derp_camera_mesh_simplified(int, const float*, int, int, double, double, double, double, float, const uint8_t*, int, int,
+                                int, float*, uint32_t*, uint64_t*, uint64_t*) {
+  g_err = "derp_camera_mesh_simplified: the oracle restatement stops before simplification; use oracle/_ref";
+  return DERP_EINVAL;
+}
+
 int oracle_resize_area(const uint16_t* src, int sw, int sh, uint16_t* dst, int dw, int dh) {
   return resizeAreaU16C3(src, sw, sh, dst, dw, dh) ? 0 : -1;
 }

@@ -37,6 +37,7 @@
 #include "source/depth_estimation/Derp.h"
 #include "source/depth_estimation/TemporalBilateralFilter.h"
 #include "source/depth_estimation/UpsampleDisparityLib.h"
+#include "source/render/MeshSimplifier.h"
 #include "source/render/MeshUtil.h"
 #include "source/util/Camera.h"
 
@@ -665,10 +666,10 @@ int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_w
   return DERP_OK;
 }
 
-int derp_camera_mesh(int /*device*/, const float* disparity, int width, int height, double depth_scale, double resolution_x,
-                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
-                     int mask_width, int mask_height, float* vertexesOut, uint32_t* facesOut, uint64_t* num_vertexes,
-                     uint64_t* num_faces) {
+static int cameraMeshRef(const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                         double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                         int mask_width, int mask_height, int triangles, float* vertexesOut, uint32_t* facesOut,
+                         uint64_t* num_vertexes, uint64_t* num_faces) {
   int W = 0, H = 0;
   if (derp_camera_mesh_size(width, height, depth_scale, &W, &H) || !disparity || !vertexesOut || !facesOut ||
       !num_vertexes || !num_faces || W < 1 || H < 1 || (foreground_mask && (mask_width < 1 || mask_height < 1)))
@@ -692,12 +693,69 @@ int derp_camera_mesh(int /*device*/, const float* disparity, int width, int heig
       vertexMask = vertexMask & foregroundMask;
     }
     mesh_util::applyMaskToVertexesAndFaces(vertexes, faces, vertexMask);
+    if (triangles > 0) {  // ConvertToBinary.cpp:186-203
+      static const bool kIsEquierror = true;
+      static const int kThreads = 1;
+      render::MeshSimplifier ms(vertexes, faces, kIsEquierror, kThreads);
+      static const float kStrictness = 0.2;
+      static const bool kRemoveBoundaryEdges = false;
+      ms.simplify(triangles, kStrictness, kRemoveBoundaryEdges);
+      vertexes = ms.getVertexes();
+      faces = ms.getFaces();
+      for (int i = 0; i < vertexes.rows(); ++i) {
+        if (vertexes.row(i).z() < 0) {
+          vertexes.row(i).z() = FLT_MIN;
+        }
+      }
+    }
     Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> v = vertexes.cast<float>();  // writeDepth
     Eigen::Matrix<uint32_t, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> f = faces.cast<uint32_t>();
     std::memcpy(vertexesOut, v.data(), v.size() * sizeof(float));
     std::memcpy(facesOut, f.data(), f.size() * sizeof(uint32_t));
     *num_vertexes = (uint64_t)vertexes.rows();
     *num_faces = (uint64_t)faces.rows();
+    return (int)DERP_OK;
+  });
+}
+
+int derp_camera_mesh(int /*device*/, const float* disparity, int width, int height, double depth_scale, double resolution_x,
+                     double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
+                     int mask_width, int mask_height, float* vertexes, uint32_t* faces, uint64_t* num_vertexes,
+                     uint64_t* num_faces) {
+  return cameraMeshRef(disparity, width, height, depth_scale, resolution_x, resolution_y, scalar_focal, tear_ratio,
+                       foreground_mask, mask_width, mask_height, 0, vertexes, faces, num_vertexes, num_faces);
+}
+
+/* + the reference's own MeshSimplifier (source/render/MeshSimplifier.cpp, compiled unmodified) with convertDepth's
+ * constants: equi-error costs, one thread, strictness 0.2, boundary edges kept, negative z -> FLT_MIN. */
+int derp_camera_mesh_simplified(int /*device*/, const float* disparity, int width, int height, double depth_scale,
+                                double resolution_x, double resolution_y, double scalar_focal, float tear_ratio,
+                                const uint8_t* foreground_mask, int mask_width, int mask_height, int triangles,
+                                float* vertexes, uint32_t* faces, uint64_t* num_vertexes, uint64_t* num_faces) {
+  return cameraMeshRef(disparity, width, height, depth_scale, resolution_x, resolution_y, scalar_focal, tear_ratio,
+                       foreground_mask, mask_width, mask_height, triangles, vertexes, faces, num_vertexes, num_faces);
+}
+
+/* test hook (not part of derp_b200.h): the reference's MeshSimplifier on an arbitrary mesh */
+int derp_ref_simplify(const double* xyz, uint64_t nv, const uint32_t* idx, uint64_t nf, int triangles, float strictness,
+                      int remove_boundary_edges, double* out_xyz, uint32_t* out_idx, uint64_t* out_nv, uint64_t* out_nf) {
+  return guarded([&] {
+    Eigen::MatrixXd vertexes((Eigen::Index)nv, 3);
+    Eigen::MatrixXi faces((Eigen::Index)nf, 3);
+    for (uint64_t i = 0; i < nv; ++i)
+      for (int j = 0; j < 3; ++j) vertexes((Eigen::Index)i, j) = xyz[3 * i + j];
+    for (uint64_t i = 0; i < nf; ++i)
+      for (int j = 0; j < 3; ++j) faces((Eigen::Index)i, j) = (int)idx[3 * i + j];
+    render::MeshSimplifier ms(vertexes, faces, true, 1);
+    ms.simplify(triangles, strictness, remove_boundary_edges != 0);
+    vertexes = ms.getVertexes();
+    faces = ms.getFaces();
+    for (Eigen::Index i = 0; i < vertexes.rows(); ++i)
+      for (int j = 0; j < 3; ++j) out_xyz[3 * i + j] = vertexes(i, j);
+    for (Eigen::Index i = 0; i < faces.rows(); ++i)
+      for (int j = 0; j < 3; ++j) out_idx[3 * i + j] = (uint32_t)faces(i, j);
+    *out_nv = (uint64_t)vertexes.rows();
+    *out_nf = (uint64_t)faces.rows();
     return (int)DERP_OK;
   });
 }

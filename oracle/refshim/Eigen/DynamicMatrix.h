@@ -8,6 +8,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 
 namespace Eigen {
 
@@ -137,11 +138,56 @@ class Matrix<S, 2, 2> {
   Solver colPivHouseholderQr() const { return Solver{*this}; }
 };
 
+// ---- 4 x 4 (the quadrics of source/render/MeshSimplifier.cpp) ---------------------------------------------------
+template <class S>
+class Matrix<S, 4, 4> {
+ public:
+  S m[4][4];
+  static Matrix Zero() {
+    Matrix r;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) r.m[i][j] = 0;
+    return r;
+  }
+  S& operator()(Index i, Index j) { return m[i][j]; }
+  const S& operator()(Index i, Index j) const { return m[i][j]; }
+  Matrix operator+(const Matrix& o) const {
+    Matrix r;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) r.m[i][j] = m[i][j] + o.m[i][j];
+    return r;
+  }
+  Matrix& operator+=(const Matrix& o) {
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) m[i][j] = m[i][j] + o.m[i][j];
+    return *this;
+  }
+  template <int R2, int C2>
+  Matrix<S, R2, C2> block(Index i0, Index j0) const {
+    Matrix<S, R2, C2> r;
+    for (int i = 0; i < R2; ++i)
+      for (int j = 0; j < C2; ++j) r(i, j) = m[i0 + i][j0 + j];
+    return r;
+  }
+};
+// q * q.transpose(): outer product of a 4-vector with itself (exact products, no sums)
+template <class S>
+inline Matrix<S, 4, 4> operator*(const Matrix<S, 4, 1>& a, const typename Matrix<S, 4, 1>::Transposed& b) {
+  Matrix<S, 4, 4> r;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) r.m[i][j] = a.v[i] * b.m->v[j];
+  return r;
+}
+template <class T>
+using aligned_allocator = std::allocator<T>;
+
 inline Matrix<double, 3, 1> operator*(float s, const Matrix<double, 3, 1>& m) { return m * (double)s; }
 
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<int, 3, 1> Vector3i;
+typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<double, 4, 4> Matrix4d;
 typedef Matrix<double, 2, 2> Matrix2d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;

@@ -449,16 +449,16 @@ def _mesh_dataset(tmp_path, W=96, H=80, S=3, F=2):
 
 
 def test_convert_to_binary_refuses_unbuilt_parts(tmp_path):
-    """The reference's defaults ask for simplification to 150 k triangles and BC7 colour: neither is built, and the
-    executable says so instead of writing something else (no GPU needed to get that far)."""
+    """The reference's default formats ask for BC7 colour, which is not built: with a --color directory the executable
+    says so instead of writing something else (no GPU needed to get that far); same for the rasterised pfm format."""
     rig, _ = _mesh_dataset(tmp_path, F=1)
     base = ["--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
             "--disparity=" + str(tmp_path / "disparity"), "--bin=" + str(tmp_path / "bin")]
-    p = run("ConvertToBinary", *base, check=False)
-    assert p.returncode != 0 and "--triangles=0" in p.stderr
     os.makedirs(tmp_path / "color" / rig["cameras"][0]["id"], exist_ok=True)
-    p = run("ConvertToBinary", *base, "--triangles=0", "--color=" + str(tmp_path / "color"), check=False)
+    p = run("ConvertToBinary", *base, "--color=" + str(tmp_path / "color"), check=False)
     assert p.returncode != 0 and "bc7" in p.stderr
+    p = run("ConvertToBinary", *base, "--output_formats=idx,vtx,pfm", check=False)
+    assert p.returncode != 0 and "pfm" in p.stderr
 
 
 @pytest.mark.gpu
@@ -517,6 +517,17 @@ def test_convert_to_binary_meshes(tmp_path, cuda, oracle):
             end = entry["offset"] + entry["size"]
             pad = fused_bytes(end, -end % stripe)
             assert pad == b"\x5a" * len(pad)
+    # default --triangles (150 000 > these meshes: untouched) and a real target: files equal the reference's sequence
+    if checker.backend == "reference-cpu":
+        run("ConvertToBinary", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
+            "--disparity=" + str(tmp_path / "disparity"), "--bin=" + str(tmp_path / "bin2"), "--triangles=3000",
+            "--output_formats=idx,vtx")
+        for cam in rig["cameras"]:
+            v, i = checker.camera_mesh(disps[cam["id"], 0], cam["resolution"], cam["focal"][0], triangles=3000)
+            stem = tmp_path / "bin2" / cam["id"] / "000000"
+            assert len(i) <= 3000 or len(i) < 2 * (W - 1) * (H - 1)
+            assert open(str(stem) + ".vtx", "rb").read() == v.tobytes()
+            assert open(str(stem) + ".idx", "rb").read() == i.tobytes()
     fused_rig = json.load(open(tmp_path / "fused" / "rig_fused.json"))
     assert [c["id"] for c in fused_rig["cameras"]] == [c["id"] for c in rig["cameras"]]
     assert np.allclose(fused_rig["cameras"][0]["focal"], rig["cameras"][0]["focal"])

@@ -112,3 +112,71 @@ def test_gpu_mesh_full_size(cuda, oracle):
     assert np.array_equal(gi, oi)
     assert np.array_equal(gv.view(np.uint32), ov.view(np.uint32))
     check_mesh_invariants(gv, gi, w, h)
+
+
+# ---- mesh simplification (ConvertToBinary.cpp:186-203): product host code vs the reference's MeshSimplifier.cpp ------
+def _simplify(lib, name, xyz, idx, triangles, strictness=0.2, remove_boundary=False):
+    import ctypes as C
+    f = getattr(lib.lib, name)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    idx = np.ascontiguousarray(idx, np.uint32)
+    ov, oi = np.empty_like(xyz), np.empty_like(idx)
+    nv, nf = C.c_uint64(), C.c_uint64()
+    assert f(xyz.ctypes.data, len(xyz), idx.ctypes.data, len(idx), triangles, strictness, int(remove_boundary),
+             ov.ctypes.data, oi.ctypes.data, C.byref(nv), C.byref(nf)) == 0
+    return ov[:nv.value].copy(), oi[:nf.value].copy()
+
+
+def _surface_mesh(oracle, seed, w, h, smooth):
+    rng = np.random.RandomState(seed)
+    if smooth:  # one sheet, interior edges contract freely
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        d = (0.4 + 0.05 * np.sin(xx / 13.0) * np.cos(yy / 9.0) + rng.uniform(-0.002, 0.002, (h, w))).astype(np.float32)
+    else:  # tears and holes: many boundaries
+        d = disparity_case(rng, w, h, nan_frac=0.01, zero_frac=0.0)
+    v, i = oracle.camera_mesh(d, (w * 4.0, h * 4.0), 300.0)
+    return v.astype(np.float64), i
+
+
+SIMPLIFY_CASES = [(0, 64, 48, True, 2000, False), (1, 96, 72, True, 1500, True), (2, 80, 60, False, 3000, False),
+                  (3, 120, 90, False, 100, True), (4, 33, 27, True, 10, False), (5, 150, 110, True, 6000, False)]
+
+
+@pytest.mark.parametrize("seed,w,h,smooth,target,rb", SIMPLIFY_CASES)
+def test_simplifier_equals_reference(oracle, seed, w, h, smooth, target, rb):
+    """The library's host simplifier (derp_simplify.h, through its test hook — no GPU involved) against the reference's own
+    MeshSimplifier.cpp compiled into oracle/_ref, on meshes with and without boundaries: same vertex bits, same faces."""
+    from facebook360_dep_b200 import capi
+    ref = oracle_libs.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    prod = capi.load_cuda()
+    xyz, idx = _surface_mesh(oracle, seed, w, h, smooth)
+    pv, pi = _simplify(prod, "derp_test_simplify", xyz, idx, target, remove_boundary=rb)
+    rv, ri = _simplify(ref, "derp_ref_simplify", xyz, idx, target, remove_boundary=rb)
+    assert len(ri) < len(idx)  # something was contracted
+    assert np.array_equal(pi, ri)
+    assert np.array_equal(pv.view(np.uint64), rv.view(np.uint64))
+
+
+@pytest.mark.gpu
+def test_gpu_mesh_simplified_equals_reference(cuda):
+    """derp_camera_mesh_simplified end to end (GPU mesh in double precision -> host contraction sweeps -> float32 / uint32)
+    against convertDepth's sequence on the reference's own code."""
+    ref = oracle_libs.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.RandomState(2)
+    yy, xx = np.mgrid[0:150, 0:200].astype(np.float32)
+    d = (0.4 + 0.05 * np.sin(xx / 13.0) * np.cos(yy / 9.0) + rng.uniform(-0.002, 0.002, xx.shape)).astype(np.float32)
+    d[(xx > 90) & (xx < 100)] *= 1.4  # a tear
+    d[rng.uniform(size=d.shape) < 0.002] = np.nan
+    for tri in (20000, 5000):
+        gv, gi = cuda.camera_mesh(d, (800.0, 600.0), 300.0, triangles=tri)
+        rv, ri = ref.camera_mesh(d, (800.0, 600.0), 300.0, triangles=tri)
+        assert len(ri) <= max(tri, 1) or len(ri) < 2 * 199 * 149
+        assert np.array_equal(gi, ri)
+        assert np.array_equal(gv.view(np.uint32), rv.view(np.uint32))
