@@ -1502,6 +1502,7 @@ static int cameraMesh(int device, const float* disparity, int width, int height,
   g.stepY = resolution_y / H;
   g.scale = scalar_focal * 1.0;  // kRadius = 1 (MeshUtil.h:316)
   g.tearRatio = tear_ratio;
+  g.floorZ = 0;
   meshQuadKernel<<<grid2(W, H), block2()>>>(g, dQuad.p, dUsed.p);
   meshTileCountKernel<<<tiles, kScanThreads>>>(n, dQuad.p, dUsed.p, dTiles.p, dTiles.p + tiles);
   meshTileScanKernel<<<1, kScanThreads>>>(tiles, dTiles.p, dTiles.p + tiles, dTotals.p);
@@ -1514,6 +1515,7 @@ static int cameraMesh(int device, const float* disparity, int width, int height,
     DevBuf<double>& dVtx64 = sc.dVtx64;
     CU(dVtx64.ensure(std::max<size_t>(1, totals[1] * 3)));
     CU(dFaces.ensure(std::max<size_t>(1, totals[0] * 3)));
+    g.floorZ = 0;  // the simplifier works on the raw values; the floor is applied to its output below
     meshEmitVertexesKernel<double><<<tiles, kScanThreads>>>(g, dUsed.p, dTiles.p + tiles, dIndex.p, dVtx64.p);
     meshEmitFacesKernel<<<tiles, kScanThreads>>>(W, n, dQuad.p, dTiles.p, dIndex.p, dFaces.p);
     CU(cudaGetLastError());
@@ -1539,6 +1541,7 @@ static int cameraMesh(int device, const float* disparity, int width, int height,
     *num_faces = mesh.faces.size();
     return DERP_OK;
   }
+  g.floorZ = triangles > 0;  // the reference applies it after the (here: no-op) simplification
   // outputs: written in place when the caller's buffers are device memory, else staged
   float* vtx = vertexes;
   uint32_t* fac = faces;

@@ -26,6 +26,7 @@ struct MeshGrid {
   double stepX, stepY; // camera.resolution / grid size (MeshUtil.h:324-325)
   double scale;        // camera.getScalarFocal() * kRadius (MeshUtil.h:317)
   float tearRatio;
+  int floorZ;          // write z < 0 as FLT_MIN (ConvertToBinary.cpp:199-203, whenever --triangles > 0)
 };
 
 // depth(y, x) = 1.0f / disparity (cv::divide on floats, IEEE), ConvertToBinary.cpp:152-156
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kScanThreads) meshEmitVertexesKernel(const Mes
     newIndex[i] = at;
     vertexes[(size_t)at * 3 + 0] = (T)(g.stepX * (x + 0.5));
     vertexes[(size_t)at * 3 + 1] = (T)(g.stepY * (y + 0.5));
-    vertexes[(size_t)at * 3 + 2] = (T)z;
+    vertexes[(size_t)at * 3 + 2] = (g.floorZ && z < 0) ? (T)1.17549435e-38f : (T)z;
   }
 }
 

@@ -317,12 +317,17 @@ int main(int argc, char** argv) {
     for (int f = 0; f < numFrames; ++f)
       for (int c : cams) tasks.push_back(Task{c, firstFrame + f});
     const int G = std::max(1, std::min<int>(FLAGS_gpus, (int)tasks.size()));
-    LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s)";
+    // --threads like ThreadPool.h:30-45 (-1 = all cores, 0 = inline): one (frame, camera) conversion per task as in the
+    // reference (ConvertToBinary.cpp:361-368).  The contraction sweeps of the simplifier are host work, so the workers
+    // are host threads; worker k sends its meshes to GPU k mod --gpus.
+    const int want = FLAGS_threads < 0 ? (int)std::max(1u, std::thread::hardware_concurrency()) : std::max(1, FLAGS_threads);
+    const int workers = std::max(G, std::min<int>(std::min(want, 64), (int)tasks.size()));
+    LOG(INFO) << "backend " << derp_backend() << ", " << G << " GPU(s), " << workers << " host worker(s)";
     std::vector<std::thread> threads;
-    for (int g = 0; g < G && wantDepth; ++g)
-      threads.emplace_back([&, g] {
-        const int device = FLAGS_gpu + g;
-        for (size_t t = g; t < tasks.size(); t += G) {
+    for (int k = 0; k < workers && wantDepth; ++k)
+      threads.emplace_back([&, k] {
+        const int device = FLAGS_gpu + k % G;
+        for (size_t t = k; t < tasks.size(); t += workers) {
           const std::string &id = rig.ids[tasks[t].cam], frame = io::zeroPad(tasks[t].frame);
           LOG(INFO) << "Converting depth: frame " << frame << ", camera " << id << "...";
           int w, h, mw = 0, mh = 0, gw, gh;
