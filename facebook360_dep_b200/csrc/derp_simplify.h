@@ -59,9 +59,9 @@ class Mesh {
     Quadric q{};
     bool boundary = false;
   };
-  struct Face {
+  struct Face {  // (the plane quadric of a face is only needed to seed the vertex quadrics: it is not kept here,
+                 // which makes the per-sweep compaction of the face list three times lighter than the reference's)
     int v[3];
-    Quadric q{};
     V3 normal{0, 0, 0};
     double cost[3];
     bool deleted = false, touched = false;
@@ -105,17 +105,17 @@ class Mesh {
   }
 
   void initialQuadrics() {
-    for (Face& f : faces) {
+    for (Face& f : faces) {  // face order = accumulation order of the vertex quadrics, as in the reference
       f.deleted = false;
       const V3 &p0 = verts[f.v[0]].p, &p1 = verts[f.v[1]].p, &p2 = verts[f.v[2]].p;
       const V3 n = unit(cross(sub(p1, p0), sub(p2, p0)));
       f.normal = n;
       const double plane[4] = {n.x, n.y, n.z, -dot(n, p0)};
+      Quadric q;
       for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) f.q.m[i][j] = plane[i] * plane[j];
+        for (int j = 0; j < 4; ++j) q.m[i][j] = plane[i] * plane[j];
+      for (int j = 0; j < 3; ++j) addInto(verts[f.v[j]].q, q);
     }
-    for (const Face& f : faces)
-      for (int j = 0; j < 3; ++j) addInto(verts[f.v[j]].q, f.q);
     for (Face& f : faces) refreshCosts(f);
   }
   void refreshCosts(Face& f) {
