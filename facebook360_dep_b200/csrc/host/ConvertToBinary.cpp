@@ -4,8 +4,8 @@
 // (derp_camera_mesh_simplified: mesh_util::getVertexesEquiError / getFaces / applyMaskToVertexesAndFaces on the GPU, then
 // render::MeshSimplifier's contraction sweeps down to --triangles, sequential host code like the reference's), the rescaled
 // `<rig>_fused.json`, and the striped fusion of the produced files (BinaryFusionUtil.h).
-// NOT built, and refused loudly instead of silently skipped: BC7 / RGBA colour (bc7, rgba formats; the vendored ISPC
-// texture compressor) and the rasterised pfm format.  With the reference's default --output_formats=idx,vtx,bc7 AND a
+// Colour: the uncompressed .rgba stream (host bytes, --color_scale = 1).  NOT built, and refused loudly instead of silently
+// skipped: BC7 colour (bc7 format; the vendored ISPC texture compressor) and the rasterised pfm format.  With the reference's default --output_formats=idx,vtx,bc7 AND a
 // --color directory this executable therefore stops with a message naming the flag to change: --output_formats=idx,vtx.
 #include <set>
 #include <thread>
@@ -268,8 +268,10 @@ int main(int argc, char** argv) {
   for (const std::string& f : formats) CHECK(f.empty() || supported.count(f)) << "Invalid output format specified: " << f;
   const int firstFrame = std::stoi(FLAGS_first), numFrames = std::stoi(FLAGS_last) - firstFrame + 1;
   CHECK_GT(numFrames, 0);
-  const bool wantColor = !FLAGS_color.empty() && (contains(formats, "bc7") || contains(formats, "rgba"));
-  CHECK(!wantColor) << "colour formats (bc7, rgba) are not built in this port: pass --output_formats=idx,vtx[,obj]";
+  CHECK(FLAGS_color.empty() || !contains(formats, "bc7"))
+      << "the bc7 colour format (ISPC texture compressor) is not built in this port: pass --output_formats=idx,vtx[,rgba,obj]";
+  const bool wantRgba = !FLAGS_color.empty() && contains(formats, "rgba");
+  CHECK(!wantRgba || FLAGS_color_scale >= 1) << "rgba with --color_scale < 1 is not built in this port";
   CHECK(FLAGS_disparity.empty() || !contains(formats, "pfm")) << "the rasterised pfm format is not built in this port";
   const bool wantDepth = !FLAGS_disparity.empty() && (contains(formats, "idx") || contains(formats, "vtx") || contains(formats, "obj"));
 
@@ -359,6 +361,17 @@ int main(int argc, char** argv) {
         }
       });
     for (auto& t : threads) t.join();
+
+    if (wantRgba)  // convertColor (ConvertToBinary.cpp:122-147): ".rgba is just uncompressed 8-bit color"
+      for (const Task& t : tasks) {
+        const std::string &id = rig.ids[t.cam], frame = io::zeroPad(t.frame);
+        LOG(INFO) << "Converting color: frame " << frame << ", camera " << id << "...";
+        int w, h;
+        const std::vector<uint8_t> rgba = io::loadRgba8(io::imagePath(FLAGS_color, id, frame), &w, &h);
+        const fs::path out = io::imagePath(FLAGS_bin, id, frame, ".rgba");
+        fs::create_directories(out.parent_path());
+        std::ofstream(out, std::ios::binary).write(reinterpret_cast<const char*>(rgba.data()), rgba.size());
+      }
 
     fs::create_directories(FLAGS_bin);
     io::Json root = jobj(), arr;

@@ -7,7 +7,7 @@
 #include "io.h"
 
 DEFINE_string(in, "", "input image");
-DEFINE_string(mode, "color", "color | float | mask | rig | exchange");
+DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange");
 DEFINE_string(out, "", "output file (raw samples, or .png/.pfm for mode=float)");
 
 int main(int argc, char** argv) {
@@ -30,6 +30,10 @@ int main(int argc, char** argv) {
       o.open(FLAGS_out, std::ios::binary);
       o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size() * 4);
     }
+  } else if (FLAGS_mode == "rgba") {
+    const auto v = io::loadRgba8(FLAGS_in, &w, &h);
+    o.open(FLAGS_out, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size());
   } else if (FLAGS_mode == "mask") {
     const auto v = io::loadMask(FLAGS_in, &w, &h);
     o.open(FLAGS_out, std::ios::binary);

@@ -626,6 +626,33 @@ inline std::vector<uint16_t> loadColor16(const fs::path& path, int* w, int* h) {
   return out;
 }
 
+// loadImage<cv::Vec4b> followed by cv::cvtColor(BGRA2RGBA) (ConvertToBinary.cpp:138-146, the ".rgba" stream): depth -> 8U
+// (16U scaled by the float 255/65535 with rounding and saturation, cv::Mat::convertTo), channels -> 4 (alpha 255 when
+// the file has none, gray replicated), then B and R swapped.  Bytes R, G, B, A per pixel.
+inline std::vector<uint8_t> loadRgba8(const fs::path& path, int* w, int* h) {
+  const Image img = loadUnchanged(path);
+  CHECK(img.bits == 8 || img.bits == 16) << "colour image expected: " << path.string();
+  *w = img.w;
+  *h = img.h;
+  const size_t n = (size_t)img.w * img.h;
+  const float a = 255.0f / 65535.0f;
+  auto conv = [&](size_t idx) -> uint8_t {
+    if (img.bits == 8) return (uint8_t)img.u[idx];
+    const int r = (int)std::lrintf((float)img.u[idx] * a);  // saturate_cast<uchar>(src * alpha) in float
+    return (uint8_t)(r > 255 ? 255 : r);
+  };
+  std::vector<uint8_t> out(n * 4);
+  for (size_t i = 0; i < n; ++i) {
+    const size_t at = i * img.channels;
+    const uint8_t b = conv(at), g = img.channels >= 3 ? conv(at + 1) : b, r = img.channels >= 3 ? conv(at + 2) : b;
+    out[i * 4 + 0] = r;
+    out[i * 4 + 1] = g;
+    out[i * 4 + 2] = b;
+    out[i * 4 + 3] = img.channels == 4 ? conv(at + 3) : (img.channels == 2 ? conv(at + 1) : 255);
+  }
+  return out;
+}
+
 // loadImage<float>: .pfm as-is; integer images scaled by 1/max
 inline std::vector<float> loadFloat(const fs::path& path, int* w, int* h) {
   const Image img = loadUnchanged(path);

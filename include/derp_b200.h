@@ -297,7 +297,7 @@ int derp_foreground_mask(int device, const uint16_t* templ, const uint16_t* fram
  * down to `triangles` faces when the mesh has more, then z < 0 -> FLT_MIN.  That stage is a chain of dependent
  * contractions (one thread in the reference's call): the GPU builds the mesh in double precision, the contraction sweeps
  * run on the host inside the library.
- * Not built: BC7 / RGBA colour. */
+ * Not built: BC7 colour. */
 int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_width, int* mesh_height);
 int derp_camera_mesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
                      double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,

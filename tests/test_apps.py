@@ -531,3 +531,61 @@ def test_convert_to_binary_meshes(tmp_path, cuda, oracle):
     fused_rig = json.load(open(tmp_path / "fused" / "rig_fused.json"))
     assert [c["id"] for c in fused_rig["cameras"]] == [c["id"] for c in rig["cameras"]]
     assert np.allclose(fused_rig["cameras"][0]["focal"], rig["cameras"][0]["focal"])
+
+
+def test_rgba_stream_matches_opencv(tmp_path):
+    """The ".rgba" stream of ConvertToBinary (convertColor, ConvertToBinary.cpp:138-146): loadImage<Vec4b> = convertTo 8U
+    with the float scale 255/65535, BGR -> BGRA (alpha 255), then BGRA -> RGBA; the host loader against the same cv2 calls
+    on 16-bit and 8-bit, 3- and 4-channel and gray PNGs."""
+    rng = np.random.RandomState(3)
+    cases = {
+        "c16": rng.randint(0, 65536, (9, 13, 3)).astype(np.uint16),
+        "c8": rng.randint(0, 256, (9, 13, 3)).astype(np.uint8),
+        "a16": rng.randint(0, 65536, (7, 5, 4)).astype(np.uint16),
+        "g16": rng.randint(0, 65536, (6, 8)).astype(np.uint16),
+    }
+    cases["c16"][0, :4] = [[0, 128, 65535], [127, 129, 386], [65407, 65408, 65409], [32767, 32768, 32896]]  # rounding edges
+    for name, img in cases.items():
+        p = str(tmp_path / (name + ".png"))
+        assert cv2.imwrite(p, img)
+        out = str(tmp_path / (name + ".rgba"))
+        r = run("IoSelfTest", "--in=" + p, "--mode=rgba", "--out=" + out)
+        w, h = map(int, r.stdout.split()[-2:])
+        got = np.fromfile(out, np.uint8).reshape(h, w, 4)
+        src = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+        if src.dtype == np.uint16:  # cv::Mat::convertTo(CV_8U, 255.0f / 65535.0f)
+            src = cv2.convertScaleAbs(src, alpha=float(np.float32(255.0) / np.float32(65535.0)))
+        code = {2: cv2.COLOR_GRAY2BGRA, 3: cv2.COLOR_BGR2BGRA}.get(src.ndim if src.ndim == 2 else src.shape[2])
+        bgra = src if code is None else cv2.cvtColor(src, code)
+        assert np.array_equal(got, cv2.cvtColor(bgra, cv2.COLOR_BGRA2RGBA)), name
+
+
+def test_convert_to_binary_rgba_only(tmp_path):
+    """ConvertToBinary with a colour directory and --output_formats=rgba touches no GPU stage: .rgba files = the cv2
+    sequence, the rig is rescaled to the colour resolution (resizeRig, ConvertToBinary.cpp:322-343), the fused stream holds
+    the files."""
+    W, H = 48, 40
+    rig = synth.ring_rig(2, 2 * W, 2 * H, kind="FTHETA")  # rig at twice the colour resolution -> rescale by 0.5
+    os.makedirs(tmp_path / "rigs", exist_ok=True)
+    json.dump(rig, open(tmp_path / "rigs" / "rig.json", "w"))
+    rng = np.random.RandomState(8)
+    imgs = {}
+    for cam in rig["cameras"]:
+        d = tmp_path / "color" / cam["id"]
+        os.makedirs(d, exist_ok=True)
+        imgs[cam["id"]] = rng.randint(0, 65536, (H, W, 3)).astype(np.uint16)
+        assert cv2.imwrite(str(d / "000000.png"), imgs[cam["id"]])
+    run("ConvertToBinary", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
+        "--color=" + str(tmp_path / "color"), "--bin=" + str(tmp_path / "bin"), "--fused=" + str(tmp_path / "fused"),
+        "--output_formats=rgba")
+    for cam in rig["cameras"]:
+        got = np.fromfile(tmp_path / "bin" / cam["id"] / "000000.rgba", np.uint8).reshape(H, W, 4)
+        src = cv2.convertScaleAbs(imgs[cam["id"]], alpha=float(np.float32(255.0) / np.float32(65535.0)))
+        assert np.array_equal(got, cv2.cvtColor(cv2.cvtColor(src, cv2.COLOR_BGR2BGRA), cv2.COLOR_BGRA2RGBA))
+    fused_rig = json.load(open(tmp_path / "fused" / "rig_fused.json"))
+    c0, r0 = fused_rig["cameras"][0], rig["cameras"][0]
+    assert c0["resolution"] == [W, H] and np.allclose(c0["focal"], np.array(r0["focal"]) * 0.5)
+    assert np.allclose(c0.get("principal", [W / 2, H / 2]), [W / 2, H / 2])
+    catalog = json.load(open(tmp_path / "fused" / "fused.json"))
+    e = catalog["frames"]["000000"][rig["cameras"][1]["id"]][".rgba"]
+    assert e["size"] == W * H * 4 and e["offset"] % (512 * 1024) == 0
