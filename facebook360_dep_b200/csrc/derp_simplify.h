@@ -243,6 +243,10 @@ class Mesh {
       } else {
         threshold *= 2 * ++stuck;  // nothing was contracted in the last sweep: open the threshold
         if (std::isinf(threshold)) break;
+        // A threshold of exactly 0 (exactly planar patches: constant-disparity regions) or NaN never grows: the
+        // reference's loop spins forever there (MeshSimplifier.cpp:505-512, reproduced with its own code in
+        // tests/test_mesh.py).  Nothing more can be contracted under the reference's rules, so stop with the mesh as it is.
+        if (!(threshold != 0) || threshold != threshold) break;
       }
       gonePrev = gone;
       for (size_t fi = 0; fi < faces.size(); ++fi) {

@@ -180,3 +180,45 @@ def test_gpu_mesh_simplified_equals_reference(cuda):
         rv, ri = ref.camera_mesh(d, (800.0, 600.0), 300.0, triangles=tri)
         assert np.array_equal(gi, ri)
         assert np.array_equal(gv.view(np.uint32), rv.view(np.uint32))
+
+
+def _flat_grid(w, h):
+    """An exactly planar w x h vertex grid (z = 1) split into 2 (w-1)(h-1) triangles: every quadric error is exactly 0."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    xyz = np.stack([xx.ravel(), yy.ravel(), np.ones(w * h)], 1)
+    q = (np.arange(h - 1)[:, None] * w + np.arange(w - 1)[None, :]).ravel().astype(np.uint32)
+    idx = np.concatenate([np.stack([q, q + 1, q + w], 1), np.stack([q + 1, q + w + 1, q + w], 1)])
+    return xyz, idx
+
+
+_PLANAR_CHILD = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+from tests import oracle_libs, test_mesh
+from facebook360_dep_b200 import capi
+lib, name = (capi.load_cuda(), "derp_test_simplify") if sys.argv[1] == "product" else (oracle_libs.load_ref(), "derp_ref_simplify")
+xyz, idx = test_mesh._flat_grid(12, 10)
+v, i = test_mesh._simplify(lib, name, xyz, idx, 4)
+np.save(sys.argv[2], i)
+"""
+
+
+def test_simplifier_terminates_on_planar_mesh(tmp_path):
+    """A constant-disparity region is exactly planar: every edge cost is 0, the interior contracts, and once only boundary
+    edges are left the percentile threshold is exactly 0 and `threshold *= 2 * ++count` never grows -- the reference's loop
+    (MeshSimplifier.cpp:483-493) never ends (shown here with its own code, in a child process with a time limit).  The
+    library stops with the mesh it has (derp_simplify.h, documented deviation), and that mesh is a valid one."""
+    import subprocess
+    import sys
+    root = oracle_libs.ROOT
+    out = str(tmp_path / "faces.npy")
+    subprocess.run([sys.executable, "-c", _PLANAR_CHILD % root, "product", out], check=True, timeout=60)
+    faces = np.load(out)
+    xyz, idx = _flat_grid(12, 10)
+    assert 0 < len(faces) < len(idx)
+    # boundary vertices are never contracted (removeBoundaryEdges = false): all 40 rim vertices survive
+    assert len(np.unique(faces)) >= 2 * (12 + 10) - 4
+    assert all(len(set(f)) == 3 for f in faces.tolist())
+    if oracle_libs.load_ref() is not None:
+        with pytest.raises(subprocess.TimeoutExpired):
+            subprocess.run([sys.executable, "-c", _PLANAR_CHILD % root, "reference", out], check=True, timeout=8)
