@@ -169,6 +169,8 @@ _SIGS = {
     "derp_camera_mesh_simplified": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                               C.c_double, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                               C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "derp_bc7_compress": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "derp_bc7_compress_image": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
 }
 
 ABI_SYMBOLS = sorted(_SIGS)
@@ -265,6 +267,27 @@ class Library:
         else:
             self.check(self.lib.derp_camera_mesh(*head, *tail))
         return vtx[:nv.value].copy(), idx[:nf.value].copy()
+
+    def bc7_compress(self, rgba, device=0):
+        """CompressBlocksBC7 with the veryfast profile (BC7Util.h:69-76) of an opaque RGBA8 surface [h, w, 4]:
+        returns the w * h output bytes as [w * h / 16, 16] (16-byte blocks; rows of partial blocks stay zero)."""
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        h, w, c = rgba.shape
+        assert c == 4
+        out = np.empty(w * h, np.uint8)
+        self.check(self.lib.derp_bc7_compress(device, rgba.ctypes.data, w, h, out.ctypes.data))
+        return out
+
+    def bc7_compress_image(self, pixels, gamma=2.2 / 1.8, device=0):
+        """bc7_util::compressBC7 up to the file write (BC7Util.h:45-76) of an image as cv2.imread(IMREAD_UNCHANGED)
+        returns it: uint8 / uint16 [h, w, 3 or 4] in B, G, R[, A] order.  Returns the w * h bytes of the .bc7 file."""
+        pixels = np.ascontiguousarray(pixels)
+        assert pixels.dtype in (np.uint8, np.uint16) and pixels.ndim == 3 and pixels.shape[2] in (3, 4)
+        h, w, c = pixels.shape
+        out = np.empty(w * h, np.uint8)
+        self.check(self.lib.derp_bc7_compress_image(device, pixels.ctypes.data, pixels.dtype.itemsize * 8, c, w, h, gamma,
+                                                    out.ctypes.data))
+        return out
 
     def upsample_disparity(self, cam_desc, coarse, out_w, out_h, background_up=None, coarse_mask=None,
                            fine_mask=None, use_foreground_masks=False, device=0):

@@ -20,6 +20,7 @@
 #include "derp_refine.cuh"
 #include "derp_mesh.cuh"
 #include "derp_simplify.h"
+#include "derp_bc7.cuh"
 
 using namespace derp;
 
@@ -1967,6 +1968,67 @@ int derp_joint_bilateral_f32(int device, int width, int height, const float* ima
   return DERP_OK;
 }
 
+
+// ---- BC7 colour (ConvertToBinary's default colour format) ----
+static int bc7Launch(int device, const void* src, size_t srcBytes, int mode, int channels, int width, int height,
+                     const uint8_t* lutHost, size_t lutBytes, uint8_t* blocks) {
+  CU(cudaSetDevice(device));
+  const size_t outBytes = (size_t)width * height;
+  DevBuf<uint8_t> dSrc, dOut, dLut;
+  const void* s = src;
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, src) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    (void)cudaGetLastError();
+    CU(dSrc.ensure(srcBytes));
+    CU(cudaMemcpy(dSrc.p, src, srcBytes, cudaMemcpyDefault));
+    s = dSrc.p;
+  }
+  uint8_t* o = blocks;
+  const bool outOnDevice = cudaPointerGetAttributes(&at, blocks) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+  if (!outOnDevice) {
+    (void)cudaGetLastError();
+    CU(dOut.ensure(outBytes));
+    o = dOut.p;
+  }
+  CU(cudaMemset(o, 0, outBytes));  // the reference's output vector starts zeroed; partial edge blocks are never written
+  const int bx = width / 4, by = height / 4;
+  if (bx > 0 && by > 0) {
+    const unsigned grid = (unsigned)(((size_t)bx * by + derp::bc7::kBc7Threads - 1) / derp::bc7::kBc7Threads);
+    if (mode == 0) {
+      derp::bc7::bc7Kernel<<<grid, derp::bc7::kBc7Threads>>>(derp::bc7::Rgba8Source{(const uint8_t*)s, width}, width, bx, by, o);
+    } else {
+      CU(dLut.ensure(lutBytes));
+      CU(cudaMemcpy(dLut.p, lutHost, lutBytes, cudaMemcpyHostToDevice));
+      if (mode == 8)
+        derp::bc7::bc7Kernel<<<grid, derp::bc7::kBc7Threads>>>(
+            derp::bc7::BgrSource<uint8_t>{(const uint8_t*)s, width, channels, dLut.p}, width, bx, by, o);
+      else
+        derp::bc7::bc7Kernel<<<grid, derp::bc7::kBc7Threads>>>(
+            derp::bc7::BgrSource<uint16_t>{(const uint16_t*)s, width, channels, dLut.p}, width, bx, by, o);
+    }
+    CU(cudaGetLastError());
+  }
+  if (!outOnDevice) CU(cudaMemcpy(blocks, o, outBytes, cudaMemcpyDeviceToHost));
+  else CU(cudaDeviceSynchronize());
+  return DERP_OK;
+}
+
+int derp_bc7_compress(int device, const uint8_t* rgba, int width, int height, uint8_t* blocks) {
+  if (!rgba || !blocks || width < 1 || height < 1) return fail(DERP_EINVAL, "derp_bc7_compress: bad arguments");
+  return bc7Launch(device, rgba, (size_t)width * height * 4, 0, 4, width, height, nullptr, 0, blocks);
+}
+
+int derp_bc7_compress_image(int device, const void* pixels, int bits_per_channel, int channels, int width, int height,
+                            float gamma, uint8_t* blocks) {
+  if (!pixels || !blocks || width < 1 || height < 1 || (bits_per_channel != 8 && bits_per_channel != 16) ||
+      (channels != 3 && channels != 4))
+    return fail(DERP_EINVAL, "derp_bc7_compress_image: 8 or 16 bits per channel, 3 (BGR) or 4 (BGRA) channels");
+  std::vector<uint8_t> lut((size_t)1 << bits_per_channel);
+  derp::bc7::gammaTable(bits_per_channel, gamma, lut.data());
+  return bc7Launch(device, pixels, (size_t)width * height * channels * (bits_per_channel / 8), bits_per_channel, channels,
+                   width, height, lut.data(), lut.size(), blocks);
+}
+
 }  // extern "C"
 
 // ---- host-side test hooks ---------------------------------------------------------------------------
@@ -2022,6 +2084,20 @@ int derp_test_simplify(const double* xyz, uint64_t nv, const uint32_t* idx, uint
   *out_nv = mesh.verts.size();
   *out_nf = mesh.faces.size();
   return 0;
+}
+
+// HOST instantiation of the BC7 block encoder (derp_bc7.cuh) for tests/test_bc7.py -m "not gpu"; the apps call
+// derp_bc7_compress* (CUDA) only.
+int derp_test_bc7_blocks_host(const uint8_t* rgba, int width, int height, uint8_t* blocks) {
+  if (!rgba || !blocks || width < 1 || height < 1) return DERP_EINVAL;
+  std::memset(blocks, 0, (size_t)width * height);
+  derp::bc7::encodeSurfaceOnHost(rgba, width, height, blocks);
+  return DERP_OK;
+}
+int derp_test_bc7_gamma_table(int bits_per_channel, float gamma, uint8_t* lut) {
+  if ((bits_per_channel != 8 && bits_per_channel != 16) || !lut) return DERP_EINVAL;
+  derp::bc7::gammaTable(bits_per_channel, gamma, lut);
+  return DERP_OK;
 }
 
 float derp_test_robust_sum(const float* first, const float* second, int n, int keep) {

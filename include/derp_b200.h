@@ -296,8 +296,7 @@ int derp_foreground_mask(int device, const uint16_t* templ, const uint16_t* fram
  * (source/render/MeshSimplifier.cpp: quadric-error edge contraction, equi-error costs, strictness 0.2, boundary edges kept)
  * down to `triangles` faces when the mesh has more, then z < 0 -> FLT_MIN.  That stage is a chain of dependent
  * contractions (one thread in the reference's call): the GPU builds the mesh in double precision, the contraction sweeps
- * run on the host inside the library.
- * Not built: BC7 colour. */
+ * run on the host inside the library. */
 int derp_camera_mesh_size(int width, int height, double depth_scale, int* mesh_width, int* mesh_height);
 int derp_camera_mesh(int device, const float* disparity, int width, int height, double depth_scale, double resolution_x,
                      double resolution_y, double scalar_focal, float tear_ratio, const uint8_t* foreground_mask,
@@ -307,6 +306,24 @@ int derp_camera_mesh_simplified(int device, const float* disparity, int width, i
                                 double resolution_x, double resolution_y, double scalar_focal, float tear_ratio,
                                 const uint8_t* foreground_mask, int mask_width, int mask_height, int triangles,
                                 float* vertexes, uint32_t* faces, uint64_t* num_vertexes, uint64_t* num_faces);
+
+/* BC7 colour of ConvertToBinary's convertColor (ConvertToBinary.cpp:122-138; the default --output_formats holds bc7).
+ * derp_bc7_compress replaces CompressBlocksBC7(&surface, out, &settings) with GetProfile_veryfast(&settings)
+ * (source/conversion/BC7Util.h:69-76; the ISPC texture compressor vendored under source/thirdparty/bc7_compressor,
+ * ispc_texcomp.cpp:61-93, kernel.ispc:615-2036): an RGBA8 surface (width * 4 bytes per row, alpha ignored = opaque) to
+ * 16-byte blocks, block row r starting at byte r * width * 4; `blocks` holds width * height bytes and is zeroed first,
+ * partial edge blocks (width or height not a multiple of 4) are not encoded — all as the reference does.
+ * derp_bc7_compress_image replaces bc7_util::compressBC7(image, ...) up to the file write (BC7Util.h:45-76): `pixels` is the
+ * image as cv::imread(IMREAD_UNCHANGED) returns it (B, G, R[, A] interleaved, 8 or 16 bits per channel); conversion to
+ * [0, 1] floats (CvUtil.h:196-207), bc7_util::gammaCorrect (BC7Util.h:41-43) and the RGBA packing are fused into the
+ * block loads through a lookup table over the stored channel values, built on the host with the host's powf.
+ * Modes tried: 1 and 3 (best 3 / 1 of the 64 partitions by the residual bound), 6; same operation order, x86 conversion
+ * semantics and end-point quantisation as the reference BUILD, IEEE division / square root where that build uses the
+ * RCPPS / RSQRTPS estimates (so individual blocks can differ where an estimate's last bit decides; see derp_bc7.cuh).
+ * All pointers may be host or device memory. */
+int derp_bc7_compress(int device, const uint8_t* rgba, int width, int height, uint8_t* blocks);
+int derp_bc7_compress_image(int device, const void* pixels, int bits_per_channel, int channels, int width, int height,
+                            float gamma, uint8_t* blocks);
 
 #ifdef __cplusplus
 }

@@ -1525,6 +1525,17 @@ int derp_camera_mesh_simplified(int, const float*, int, int, double, double, dou
   return DERP_EINVAL;
 }
 
+// BC7 colour is checked against the reference's own encoder (oracle/_ref: kernel.ispc compiled by the ispc binary the
+// reference vendors) and, for arithmetic identity, oracle/libbc7_x86.so: no second restatement here.
+int derp_bc7_compress(int, const uint8_t*, int, int, uint8_t*) {
+  g_err = "derp_bc7_compress: no oracle restatement; the checker is oracle/_ref (the reference's own encoder)";
+  return DERP_EINVAL;
+}
+int derp_bc7_compress_image(int, const void*, int, int, int, int, float, uint8_t*) {
+  g_err = "derp_bc7_compress_image: no oracle restatement; the checker is oracle/_ref (the reference's own encoder)";
+  return DERP_EINVAL;
+}
+
 int oracle_resize_area(const uint16_t* src, int sw, int sh, uint16_t* dst, int dw, int dh) {
   return resizeAreaU16C3(src, sw, sh, dst, dw, dh) ? 0 : -1;
 }
