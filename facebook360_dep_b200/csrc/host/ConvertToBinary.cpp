@@ -1,12 +1,14 @@
-// ConvertToBinary — drop-in for the geometry half of source/mesh_stream/ConvertToBinary.cpp on B200.
+// ConvertToBinary — drop-in for source/mesh_stream/ConvertToBinary.cpp on B200.
 //
-// Built: disparity PFM -> camera mesh (.vtx float32 xyz, .idx uint32 x 3, optional .obj) through libderp_b200.so
+// Geometry: disparity PFM -> camera mesh (.vtx float32 xyz, .idx uint32 x 3, optional .obj) through libderp_b200.so
 // (derp_camera_mesh_simplified: mesh_util::getVertexesEquiError / getFaces / applyMaskToVertexesAndFaces on the GPU, then
 // render::MeshSimplifier's contraction sweeps down to --triangles, sequential host code like the reference's), the rescaled
 // `<rig>_fused.json`, and the striped fusion of the produced files (BinaryFusionUtil.h).
-// Colour: the uncompressed .rgba stream (host bytes, --color_scale = 1).  NOT built, and refused loudly instead of silently
-// skipped: BC7 colour (bc7 format; the vendored ISPC texture compressor) and the rasterised pfm format.  With the reference's default --output_formats=idx,vtx,bc7 AND a
-// --color directory this executable therefore stops with a message naming the flag to change: --output_formats=idx,vtx.
+// Colour: .bc7 (the reference's default; derp_bc7_compress_image: conversion, gamma correction, packing and the block encoder
+// of bc7_util::compressBC7 in one CUDA kernel) and the uncompressed .rgba stream (host bytes); both with --color_scale = 1.
+// NOT built, and refused with a message instead of silently skipped: the rasterised pfm format (mesh_util::writePfm samples
+// the mesh exactly ON its vertexes and edges, so which pixels it covers is decided by the rounding noise of Eigen's
+// column-pivoting QR — not reproducible without Eigen itself) and colour conversion with --color_scale < 1.
 #include <set>
 #include <thread>
 
@@ -268,11 +270,10 @@ int main(int argc, char** argv) {
   for (const std::string& f : formats) CHECK(f.empty() || supported.count(f)) << "Invalid output format specified: " << f;
   const int firstFrame = std::stoi(FLAGS_first), numFrames = std::stoi(FLAGS_last) - firstFrame + 1;
   CHECK_GT(numFrames, 0);
-  CHECK(FLAGS_color.empty() || !contains(formats, "bc7"))
-      << "the bc7 colour format (ISPC texture compressor) is not built in this port: pass --output_formats=idx,vtx[,rgba,obj]";
   const bool wantRgba = !FLAGS_color.empty() && contains(formats, "rgba");
-  CHECK(!wantRgba || FLAGS_color_scale >= 1) << "rgba with --color_scale < 1 is not built in this port";
-  CHECK(FLAGS_disparity.empty() || !contains(formats, "pfm")) << "the rasterised pfm format is not built in this port";
+  const bool wantBc7 = !FLAGS_color.empty() && contains(formats, "bc7");
+  CHECK((!wantRgba && !wantBc7) || FLAGS_color_scale >= 1) << "colour conversion with --color_scale < 1 is not built in this port";
+  CHECK(FLAGS_disparity.empty() || !contains(formats, "pfm")) << "the rasterised pfm format is not built in this port (pass --output_formats without pfm)";
   const bool wantDepth = !FLAGS_disparity.empty() && (contains(formats, "idx") || contains(formats, "vtx") || contains(formats, "obj"));
 
   // resizeRig (ConvertToBinary.cpp:322-343): camera resolutions follow the (scaled) colour images
@@ -361,6 +362,41 @@ int main(int argc, char** argv) {
         }
       });
     for (auto& t : threads) t.join();
+
+    // convertColor, bc7 (ConvertToBinary.cpp:131-137): bc7_util::compressBC7(image, path, --gamma_correction, no DDS header).
+    // The image goes to the GPU as stored (B, G, R, 8 or 16 bits); conversion to float, gamma correction, RGBA packing and the
+    // block encoder are one kernel (derp_bc7_compress_image).  PNG decoding is the host cost: one worker per image.
+    if (wantBc7) {
+      threads.clear();
+      for (int k = 0; k < workers; ++k)
+        threads.emplace_back([&, k] {
+          const int device = FLAGS_gpu + k % G;
+          for (size_t t = k; t < tasks.size(); t += workers) {
+            const std::string &id = rig.ids[tasks[t].cam], frame = io::zeroPad(tasks[t].frame);
+            LOG(INFO) << "Converting color: frame " << frame << ", camera " << id << "...";
+            const io::Image img = io::loadUnchanged(io::imagePath(FLAGS_color, id, frame));
+            CHECK((img.bits == 8 || img.bits == 16) && (img.channels == 1 || img.channels == 3 || img.channels == 4))
+                << "Conversion from " << img.channels << " channels to 4 channels not supported";  // CvUtil.h:261-262
+            const size_t n = (size_t)img.w * img.h;
+            std::vector<uint8_t> pixels(n * 3 * (img.bits / 8));  // B, G, R as cv::cvtColor(GRAY2BGRA / BGRA2BGR) leave them
+            for (size_t i = 0; i < n; ++i)
+              for (int c = 0; c < 3; ++c) {
+                const uint16_t v = img.u[i * img.channels + (img.channels == 1 ? 0 : c)];
+                if (img.bits == 8)
+                  pixels[i * 3 + c] = (uint8_t)v;
+                else
+                  std::memcpy(&pixels[(i * 3 + c) * 2], &v, 2);
+              }
+            std::vector<uint8_t> blocks(n);
+            DERP_CALL(derp_bc7_compress_image(device, pixels.data(), img.bits, 3, img.w, img.h, (float)FLAGS_gamma_correction,
+                                              blocks.data()));
+            const fs::path out = io::imagePath(FLAGS_bin, id, frame, ".bc7");
+            fs::create_directories(out.parent_path());
+            std::ofstream(out, std::ios::binary).write(reinterpret_cast<const char*>(blocks.data()), blocks.size());
+          }
+        });
+      for (auto& t : threads) t.join();
+    }
 
     if (wantRgba)  // convertColor (ConvertToBinary.cpp:122-147): ".rgba is just uncompressed 8-bit color"
       for (const Task& t : tasks) {

@@ -449,16 +449,70 @@ def _mesh_dataset(tmp_path, W=96, H=80, S=3, F=2):
 
 
 def test_convert_to_binary_refuses_unbuilt_parts(tmp_path):
-    """The reference's default formats ask for BC7 colour, which is not built: with a --color directory the executable
-    says so instead of writing something else (no GPU needed to get that far); same for the rasterised pfm format."""
+    """What this build does not do is refused with a message instead of skipped or approximated (no GPU needed to get that
+    far): the rasterised pfm format, and colour conversion with --color_scale < 1.  Without a GPU the BC7 colour format
+    stops with the CUDA error — there is no host encoder behind the executable."""
     rig, _ = _mesh_dataset(tmp_path, F=1)
     base = ["--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
             "--disparity=" + str(tmp_path / "disparity"), "--bin=" + str(tmp_path / "bin")]
-    os.makedirs(tmp_path / "color" / rig["cameras"][0]["id"], exist_ok=True)
-    p = run("ConvertToBinary", *base, "--color=" + str(tmp_path / "color"), check=False)
-    assert p.returncode != 0 and "bc7" in p.stderr
     p = run("ConvertToBinary", *base, "--output_formats=idx,vtx,pfm", check=False)
     assert p.returncode != 0 and "pfm" in p.stderr
+    H, W = 80, 96
+    for cam in rig["cameras"]:
+        os.makedirs(tmp_path / "color" / cam["id"], exist_ok=True)
+        assert cv2.imwrite(str(tmp_path / "color" / cam["id"] / "000000.png"), np.full((H, W, 3), 1000, np.uint16))
+    p = run("ConvertToBinary", *base, "--color=" + str(tmp_path / "color"), "--color_scale=0.5", check=False)
+    assert p.returncode != 0 and "color_scale" in p.stderr
+    import torch
+    if not torch.cuda.is_available():
+        p = run("ConvertToBinary", base[0], base[1], base[2], base[4], "--color=" + str(tmp_path / "color"),
+                "--output_formats=bc7", check=False)
+        assert p.returncode != 0 and "cuda" in p.stderr.lower() and not os.path.exists(tmp_path / "bin" / "cam0" / "000000.bc7")
+
+
+@pytest.mark.gpu
+def test_convert_to_binary_bc7(tmp_path, cuda):
+    """The reference's DEFAULT --output_formats (idx, vtx, bc7) with a colour directory: the .bc7 files are the library's
+    blocks of the image as cv2.imread(IMREAD_UNCHANGED) holds it (16-bit BGR, 8-bit BGRA and gray PNGs), the fused stream
+    carries them; against the reference's own bc7_util::compressBC7 the files agree as far as IEEE vs estimate arithmetic
+    allows (tests/test_bc7.py)."""
+    from tests import bc7_decode, oracle_libs
+    rig, disps = _mesh_dataset(tmp_path, F=1)
+    H, W = next(iter(disps.values())).shape
+    rng = np.random.RandomState(6)
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = np.stack([0.5 + 0.4 * np.sin(xx / 9.), 0.5 + 0.4 * np.cos(yy / 7.), (xx + yy) / float(W + H)], -1)
+    imgs = {}
+    for n, cam in enumerate(rig["cameras"]):
+        img = (base + rng.normal(0, 0.01, base.shape)).clip(0, 1)
+        if n == 0:
+            img = (img * 65535).astype(np.uint16)
+        elif n == 1:
+            img = np.concatenate([(img * 255).astype(np.uint8), np.full((H, W, 1), 200, np.uint8)], -1)
+        else:
+            img = (img[..., 0] * 65535).astype(np.uint16)
+        os.makedirs(tmp_path / "color" / cam["id"], exist_ok=True)
+        assert cv2.imwrite(str(tmp_path / "color" / cam["id"] / "000000.png"), img)
+        imgs[cam["id"]] = img
+    run("ConvertToBinary", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
+        "--disparity=" + str(tmp_path / "disparity"), "--color=" + str(tmp_path / "color"), "--bin=" + str(tmp_path / "bin"),
+        "--fused=" + str(tmp_path / "fused"))
+    catalog = json.load(open(tmp_path / "fused" / "fused.json"))
+    disk = open(tmp_path / "fused" / "fused_0.bin", "rb").read()
+    ref = oracle_libs.load_ref()
+    for cam in rig["cameras"]:
+        img = imgs[cam["id"]]
+        stored = img if img.ndim == 3 else np.repeat(img[..., None], 3, -1)  # GRAY2BGRA replicates the channel
+        got = np.fromfile(str(tmp_path / "bin" / cam["id"] / "000000.bc7"), np.uint8)
+        assert got.size == W * H
+        assert np.array_equal(got, cuda.bc7_compress_image(stored[..., :3].copy(), 2.2 / 1.8))
+        e = catalog["frames"]["000000"][cam["id"]][".bc7"]
+        assert disk[e["offset"]:e["offset"] + e["size"]] == got.tobytes()
+        assert os.path.exists(tmp_path / "bin" / cam["id"] / "000000.vtx")
+        if ref is not None:
+            want = ref.bc7_compress_image(stored[..., :3].copy(), 2.2 / 1.8)
+            assert (got.reshape(-1, 16) == want.reshape(-1, 16)).all(1).mean() > 0.9
+            assert {bc7_decode.block_mode(b) for b in got.reshape(-1, 16)} <= {1, 3, 6}
 
 
 @pytest.mark.gpu
