@@ -24,6 +24,13 @@
 #include <cstdint>
 #include <cstring>
 
+#ifndef DERP_BC7_MIN_CTAS  // build-time experiment knobs (profiles/README.md has the A/B)
+#define DERP_BC7_MIN_CTAS 2
+#endif
+#ifndef DERP_BC7_RANK_UNROLL
+#define DERP_BC7_RANK_UNROLL 1
+#endif
+
 namespace derp {
 namespace bc7 {
 
@@ -544,6 +551,8 @@ BC7_FN void encodeBlock(const Pixels& px, uint32_t (&out)[4]) {
   {
     const Moments all = momentsOf(px, 0xFFFFu);
     int key0 = INT_MAX, key1 = INT_MAX, key2 = INT_MAX;
+    constexpr int kRankUnroll = DERP_BC7_RANK_UNROLL;
+#pragma unroll kRankUnroll
     for (int part = 0; part < 64; ++part) {
       const Moments first = momentsOf(px, ~subset1Mask(part) & 0xFFFFu);
       float bound = 0;
@@ -652,7 +661,7 @@ struct BgrSource {
 };
 constexpr int kBc7Threads = 128;
 template <typename Source>
-__global__ void __launch_bounds__(kBc7Threads, 3) bc7Kernel(Source src, int width, int blocksX, int blocksY, uint8_t* out) {
+__global__ void __launch_bounds__(kBc7Threads, DERP_BC7_MIN_CTAS) bc7Kernel(Source src, int width, int blocksX, int blocksY, uint8_t* out) {
   const int b = blockIdx.x * kBc7Threads + threadIdx.x;
   if (b >= blocksX * blocksY) return;
   const int bx = b % blocksX, by = b / blocksX;
