@@ -36,9 +36,15 @@ namespace bc7 {
 
 #ifdef __CUDACC__
 #define BC7_FN __host__ __device__ __forceinline__
+// The stages called from several places (line fit, index choice, least-squares refit) are NOT inlined on the device and
+// their per-pixel loops stay rolled: fully inlined and unrolled the kernel was 24 208 instructions (387 KB) and stalled on
+// instruction fetch (ncu: no_instruction 3.8 per issued instruction, profiles/r2_bc7Kernel_ncu_full.txt).
+#define BC7_STAGE __host__ __device__ __noinline__
 #else  // plain C++ build of the same functions: oracle/bc7_x86.cpp (test infrastructure)
 #define BC7_FN inline
+#define BC7_STAGE inline
 #endif
+#define BC7_PIXEL_LOOP _Pragma("unroll 2")
 
 // Division and reciprocal square root.  Product: IEEE.  -DDERP_BC7_X86_ESTIMATES (host only, used by the test build
 // oracle/bc7_x86.cpp): the instruction sequences the reference's ispc build emits for `a / b` and rsqrt() — RCPPS / RSQRTPS
@@ -113,18 +119,32 @@ BC7_FN float clampPs(float v, float lo, float hi) { return minPs(maxPs(v, lo), h
 BC7_FN int clampInt(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 BC7_FN float sq(float v) { return v * v; }
 
-typedef float Pixels[3][16];  // [channel R, G, B][pixel y * 4 + x], values 0..255
+// The 16 pixels of a block, values 0..255 as floats: px(channel R / G / B, pixel y * 4 + x).  On the device they live in
+// shared memory, [channel * 16 + pixel][thread] (conflict-free: consecutive threads, consecutive words), so that the loops
+// over pixels can stay rolled and the stages can be real functions; on the host a plain array.
+struct HostPixels {
+  float v[3][16];
+  BC7_FN float operator()(int c, int k) const { return v[c][k]; }
+};
+#ifdef __CUDACC__
+constexpr int kBc7Threads = 128;
+__shared__ float bc7Tile[48 * kBc7Threads];  // 24 KB per CTA; a thread only ever touches its own 48 words: no barriers
+struct SharedPixels {
+  __device__ __forceinline__ float operator()(int c, int k) const { return bc7Tile[(c * 16 + k) * kBc7Threads + threadIdx.x]; }
+};
+#endif
 
 // ---- first and second moments of the pixels selected by a 16-bit mask (kernel.ispc:762-802) ----
 struct Moments {
   float rr, rg, rb, gg, gb, bb, r, g, b, n;
 };
-BC7_FN Moments momentsOf(const Pixels& px, uint32_t mask) {
+template <class Px>
+BC7_FN Moments momentsOf(const Px& px, uint32_t mask) {
   Moments m = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
+  BC7_PIXEL_LOOP
   for (int k = 0; k < 16; ++k) {
     const float in = (float)((mask >> k) & 1u);
-    const float r = px[0][k] * in, g = px[1][k] * in, b = px[2][k] * in;
+    const float r = px(0, k) * in, g = px(1, k) * in, b = px(2, k) * in;
     m.n += in;
     m.r += r;
     m.g += g;
@@ -215,20 +235,21 @@ BC7_FN float residualBound(const Moments& m) {
 }
 
 // ---- one line per subset: end points on the principal axis, clamped to the byte range (kernel.ispc:856-904) ----
-BC7_FN void fitLine(const Pixels& px, uint32_t mask, float (&ends)[2][3]) {
+template <class Px>
+BC7_STAGE void fitLine(const Px& px, uint32_t mask, float (&ends)[2][3]) {
   const Moments m = momentsOf(px, mask);
   const Cov c = scaledCovariance(m);
   const float mean[3] = {divide(m.r, m.n), divide(m.g, m.n), divide(m.b, m.n)};
   float axis[3];
   principalAxis<8>(c, axis);
   float lo = INFINITY, hi = -INFINITY;
-#pragma unroll
+  BC7_PIXEL_LOOP
   for (int k = 0; k < 16; ++k) {
     if (!((mask >> k) & 1u)) continue;
     float t = 0;
-    t += axis[0] * (px[0][k] - mean[0]);
-    t += axis[1] * (px[1][k] - mean[1]);
-    t += axis[2] * (px[2][k] - mean[2]);
+    t += axis[0] * (px(0, k) - mean[0]);
+    t += axis[1] * (px(1, k) - mean[1]);
+    t += axis[2] * (px(2, k) - mean[2]);
     lo = minPs(lo, t);
     hi = maxPs(hi, t);
   }
@@ -321,14 +342,15 @@ BC7_FN void quantiseLines(const float (&ends)[2][2][3], int kSubsets, Lines& out
 }
 
 // ---- pixel indexes against dequantised end points, returns the squared error (kernel.ispc:1132-1192) ----
-template <int kBits>
-BC7_FN float chooseIndexes(const Pixels& px, const float (&deq)[2][2][3], uint32_t subset1, uint32_t (&idx)[2]) {
+template <int kBits, class Px>
+BC7_STAGE float chooseIndexes(const Px& px, const float (&deq)[2][2][3], uint32_t subset1, uint32_t (&idx)[2]) {
   constexpr int kLevels = 1 << kBits;
   float total = 0;
-  idx[0] = idx[1] = 0;
-#pragma unroll
+  uint64_t packed = 0;
+  BC7_PIXEL_LOOP
   for (int k = 0; k < 16; ++k) {
     const bool second = (subset1 >> k) & 1u;
+    const float v[3] = {px(0, k), px(1, k), px(2, k)};
     float a[3], b[3];
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
@@ -338,7 +360,7 @@ BC7_FN float chooseIndexes(const Pixels& px, const float (&deq)[2][2][3], uint32
     float along = 0, len2 = 0;
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
-      along += (px[p][k] - a[p]) * (b[p] - a[p]);
+      along += (v[p] - a[p]) * (b[p] - a[p]);
       len2 += sq(b[p] - a[p]);
     }
     along /= len2;  // `/=` stays a true division in the reference build (DIVPS)
@@ -349,38 +371,42 @@ BC7_FN float chooseIndexes(const Pixels& px, const float (&deq)[2][2][3], uint32
     for (int p = 0; p < 3; ++p) {
       const float d0 = (float)(int)(((float)(64 - w0) * a[p] + (float)w0 * b[p] + 32.0f) * (1.0f / 64.0f));
       const float d1 = (float)(int)(((float)(64 - w1) * a[p] + (float)w1 * b[p] + 32.0f) * (1.0f / 64.0f));
-      err0 += sq(d0 - px[p][k]);
-      err1 += sq(d1 - px[p][k]);
+      err0 += sq(d0 - v[p]);
+      err1 += sq(d1 - v[p]);
     }
     int err = (int)err1, q = upper;  // the reference accumulates the error through an int
     if (err0 < err1) {
       err = (int)err0;
       q = upper - 1;
     }
-    idx[k >> 3] += (uint32_t)q << (4 * (k & 7));
+    packed += (uint64_t)q << (4 * k);
     total += (float)err;
   }
+  idx[0] = (uint32_t)packed;
+  idx[1] = (uint32_t)(packed >> 32);
   return total;
 }
 
 // ---- least-squares end points for fixed indexes (kernel.ispc:1197-1261) ----
-template <int kBits>
-BC7_FN void refitLine(const Pixels& px, const uint32_t (&idx)[2], uint32_t mask, float (&ends)[2][3]) {
+template <int kBits, class Px>
+BC7_STAGE void refitLine(const Px& px, const uint32_t (&idx)[2], uint32_t mask, float (&ends)[2][3]) {
   constexpr int kTop = (1 << kBits) - 1;
   float xb[3] = {0, 0, 0}, sum[3] = {0, 0, 0};
   float sumQ = 0, sumQQ = 0, count = 0;
-#pragma unroll
+  const uint64_t packed = (uint64_t)idx[0] | ((uint64_t)idx[1] << 32);
+  BC7_PIXEL_LOOP
   for (int k = 0; k < 16; ++k) {
     if (!((mask >> k) & 1u)) continue;
-    const float q = (float)(int)((idx[k >> 3] >> (4 * (k & 7))) & 15u);
+    const float q = (float)(int)((packed >> (4 * k)) & 15u);
+    const float v[3] = {px(0, k), px(1, k), px(2, k)};
     const float x = (float)(int)((float)kTop - q);
     sumQ += q;
     sumQQ += q * q;
     count += 1;
 #pragma unroll
-    for (int p = 0; p < 3; ++p) sum[p] += px[p][k];
+    for (int p = 0; p < 3; ++p) sum[p] += v[p];
 #pragma unroll
-    for (int p = 0; p < 3; ++p) xb[p] += x * px[p][k];
+    for (int p = 0; p < 3; ++p) xb[p] += x * v[p];
   }
   float yb[3];
 #pragma unroll
@@ -455,7 +481,7 @@ BC7_FN void packTwoSubsets(Lines c, int part, uint32_t (&out)[4]) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) w.put((uint32_t)c.q[e >> 1][e & 1][0] & 1u, 1);
   }
-#pragma unroll
+  BC7_PIXEL_LOOP
   for (int k = 0; k < 16; ++k) {
     uint32_t q = indexAt(c.idx, k);
     if ((mirrored >> k) & 1u) q = (uint32_t)(kLevels - 1) - q;
@@ -501,8 +527,8 @@ BC7_FN void packMode6(const int (&q)[2][3], const int (&alpha)[2], const uint32_
 }
 
 // ---- a two-subset mode over a short list of partitions, then refinement of the winner (kernel.ispc:1278-1362) ----
-template <int kMode>
-BC7_FN float tryTwoSubsets(const Pixels& px, int part0, int part1, int part2, int count, int refinements, Lines& best,
+template <int kMode, class Px>
+BC7_FN float tryTwoSubsets(const Px& px, int part0, int part1, int part2, int count, int refinements, Lines& best,
                            int& bestPart) {
   constexpr int kBits = kMode == 1 ? 3 : 2;
   float bestErr = INFINITY;
@@ -543,7 +569,8 @@ BC7_FN float tryTwoSubsets(const Pixels& px, int part0, int part1, int part2, in
 BC7_FN int quantiseAlpha(float a, int parity) { return quantiseWithParity<255>(a, parity); }
 
 // ---- one block: the veryfast profile on an opaque RGB surface (kernel.ispc:1969-1976, ispc_texcomp.cpp:61-93) ----
-BC7_FN void encodeBlock(const Pixels& px, uint32_t (&out)[4]) {
+template <class Px>
+BC7_FN void encodeBlock(const Px& px, uint32_t (&out)[4]) {
   float bestErr = INFINITY;
   out[0] = out[1] = out[2] = out[3] = 0;
 
@@ -618,7 +645,7 @@ BC7_FN void encodeBlock(const Pixels& px, uint32_t (&out)[4]) {
 struct Rgba8Source {
   const uint8_t* rgba;  // width * 4 bytes per row
   int width;
-  __device__ __forceinline__ void load(int bx, int by, Pixels& px) const {
+  __device__ __forceinline__ void load(int bx, int by, float* mine) const {
 #pragma unroll
     for (int y = 0; y < 4; ++y) {
       const uint32_t* row = reinterpret_cast<const uint32_t*>(rgba + ((size_t)(by * 4 + y) * width + (size_t)bx * 4) * 4);
@@ -634,11 +661,9 @@ struct Rgba8Source {
         for (int x = 0; x < 4; ++x) t[x] = __ldg(row + x);
       }
 #pragma unroll
-      for (int x = 0; x < 4; ++x) {
-        px[0][y * 4 + x] = (float)(int)(t[x] & 255u);
-        px[1][y * 4 + x] = (float)(int)((t[x] >> 8) & 255u);
-        px[2][y * 4 + x] = (float)(int)((t[x] >> 16) & 255u);
-      }
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mine[(c * 16 + y * 4 + x) * kBc7Threads] = (float)(int)((t[x] >> (8 * c)) & 255u);
     }
   }
 };
@@ -647,26 +672,24 @@ struct BgrSource {
   const T* bgr;  // width * channels values per row
   int width, channels;
   const uint8_t* lut;  // stored value -> gamma-corrected byte
-  __device__ __forceinline__ void load(int bx, int by, Pixels& px) const {
+  __device__ __forceinline__ void load(int bx, int by, float* mine) const {
 #pragma unroll
     for (int y = 0; y < 4; ++y)
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         const T* t = bgr + ((size_t)(by * 4 + y) * width + (size_t)bx * 4 + x) * channels;
-        px[0][y * 4 + x] = (float)__ldg(lut + t[2]);
-        px[1][y * 4 + x] = (float)__ldg(lut + t[1]);
-        px[2][y * 4 + x] = (float)__ldg(lut + t[0]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mine[(c * 16 + y * 4 + x) * kBc7Threads] = (float)__ldg(lut + t[2 - c]);
       }
   }
 };
-constexpr int kBc7Threads = 128;
 template <typename Source>
 __global__ void __launch_bounds__(kBc7Threads, DERP_BC7_MIN_CTAS) bc7Kernel(Source src, int width, int blocksX, int blocksY, uint8_t* out) {
   const int b = blockIdx.x * kBc7Threads + threadIdx.x;
   if (b >= blocksX * blocksY) return;
   const int bx = b % blocksX, by = b / blocksX;
-  Pixels px;
-  src.load(bx, by, px);
+  src.load(bx, by, bc7Tile + threadIdx.x);
+  const SharedPixels px = {};
   uint32_t data[4];
   encodeBlock(px, data);
   // the reference's store_data: block row `by` starts at byte by * width * 4 (kernel.ispc:152-159)
@@ -678,18 +701,17 @@ __global__ void __launch_bounds__(kBc7Threads, DERP_BC7_MIN_CTAS) bc7Kernel(Sour
     for (int i = 0; i < 4; ++i) dst[i] = data[i];
   }
 }
-
 #endif  // __CUDACC__
 
 // host instantiation for the CPU test hook (not reachable from the apps)
 inline void encodeSurfaceOnHost(const uint8_t* rgba, int width, int height, uint8_t* out) {
   for (int by = 0; by < height / 4; ++by)
     for (int bx = 0; bx < width / 4; ++bx) {
-      Pixels px;
+      HostPixels px;
       for (int y = 0; y < 4; ++y)
         for (int x = 0; x < 4; ++x) {
           const uint8_t* t = rgba + ((size_t)(by * 4 + y) * width + (size_t)bx * 4 + x) * 4;
-          for (int p = 0; p < 3; ++p) px[p][y * 4 + x] = (float)t[p];
+          for (int p = 0; p < 3; ++p) px.v[p][y * 4 + x] = (float)t[p];
         }
       uint32_t data[4];
       encodeBlock(px, data);
