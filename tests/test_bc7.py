@@ -19,6 +19,7 @@ import pytest
 from tests import bc7_decode, oracle_libs
 
 KINDS = ["smooth", "noise", "flat", "edges", "ramp"]
+HARD_KINDS = ["twocolour", "extremes", "nearflat", "channel", "dark"]
 
 
 def surface(seed, w, h, kind):
@@ -35,6 +36,23 @@ def surface(seed, w, h, kind):
     elif kind == "edges":
         img = np.where(((xx // 5 + yy // 7) % 2)[..., None] > 0, rng.uniform(0, 255, 3), rng.uniform(0, 255, 3)) + \
             rng.normal(0, 3, (h, w, 3))
+    elif kind == "twocolour":  # every block: two random colours split along a random line (what the partitions are for)
+        by, bx = (h + 3) // 4, (w + 3) // 4
+        c0 = rng.randint(0, 256, (by, bx, 3)).repeat(4, 0).repeat(4, 1)[:h, :w]
+        c1 = rng.randint(0, 256, (by, bx, 3)).repeat(4, 0).repeat(4, 1)[:h, :w]
+        ang = rng.uniform(0, np.pi, (by, bx)).repeat(4, 0).repeat(4, 1)[:h, :w]
+        side = ((xx % 4) - 1.5) * np.cos(ang) + ((yy % 4) - 1.5) * np.sin(ang) > 0
+        img = np.where(side[..., None], c0, c1).astype(np.float64)
+    elif kind == "extremes":  # 0 / 255 per pixel and channel: clamps and saturated end points
+        img = rng.randint(0, 2, (h, w, 3)) * 255.0
+    elif kind == "nearflat":  # constant blocks with one pixel one grey level off: zero-length lines, degenerate covariances
+        img = np.zeros((h, w, 3)) + rng.randint(0, 256, ((h + 3) // 4, (w + 3) // 4, 3)).repeat(4, 0).repeat(4, 1)[:h, :w]
+        img[1::4, 2::4, 1] += 1
+    elif kind == "channel":  # only red varies
+        img = np.stack([rng.uniform(0, 255, (h, w)), np.full((h, w), 77.0), np.full((h, w), 200.0)], -1)
+    elif kind == "dark":  # values 0..3 and 252..255: the parity-bit grid at both ends of the range
+        img = rng.randint(0, 4, (h, w, 3)).astype(np.float64)
+        img[:, w // 2:] += 252
     else:  # ramp: black to white, saturated corners
         img = np.stack([xx * 255. / max(w - 1, 1), yy * 255. / max(h - 1, 1), (xx + yy) * 255. / max(w + h - 2, 1)], -1)
     return np.concatenate([img.clip(0, 255).astype(np.uint8), np.full((h, w, 1), 255, np.uint8)], -1).copy()
@@ -77,7 +95,7 @@ def psnr(decoded, rgba):
     return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
 
 
-@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("kind", KINDS + HARD_KINDS)
 @pytest.mark.parametrize("size", [(128, 96), (70, 50)])  # the second: neither side a multiple of 4
 def test_same_arithmetic_gives_the_reference_bytes(ref, kind, size):
     rgba = surface(3, size[0], size[1], kind)
