@@ -63,14 +63,16 @@ class Mesh {
                  // which makes the per-sweep compaction of the face list three times lighter than the reference's)
     int v[3];
     V3 normal{0, 0, 0};
-    double cost[3];
-    bool deleted = false, touched = false;
   };
   std::vector<Vertex> verts;
   std::vector<Face> faces;
+  // what the sweeps scan, apart from the face records: 3 edge costs per face (edge j = v[j] -> v[j + 1]) and the flags
+  std::vector<double> cost;
+  std::vector<uint8_t> flag;
+  enum : uint8_t { kDeleted = 1, kTouched = 2 };
 
   // xyz: 3 doubles per vertex; idx: 3 indices per face
-  Mesh(const double* xyz, size_t nv, const uint32_t* idx, size_t nf) : verts(nv), faces(nf) {
+  Mesh(const double* xyz, size_t nv, const uint32_t* idx, size_t nf) : verts(nv), faces(nf), cost(3 * nf), flag(nf, 0) {
     for (size_t i = 0; i < nv; ++i) verts[i].p = V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     for (size_t i = 0; i < nf; ++i)
       for (int j = 0; j < 3; ++j) faces[i].v[j] = (int)idx[3 * i + j];
@@ -106,7 +108,6 @@ class Mesh {
 
   void initialQuadrics() {
     for (Face& f : faces) {  // face order = accumulation order of the vertex quadrics, as in the reference
-      f.deleted = false;
       const V3 &p0 = verts[f.v[0]].p, &p1 = verts[f.v[1]].p, &p2 = verts[f.v[2]].p;
       const V3 n = unit(cross(sub(p1, p0), sub(p2, p0)));
       f.normal = n;
@@ -116,21 +117,28 @@ class Mesh {
         for (int j = 0; j < 4; ++j) q.m[i][j] = plane[i] * plane[j];
       for (int j = 0; j < 3; ++j) addInto(verts[f.v[j]].q, q);
     }
-    for (Face& f : faces) refreshCosts(f);
+    for (size_t fi = 0; fi < faces.size(); ++fi) refreshCosts(fi);
   }
-  void refreshCosts(Face& f) {
+  void refreshCosts(size_t fi) {
+    const Face& f = faces[fi];
     for (int j = 0; j < 3; ++j) {
       V3 unused;
-      f.cost[j] = contraction(verts[f.v[j]], verts[f.v[(j + 1) % 3]], &unused);
+      cost[3 * fi + j] = contraction(verts[f.v[j]], verts[f.v[(j + 1) % 3]], &unused);
     }
   }
   void dropDeletedFaces() {
     size_t keep = 0;
-    for (Face& f : faces) {
-      f.touched = false;
-      if (!f.deleted) faces[keep++] = f;
+    for (size_t fi = 0; fi < faces.size(); ++fi) {
+      if (flag[fi] & kDeleted) continue;
+      if (keep != fi) {
+        faces[keep] = faces[fi];
+        for (int j = 0; j < 3; ++j) cost[3 * keep + j] = cost[3 * fi + j];
+      }
+      ++keep;
     }
     faces.resize(keep);
+    cost.resize(3 * keep);
+    flag.assign(keep, 0);
   }
   void rebuildIncidence() {
     for (Vertex& v : verts) v.faces.clear();
@@ -168,9 +176,7 @@ class Mesh {
     }
   }
   double costPercentile(float strictness) const {
-    std::vector<double> all(faces.size() * 3);
-    for (size_t i = 0; i < faces.size(); ++i)
-      for (int j = 0; j < 3; ++j) all[i * 3 + j] = faces[i].cost[j];
+    std::vector<double> all(cost);  // called right after the compaction: every face is live
     const int at = strictness * (all.size() - 1);  // float * size_t -> float -> int, as written in getThreshold
     std::nth_element(all.begin(), all.begin() + at, all.end());
     return all[at];
@@ -178,8 +184,8 @@ class Mesh {
   // would moving vertex a (edge a-b contracting) to p flip the normal of a face around a?
   bool flips(const V3& p, int a, int b) {
     for (size_t k = 0; k < verts[a].faces.size(); ++k) {
+      if (flag[verts[a].faces[k]] & kDeleted) continue;
       const Face& f = faces[verts[a].faces[k]];
-      if (f.deleted) continue;
       int at = 0;
       for (int j = 0; j < 3; ++j)
         if (f.v[j] == a) {
@@ -199,15 +205,15 @@ class Mesh {
     std::vector<int> around(verts[a].faces);
     around.insert(around.end(), verts[b].faces.begin(), verts[b].faces.end());
     for (int fi : around) {
+      if (flag[fi] & kDeleted) continue;
       Face& f = faces[fi];
-      if (f.deleted) continue;
       for (int j = 0; j < 3; ++j)
         if (f.v[j] == a || f.v[j] == b) {
           f.v[j] = a;
-          f.touched = true;
+          flag[fi] |= kTouched;
           break;
         }
-      refreshCosts(f);
+      refreshCosts(fi);
     }
   }
   void compact() {
@@ -233,9 +239,17 @@ class Mesh {
     const int facesIn = (int)faces.size();
     int gone = 0, gonePrev = 0, stuck = 0, iteration = 0;
     double threshold = 0;
+    // A sweep that contracts nothing leaves the mesh as it found it, and every edge it tried (all edges with cost <= its
+    // threshold) failed for reasons that do not depend on the threshold (boundary rules, flipped normals).  The next sweep
+    // then needs neither the compaction nor the incidence lists rebuilt, and only has to try the edges the larger
+    // threshold newly admits; trying the others again is pure (no side effects) and would fail again.
+    bool unchanged = false;  // the previous sweep contracted nothing
+    double failedUpTo = 0;   // ... and every edge with cost <= failedUpTo was tried in it
     while ((int)faces.size() > facesOut) {
-      dropDeletedFaces();
-      rebuildIncidence();
+      if (!unchanged) {
+        dropDeletedFaces();
+        rebuildIncidence();
+      }
       if (iteration == 0) markBoundaries();
       if (iteration == 0 || gonePrev != gone) {
         threshold = costPercentile(strictness);
@@ -249,11 +263,16 @@ class Mesh {
         if (!(threshold != 0) || threshold != threshold) break;
       }
       gonePrev = gone;
+      bool skipKnown = unchanged;
+      double maxCost = -std::numeric_limits<double>::infinity();
       for (size_t fi = 0; fi < faces.size(); ++fi) {
         // by index: contract() may not grow `faces`, but it writes through references into it
-        if (faces[fi].deleted || faces[fi].touched) continue;
+        if (flag[fi]) continue;  // deleted or touched in this sweep
         for (int j = 0; j < 3; ++j) {
-          if (faces[fi].cost[j] > threshold) continue;
+          const double c = cost[3 * fi + j];
+          if (!(c <= maxCost)) maxCost = c > maxCost ? c : std::numeric_limits<double>::quiet_NaN();
+          if (c > threshold) continue;
+          if (skipKnown && c <= failedUpTo) continue;
           const int a = faces[fi].v[j], b = faces[fi].v[(j + 1) % 3];
           if (verts[a].boundary != verts[b].boundary) continue;
           if (!removeBoundaryEdges && (verts[a].boundary || verts[b].boundary)) continue;
@@ -261,14 +280,21 @@ class Mesh {
           contraction(verts[a], verts[b], &p);
           if (flips(p, a, b) || flips(p, b, a)) continue;
           const std::vector<int> shared = sharedFaces(a, b);
-          for (int s : shared) faces[s].deleted = true;
+          for (int s : shared) flag[s] |= kDeleted;
           gone += (int)shared.size();
           contract(a, b, p);
+          skipKnown = false;  // the mesh moved: what failed before may succeed now
           break;
         }
         if (facesIn - gone <= facesOut) break;
       }
       ++iteration;
+      unchanged = gone == gonePrev;
+      if (unchanged) {
+        failedUpTo = threshold;
+        // every edge there is was tried and failed: larger thresholds change nothing until the reference's loop ends at inf
+        if (maxCost <= threshold) break;
+      }
     }
     compact();
   }

@@ -142,7 +142,9 @@ def _surface_mesh(oracle, seed, w, h, smooth):
 
 
 SIMPLIFY_CASES = [(0, 64, 48, True, 2000, False), (1, 96, 72, True, 1500, True), (2, 80, 60, False, 3000, False),
-                  (3, 120, 90, False, 100, True), (4, 33, 27, True, 10, False), (5, 150, 110, True, 6000, False)]
+                  (3, 120, 90, False, 100, True), (4, 33, 27, True, 10, False), (5, 150, 110, True, 6000, False),
+                  # torn meshes that cannot reach the target: long runs of sweeps that contract nothing (the fast path of run())
+                  (11, 160, 120, False, 50, False), (16, 250, 180, False, 10000, False), (15, 96, 200, False, 1, True)]
 
 
 @pytest.mark.parametrize("seed,w,h,smooth,target,rb", SIMPLIFY_CASES)
