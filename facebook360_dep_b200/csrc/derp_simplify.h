@@ -5,6 +5,10 @@
 // the reference's result is defined by that sequential order and the stage is host code here exactly as it is there
 // (kThreads = 1 in the reference's call); the GPU delivers the mesh it starts from (derp_mesh.cuh) in double precision.
 //
+// What this version does NOT repeat of the reference's work (same result, tests/test_mesh.py against the reference's own code
+// on 100+ meshes): attempts that are known to fail again, and the per-sweep passes of sweeps that cannot contract anything
+// — see run() and the `failed` / `stamped` members.
+//
 // Arithmetic conventions (they decide threshold comparisons, hence the output): IEEE double, no FMA contraction,
 // 3-term sums left to right, cross product and 3 x 3 determinant in the textbook cofactor order Eigen's fixed-size
 // kernels use.  Checked against the reference's own MeshSimplifier.cpp compiled into oracle/_ref (tests/test_mesh.py).
@@ -54,7 +58,6 @@ inline double quadricError(const Quadric& q, const V3& v) {
 class Mesh {
  public:
   struct Vertex {
-    std::vector<int> faces;
     V3 p{0, 0, 0};
     Quadric q{};
     bool boundary = false;
@@ -67,12 +70,31 @@ class Mesh {
   std::vector<Vertex> verts;
   std::vector<Face> faces;
   // what the sweeps scan, apart from the face records: 3 edge costs per face (edge j = v[j] -> v[j + 1]) and the flags
+  // faces around every vertex as of the start of the sweep, ascending (the reference rebuilds its per-vertex lists once per
+  // sweep and does not update them inside it): one flat array + offsets
+  std::vector<int> around0, aroundAt;
+  struct FaceRange {
+    const int *first, *last;
+    const int* begin() const { return first; }
+    const int* end() const { return last; }
+    size_t size() const { return (size_t)(last - first); }
+  };
+  FaceRange facesOf(int v) const { return FaceRange{around0.data() + aroundAt[v], around0.data() + aroundAt[v + 1]}; }
   std::vector<double> cost;
   std::vector<uint8_t> flag;
   enum : uint8_t { kDeleted = 1, kTouched = 2 };
+  // Memory of failed attempts.  Whether edge a-b can be contracted is a pure function of the two vertexes (position, quadric,
+  // boundary flag, face lists) and of the faces around them (vertex ids, normals, deleted flags, positions of their
+  // vertexes) — the closed 1-rings of a and b.  A contraction x <- y changes exactly the closed 1-rings of x and y, so it
+  // stamps every vertex of every face around x and y; an edge that failed after `failed[e] - 1` contractions still fails as
+  // long as neither end has been stamped since.  The reference tries such edges again in every sweep (a failed attempt has
+  // no side effects, so skipping it changes nothing): on torn meshes that is where its time goes.
+  std::vector<uint32_t> failed;   // per edge (3 per face): 1 + number of contractions done when it last failed, 0 = not known
+  std::vector<uint32_t> stamped;  // per vertex: number of the last contraction that touched its closed 1-ring
+  uint32_t contractions = 0;
 
   // xyz: 3 doubles per vertex; idx: 3 indices per face
-  Mesh(const double* xyz, size_t nv, const uint32_t* idx, size_t nf) : verts(nv), faces(nf), cost(3 * nf), flag(nf, 0) {
+  Mesh(const double* xyz, size_t nv, const uint32_t* idx, size_t nf) : verts(nv), faces(nf), cost(3 * nf), flag(nf, 0), failed(3 * nf, 0), stamped(nv, 0) {
     for (size_t i = 0; i < nv; ++i) verts[i].p = V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     for (size_t i = 0; i < nf; ++i)
       for (int j = 0; j < 3; ++j) faces[i].v[j] = (int)idx[3 * i + j];
@@ -133,22 +155,29 @@ class Mesh {
       if (keep != fi) {
         faces[keep] = faces[fi];
         for (int j = 0; j < 3; ++j) cost[3 * keep + j] = cost[3 * fi + j];
+        for (int j = 0; j < 3; ++j) failed[3 * keep + j] = failed[3 * fi + j];
       }
       ++keep;
     }
     faces.resize(keep);
     cost.resize(3 * keep);
+    failed.resize(3 * keep);
     flag.assign(keep, 0);
   }
   void rebuildIncidence() {
-    for (Vertex& v : verts) v.faces.clear();
+    aroundAt.assign(verts.size() + 1, 0);
+    for (const Face& f : faces)
+      for (int j = 0; j < 3; ++j) ++aroundAt[f.v[j] + 1];
+    for (size_t v = 0; v < verts.size(); ++v) aroundAt[v + 1] += aroundAt[v];
+    around0.resize(3 * faces.size());
+    std::vector<int> fill(aroundAt.begin(), aroundAt.end() - 1);
     for (size_t i = 0; i < faces.size(); ++i)
-      for (int j = 0; j < 3; ++j) verts[faces[i].v[j]].faces.push_back((int)i);
+      for (int j = 0; j < 3; ++j) around0[fill[faces[i].v[j]]++] = (int)i;
   }
   std::vector<int> sharedFaces(int a, int b) const {
     std::vector<int> out;
-    for (int fa : verts[a].faces)
-      for (int fb : verts[b].faces)
+    for (int fa : facesOf(a))
+      for (int fb : facesOf(b))
         if (fa == fb) out.push_back(fa);
     return out;
   }
@@ -157,17 +186,17 @@ class Mesh {
     for (Vertex& v : verts) v.boundary = false;
     for (int i = 0; i < (int)verts.size(); ++i) {
       if (verts[i].boundary) continue;
-      if (verts[i].faces.size() == 1) {
+      if (facesOf(i).size() == 1) {
         verts[i].boundary = true;
         continue;
       }
       bool border = false;
       std::set<int> seen;
-      for (int fi : verts[i].faces)
+      for (int fi : facesOf(i))
         for (int j = 0; j < 3; ++j) {
           const int o = faces[fi].v[j];
           if (o == i || !seen.insert(o).second) continue;
-          if (verts[o].faces.size() == 1 || sharedFaces(i, o).size() == 1) {
+          if (facesOf(o).size() == 1 || sharedFaces(i, o).size() == 1) {
             verts[o].boundary = true;
             border = true;
           }
@@ -183,9 +212,9 @@ class Mesh {
   }
   // would moving vertex a (edge a-b contracting) to p flip the normal of a face around a?
   bool flips(const V3& p, int a, int b) {
-    for (size_t k = 0; k < verts[a].faces.size(); ++k) {
-      if (flag[verts[a].faces[k]] & kDeleted) continue;
-      const Face& f = faces[verts[a].faces[k]];
+    for (int fi : facesOf(a)) {
+      if (flag[fi] & kDeleted) continue;
+      const Face& f = faces[fi];
       int at = 0;
       for (int j = 0; j < 3; ++j)
         if (f.v[j] == a) {
@@ -202,8 +231,13 @@ class Mesh {
   void contract(int a, int b, const V3& p) {  // vertex a becomes the merged vertex
     verts[a].p = p;
     addInto(verts[a].q, verts[b].q);
-    std::vector<int> around(verts[a].faces);
-    around.insert(around.end(), verts[b].faces.begin(), verts[b].faces.end());
+    const FaceRange fa = facesOf(a), fb = facesOf(b);
+    std::vector<int> around(fa.begin(), fa.end());
+    around.insert(around.end(), fb.begin(), fb.end());
+    ++contractions;
+    stamped[b] = contractions;
+    for (int fi : around)  // before b is renamed to a; the faces the edge shared (just deleted) count: their third vertex
+      for (int j = 0; j < 3; ++j) stamped[faces[fi].v[j]] = contractions;  // loses a face
     for (int fi : around) {
       if (flag[fi] & kDeleted) continue;
       Face& f = faces[fi];
@@ -233,67 +267,112 @@ class Mesh {
       for (int j = 0; j < 3; ++j) f.v[j] = renumber[f.v[j]];
   }
 
-  // MeshSimplifier::simplify
+  // one attempt at contracting edge j of face fi (MeshSimplifier.cpp:519-553); true if it was contracted.  A failed attempt
+  // changes nothing.
+  bool tryEdge(size_t fi, int j, bool removeBoundaryEdges, int* gone) {
+    const int a = faces[fi].v[j], b = faces[fi].v[(j + 1) % 3];
+    if (verts[a].boundary != verts[b].boundary) return false;
+    if (!removeBoundaryEdges && (verts[a].boundary || verts[b].boundary)) return false;
+    uint32_t& memo = failed[3 * fi + j];
+    if (memo > stamped[a] && memo > stamped[b]) return false;  // failed before, and nothing around it has changed since
+    V3 p;
+    contraction(verts[a], verts[b], &p);
+    if (flips(p, a, b) || flips(p, b, a)) {
+      memo = contractions + 1;
+      return false;
+    }
+    const std::vector<int> shared = sharedFaces(a, b);
+    for (int s : shared) flag[s] |= kDeleted;
+    *gone += (int)shared.size();
+    contract(a, b, p);
+    return true;
+  }
+  // a sweep over the faces from `from` on: every edge whose cost is under the threshold is tried, in order
+  void sweepFrom(size_t from, double threshold, bool removeBoundaryEdges, int facesIn, int facesOut, int* gone) {
+    for (size_t fi = from; fi < faces.size(); ++fi) {
+      // by index: contract() may not grow `faces`, but it writes through references into it
+      if (flag[fi]) continue;  // deleted, or touched in this sweep
+      for (int j = 0; j < 3; ++j) {
+        if (cost[3 * fi + j] > threshold) continue;
+        if (tryEdge(fi, j, removeBoundaryEdges, gone)) break;
+      }
+      if (facesIn - *gone <= facesOut) break;
+    }
+  }
+
+  // MeshSimplifier::simplify.  The reference runs sweep after sweep: compaction, incidence lists, threshold (a percentile
+  // of the edge costs after a sweep that contracted something, the previous threshold times 2, 4, 6, ... after one that
+  // did not, until it overflows to inf), then the pass over the faces.  Sweeps that contract nothing are the bulk on torn
+  // meshes (boundary edges are kept, so the target is out of reach and the loop only ends at inf: hundreds of sweeps), and
+  // they are where this version does less work for the same result: such a sweep leaves the mesh as it found it, every
+  // edge it tried failed for reasons that do not depend on the threshold, and a failed attempt has no side effects — so
+  // the following sweeps need no compaction, no incidence rebuild and no pass over the faces, only attempts at the edges
+  // their larger thresholds newly admit, in face order.  One pass sorts those edges into the sweeps that will admit them.
   void run(int facesOut, float strictness, bool removeBoundaryEdges) {
     initialQuadrics();
     const int facesIn = (int)faces.size();
-    int gone = 0, gonePrev = 0, stuck = 0, iteration = 0;
+    int gone = 0, stuck = 0, iteration = 0;
     double threshold = 0;
-    // A sweep that contracts nothing leaves the mesh as it found it, and every edge it tried (all edges with cost <= its
-    // threshold) failed for reasons that do not depend on the threshold (boundary rules, flipped normals).  The next sweep
-    // then needs neither the compaction nor the incidence lists rebuilt, and only has to try the edges the larger
-    // threshold newly admits; trying the others again is pure (no side effects) and would fail again.
-    bool unchanged = false;  // the previous sweep contracted nothing
-    double failedUpTo = 0;   // ... and every edge with cost <= failedUpTo was tried in it
-    while ((int)faces.size() > facesOut) {
-      if (!unchanged) {
-        dropDeletedFaces();
-        rebuildIncidence();
-      }
+    bool done = false;
+    while (!done && (int)faces.size() > facesOut) {
+      // ---- a sweep after a change (or the first one): the reference's sweep as it is
+      dropDeletedFaces();
+      rebuildIncidence();
       if (iteration == 0) markBoundaries();
-      if (iteration == 0 || gonePrev != gone) {
-        threshold = costPercentile(strictness);
-        stuck = 0;
-      } else {
-        threshold *= 2 * ++stuck;  // nothing was contracted in the last sweep: open the threshold
-        if (std::isinf(threshold)) break;
-        // A threshold of exactly 0 (exactly planar patches: constant-disparity regions) or NaN never grows: the
-        // reference's loop spins forever there (MeshSimplifier.cpp:505-512, reproduced with its own code in
-        // tests/test_mesh.py).  Nothing more can be contracted under the reference's rules, so stop with the mesh as it is.
-        if (!(threshold != 0) || threshold != threshold) break;
+      threshold = costPercentile(strictness);
+      stuck = 0;
+      int gonePrev = gone;
+      sweepFrom(0, threshold, removeBoundaryEdges, facesIn, facesOut, &gone);
+      ++iteration;
+      if (gone != gonePrev) continue;
+      if (!((int)faces.size() > facesOut)) break;  // the reference tests its loop condition before every sweep
+
+      // ---- nothing was contracted: the sweeps that follow, until one contracts something or the threshold overflows.
+      // No face is deleted or touched here (the compaction cleared the flags and nothing has happened since).
+      std::vector<double> levels;  // thresholds of the coming sweeps, computed the way the reference computes them
+      {
+        double t = threshold;
+        int s = stuck;
+        do {
+          t *= 2 * ++s;
+          levels.push_back(t);
+        } while (!std::isinf(t) && t != 0 && t == t && levels.size() < 4096);
       }
-      gonePrev = gone;
-      bool skipKnown = unchanged;
-      double maxCost = -std::numeric_limits<double>::infinity();
-      for (size_t fi = 0; fi < faces.size(); ++fi) {
-        // by index: contract() may not grow `faces`, but it writes through references into it
-        if (flag[fi]) continue;  // deleted or touched in this sweep
+      // A threshold of exactly 0 (exactly planar patches: constant-disparity regions) or NaN never grows: the reference's
+      // loop spins forever there (MeshSimplifier.cpp:483-493, reproduced with its own code in tests/test_mesh.py).  Nothing
+      // more can be contracted under the reference's rules, so stop with the mesh as it is.
+      if (!(levels[0] != 0) || levels[0] != levels[0]) break;
+      // edges not tried yet (cost above the last threshold; NaN costs pass every threshold test and were tried), filed under
+      // the first coming sweep that admits them; the pass runs in face order, so every list is in face order
+      std::vector<std::vector<uint32_t>> admitted(levels.size());
+      for (size_t fi = 0; fi < faces.size(); ++fi)
         for (int j = 0; j < 3; ++j) {
           const double c = cost[3 * fi + j];
-          if (!(c <= maxCost)) maxCost = c > maxCost ? c : std::numeric_limits<double>::quiet_NaN();
-          if (c > threshold) continue;
-          if (skipKnown && c <= failedUpTo) continue;
-          const int a = faces[fi].v[j], b = faces[fi].v[(j + 1) % 3];
-          if (verts[a].boundary != verts[b].boundary) continue;
-          if (!removeBoundaryEdges && (verts[a].boundary || verts[b].boundary)) continue;
-          V3 p;
-          contraction(verts[a], verts[b], &p);
-          if (flips(p, a, b) || flips(p, b, a)) continue;
-          const std::vector<int> shared = sharedFaces(a, b);
-          for (int s : shared) flag[s] |= kDeleted;
-          gone += (int)shared.size();
-          contract(a, b, p);
-          skipKnown = false;  // the mesh moved: what failed before may succeed now
+          if (!(c > threshold)) continue;
+          const size_t k = std::lower_bound(levels.begin(), levels.end(), c) - levels.begin();  // first level >= c
+          if (k + 1 < levels.size()) admitted[k].push_back((uint32_t)(3 * fi + j));  // the last level is inf: the loop ends there
+        }
+      size_t pending = 0;
+      for (const auto& list : admitted) pending += list.size();
+      for (size_t k = 0; k < levels.size(); ++k) {
+        threshold = levels[k];
+        ++stuck;
+        if (std::isinf(threshold) || pending == 0) {  // the reference's loop ends at inf; with nothing left to try the sweeps
+          done = true;                                // up to there change nothing
           break;
         }
-        if (facesIn - gone <= facesOut) break;
-      }
-      ++iteration;
-      unchanged = gone == gonePrev;
-      if (unchanged) {
-        failedUpTo = threshold;
-        // every edge there is was tried and failed: larger thresholds change nothing until the reference's loop ends at inf
-        if (maxCost <= threshold) break;
+        gonePrev = gone;
+        bool contracted = false;
+        for (uint32_t e : admitted[k]) {
+          const size_t fi = e / 3;
+          if (!tryEdge(fi, (int)(e % 3), removeBoundaryEdges, &gone)) continue;
+          contracted = true;  // the mesh moved: the rest of this sweep is an ordinary one (what failed before may succeed now)
+          if (facesIn - gone > facesOut) sweepFrom(fi + 1, threshold, removeBoundaryEdges, facesIn, facesOut, &gone);
+          break;
+        }
+        pending -= admitted[k].size();
+        ++iteration;
+        if (contracted) break;
       }
     }
     compact();

@@ -164,6 +164,28 @@ def test_simplifier_equals_reference(oracle, seed, w, h, smooth, target, rb):
     assert np.array_equal(pv.view(np.uint64), rv.view(np.uint64))
 
 
+def test_simplifier_equals_reference_on_random_meshes(oracle):
+    """96 more meshes against the reference's MeshSimplifier.cpp: random sizes, sheets and torn meshes, targets of 1 face, a
+    few hundred, a few thousand and more than there are (nothing to do), boundary edges kept or removed — the combinations
+    that decide how the sweep loop ends (target reached inside a sweep, exactly at a sweep's end, never)."""
+    from facebook360_dep_b200 import capi
+    ref = oracle_libs.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    prod = capi.load_cuda()
+    for seed in range(20, 32):
+        rng = np.random.RandomState(seed)
+        w, h = int(rng.randint(20, 140)), int(rng.randint(20, 140))
+        smooth = bool(rng.randint(0, 2))
+        xyz, idx = _surface_mesh(oracle, seed, w, h, smooth)
+        for target in (1, int(rng.randint(2, 400)), int(rng.randint(400, 20000)), 10 ** 7):
+            for rb in (False, True):
+                pv, pi = _simplify(prod, "derp_test_simplify", xyz, idx, target, remove_boundary=rb)
+                rv, ri = _simplify(ref, "derp_ref_simplify", xyz, idx, target, remove_boundary=rb)
+                assert np.array_equal(pi, ri), (seed, w, h, smooth, target, rb)
+                assert np.array_equal(pv.view(np.uint64), rv.view(np.uint64)), (seed, w, h, smooth, target, rb)
+
+
 @pytest.mark.gpu
 def test_gpu_mesh_simplified_equals_reference(cuda):
     """derp_camera_mesh_simplified end to end (GPU mesh in double precision -> host contraction sweeps -> float32 / uint32)
