@@ -184,6 +184,7 @@ class Mesh {
   // a vertex is on the boundary when an edge at it has a single face (identifySubBoundaries, whole range in one thread)
   void markBoundaries() {
     for (Vertex& v : verts) v.boundary = false;
+    std::vector<std::pair<int, int>> near;
     for (int i = 0; i < (int)verts.size(); ++i) {
       if (verts[i].boundary) continue;
       if (facesOf(i).size() == 1) {
@@ -191,15 +192,24 @@ class Mesh {
         continue;
       }
       bool border = false;
-      std::set<int> seen;
+      // neighbours of i with the number of faces they share with it (= how often they occur among the vertexes of i's
+      // faces: a face has three different vertexes); the reference looks every neighbour up once, in this order
+      near.clear();
       for (int fi : facesOf(i))
         for (int j = 0; j < 3; ++j) {
           const int o = faces[fi].v[j];
-          if (o == i || !seen.insert(o).second) continue;
-          if (facesOf(o).size() == 1 || sharedFaces(i, o).size() == 1) {
-            verts[o].boundary = true;
-            border = true;
-          }
+          if (o == i) continue;
+          size_t k = 0;
+          while (k < near.size() && near[k].first != o) ++k;
+          if (k == near.size())
+            near.emplace_back(o, 1);
+          else
+            ++near[k].second;
+        }
+      for (const std::pair<int, int>& n : near)
+        if (facesOf(n.first).size() == 1 || n.second == 1) {
+          verts[n.first].boundary = true;
+          border = true;
         }
       if (border) verts[i].boundary = true;
     }
