@@ -320,9 +320,12 @@ struct Image {
 inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
 
 inline Image readPng(const fs::path& path) {
-  std::ifstream f(path, std::ios::binary);
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
   CHECK(f.good()) << "failed to load image: " << path.string();
-  std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  std::vector<uint8_t> buf((size_t)f.tellg());
+  f.seekg(0);
+  f.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)buf.size());
+  CHECK(f.good()) << "failed to read image: " << path.string();
   static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
   CHECK(buf.size() > 8 && std::memcmp(buf.data(), sig, 8) == 0) << "not a PNG file: " << path.string();
   size_t p = 8;
@@ -366,30 +369,38 @@ inline Image readPng(const fs::path& path) {
   uLongf outLen = (uLongf)raw.size();
   const int zr = uncompress(raw.data(), &outLen, idat.data(), (uLong)idat.size());
   CHECK(zr == Z_OK && outLen == raw.size()) << "PNG inflate failed: " << path.string();
+  // undo the row filters (PNG specification, section 9): one tight loop per filter type; the first bpp bytes of a row have
+  // no left neighbour, the first row has no row above
   std::vector<uint8_t> pix(stride * h);
+  const std::vector<uint8_t> zeros(stride, 0);
   for (int y = 0; y < h; ++y) {
     const uint8_t ft = raw[y * (stride + 1)];
     const uint8_t* in = &raw[y * (stride + 1) + 1];
     uint8_t* out = &pix[y * stride];
-    const uint8_t* up = y ? out - stride : nullptr;
-    for (size_t i = 0; i < stride; ++i) {
-      const int a = i >= (size_t)bpp ? out[i - bpp] : 0;
-      const int b = up ? up[i] : 0;
-      const int c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
-      int v = in[i];
-      switch (ft) {
-        case 0: break;
-        case 1: v += a; break;
-        case 2: v += b; break;
-        case 3: v += (a + b) >> 1; break;
-        case 4: {
+    const uint8_t* up = y ? out - stride : zeros.data();
+    const size_t head = std::min<size_t>(bpp, stride);
+    switch (ft) {
+      case 0: std::memcpy(out, in, stride); break;
+      case 1:
+        for (size_t i = 0; i < head; ++i) out[i] = in[i];
+        for (size_t i = head; i < stride; ++i) out[i] = (uint8_t)(in[i] + out[i - bpp]);
+        break;
+      case 2:
+        for (size_t i = 0; i < stride; ++i) out[i] = (uint8_t)(in[i] + up[i]);
+        break;
+      case 3:
+        for (size_t i = 0; i < head; ++i) out[i] = (uint8_t)(in[i] + (up[i] >> 1));
+        for (size_t i = head; i < stride; ++i) out[i] = (uint8_t)(in[i] + ((out[i - bpp] + up[i]) >> 1));
+        break;
+      case 4:
+        for (size_t i = 0; i < head; ++i) out[i] = (uint8_t)(in[i] + up[i]);  // a = c = 0: the predictor is b
+        for (size_t i = head; i < stride; ++i) {
+          const int a = out[i - bpp], b = up[i], c = up[i - bpp];
           const int pa = std::abs(b - c), pb = std::abs(a - c), pc = std::abs(a + b - 2 * c);
-          v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-          break;
+          out[i] = (uint8_t)(in[i] + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)));
         }
-        default: LOG(FATAL) << "bad PNG filter";
-      }
-      out[i] = (uint8_t)v;
+        break;
+      default: LOG(FATAL) << "bad PNG filter";
     }
   }
   Image img;
@@ -403,14 +414,28 @@ inline Image readPng(const fs::path& path) {
     for (size_t i = 0; i < (size_t)w * h; ++i)
       for (int c = 0; c < 3; ++c) img.u[i * 3 + c] = palette[pix[i] * 3 + c];
   } else {
+    // samples are big-endian; PNG stores RGB(A), OpenCV hands out BGR(A) (cv::imread IMREAD_UNCHANGED): one pass does both
     img.channels = ch;
     img.u.resize((size_t)w * h * ch);
-    for (size_t i = 0; i < img.u.size(); ++i)
-      img.u[i] = depth == 8 ? pix[i] : (uint16_t)((pix[2 * i] << 8) | pix[2 * i + 1]);
+    const size_t n = (size_t)w * h;
+    uint16_t* dst = img.u.data();
+    const uint8_t* src = pix.data();
+    auto sample = [&](size_t k) -> uint16_t { return depth == 8 ? src[k] : (uint16_t)((src[2 * k] << 8) | src[2 * k + 1]); };
+    if (ch >= 3) {
+      for (size_t i = 0; i < n; ++i) {
+        const size_t at = i * ch;
+        dst[at] = sample(at + 2);
+        dst[at + 1] = sample(at + 1);
+        dst[at + 2] = sample(at);
+        if (ch == 4) dst[at + 3] = sample(at + 3);
+      }
+    } else {
+      for (size_t k = 0; k < n * ch; ++k) dst[k] = sample(k);
+    }
+    return img;
   }
-  // PNG stores RGB(A); OpenCV hands out BGR(A) (cv::imread IMREAD_UNCHANGED)
-  if (img.channels >= 3)
-    for (size_t i = 0; i < (size_t)w * h; ++i) std::swap(img.u[i * img.channels], img.u[i * img.channels + 2]);
+  // palette: R, G, B entries -> B, G, R
+  for (size_t i = 0; i < (size_t)w * h; ++i) std::swap(img.u[i * 3], img.u[i * 3 + 2]);
   return img;
 }
 
