@@ -1,13 +1,15 @@
 // Test helper (not a reference app): loads an image with the apps' loaders and dumps the converted
 // samples, so tests can compare the PNG/PFM readers and writers with cv2.
 #include <atomic>
+#include <chrono>
 #include <thread>
 
 #include "exchange.h"
 #include "io.h"
 
 DEFINE_string(in, "", "input image");
-DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange");
+DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange | inflate");
+DEFINE_int32(size, 0, "mode=inflate: number of bytes the zlib stream in --in decodes to");
 DEFINE_string(out, "", "output file (raw samples, or .png/.pfm for mode=float)");
 
 int main(int argc, char** argv) {
@@ -43,6 +45,24 @@ int main(int argc, char** argv) {
     o.open(FLAGS_out, std::ios::binary);
     o.write(reinterpret_cast<const char*>(rig.cams.data()), (std::streamsize)(rig.cams.size() * sizeof(DerpCameraDesc)));
     for (const auto& id : rig.ids) std::printf("%s\n", id.c_str());
+  } else if (FLAGS_mode == "inflate") {
+    // the PNG reader's own inflate (inflate.h) against zlib on a raw zlib stream: accepted streams must decode to zlib's
+    // bytes; prints "same" / "declined" / "DIFFERENT" and both times
+    std::ifstream f(FLAGS_in, std::ios::binary);
+    const std::vector<uint8_t> z((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<uint8_t> mine((size_t)FLAGS_size + 1, 0xCD), theirs((size_t)FLAGS_size + 1, 0xEF);
+    auto t0 = std::chrono::steady_clock::now();
+    const bool accepted = io::inflate::zlibDecode(z.data(), z.size(), mine.data(), (size_t)FLAGS_size);
+    auto t1 = std::chrono::steady_clock::now();
+    uLongf outLen = (uLongf)FLAGS_size;
+    const int zr = uncompress(theirs.data(), &outLen, z.data(), (uLong)z.size());
+    auto t2 = std::chrono::steady_clock::now();
+    const bool zok = zr == Z_OK && outLen == (uLongf)FLAGS_size;
+    const bool guard = mine[(size_t)FLAGS_size] == 0xCD;  // nothing written past the end
+    const char* verdict = !guard ? "OVERRUN" : !accepted ? "declined" : (zok && std::memcmp(mine.data(), theirs.data(), (size_t)FLAGS_size) == 0) ? "same" : "DIFFERENT";
+    std::printf("%s zlib_ok=%d own %.4f s zlib %.4f s\n", verdict, (int)zok, std::chrono::duration<double>(t1 - t0).count(),
+                std::chrono::duration<double>(t2 - t1).count());
+    return 0;
   } else if (FLAGS_mode == "exchange") {
     // 5 threads x 200 rounds through the workers' rendezvous: between two barriers every thread must observe the
     // values all threads published before the first one (the protocol of DerpCLI's camera-sharded mismatch levels)

@@ -6,6 +6,8 @@
 
 #include <zlib.h>
 
+#include "inflate.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -366,9 +368,11 @@ inline Image readPng(const fs::path& path) {
   const int bpp = ch * depth / 8;
   const size_t stride = (size_t)w * bpp;
   std::vector<uint8_t> raw((stride + 1) * h);
-  uLongf outLen = (uLongf)raw.size();
-  const int zr = uncompress(raw.data(), &outLen, idat.data(), (uLong)idat.size());
-  CHECK(zr == Z_OK && outLen == raw.size()) << "PNG inflate failed: " << path.string();
+  if (!inflate::zlibDecode(idat.data(), idat.size(), raw.data(), raw.size())) {  // declined: let zlib decide
+    uLongf outLen = (uLongf)raw.size();
+    const int zr = uncompress(raw.data(), &outLen, idat.data(), (uLong)idat.size());
+    CHECK(zr == Z_OK && outLen == raw.size()) << "PNG inflate failed: " << path.string();
+  }
   // undo the row filters (PNG specification, section 9): one tight loop per filter type; the first bpp bytes of a row have
   // no left neighbour, the first row has no row above
   std::vector<uint8_t> pix(stride * h);

@@ -587,6 +587,45 @@ def test_convert_to_binary_meshes(tmp_path, cuda, oracle):
     assert np.allclose(fused_rig["cameras"][0]["focal"], rig["cameras"][0]["focal"])
 
 
+def test_png_inflate_equals_zlib(tmp_path):
+    """The PNG reader's own inflate (csrc/host/inflate.h) against zlib: stored, fixed and dynamic blocks from every
+    compression level and strategy, two window sizes, empty and one-byte inputs, incompressible and highly repetitive data,
+    matches at the maximum distance, flush points inside the stream; malformed streams (truncated, corrupted, wrong size) are
+    declined (the reader then lets zlib report the error) and nothing is written past the output."""
+    import zlib
+    rng = np.random.RandomState(0)
+    yy, xx = np.mgrid[0:256, 0:256]
+    data = {
+        "empty": b"", "one": b"x", "zeros": bytes(200000), "random": rng.bytes(100000),
+        "text": b"the quick brown fox jumps over the lazy dog " * 3000,
+        "lowent": bytes(rng.randint(0, 4, 150000).astype(np.uint8)),
+        "u16smooth": ((np.sin(xx / 30.) * np.cos(yy / 17.) * 20000 + 30000) + rng.normal(0, 50, xx.shape)).astype(">u2").tobytes(),
+        "maxdist": rng.bytes(32768) * 4,
+        "short_runs": b"".join(bytes([i % 251]) * ((i % 7) + 1) for i in range(30000)),
+    }
+    z_path = str(tmp_path / "z.bin")
+
+    def verdict(z, n):
+        open(z_path, "wb").write(z)
+        return run("IoSelfTest", "--in=" + z_path, "--mode=inflate", "--size=%d" % n).stdout.strip().splitlines()[-1].split()[0]
+
+    for name, d in data.items():
+        for level in (0, 1, 9):
+            for k, strategy in enumerate((zlib.Z_DEFAULT_STRATEGY, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED)):
+                wbits = 15 if (k + level) % 2 else 9
+                c = zlib.compressobj(level, zlib.DEFLATED, wbits, 8, strategy)
+                assert verdict(c.compress(d) + c.flush(), len(d)) == "same", (name, level, strategy, wbits)
+    c = zlib.compressobj(6)
+    d = data["random"] + data["zeros"]
+    z = c.compress(d[:30000]) + c.flush(zlib.Z_SYNC_FLUSH) + c.compress(d[30000:]) + c.flush(zlib.Z_FULL_FLUSH) + c.flush()
+    assert verdict(z, len(d)) == "same"
+    z = zlib.compress(b"hello world" * 1000)
+    assert verdict(z[:-9], 11000) == "declined" and verdict(z, 10999) == "declined"
+    corrupt = bytearray(z)
+    corrupt[20] ^= 0x55
+    assert verdict(bytes(corrupt), 11000) in ("declined", "same")  # a flipped bit may still decode, but then the checksum fails
+
+
 def test_rgba_stream_matches_opencv(tmp_path):
     """The ".rgba" stream of ConvertToBinary (convertColor, ConvertToBinary.cpp:138-146): loadImage<Vec4b> = convertTo 8U
     with the float scale 255/65535, BGR -> BGRA (alpha 255), then BGRA -> RGBA; the host loader against the same cv2 calls
