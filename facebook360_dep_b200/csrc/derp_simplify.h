@@ -18,6 +18,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <limits>
 #include <map>
 #include <set>
@@ -89,12 +90,17 @@ class Mesh {
   // stamps every vertex of every face around x and y; an edge that failed after `failed[e] - 1` contractions still fails as
   // long as neither end has been stamped since.  The reference tries such edges again in every sweep (a failed attempt has
   // no side effects, so skipping it changes nothing): on torn meshes that is where its time goes.
+  // whether the boundary rules admit the edge at all (MeshSimplifier.cpp:512-521: both ends on the boundary or neither, and
+  // boundary edges only when asked to remove them): a property of the two end points' boundary flags, refreshed with the
+  // costs; kept per edge so that the sweeps do not have to fetch two vertex records to find out
+  std::vector<uint8_t> admissible;
+  bool removeBoundary = false;
   std::vector<uint32_t> failed;   // per edge (3 per face): 1 + number of contractions done when it last failed, 0 = not known
   std::vector<uint32_t> stamped;  // per vertex: number of the last contraction that touched its closed 1-ring
   uint32_t contractions = 0;
 
   // xyz: 3 doubles per vertex; idx: 3 indices per face
-  Mesh(const double* xyz, size_t nv, const uint32_t* idx, size_t nf) : verts(nv), faces(nf), cost(3 * nf), flag(nf, 0), failed(3 * nf, 0), stamped(nv, 0) {
+  Mesh(const double* xyz, size_t nv, const uint32_t* idx, size_t nf) : verts(nv), faces(nf), cost(3 * nf), flag(nf, 0), admissible(3 * nf, 1), failed(3 * nf, 0), stamped(nv, 0) {
     for (size_t i = 0; i < nv; ++i) verts[i].p = V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     for (size_t i = 0; i < nf; ++i)
       for (int j = 0; j < 3; ++j) faces[i].v[j] = (int)idx[3 * i + j];
@@ -145,7 +151,9 @@ class Mesh {
     const Face& f = faces[fi];
     for (int j = 0; j < 3; ++j) {
       V3 unused;
-      cost[3 * fi + j] = contraction(verts[f.v[j]], verts[f.v[(j + 1) % 3]], &unused);
+      const Vertex &a = verts[f.v[j]], &b = verts[f.v[(j + 1) % 3]];
+      cost[3 * fi + j] = contraction(a, b, &unused);
+      admissible[3 * fi + j] = a.boundary == b.boundary && (removeBoundary || !(a.boundary || b.boundary));
     }
   }
   void dropDeletedFaces() {
@@ -156,12 +164,14 @@ class Mesh {
         faces[keep] = faces[fi];
         for (int j = 0; j < 3; ++j) cost[3 * keep + j] = cost[3 * fi + j];
         for (int j = 0; j < 3; ++j) failed[3 * keep + j] = failed[3 * fi + j];
+        for (int j = 0; j < 3; ++j) admissible[3 * keep + j] = admissible[3 * fi + j];
       }
       ++keep;
     }
     faces.resize(keep);
     cost.resize(3 * keep);
     failed.resize(3 * keep);
+    admissible.resize(3 * keep);
     flag.assign(keep, 0);
   }
   void rebuildIncidence() {
@@ -214,11 +224,42 @@ class Mesh {
       if (border) verts[i].boundary = true;
     }
   }
+  // getThreshold: the cost at rank strictness * (number of costs - 1).  The reference copies the costs and calls
+  // std::nth_element; the value at a rank does not depend on how it is found, so this is a two-level radix selection on
+  // the order-preserving integer image of the doubles (one counting pass over 16 bits, then nth_element inside the one
+  // bucket that holds the rank).  NaN costs have no rank: then the reference's call is reproduced literally.
   double costPercentile(float strictness) const {
-    std::vector<double> all(cost);  // called right after the compaction: every face is live
-    const int at = strictness * (all.size() - 1);  // float * size_t -> float -> int, as written in getThreshold
-    std::nth_element(all.begin(), all.begin() + at, all.end());
-    return all[at];
+    const size_t n = cost.size();  // called right after the compaction: every face is live
+    const int at = strictness * (n - 1);  // float * size_t -> float -> int, as written in getThreshold
+    auto key = [](double d) {
+      uint64_t u;
+      std::memcpy(&u, &d, 8);
+      return (u >> 63) ? ~u : (u | 0x8000000000000000ull);  // negatives reversed below the positives
+    };
+    std::vector<uint32_t> count(65536, 0);
+    bool nan = false;
+    for (size_t i = 0; i < n; ++i) {
+      const double c = cost[i];
+      nan |= c != c;
+      ++count[key(c) >> 48];
+    }
+    if (nan) {
+      std::vector<double> all(cost);
+      std::nth_element(all.begin(), all.begin() + at, all.end());
+      return all[at];
+    }
+    size_t below = 0;
+    uint32_t bucket = 0;
+    for (;; ++bucket) {
+      if (below + count[bucket] > (size_t)at) break;
+      below += count[bucket];
+    }
+    std::vector<double> in;
+    in.reserve(count[bucket]);
+    for (size_t i = 0; i < n; ++i)
+      if ((key(cost[i]) >> 48) == bucket) in.push_back(cost[i]);
+    std::nth_element(in.begin(), in.begin() + ((size_t)at - below), in.end());
+    return in[(size_t)at - below];
   }
   // would moving vertex a (edge a-b contracting) to p flip the normal of a face around a?
   bool flips(const V3& p, int a, int b) {
@@ -279,10 +320,9 @@ class Mesh {
 
   // one attempt at contracting edge j of face fi (MeshSimplifier.cpp:519-553); true if it was contracted.  A failed attempt
   // changes nothing.
-  bool tryEdge(size_t fi, int j, bool removeBoundaryEdges, int* gone) {
+  bool tryEdge(size_t fi, int j, int* gone) {
+    if (!admissible[3 * fi + j]) return false;
     const int a = faces[fi].v[j], b = faces[fi].v[(j + 1) % 3];
-    if (verts[a].boundary != verts[b].boundary) return false;
-    if (!removeBoundaryEdges && (verts[a].boundary || verts[b].boundary)) return false;
     uint32_t& memo = failed[3 * fi + j];
     if (memo > stamped[a] && memo > stamped[b]) return false;  // failed before, and nothing around it has changed since
     V3 p;
@@ -298,13 +338,13 @@ class Mesh {
     return true;
   }
   // a sweep over the faces from `from` on: every edge whose cost is under the threshold is tried, in order
-  void sweepFrom(size_t from, double threshold, bool removeBoundaryEdges, int facesIn, int facesOut, int* gone) {
+  void sweepFrom(size_t from, double threshold, int facesIn, int facesOut, int* gone) {
     for (size_t fi = from; fi < faces.size(); ++fi) {
       // by index: contract() may not grow `faces`, but it writes through references into it
       if (flag[fi]) continue;  // deleted, or touched in this sweep
       for (int j = 0; j < 3; ++j) {
         if (cost[3 * fi + j] > threshold) continue;
-        if (tryEdge(fi, j, removeBoundaryEdges, gone)) break;
+        if (tryEdge(fi, j, gone)) break;
       }
       if (facesIn - *gone <= facesOut) break;
     }
@@ -328,11 +368,19 @@ class Mesh {
       // ---- a sweep after a change (or the first one): the reference's sweep as it is
       dropDeletedFaces();
       rebuildIncidence();
-      if (iteration == 0) markBoundaries();
+      if (iteration == 0) {
+        markBoundaries();
+        removeBoundary = removeBoundaryEdges;
+        for (size_t fi = 0; fi < faces.size(); ++fi)
+          for (int j = 0; j < 3; ++j) {
+            const Vertex &a = verts[faces[fi].v[j]], &b = verts[faces[fi].v[(j + 1) % 3]];
+            admissible[3 * fi + j] = a.boundary == b.boundary && (removeBoundary || !(a.boundary || b.boundary));
+          }
+      }
       threshold = costPercentile(strictness);
       stuck = 0;
       int gonePrev = gone;
-      sweepFrom(0, threshold, removeBoundaryEdges, facesIn, facesOut, &gone);
+      sweepFrom(0, threshold, facesIn, facesOut, &gone);
       ++iteration;
       if (gone != gonePrev) continue;
       if (!((int)faces.size() > facesOut)) break;  // the reference tests its loop condition before every sweep
@@ -358,7 +406,7 @@ class Mesh {
       for (size_t fi = 0; fi < faces.size(); ++fi)
         for (int j = 0; j < 3; ++j) {
           const double c = cost[3 * fi + j];
-          if (!(c > threshold)) continue;
+          if (!(c > threshold) || !admissible[3 * fi + j]) continue;
           const size_t k = std::lower_bound(levels.begin(), levels.end(), c) - levels.begin();  // first level >= c
           if (k + 1 < levels.size()) admitted[k].push_back((uint32_t)(3 * fi + j));  // the last level is inf: the loop ends there
         }
@@ -375,9 +423,9 @@ class Mesh {
         bool contracted = false;
         for (uint32_t e : admitted[k]) {
           const size_t fi = e / 3;
-          if (!tryEdge(fi, (int)(e % 3), removeBoundaryEdges, &gone)) continue;
+          if (!tryEdge(fi, (int)(e % 3), &gone)) continue;
           contracted = true;  // the mesh moved: the rest of this sweep is an ordinary one (what failed before may succeed now)
-          if (facesIn - gone > facesOut) sweepFrom(fi + 1, threshold, removeBoundaryEdges, facesIn, facesOut, &gone);
+          if (facesIn - gone > facesOut) sweepFrom(fi + 1, threshold, facesIn, facesOut, &gone);
           break;
         }
         pending -= admitted[k].size();
