@@ -3,8 +3,10 @@
 // literal / length symbol (11 index bits, second-level tables for longer codes), 8-byte-chunk match copies.  With 80 PNGs
 // per 16-camera frame, inflate on the host threads is the largest share of DerpCLI's files-in -> files-out time once the
 // GPU work is 0.2 s (profiles/README.md).  The reader falls back to zlib's uncompress() whenever this decoder declines a
-// stream (it never produces different bytes for a stream it accepts: tests/test_host_units.py checks it against zlib on
-// stored / fixed / dynamic blocks, every compression level and strategy, long matches at the maximum distance, and PNGs).
+// stream (it never produces different bytes for a stream it accepts: tests/test_apps.py::test_png_inflate_equals_zlib checks
+// it against zlib on stored / fixed / dynamic blocks, compression levels and strategies, long matches at the maximum
+// distance and flush points; an AddressSanitizer run over 30 000 valid and mutated streams found no overrun).  Little-endian
+// hosts only (8-byte loads into the bit buffer).
 #pragma once
 #include <cstddef>
 #include <cstdint>
