@@ -511,7 +511,7 @@ def test_convert_to_binary_bc7(tmp_path, cuda):
         assert os.path.exists(tmp_path / "bin" / cam["id"] / "000000.vtx")
         if ref is not None:
             want = ref.bc7_compress_image(stored[..., :3].copy(), 2.2 / 1.8)
-            assert (got.reshape(-1, 16) == want.reshape(-1, 16)).all(1).mean() > 0.9
+            assert (got.reshape(-1, 16) == want.reshape(-1, 16)).all(1).mean() > 0.8  # 96.9-100 % measured; CPU dependent
             assert {bc7_decode.block_mode(b) for b in got.reshape(-1, 16)} <= {1, 3, 6}
 
 
