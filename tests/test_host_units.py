@@ -1,3 +1,4 @@
+import os
 """CPU-only checks of the PRODUCT library (libderp_b200.so): it must load without a GPU, export every
 symbol include/derp_b200.h declares, fail loudly on compute calls, and the host instantiations of its
 __host__ __device__ building blocks (introselect emulation, minstd skip-ahead, camera) must agree with
@@ -27,6 +28,21 @@ def test_exports_every_declared_symbol(prod, oracle):
             assert hasattr(lib.lib, name), "%s misses %s" % (lib.path, name)
     assert set(declared) == set(capi.ABI_SYMBOLS), set(declared) ^ set(capi.ABI_SYMBOLS)
     assert prod.backend == "cuda-sm_100a" and oracle.backend == "oracle-cpu"
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/derp_b200.h must compile as C99 (no C++ or CUDA types in the signatures) and a C
+    program must link against the library with nothing but that header."""
+    import subprocess
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "derp_b200.h"\n#include <stdio.h>\nint main(void) { printf("%s\\n", derp_backend()); '
+                   'return derp_bc7_compress(0, 0, 0, 0, 0) == 0; }\n')
+    exe = tmp_path / "cabi"
+    libdir = os.path.dirname(capi.CUDA_LIB)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", capi.ROOT + "/include", str(src),
+                           "-o", str(exe), "-L", libdir, "-lderp_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "cuda-sm_100a"  # bad arguments -> DERP_EINVAL, no CUDA call needed
 
 
 def test_no_cpu_fallback_without_gpu(prod):
