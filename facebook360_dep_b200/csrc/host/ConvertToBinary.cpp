@@ -6,9 +6,9 @@
 // `<rig>_fused.json`, and the striped fusion of the produced files (BinaryFusionUtil.h).
 // Colour: .bc7 (the reference's default; derp_bc7_compress_image: conversion, gamma correction, packing and the block encoder
 // of bc7_util::compressBC7 in one CUDA kernel) and the uncompressed .rgba stream (host bytes); both with --color_scale = 1.
-// NOT built, and refused with a message instead of silently skipped: the rasterised pfm format (mesh_util::writePfm samples
-// the mesh exactly ON its vertexes and edges, so which pixels it covers is decided by the rounding noise of Eigen's
-// column-pivoting QR — not reproducible without Eigen itself) and colour conversion with --color_scale < 1.
+// The rasterised pfm format (mesh_util::writePfm) is host code like the reference's (io.h rasterMesh; its 2 x 2 solves are by
+// elimination, not Eigen's QR: pixel centres exactly on an edge can fall the other way, values agree to float rounding).
+// NOT built, and refused with a message instead of silently skipped: colour conversion with --color_scale < 1.
 #include <set>
 #include <thread>
 
@@ -273,8 +273,8 @@ int main(int argc, char** argv) {
   const bool wantRgba = !FLAGS_color.empty() && contains(formats, "rgba");
   const bool wantBc7 = !FLAGS_color.empty() && contains(formats, "bc7");
   CHECK((!wantRgba && !wantBc7) || FLAGS_color_scale >= 1) << "colour conversion with --color_scale < 1 is not built in this port";
-  CHECK(FLAGS_disparity.empty() || !contains(formats, "pfm")) << "the rasterised pfm format is not built in this port (pass --output_formats without pfm)";
-  const bool wantDepth = !FLAGS_disparity.empty() && (contains(formats, "idx") || contains(formats, "vtx") || contains(formats, "obj"));
+  const bool wantDepth = !FLAGS_disparity.empty() &&
+      (contains(formats, "idx") || contains(formats, "vtx") || contains(formats, "obj") || contains(formats, "pfm"));
 
   // resizeRig (ConvertToBinary.cpp:322-343): camera resolutions follow the (scaled) colour images
   if (!FLAGS_color.empty()) {
@@ -357,6 +357,11 @@ int main(int argc, char** argv) {
           if (contains(formats, "idx") || contains(formats, "vtx")) {  // mesh_util::writeDepth writes both
             std::ofstream(fnVtx, std::ios::binary).write(reinterpret_cast<const char*>(vtx.data()), vtx.size() * sizeof(float));
             std::ofstream(fnIdx, std::ios::binary).write(reinterpret_cast<const char*>(idx.data()), idx.size() * sizeof(uint32_t));
+          }
+          if (contains(formats, "pfm")) {  // mesh_util::writePfm(depth, cam.resolution, vertexes, faces, ...): the mesh rasterised
+            const std::vector<float> raster =  // back onto the (possibly --depth_scale'd) depth grid; host code like the reference's
+                io::rasterMesh(vtx.data(), idx.data(), nf, gw, gh, cam.resolution[0], cam.resolution[1]);
+            io::writePfm(io::imagePath(FLAGS_bin, id, frame, ".pfm"), raster.data(), gw, gh);
           }
           if (contains(formats, "obj")) writeObj(vtx, idx, io::imagePath(FLAGS_bin, id, frame, ".obj"));
         }

@@ -8,8 +8,13 @@
 #include "io.h"
 
 DEFINE_string(in, "", "input image");
-DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange | inflate");
+DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange | inflate | raster");
 DEFINE_int32(size, 0, "mode=inflate: number of bytes the zlib stream in --in decodes to");
+DEFINE_string(faces, "", "mode=raster: .idx file (uint32 x 3 per face); --in is the .vtx file (float32 x 3 per vertex)");
+DEFINE_int32(width, 0, "mode=raster: depth grid width");
+DEFINE_int32(height, 0, "mode=raster: depth grid height");
+DEFINE_double(resolution_x, 0, "mode=raster: camera resolution");
+DEFINE_double(resolution_y, 0, "mode=raster: camera resolution");
 DEFINE_string(out, "", "output file (raw samples, or .png/.pfm for mode=float)");
 
 int main(int argc, char** argv) {
@@ -45,6 +50,18 @@ int main(int argc, char** argv) {
     o.open(FLAGS_out, std::ios::binary);
     o.write(reinterpret_cast<const char*>(rig.cams.data()), (std::streamsize)(rig.cams.size() * sizeof(DerpCameraDesc)));
     for (const auto& id : rig.ids) std::printf("%s\n", id.c_str());
+  } else if (FLAGS_mode == "raster") {
+    // ConvertToBinary's "pfm" format: the mesh of --in (.vtx) / --faces (.idx) rasterised onto a --width x --height grid
+    auto slurp = [](const std::string& path) {
+      std::ifstream f(path, std::ios::binary);
+      return std::vector<char>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    };
+    const std::vector<char> v = slurp(FLAGS_in), i = slurp(FLAGS_faces);
+    const std::vector<float> r = io::rasterMesh(reinterpret_cast<const float*>(v.data()), reinterpret_cast<const uint32_t*>(i.data()),
+                                                i.size() / 12, FLAGS_width, FLAGS_height, FLAGS_resolution_x, FLAGS_resolution_y);
+    io::writePfm(FLAGS_out, r.data(), FLAGS_width, FLAGS_height);
+    w = FLAGS_width;
+    h = FLAGS_height;
   } else if (FLAGS_mode == "inflate") {
     // the PNG reader's own inflate (inflate.h) against zlib on a raw zlib stream: accepted streams must decode to zlib's
     // bytes; prints "same" / "declined" / "DIFFERENT" and both times

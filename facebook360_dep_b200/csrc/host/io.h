@@ -4,6 +4,7 @@
 // (ImageUtil.h:42-107, CvUtil.h:227-284 convertImage semantics).
 #pragma once
 
+#include <cfloat>
 #include <zlib.h>
 
 #include "inflate.h"
@@ -614,6 +615,49 @@ inline void writePng16(const fs::path& path, const uint16_t* data, int w, int h,
   comp.resize(clen);
   pngChunk(f, "IDAT", comp);
   pngChunk(f, "IEND", {});
+}
+
+// ---- mesh_util::writePfm (MeshUtil.h:24-70): the "pfm" output of ConvertToBinary, the mesh rasterised back onto the depth
+// grid.  Faces in order, the last one covering a pixel centre wins; a pixel is covered when its three barycentric
+// coordinates are >= 0 ("ignore rasterization rules, just include all edges"); uncovered pixels stay -FLT_MAX.  The 2 x 2
+// system of calcBarycentrics is solved by elimination with partial pivoting — the reference calls Eigen's
+// colPivHouseholderQr, whose last-bit rounding decides coverage for pixel centres that lie exactly ON an edge or a vertex
+// (which they do for an unsimplified mesh: its vertexes ARE the pixel centres); values agree to float rounding either way.
+// vtx: x, y, z per vertex as written to .vtx (float32); width / height: the depth grid; resolution: the camera's.
+inline std::vector<float> rasterMesh(const float* vtx, const uint32_t* idx, size_t numFaces, int width, int height,
+                                     double resolutionX, double resolutionY) {
+  std::vector<float> dst((size_t)width * height, -FLT_MAX);
+  const double sx = width / resolutionX, sy = height / resolutionY;
+  for (size_t f = 0; f < numFaces; ++f) {
+    double t[3][3];
+    for (int i = 0; i < 3; ++i) {
+      const float* v = vtx + 3 * (size_t)idx[3 * f + i];
+      t[i][0] = (double)v[0] * sx;
+      t[i][1] = (double)v[1] * sy;
+      t[i][2] = (double)v[2];
+    }
+    const double minX = std::min(std::min(t[0][0], t[1][0]), t[2][0]), maxX = std::max(std::max(t[0][0], t[1][0]), t[2][0]);
+    const double minY = std::min(std::min(t[0][1], t[1][1]), t[2][1]), maxY = std::max(std::max(t[0][1], t[1][1]), t[2][1]);
+    const double bx = t[2][0], by = t[2][1];
+    // m^T of calcBarycentrics: columns are (row 0 - base) and (row 1 - base)
+    const double a00 = t[0][0] - bx, a01 = t[1][0] - bx, a10 = t[0][1] - by, a11 = t[1][1] - by;
+    for (int y = (int)std::floor(minY); y < std::ceil(maxY); ++y)
+      for (int x = (int)std::floor(minX); x < std::ceil(maxX); ++x) {
+        double A[2][3] = {{a00, a01, (x + 0.5) - bx}, {a10, a11, (y + 0.5) - by}};
+        if (std::abs(A[1][0]) > std::abs(A[0][0]))
+          for (int j = 0; j < 3; ++j) std::swap(A[0][j], A[1][j]);
+        const double fct = A[1][0] / A[0][0];
+        const double b1 = (A[1][2] - fct * A[0][2]) / (A[1][1] - fct * A[0][1]);
+        const double b0 = (A[0][2] - A[0][1] * b1) / A[0][0];
+        const double b2 = 1 - b0 - b1;
+        if (b0 >= 0 && b1 >= 0 && b2 >= 0) {
+          CHECK(0 <= x && x < width) << x << width;
+          CHECK(0 <= y && y < height) << y << height;
+          dst[(size_t)y * width + x] = (float)((t[0][2] * b0 + t[1][2] * b1) + t[2][2] * b2);
+        }
+      }
+  }
+  return dst;
 }
 
 // ---- cv_util::loadImage<T> semantics (CvUtil.h:171-284) -----------------------------------------------

@@ -760,6 +760,24 @@ int derp_ref_simplify(const double* xyz, uint64_t nv, const uint32_t* idx, uint6
   });
 }
 
+/* test hook: mesh_util::writePfm (MeshUtil.h:35-70), the rasterised "pfm" format of ConvertToBinary, on a mesh given as
+ * arrays.  calcBarycentrics solves its 2 x 2 system with Eigen's colPivHouseholderQr; the stand-in header solves it by
+ * elimination with partial pivoting, so coverage exactly ON triangle edges can differ from a build with Eigen itself. */
+int derp_ref_write_raster_pfm(const double* xyz, uint64_t nv, const uint32_t* idx, uint64_t nf, int width, int height,
+                              double resolution_x, double resolution_y, const char* path) {
+  return guarded([&] {
+    Eigen::MatrixXd vertexes((Eigen::Index)nv, 3);
+    Eigen::MatrixXi faces((Eigen::Index)nf, 3);
+    for (uint64_t i = 0; i < nv; ++i)
+      for (int j = 0; j < 3; ++j) vertexes((Eigen::Index)i, j) = xyz[3 * i + j];
+    for (uint64_t i = 0; i < nf; ++i)
+      for (int j = 0; j < 3; ++j) faces((Eigen::Index)i, j) = (int)idx[3 * i + j];
+    const cv::Mat_<float> original(height, width, 0.0f);
+    mesh_util::writePfm(original, Camera::Vector2(resolution_x, resolution_y), vertexes, faces, filesystem::path(path));
+    return (int)DERP_OK;
+  });
+}
+
 /* bench / test hook (not part of derp_b200.h): candidate slices of the brute-force cost volume the way the reference
  * builds them (Derp.cpp:288-304): ONE ThreadPool task per candidate, each writing a full-size cost and confidence map
  * (NaN where ignored).  Rows [y0, y1) only, so that a bench step can be a bounded band of the frame: with the full

@@ -450,13 +450,13 @@ def _mesh_dataset(tmp_path, W=96, H=80, S=3, F=2):
 
 def test_convert_to_binary_refuses_unbuilt_parts(tmp_path):
     """What this build does not do is refused with a message instead of skipped or approximated (no GPU needed to get that
-    far): the rasterised pfm format, and colour conversion with --color_scale < 1.  Without a GPU the BC7 colour format
-    stops with the CUDA error — there is no host encoder behind the executable."""
+    far): colour conversion with --color_scale < 1, and unknown formats like the reference.  Without a GPU the BC7 colour
+    format stops with the CUDA error — there is no host encoder behind the executable."""
     rig, _ = _mesh_dataset(tmp_path, F=1)
     base = ["--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
             "--disparity=" + str(tmp_path / "disparity"), "--bin=" + str(tmp_path / "bin")]
-    p = run("ConvertToBinary", *base, "--output_formats=idx,vtx,pfm", check=False)
-    assert p.returncode != 0 and "pfm" in p.stderr
+    p = run("ConvertToBinary", *base, "--output_formats=idx,vtx,exr", check=False)
+    assert p.returncode != 0 and "Invalid output format" in p.stderr
     H, W = 80, 96
     for cam in rig["cameras"]:
         os.makedirs(tmp_path / "color" / cam["id"], exist_ok=True)

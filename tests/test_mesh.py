@@ -2,6 +2,8 @@
 before simplification — ConvertToBinary.cpp:150-183, MeshUtil.h).  CPU: the oracle restatement against the reference's own
 MeshUtil.h (oracle/_ref) and hand-checked small cases.  GPU: the CUDA library against the checker, exactly (index work and
 IEEE fp64 divisions only — no tolerance)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -184,6 +186,52 @@ def test_simplifier_equals_reference_on_random_meshes(oracle):
                 rv, ri = _simplify(ref, "derp_ref_simplify", xyz, idx, target, remove_boundary=rb)
                 assert np.array_equal(pi, ri), (seed, w, h, smooth, target, rb)
                 assert np.array_equal(pv.view(np.uint64), rv.view(np.uint64)), (seed, w, h, smooth, target, rb)
+
+
+def test_raster_pfm_equals_reference_write_pfm(oracle, tmp_path):
+    """ConvertToBinary's "pfm" format (mesh_util::writePfm, MeshUtil.h:24-70): the host rasteriser of the apps (io.h
+    rasterMesh, through IoSelfTest) against the reference's own function compiled into oracle/_ref, on a camera mesh as
+    written to .vtx / .idx and on the same mesh simplified — bit for bit (both sides solve calcBarycentrics' 2 x 2 system by
+    elimination: oracle/_ref has a stand-in for Eigen, see io.h) — and against the mesh itself: the vertexes of an
+    unsimplified mesh are pixel centres, and those pixels show their z."""
+    import ctypes as C
+    import subprocess
+    from facebook360_dep_b200 import capi
+    ref = oracle_libs.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    w, h = 72, 56
+    d = disparity_case(np.random.RandomState(9), w, h, nan_frac=0.02, zero_frac=0.0)
+    res = (w * 4.0, h * 4.0)
+    v32, idx = oracle.camera_mesh(d, res, 300.0)
+    sv, si = _simplify(capi.load_cuda(), "derp_test_simplify", v32.astype(np.float64), idx, 1500)
+    f = ref.lib.derp_ref_write_raster_pfm
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_char_p]
+    exe = os.path.join(capi.ROOT, "facebook360_dep_b200", "bin", "IoSelfTest")
+    for name, vv, ii in (("full", v32, idx), ("simplified", sv.astype(np.float32), si)):
+        vv = np.ascontiguousarray(vv, np.float32)
+        ii = np.ascontiguousarray(ii, np.uint32)
+        vv.tofile(str(tmp_path / "m.vtx"))
+        ii.tofile(str(tmp_path / "m.idx"))
+        out = str(tmp_path / (name + ".pfm"))
+        subprocess.run([exe, "--mode=raster", "--in=" + str(tmp_path / "m.vtx"), "--faces=" + str(tmp_path / "m.idx"),
+                        "--width=%d" % w, "--height=%d" % h, "--resolution_x=%r" % res[0], "--resolution_y=%r" % res[1],
+                        "--out=" + out], check=True, capture_output=True)
+        v64 = vv.astype(np.float64)
+        want = str(tmp_path / (name + "_ref.pfm"))
+        assert f(v64.ctypes.data, len(v64), ii.ctypes.data, len(ii), w, h, res[0], res[1], want.encode()) == 0
+        got_bytes, want_bytes = open(out, "rb").read(), open(want, "rb").read()
+        assert got_bytes == want_bytes, name
+        raster = np.frombuffer(got_bytes[-w * h * 4:], np.float32).reshape(h, w)
+        covered = raster > -3e38
+        assert covered.mean() > 0.5
+        if name == "full":  # every vertex of the unsimplified mesh sits on a pixel centre: that pixel shows the vertex's z
+            px = np.rint(v32[:, 0] / 4.0 - 0.5).astype(int)
+            py = np.rint(v32[:, 1] / 4.0 - 0.5).astype(int)
+            assert np.allclose(v32[:, 0] / 4.0 - 0.5, px, atol=1e-4) and np.allclose(v32[:, 1] / 4.0 - 0.5, py, atol=1e-4)
+            seen = covered[py, px]
+            assert seen.mean() > 0.95 and np.allclose(raster[py, px][seen], v32[seen, 2], rtol=2e-6)
 
 
 @pytest.mark.gpu
