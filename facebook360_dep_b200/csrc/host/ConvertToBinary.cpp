@@ -5,10 +5,11 @@
 // render::MeshSimplifier's contraction sweeps down to --triangles, sequential host code like the reference's), the rescaled
 // `<rig>_fused.json`, and the striped fusion of the produced files (BinaryFusionUtil.h).
 // Colour: .bc7 (the reference's default; derp_bc7_compress_image: conversion, gamma correction, packing and the block encoder
-// of bc7_util::compressBC7 in one CUDA kernel) and the uncompressed .rgba stream (host bytes); both with --color_scale = 1.
+// of bc7_util::compressBC7 in one CUDA kernel) and the uncompressed .rgba stream (host bytes).
 // The rasterised pfm format (mesh_util::writePfm) is host code like the reference's (io.h rasterMesh; its 2 x 2 solves are by
 // elimination, not Eigen's QR: pixel centres exactly on an edge can fall the other way, values agree to float rounding).
-// NOT built, and refused with a message instead of silently skipped: colour conversion with --color_scale < 1.
+// --color_scale < 1 (the UI's export below full width): conversion, cv::resize INTER_AREA and gamma are host stages pinned to
+// cv2 (area_resize.h), the encoder takes the packed RGBA8 surface.
 #include <set>
 #include <thread>
 
@@ -272,7 +273,6 @@ int main(int argc, char** argv) {
   CHECK_GT(numFrames, 0);
   const bool wantRgba = !FLAGS_color.empty() && contains(formats, "rgba");
   const bool wantBc7 = !FLAGS_color.empty() && contains(formats, "bc7");
-  CHECK((!wantRgba && !wantBc7) || FLAGS_color_scale >= 1) << "colour conversion with --color_scale < 1 is not built in this port";
   const bool wantDepth = !FLAGS_disparity.empty() &&
       (contains(formats, "idx") || contains(formats, "vtx") || contains(formats, "obj") || contains(formats, "pfm"));
 
@@ -281,10 +281,7 @@ int main(int argc, char** argv) {
     for (int c : cams) {
       int w, h;
       pngSize(io::imagePath(FLAGS_color, rig.ids[c], FLAGS_first), &w, &h);
-      if (FLAGS_color_scale < 1) {  // cv::resize(fx, fy): dsize = cvRound(size * scale)
-        w = io::cvRoundD(w * FLAGS_color_scale);
-        h = io::cvRoundD(h * FLAGS_color_scale);
-      }
+      if (FLAGS_color_scale < 1) io::scaledSize(w, h, FLAGS_color_scale, &w, &h);  // cv_util::scaleImage
       DerpCameraDesc& cam = rig.cams[c];
       const float xScale = float(w) / cam.resolution[0], yScale = float(h) / cam.resolution[1];
       CHECK_EQ(xScale, yScale) << "Aspect ratio must be kept. " << cam.resolution[0] << "x" << cam.resolution[1] << " vs " << w << "x" << h;
@@ -380,6 +377,18 @@ int main(int argc, char** argv) {
             const std::string &id = rig.ids[tasks[t].cam], frame = io::zeroPad(tasks[t].frame);
             LOG(INFO) << "Converting color: frame " << frame << ", camera " << id << "...";
             const io::Image img = io::loadUnchanged(io::imagePath(FLAGS_color, id, frame));
+            if (FLAGS_color_scale < 1) {
+              // loadScaledImage<Vec4f>(..., --color_scale, INTER_AREA): conversion, area resize and gamma are host stages
+              // (the reference's arithmetic incl. its powf); the block encoder takes the packed surface
+              int sw, sh;
+              const std::vector<uint8_t> rgba = io::bc7SurfaceScaled(img, FLAGS_color_scale, (float)FLAGS_gamma_correction, &sw, &sh);
+              std::vector<uint8_t> blocks((size_t)sw * sh);
+              DERP_CALL(derp_bc7_compress(device, rgba.data(), sw, sh, blocks.data()));
+              const fs::path out = io::imagePath(FLAGS_bin, id, frame, ".bc7");
+              fs::create_directories(out.parent_path());
+              std::ofstream(out, std::ios::binary).write(reinterpret_cast<const char*>(blocks.data()), blocks.size());
+              continue;
+            }
             CHECK((img.bits == 8 || img.bits == 16) && (img.channels == 1 || img.channels == 3 || img.channels == 4))
                 << "Conversion from " << img.channels << " channels to 4 channels not supported";  // CvUtil.h:261-262
             const size_t n = (size_t)img.w * img.h;
@@ -408,7 +417,8 @@ int main(int argc, char** argv) {
         const std::string &id = rig.ids[t.cam], frame = io::zeroPad(t.frame);
         LOG(INFO) << "Converting color: frame " << frame << ", camera " << id << "...";
         int w, h;
-        const std::vector<uint8_t> rgba = io::loadRgba8(io::imagePath(FLAGS_color, id, frame), &w, &h);
+        std::vector<uint8_t> rgba = io::loadRgba8(io::imagePath(FLAGS_color, id, frame), &w, &h);
+        if (FLAGS_color_scale < 1) rgba = io::scaleRgba8(rgba, &w, &h, FLAGS_color_scale);
         const fs::path out = io::imagePath(FLAGS_bin, id, frame, ".rgba");
         fs::create_directories(out.parent_path());
         std::ofstream(out, std::ios::binary).write(reinterpret_cast<const char*>(rgba.data()), rgba.size());

@@ -4,17 +4,25 @@
 #include <chrono>
 #include <thread>
 
+#include "area_resize.h"
 #include "exchange.h"
 #include "io.h"
 
 DEFINE_string(in, "", "input image");
-DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange | inflate | raster");
+DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange | inflate | raster | area | bc7surface");
 DEFINE_int32(size, 0, "mode=inflate: number of bytes the zlib stream in --in decodes to");
 DEFINE_string(faces, "", "mode=raster: .idx file (uint32 x 3 per face); --in is the .vtx file (float32 x 3 per vertex)");
 DEFINE_int32(width, 0, "mode=raster: depth grid width");
 DEFINE_int32(height, 0, "mode=raster: depth grid height");
 DEFINE_double(resolution_x, 0, "mode=raster: camera resolution");
 DEFINE_double(resolution_y, 0, "mode=raster: camera resolution");
+DEFINE_int32(channels, 4, "mode=area: samples per pixel");
+DEFINE_int32(dst_width, 0, "mode=area: output width");
+DEFINE_int32(dst_height, 0, "mode=area: output height");
+DEFINE_string(type, "f32", "mode=area: f32 | u8 samples in the raw file --in (--width x --height pixels)");
+DEFINE_bool(simd4, false, "mode=area: float 2 x 2 formula of 4-channel images");
+DEFINE_double(scale, 1, "mode=bc7surface / rgba: --color_scale");
+DEFINE_double(gamma, 2.2 / 1.8, "mode=bc7surface: --gamma_correction");
 DEFINE_string(out, "", "output file (raw samples, or .png/.pfm for mode=float)");
 
 int main(int argc, char** argv) {
@@ -38,7 +46,8 @@ int main(int argc, char** argv) {
       o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size() * 4);
     }
   } else if (FLAGS_mode == "rgba") {
-    const auto v = io::loadRgba8(FLAGS_in, &w, &h);
+    auto v = io::loadRgba8(FLAGS_in, &w, &h);
+    if (FLAGS_scale < 1) v = io::scaleRgba8(v, &w, &h, FLAGS_scale);
     o.open(FLAGS_out, std::ios::binary);
     o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size());
   } else if (FLAGS_mode == "mask") {
@@ -62,6 +71,30 @@ int main(int argc, char** argv) {
     io::writePfm(FLAGS_out, r.data(), FLAGS_width, FLAGS_height);
     w = FLAGS_width;
     h = FLAGS_height;
+  } else if (FLAGS_mode == "bc7surface") {
+    // the RGBA8 surface ConvertToBinary feeds the BC7 encoder for --in with --color_scale = --scale (< 1)
+    const std::vector<uint8_t> v = io::bc7SurfaceScaled(io::loadUnchanged(FLAGS_in), FLAGS_scale, (float)FLAGS_gamma, &w, &h);
+    o.open(FLAGS_out, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size());
+  } else if (FLAGS_mode == "area") {
+    // cv::resize(INTER_AREA) of a raw interleaved image (area_resize.h) for comparison with cv2
+    std::ifstream f(FLAGS_in, std::ios::binary);
+    const std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const size_t n = (size_t)FLAGS_dst_width * FLAGS_dst_height * FLAGS_channels;
+    o.open(FLAGS_out, std::ios::binary);
+    if (FLAGS_type == "f32") {
+      std::vector<float> d(n);
+      io::area::resize(reinterpret_cast<const float*>(raw.data()), FLAGS_width, FLAGS_height, FLAGS_channels, d.data(), FLAGS_dst_width,
+                       FLAGS_dst_height, FLAGS_simd4);
+      o.write(reinterpret_cast<const char*>(d.data()), (std::streamsize)n * 4);
+    } else {
+      std::vector<uint8_t> d(n);
+      io::area::resize(reinterpret_cast<const uint8_t*>(raw.data()), FLAGS_width, FLAGS_height, FLAGS_channels, d.data(),
+                       FLAGS_dst_width, FLAGS_dst_height);
+      o.write(reinterpret_cast<const char*>(d.data()), (std::streamsize)n);
+    }
+    w = FLAGS_dst_width;
+    h = FLAGS_dst_height;
   } else if (FLAGS_mode == "inflate") {
     // the PNG reader's own inflate (inflate.h) against zlib on a raw zlib stream: accepted streams must decode to zlib's
     // bytes; prints "same" / "declined" / "DIFFERENT" and both times

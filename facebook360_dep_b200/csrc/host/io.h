@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <zlib.h>
 
+#include "area_resize.h"
 #include "inflate.h"
 
 #include <algorithm>
@@ -724,6 +725,58 @@ inline std::vector<uint8_t> loadRgba8(const fs::path& path, int* w, int* h) {
     out[i * 4 + 3] = img.channels == 4 ? conv(at + 3) : (img.channels == 2 ? conv(at + 1) : 255);
   }
   return out;
+}
+
+// cv_util::scaleImage's output size (CvUtil.h:150-153): std::round of the scaled extent
+inline void scaledSize(int w, int h, double scale, int* dw, int* dh) {
+  *dw = (int)std::round(w * scale);
+  *dh = (int)std::round(h * scale);
+}
+
+// image_util::loadScaledImage<cv::Vec4b>(..., --color_scale, INTER_AREA) for the ".rgba" stream (ConvertToBinary.cpp:140-142):
+// the 8-bit 4-channel image shrunk with cv::resize INTER_AREA (the channel order does not matter to a per-channel filter)
+inline std::vector<uint8_t> scaleRgba8(const std::vector<uint8_t>& rgba, int* w, int* h, double scale) {
+  int dw, dh;
+  scaledSize(*w, *h, scale, &dw, &dh);
+  CHECK(dw >= 1 && dh >= 1 && dw <= *w && dh <= *h) << "--color_scale must shrink the image";
+  if (dw == *w && dh == *h) return rgba;
+  std::vector<uint8_t> out((size_t)dw * dh * 4);
+  area::resize(rgba.data(), *w, *h, 4, out.data(), dw, dh);
+  *w = dw;
+  *h = dh;
+  return out;
+}
+
+// The RGBA8 surface bc7_util::compressBC7 hands to the block encoder when ConvertToBinary runs with --color_scale < 1
+// (ConvertToBinary.cpp:127-137, BC7Util.h:45-67): the stored image -> [0, 1] floats (CvUtil.h:196-207; grey replicated, an
+// alpha channel would be carried along and dropped later: skipped here) -> cv::resize INTER_AREA to the scaled size ->
+// gammaCorrect per channel with the host's powf, exactly the reference's call -> R, G, B, 255.
+inline std::vector<uint8_t> bc7SurfaceScaled(const Image& img, double scale, float gamma, int* outW, int* outH) {
+  CHECK((img.bits == 8 || img.bits == 16) && (img.channels == 1 || img.channels == 3 || img.channels == 4))
+      << "Conversion from " << img.channels << " channels to 4 channels not supported";  // CvUtil.h:261-262
+  const size_t n = (size_t)img.w * img.h;
+  const float toUnit = 1.0f / (img.bits == 16 ? 65535.0f : 255.0f);
+  std::vector<float> bgr(n * 3);
+  for (size_t i = 0; i < n; ++i)
+    for (int c = 0; c < 3; ++c) bgr[i * 3 + c] = (float)img.u[i * img.channels + (img.channels == 1 ? 0 : c)] * toUnit;
+  int dw, dh;
+  scaledSize(img.w, img.h, scale, &dw, &dh);
+  CHECK(dw >= 1 && dh >= 1 && dw <= img.w && dh <= img.h) << "--color_scale must shrink the image";
+  std::vector<float> small;
+  const float* px = bgr.data();
+  if (dw != img.w || dh != img.h) {  // resizeImage returns the input when the size does not change
+    small.resize((size_t)dw * dh * 3);
+    area::resize(bgr.data(), img.w, img.h, 3, small.data(), dw, dh, /*simdAsFourChannels=*/true);  // the reference resizes BGRA
+    px = small.data();
+  }
+  std::vector<uint8_t> rgba((size_t)dw * dh * 4);
+  for (size_t i = 0; i < (size_t)dw * dh; ++i) {
+    for (int c = 0; c < 3; ++c) rgba[i * 4 + c] = (uint8_t)(std::pow(px[i * 3 + 2 - c], gamma) * 255.0f + 0.5f);
+    rgba[i * 4 + 3] = 255;
+  }
+  *outW = dw;
+  *outH = dh;
+  return rgba;
 }
 
 // loadImage<float>: .pfm as-is; integer images scaled by 1/max

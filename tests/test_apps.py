@@ -449,8 +449,7 @@ def _mesh_dataset(tmp_path, W=96, H=80, S=3, F=2):
 
 
 def test_convert_to_binary_refuses_unbuilt_parts(tmp_path):
-    """What this build does not do is refused with a message instead of skipped or approximated (no GPU needed to get that
-    far): colour conversion with --color_scale < 1, and unknown formats like the reference.  Without a GPU the BC7 colour
+    """Bad command lines stop like the reference's (no GPU needed to get that far): unknown formats, --color_scale > 1.  Without a GPU the BC7 colour
     format stops with the CUDA error — there is no host encoder behind the executable."""
     rig, _ = _mesh_dataset(tmp_path, F=1)
     base = ["--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
@@ -461,8 +460,8 @@ def test_convert_to_binary_refuses_unbuilt_parts(tmp_path):
     for cam in rig["cameras"]:
         os.makedirs(tmp_path / "color" / cam["id"], exist_ok=True)
         assert cv2.imwrite(str(tmp_path / "color" / cam["id"] / "000000.png"), np.full((H, W, 3), 1000, np.uint16))
-    p = run("ConvertToBinary", *base, "--color=" + str(tmp_path / "color"), "--color_scale=0.5", check=False)
-    assert p.returncode != 0 and "color_scale" in p.stderr
+    p = run("ConvertToBinary", *base, "--color=" + str(tmp_path / "color"), "--color_scale=1.5", check=False)
+    assert p.returncode != 0  # CHECK_LE(FLAGS_color_scale, 1) like the reference (ConvertToBinary.cpp:347)
     import torch
     if not torch.cuda.is_available():
         p = run("ConvertToBinary", base[0], base[1], base[2], base[4], "--color=" + str(tmp_path / "color"),
@@ -653,6 +652,80 @@ def test_rgba_stream_matches_opencv(tmp_path):
         assert np.array_equal(got, cv2.cvtColor(bgra, cv2.COLOR_BGRA2RGBA)), name
 
 
+def test_area_resize_matches_opencv(tmp_path):
+    """cv::resize INTER_AREA of the colour streams under --color_scale < 1 (csrc/host/area_resize.h) against cv2: float and
+    8-bit images with 4 and 3 channels; ratios of exactly 2 (OpenCV's vector bodies), other integer ratios (row-order sums,
+    in groups of four for float), mixed and fractional ratios (separable taps); bit for bit."""
+    rng = np.random.RandomState(0)
+    src, out = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+
+    def resize(img, dw, dh, simd4=False):
+        h, w, c = img.shape
+        img.tofile(src)
+        run("IoSelfTest", "--mode=area", "--in=" + src, "--width=%d" % w, "--height=%d" % h, "--channels=%d" % c,
+            "--dst_width=%d" % dw, "--dst_height=%d" % dh, "--type=" + ("f32" if img.dtype == np.float32 else "u8"), "--out=" + out,
+            *(["--simd4"] if simd4 else []))
+        return np.fromfile(out, img.dtype).reshape(dh, dw, c)
+
+    for (w, h, dw, dh) in [(64, 48, 32, 24), (66, 50, 33, 25), (60, 45, 20, 15), (64, 48, 16, 12), (70, 50, 35, 10),
+                           (101, 77, 40, 31), (96, 64, 95, 63), (50, 40, 7, 3), (30, 20, 30, 10)]:
+        for dtype, c in ((np.float32, 4), (np.float32, 3), (np.uint8, 4), (np.uint8, 3)):
+            img = rng.uniform(0, 1, (h, w, c)).astype(np.float32) if dtype == np.float32 else rng.randint(0, 256, (h, w, c)).astype(np.uint8)
+            want = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA).reshape(dh, dw, c)
+            assert resize(img, dw, dh).tobytes() == want.tobytes(), (w, h, dw, dh, dtype.__name__, c)
+    # the BC7 stream resizes B, G, R with the arithmetic of the 4-channel image the reference carries
+    img4 = rng.uniform(0, 1, (48, 64, 4)).astype(np.float32)
+    want = cv2.resize(img4, (32, 24), interpolation=cv2.INTER_AREA)[..., :3]
+    assert resize(np.ascontiguousarray(img4[..., :3]), 32, 24, simd4=True).tobytes() == np.ascontiguousarray(want).tobytes()
+
+
+@pytest.mark.parametrize("scale", [0.5, 0.375, 1.0 / 3.0, 0.73])
+def test_colour_streams_with_color_scale(tmp_path, scale):
+    """--color_scale < 1 (scripts/ui/export.py:311-318 sets it for exports below full width): the RGBA8 surface handed to the
+    BC7 encoder = the reference's own sequence — cv_util::convertTo to [0, 1] floats, BGR -> BGRA, cv::resize INTER_AREA
+    (cv2), bc7_util::gammaCorrect (the reference's function, oracle/_ref) — and the .rgba stream = convertTo 8 bit, BGRA,
+    INTER_AREA, RGBA; 16-bit colour, 8-bit colour with alpha, 16-bit grey."""
+    import ctypes as C
+    from tests import oracle_libs
+    ref = oracle_libs.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    g = ref.lib.derp_ref_gamma_correct
+    g.restype, g.argtypes = C.c_uint8, [C.c_float, C.c_float]
+    gamma = 2.2 / 1.8
+    rng = np.random.RandomState(5)
+    H, W = 48, 64
+    cases = {"c16": rng.randint(0, 65536, (H, W, 3)).astype(np.uint16), "a8": rng.randint(0, 256, (H, W, 4)).astype(np.uint8),
+             "g16": rng.randint(0, 65536, (H, W)).astype(np.uint16)}
+    for name, img in cases.items():
+        png = str(tmp_path / (name + ".png"))
+        assert cv2.imwrite(png, img)
+        stored = cv2.imread(png, cv2.IMREAD_UNCHANGED)
+        dw, dh = int(np.floor(W * scale + 0.5)), int(np.floor(H * scale + 0.5))  # std::round
+        # ---- BC7 surface
+        top = np.float32(65535.0 if stored.dtype == np.uint16 else 255.0)
+        f = stored.astype(np.float32) * (np.float32(1.0) / top)
+        bgra = cv2.cvtColor(f, {2: cv2.COLOR_GRAY2BGRA, 3: cv2.COLOR_BGR2BGRA}.get(f.ndim if f.ndim == 2 else f.shape[2])) \
+            if (f.ndim == 2 or f.shape[2] == 3) else f
+        small = cv2.resize(bgra, (dw, dh), interpolation=cv2.INTER_AREA)
+        want = np.zeros((dh, dw, 4), np.uint8)
+        want[..., 3] = 255
+        for c in range(3):
+            want[..., c] = np.array([g(float(v), gamma) for v in small[..., 2 - c].ravel()], np.uint8).reshape(dh, dw)
+        out = str(tmp_path / (name + ".surface"))
+        r = run("IoSelfTest", "--mode=bc7surface", "--in=" + png, "--scale=%r" % scale, "--out=" + out)
+        assert list(map(int, r.stdout.split()[-2:])) == [dw, dh]
+        assert np.fromfile(out, np.uint8).tobytes() == want.tobytes(), name
+        # ---- .rgba stream
+        s8 = stored if stored.dtype == np.uint8 else cv2.convertScaleAbs(stored, alpha=float(np.float32(255.0) / np.float32(65535.0)))
+        code = {2: cv2.COLOR_GRAY2BGRA, 3: cv2.COLOR_BGR2BGRA}.get(s8.ndim if s8.ndim == 2 else s8.shape[2])
+        bgra8 = s8 if code is None else cv2.cvtColor(s8, code)
+        want8 = cv2.cvtColor(cv2.resize(bgra8, (dw, dh), interpolation=cv2.INTER_AREA), cv2.COLOR_BGRA2RGBA)
+        out = str(tmp_path / (name + ".rgba"))
+        run("IoSelfTest", "--mode=rgba", "--in=" + png, "--scale=%r" % scale, "--out=" + out)
+        assert np.fromfile(out, np.uint8).tobytes() == want8.tobytes(), name
+
+
 def test_convert_to_binary_rgba_only(tmp_path):
     """ConvertToBinary with a colour directory and --output_formats=rgba touches no GPU stage: .rgba files = the cv2
     sequence, the rig is rescaled to the colour resolution (resizeRig, ConvertToBinary.cpp:322-343), the fused stream holds
@@ -682,3 +755,12 @@ def test_convert_to_binary_rgba_only(tmp_path):
     catalog = json.load(open(tmp_path / "fused" / "fused.json"))
     e = catalog["frames"]["000000"][rig["cameras"][1]["id"]][".rgba"]
     assert e["size"] == W * H * 4 and e["offset"] % (512 * 1024) == 0
+    # --color_scale = 0.5 (scripts/ui/export.py:311-318): the stream is the INTER_AREA-shrunk 8-bit BGRA image, the rig follows
+    run("ConvertToBinary", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
+        "--color=" + str(tmp_path / "color"), "--bin=" + str(tmp_path / "bin_half"), "--output_formats=rgba", "--color_scale=0.5")
+    for cam in rig["cameras"]:
+        got = np.fromfile(tmp_path / "bin_half" / cam["id"] / "000000.rgba", np.uint8).reshape(H // 2, W // 2, 4)
+        src = cv2.cvtColor(cv2.convertScaleAbs(imgs[cam["id"]], alpha=float(np.float32(255.0) / np.float32(65535.0))), cv2.COLOR_BGR2BGRA)
+        assert np.array_equal(got, cv2.cvtColor(cv2.resize(src, (W // 2, H // 2), interpolation=cv2.INTER_AREA), cv2.COLOR_BGRA2RGBA))
+    half = json.load(open(tmp_path / "bin_half" / "rig_fused.json"))["cameras"][0]
+    assert half["resolution"] == [W // 2, H // 2] and np.allclose(half["focal"], np.array(r0["focal"]) * 0.25)

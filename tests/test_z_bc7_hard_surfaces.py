@@ -4,7 +4,9 @@ reference on these (tests/test_bc7.py); this file adds the GPU leg.  It was writ
 (the five surfaces of tests/test_bc7.py ARE GPU-verified), so it is named to run last under `pytest -x`.
 (2) ConvertToBinary --output_formats=...,pfm: the rasterised mesh the app writes next to its .vtx / .idx equals the
 reference's mesh_util::writePfm (oracle/_ref) of those very files; the rasteriser itself is host code and is checked
-without a GPU in tests/test_mesh.py::test_raster_pfm_equals_reference_write_pfm."""
+without a GPU in tests/test_mesh.py::test_raster_pfm_equals_reference_write_pfm.
+(3) ConvertToBinary --color_scale=0.5 with the bc7 format: the blocks of the surface that
+tests/test_apps.py::test_colour_streams_with_color_scale pins to the reference's sequence, through derp_bc7_compress."""
 import numpy as np
 import pytest
 
@@ -44,3 +46,32 @@ def test_convert_to_binary_raster_pfm(tmp_path, cuda):
         want = str(tmp_path / (cam["id"] + "_ref.pfm"))
         assert f(v.ctypes.data, len(v), i.ctypes.data, len(i), W, H, cam["resolution"][0], cam["resolution"][1], want.encode()) == 0
         assert open(stem + ".pfm", "rb").read() == open(want, "rb").read()
+
+
+@pytest.mark.gpu
+def test_convert_to_binary_bc7_with_color_scale(tmp_path, cuda):
+    import cv2
+    import json
+    import os
+    from facebook360_dep_b200 import synth
+    from tests.test_apps import run
+    W, H = 64, 48
+    rig = synth.ring_rig(2, W, H, kind="FTHETA")
+    os.makedirs(tmp_path / "rigs", exist_ok=True)
+    json.dump(rig, open(tmp_path / "rigs" / "rig.json", "w"))
+    rng = np.random.RandomState(11)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for cam in rig["cameras"]:
+        img = np.stack([0.5 + 0.4 * np.sin(xx / 9.), 0.5 + 0.4 * np.cos(yy / 7.), (xx + yy) / float(W + H)], -1)
+        img = ((img + rng.normal(0, 0.01, img.shape)).clip(0, 1) * 65535).astype(np.uint16)
+        os.makedirs(tmp_path / "color" / cam["id"], exist_ok=True)
+        assert cv2.imwrite(str(tmp_path / "color" / cam["id"] / "000000.png"), img)
+    run("ConvertToBinary", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--first=000000", "--last=000000",
+        "--color=" + str(tmp_path / "color"), "--bin=" + str(tmp_path / "bin"), "--output_formats=bc7", "--color_scale=0.5")
+    for cam in rig["cameras"]:
+        surface = str(tmp_path / (cam["id"] + ".surface"))
+        run("IoSelfTest", "--mode=bc7surface", "--in=" + str(tmp_path / "color" / cam["id"] / "000000.png"), "--scale=0.5",
+            "--out=" + surface)
+        rgba = np.fromfile(surface, np.uint8).reshape(H // 2, W // 2, 4)
+        got = np.fromfile(str(tmp_path / "bin" / cam["id"] / "000000.bc7"), np.uint8)
+        assert np.array_equal(got, cuda.bc7_compress(rgba))
