@@ -80,8 +80,14 @@ int main(int argc, char** argv) {
   const int W = std::min(bw, FLAGS_width);
   const int H = (int)std::lrint(W * bh / float(bw));
   std::vector<std::vector<uint16_t>> background(cams.size());
-  for (size_t i = 0; i < cams.size(); ++i)
+  // The library blurs with the default radius (1: its 3 x 3 kernel) or not at all; the UI's slider can ask for more: radii 2
+  // and 3 are blurred on the host (OpenCV's 5- and 7-tap table kernels, io.h) and the library is told not to blur.
+  const bool hostBlur = FLAGS_blur_radius > 1;
+  const int libraryBlur = hostBlur ? 0 : FLAGS_blur_radius;
+  for (size_t i = 0; i < cams.size(); ++i) {
     background[i] = loadResized(io::imagePath(FLAGS_background_color, rig.ids[cams[i]], FLAGS_background_frame), W, H, FLAGS_gpu);
+    if (hostBlur) background[i] = io::gaussianBlurU16C3(background[i], W, H, FLAGS_blur_radius);
+  }
   for (int c : cams) fs::create_directories(fs::path(FLAGS_foreground_masks) / rig.ids[c]);
 
   const int firstFrame = std::stoi(FLAGS_first), numFrames = std::stoi(FLAGS_last) - firstFrame + 1;
@@ -102,9 +108,10 @@ int main(int argc, char** argv) {
         LOG(INFO) << "Processing frame " << frame << "...";
         for (size_t k = 0; k < cams.size(); ++k) {
           const std::string& id = rig.ids[cams[k]];
-          const std::vector<uint16_t> color = loadResized(io::imagePath(FLAGS_color, id, frame), W, H, device);
+          std::vector<uint16_t> color = loadResized(io::imagePath(FLAGS_color, id, frame), W, H, device);
+          if (hostBlur) color = io::gaussianBlurU16C3(color, W, H, FLAGS_blur_radius);
           std::vector<uint8_t> mask((size_t)W * H);
-          DERP_CALL(derp_foreground_mask(device, background[k].data(), color.data(), W, H, FLAGS_blur_radius,
+          DERP_CALL(derp_foreground_mask(device, background[k].data(), color.data(), W, H, libraryBlur,
                                          (float)FLAGS_threshold, FLAGS_morph_closing_size, mask.data()));
           size_t count = 0;
           for (uint8_t& m : mask) {

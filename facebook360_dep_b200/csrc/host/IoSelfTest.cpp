@@ -9,7 +9,7 @@
 #include "io.h"
 
 DEFINE_string(in, "", "input image");
-DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange | inflate | raster | area | bc7surface");
+DEFINE_string(mode, "color", "color | rgba | float | mask | rig | exchange | inflate | raster | area | bc7surface | gauss");
 DEFINE_int32(size, 0, "mode=inflate: number of bytes the zlib stream in --in decodes to");
 DEFINE_string(faces, "", "mode=raster: .idx file (uint32 x 3 per face); --in is the .vtx file (float32 x 3 per vertex)");
 DEFINE_int32(width, 0, "mode=raster: depth grid width");
@@ -76,6 +76,17 @@ int main(int argc, char** argv) {
     const std::vector<uint8_t> v = io::bc7SurfaceScaled(io::loadUnchanged(FLAGS_in), FLAGS_scale, (float)FLAGS_gamma, &w, &h);
     o.open(FLAGS_out, std::ios::binary);
     o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size());
+  } else if (FLAGS_mode == "gauss") {
+    // cv::GaussianBlur((2 r + 1)^2, sigma 0) of a raw u16 x 3 image (--width x --height), r = --size
+    std::ifstream f(FLAGS_in, std::ios::binary);
+    const std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<uint16_t> img((size_t)FLAGS_width * FLAGS_height * 3);
+    std::memcpy(img.data(), raw.data(), img.size() * 2);
+    const std::vector<uint16_t> v = io::gaussianBlurU16C3(img, FLAGS_width, FLAGS_height, FLAGS_size);
+    o.open(FLAGS_out, std::ios::binary);
+    o.write(reinterpret_cast<const char*>(v.data()), (std::streamsize)v.size() * 2);
+    w = FLAGS_width;
+    h = FLAGS_height;
   } else if (FLAGS_mode == "area") {
     // cv::resize(INTER_AREA) of a raw interleaved image (area_resize.h) for comparison with cv2
     std::ifstream f(FLAGS_in, std::ios::binary);

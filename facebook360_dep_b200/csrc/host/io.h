@@ -727,6 +727,41 @@ inline std::vector<uint8_t> loadRgba8(const fs::path& path, int* w, int* h) {
   return out;
 }
 
+// cv_util::gaussianBlur(image, radius) = cv::GaussianBlur(image, (2 r + 1)^2, sigma 0) (CvUtil.h:302-312) on a 16-bit
+// 3-channel image, radius 1..3: OpenCV's fixed-point path with its table kernels for sizes up to 7 — (1 2 1) / 4,
+// (1 4 6 4 1) / 16, (2 7 14 18 14 7 2) / 64 — i.e. the integer-weighted sum, + half, shifted; BORDER_REFLECT_101 (pinned to
+// cv2 in tests/test_apps.py).  The CUDA library blurs with the default radius 1 itself (derp_foreground_mask); the larger
+// radii of the UI's slider are blurred here and handed over with blur_radius = 0.
+inline std::vector<uint16_t> gaussianBlurU16C3(const std::vector<uint16_t>& src, int w, int h, int radius) {
+  CHECK(radius >= 1 && radius <= 3) << "--blur_radius up to 3 (OpenCV's table kernels); got " << radius;
+  static const int kernels[3][7] = {{1, 2, 1}, {1, 4, 6, 4, 1}, {2, 7, 14, 18, 14, 7, 2}};
+  const int* k = kernels[radius - 1];
+  const int n = 2 * radius + 1, shift = radius == 1 ? 2 : (radius == 2 ? 4 : 6);
+  auto reflect = [](int i, int size) {
+    if (size == 1) return 0;
+    while (i < 0 || i >= size) i = i < 0 ? -i : 2 * (size - 1) - i;
+    return i;
+  };
+  std::vector<uint32_t> rows((size_t)w * h * 3);  // horizontal pass, exact: <= 65535 * 64
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      for (int c = 0; c < 3; ++c) {
+        uint32_t s = 0;
+        for (int i = 0; i < n; ++i) s += (uint32_t)k[i] * src[((size_t)y * w + reflect(x + i - radius, w)) * 3 + c];
+        rows[((size_t)y * w + x) * 3 + c] = s;
+      }
+  std::vector<uint16_t> dst((size_t)w * h * 3);
+  const uint64_t half = (uint64_t)1 << (2 * shift - 1);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      for (int c = 0; c < 3; ++c) {
+        uint64_t s = 0;
+        for (int j = 0; j < n; ++j) s += (uint64_t)k[j] * rows[((size_t)reflect(y + j - radius, h) * w + x) * 3 + c];
+        dst[((size_t)y * w + x) * 3 + c] = (uint16_t)((s + half) >> (2 * shift));
+      }
+  return dst;
+}
+
 // cv_util::scaleImage's output size (CvUtil.h:150-153): std::round of the scaled extent
 inline void scaledSize(int w, int h, double scale, int* dw, int* dh) {
   *dw = (int)std::round(w * scale);

@@ -652,6 +652,22 @@ def test_rgba_stream_matches_opencv(tmp_path):
         assert np.array_equal(got, cv2.cvtColor(bgra, cv2.COLOR_BGRA2RGBA)), name
 
 
+def test_gaussian_blur_radii_match_opencv(tmp_path):
+    """cv_util::gaussianBlur for GenerateForegroundMasks --blur_radius 2 and 3 (the host stage; radius 1 is the library's 3 x 3
+    kernel, checked on the GPU): cv2.GaussianBlur((2 r + 1)^2, sigma 0) on 16-bit 3-channel images, bit for bit, down to images
+    smaller than the kernel."""
+    rng = np.random.RandomState(1)
+    src, out = str(tmp_path / "g.raw"), str(tmp_path / "g.out")
+    for (w, h) in ((53, 37), (8, 5), (3, 3), (64, 1), (1, 9)):
+        img = rng.randint(0, 65536, (h, w, 3)).astype(np.uint16)
+        img.tofile(src)
+        for r in (1, 2, 3):
+            run("IoSelfTest", "--mode=gauss", "--in=" + src, "--width=%d" % w, "--height=%d" % h, "--size=%d" % r, "--out=" + out)
+            assert np.array_equal(np.fromfile(out, np.uint16).reshape(h, w, 3), cv2.GaussianBlur(img, (2 * r + 1, 2 * r + 1), 0)), (w, h, r)
+    p = run("IoSelfTest", "--mode=gauss", "--in=" + src, "--width=1", "--height=9", "--size=4", "--out=" + out, check=False)
+    assert p.returncode != 0 and "blur_radius" in p.stderr  # sizes above 7 use a computed kernel: not restated, refused
+
+
 def test_area_resize_matches_opencv(tmp_path):
     """cv::resize INTER_AREA of the colour streams under --color_scale < 1 (csrc/host/area_resize.h) against cv2: float and
     8-bit images with 4 and 3 channels; ratios of exactly 2 (OpenCV's vector bodies), other integer ratios (row-order sums,

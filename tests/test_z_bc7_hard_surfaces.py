@@ -6,7 +6,9 @@ reference on these (tests/test_bc7.py); this file adds the GPU leg.  It was writ
 reference's mesh_util::writePfm (oracle/_ref) of those very files; the rasteriser itself is host code and is checked
 without a GPU in tests/test_mesh.py::test_raster_pfm_equals_reference_write_pfm.
 (3) ConvertToBinary --color_scale=0.5 with the bc7 format: the blocks of the surface that
-tests/test_apps.py::test_colour_streams_with_color_scale pins to the reference's sequence, through derp_bc7_compress."""
+tests/test_apps.py::test_colour_streams_with_color_scale pins to the reference's sequence, through derp_bc7_compress.
+(4) GenerateForegroundMasks --blur_radius=2 / 3: blurred on the host (pinned to cv2 without a GPU), the library's
+verified difference + closing kernels after it."""
 import numpy as np
 import pytest
 
@@ -75,3 +77,41 @@ def test_convert_to_binary_bc7_with_color_scale(tmp_path, cuda):
         rgba = np.fromfile(surface, np.uint8).reshape(H // 2, W // 2, 4)
         got = np.fromfile(str(tmp_path / "bin" / cam["id"] / "000000.bc7"), np.uint8)
         assert np.array_equal(got, cuda.bc7_compress(rgba))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("radius", [2, 3])
+def test_generate_foreground_masks_larger_blur(tmp_path, cuda, radius):
+    import cv2
+    import json
+    import os
+    from facebook360_dep_b200 import synth
+    from tests.test_apps import run
+    S, Wf, Hf = 2, 120, 90
+    rig = synth.ring_rig(S, Wf, Hf, kind="FTHETA")
+    os.makedirs(tmp_path / "rigs", exist_ok=True)
+    json.dump(rig, open(tmp_path / "rigs" / "rig.json", "w"))
+    rng = np.random.RandomState(2)
+    bgdir, fgdir, mdir = str(tmp_path / "bg"), str(tmp_path / "fg"), str(tmp_path / "masks")
+    ids = [c["id"] for c in rig["cameras"]]
+    for s, cid in enumerate(ids):
+        bgimg = np.clip(rng.normal(30000, 9000, (Hf, Wf, 3)), 0, 65535).astype(np.uint16)
+        fr = bgimg.copy()
+        fr[20:60, 30 + 5 * s:80] = rng.randint(0, 65536, (40, 50 - 5 * s, 3)).astype(np.uint16)
+        os.makedirs(os.path.join(bgdir, cid))
+        os.makedirs(os.path.join(fgdir, cid))
+        cv2.imwrite(os.path.join(bgdir, cid, "000000.png"), bgimg)
+        cv2.imwrite(os.path.join(fgdir, cid, "000007.png"), fr)
+    run("GenerateForegroundMasks", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--color=" + fgdir, "--background_color=" + bgdir,
+        "--foreground_masks=" + mdir, "--first=000007", "--last=000007", "--width=80", "--blur_radius=%d" % radius)
+    Wo, Ho = 80, int(np.rint(80 * Hf / np.float32(Wf)))
+    a32 = np.float32(1.0) / np.float32(65535.0)
+    k = 2 * radius + 1
+    for cid in ids:
+        b = cv2.resize(cv2.imread(os.path.join(bgdir, cid, "000000.png"), cv2.IMREAD_UNCHANGED), (Wo, Ho), interpolation=cv2.INTER_AREA)
+        f = cv2.resize(cv2.imread(os.path.join(fgdir, cid, "000007.png"), cv2.IMREAD_UNCHANGED), (Wo, Ho), interpolation=cv2.INTER_AREA)
+        diff = cv2.absdiff(cv2.GaussianBlur(b, (k, k), 0).astype(np.float32) * a32, cv2.GaussianBlur(f, (k, k), 0).astype(np.float32) * a32)
+        m = (np.sqrt((diff.astype(np.float64) ** 2).sum(-1)) > np.float64(np.float32(0.04))).astype(np.uint8)
+        m = cv2.morphologyEx(m, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (4, 4)))
+        got = cv2.imread(os.path.join(mdir, cid, "000007.png"), cv2.IMREAD_UNCHANGED)
+        assert got.dtype == np.uint8 and np.array_equal(got, m * 255), cid
