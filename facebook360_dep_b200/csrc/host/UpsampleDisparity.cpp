@@ -1,9 +1,8 @@
 // UpsampleDisparity — drop-in for source/depth_estimation/UpsampleDisparity.cpp on B200.
 // Same flags and directory contract; upsampling (UpsampleDisparityLib.cpp:98-182) and the optional
-// colour-guided joint bilateral filter run in libderp_b200.so.  Colour images larger than the output are shrunk with
-// cv::resize(INTER_AREA) like cv_util::resizeImage does (UpsampleDisparity.cpp:117) — derp_downscale_area, on 16-bit
-// integer samples (8-bit inputs are widened x257 first, cv_util::loadImage's own conversion); float or smaller-than-output
-// colour images are a fatal error (the reference would interpolate those; not part of the pipeline's use).
+// colour-guided joint bilateral filter run in libderp_b200.so.  Colour images of another size than the output go through
+// cv::resize(INTER_AREA) like cv_util::resizeImage does (UpsampleDisparity.cpp:117) on the [0, 1] float image the reference
+// holds (PixelType = cv::Vec3f): a host stage (area_resize.h, bit-identical to cv2) before the guided filter on the GPU.
 #include <thread>
 
 #include "io.h"
@@ -104,14 +103,10 @@ static void upsampleFrame(const io::Rig& rig, const std::vector<int>& dst, const
       const int radius = (int)(scale * scale + 1);
       LOG(INFO) << "Applying filter with radius " << radius << " to " << W << "x" << H << " disparity to " << id << "...";
       std::vector<float> color = loadColorF32(io::imagePath(FLAGS_color, id, frame), &w, &h);
-      if (!(w == W && h == H)) {  // cv_util::resizeImage(colors[i], sizeUp): INTER_AREA
-        CHECK(w >= W && h >= H) << "colour images must be at least as large as the output (" << W << "x" << H << ")";
-        int cw2, ch2;
-        const std::vector<uint16_t> c16 = io::loadColor16(io::imagePath(FLAGS_color, id, frame), &cw2, &ch2);
-        std::vector<uint16_t> small((size_t)W * H * 3);
-        DERP_CALL(derp_downscale_area(device, c16.data(), cw2, ch2, small.data(), W, H));
-        color.resize((size_t)W * H * 3);
-        for (size_t k = 0; k < color.size(); ++k) color[k] = small[k] * (1.0f / 65535.0f);
+      if (!(w == W && h == H)) {  // cv_util::resizeImage(colors[i], sizeUp): cv::resize INTER_AREA of the Vec3f image — the
+        std::vector<float> resized((size_t)W * H * 3);  // reference's arithmetic (float area sums; the bilinear variant when
+        io::area::resize(color.data(), w, h, 3, resized.data(), W, H);  // the image has to grow), pinned to cv2
+        color.swap(resized);
       }
       std::vector<float> filtered((size_t)W * H);
       DERP_CALL(derp_joint_bilateral_f32(device, W, H, up.data(), color.data(), maskUp.data(), radius, (float)FLAGS_sigma,

@@ -1,4 +1,5 @@
-// area_resize.h — cv::resize(..., INTER_AREA), shrinking, on interleaved host images of float or 8-bit samples: what
+// area_resize.h — cv::resize(..., INTER_AREA) on interleaved host images of float or 8-bit samples: what cv_util::resizeImage
+// applies to the colour guide of UpsampleDisparity (UpsampleDisparity.cpp:117, Vec3f images, either direction) and what
 // cv_util::scaleImage / resizeImage (CvUtil.h:138-154) apply to the colour images of ConvertToBinary when --color_scale < 1
 // (image_util::loadScaledImage<Vec4f> for the BC7 stream, <Vec4b> for the .rgba stream; ConvertToBinary.cpp:127-142).  The
 // UI's export tab sets that flag whenever it exports below the full width (scripts/ui/export.py:311-318, 389).
@@ -43,10 +44,60 @@ inline uint8_t store(float v, uint8_t*) {
   return (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
 }
 
-// src: sh rows of sw pixels of cn samples; dst: dh x dw, dw <= sw and dh <= sh.  simdAsFourChannels: use the 2 x 2 float
+// INTER_AREA when an axis grows ("true area interpolation is only implemented for the case scale >= 1; in other cases it is
+// emulated using some variant of bilinear", resize.cpp): both axes then take two taps at sx = floor(dx * scale) with
+// fx = (dx + 1) - (sx + 1) / scale, fx <= 0 ? 0 : fx - floor(fx); float weights, rows first, no rounding for float images.
+inline void enlargeAxis(int ssize, int dsize, std::vector<int>& at, std::vector<float>& w0, std::vector<float>& w1) {
+  const double scale = (double)ssize / dsize, inv = (double)dsize / ssize;
+  at.resize(dsize);
+  w0.resize(dsize);
+  w1.resize(dsize);
+  for (int d = 0; d < dsize; ++d) {
+    int s = (int)std::floor(d * scale);
+    double f = (d + 1) - (s + 1) * inv;
+    f = f <= 0 ? 0. : f - std::floor(f);
+    if (s < 0) {
+      s = 0;
+      f = 0;
+    }
+    if (s >= ssize - 1) {
+      s = ssize - 1;
+      f = 0;
+    }
+    at[d] = s;
+    w1[d] = (float)f;
+    w0[d] = 1.f - w1[d];
+  }
+}
+inline void enlarge(const float* src, int sw, int sh, int cn, float* dst, int dw, int dh) {
+  std::vector<int> xat, yat;
+  std::vector<float> xa, xb, ya, yb;
+  enlargeAxis(sw, dw, xat, xa, xb);
+  enlargeAxis(sh, dh, yat, ya, yb);
+  const size_t n = (size_t)dw * cn;
+  std::vector<float> rows((size_t)sh * n);
+  for (int y = 0; y < sh; ++y)
+    for (int x = 0; x < dw; ++x) {
+      const float* S0 = src + ((size_t)y * sw + xat[x]) * cn;
+      const float* S1 = src + ((size_t)y * sw + std::min(xat[x] + 1, sw - 1)) * cn;
+      for (int c = 0; c < cn; ++c) rows[(size_t)y * n + (size_t)x * cn + c] = S0[c] * xa[x] + S1[c] * xb[x];
+    }
+  for (int y = 0; y < dh; ++y) {
+    const float* R0 = rows.data() + (size_t)yat[y] * n;
+    const float* R1 = rows.data() + (size_t)std::min(yat[y] + 1, sh - 1) * n;
+    for (size_t i = 0; i < n; ++i) dst[(size_t)y * n + i] = R0[i] * ya[y] + R1[i] * yb[y];
+  }
+}
+inline void enlarge(const uint8_t*, int, int, int, uint8_t*, int, int) {}  // 8-bit images are never enlarged here (fixed point in OpenCV)
+
+// src: sh rows of sw pixels of cn samples; dst: dh x dw (float images may also grow: see enlarge()).  simdAsFourChannels: use the 2 x 2 float
 // formula of images with 1 or 4 channels although cn differs (the caller dropped a channel the reference still carries).
 template <typename T>
 inline void resize(const T* src, int sw, int sh, int cn, T* dst, int dw, int dh, bool simdAsFourChannels = false) {
+  if (dw > sw || dh > sh) {  // an axis grows: the bilinear variant, for both axes
+    enlarge(src, sw, sh, cn, dst, dw, dh);
+    return;
+  }
   const double fx = (double)sw / dw, fy = (double)sh / dh;
   const int kx = (int)std::floor(fx + 0.5), ky = (int)std::floor(fy + 0.5);
   const bool integer = std::fabs(fx - kx) < 2.220446049250313e-16 && std::fabs(fy - ky) < 2.220446049250313e-16;

@@ -689,6 +689,12 @@ def test_area_resize_matches_opencv(tmp_path):
             img = rng.uniform(0, 1, (h, w, c)).astype(np.float32) if dtype == np.float32 else rng.randint(0, 256, (h, w, c)).astype(np.uint8)
             want = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA).reshape(dh, dw, c)
             assert resize(img, dw, dh).tobytes() == want.tobytes(), (w, h, dw, dh, dtype.__name__, c)
+    # an axis that grows (UpsampleDisparity's colour guide smaller than the output): OpenCV's bilinear variant, float images
+    for (w, h, dw, dh) in [(20, 15, 40, 30), (20, 15, 33, 21), (17, 13, 50, 29), (20, 15, 40, 10), (20, 15, 10, 30), (31, 7, 32, 8),
+                           (16, 16, 17, 16), (5, 4, 64, 48)]:
+        img = rng.uniform(0, 1, (h, w, 3)).astype(np.float32)
+        want = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_AREA)
+        assert resize(img, dw, dh).tobytes() == want.tobytes(), (w, h, dw, dh)
     # the BC7 stream resizes B, G, R with the arithmetic of the 4-channel image the reference carries
     img4 = rng.uniform(0, 1, (48, 64, 4)).astype(np.float32)
     want = cv2.resize(img4, (32, 24), interpolation=cv2.INTER_AREA)[..., :3]

@@ -8,7 +8,9 @@ without a GPU in tests/test_mesh.py::test_raster_pfm_equals_reference_write_pfm.
 (3) ConvertToBinary --color_scale=0.5 with the bc7 format: the blocks of the surface that
 tests/test_apps.py::test_colour_streams_with_color_scale pins to the reference's sequence, through derp_bc7_compress.
 (4) GenerateForegroundMasks --blur_radius=2 / 3: blurred on the host (pinned to cv2 without a GPU), the library's
-verified difference + closing kernels after it."""
+verified difference + closing kernels after it.
+(5) UpsampleDisparity with a colour guide larger / smaller than the output: the guide resized like cv_util::resizeImage
+(cv2.resize INTER_AREA of the float image), then the oracle's upsampling and guided filter."""
 import numpy as np
 import pytest
 
@@ -115,3 +117,38 @@ def test_generate_foreground_masks_larger_blur(tmp_path, cuda, radius):
         m = cv2.morphologyEx(m, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (4, 4)))
         got = cv2.imread(os.path.join(mdir, cid, "000007.png"), cv2.IMREAD_UNCHANGED)
         assert got.dtype == np.uint8 and np.array_equal(got, m * 255), cid
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("guide_size", [192, 64])  # larger than the 96-wide output (area sums), smaller (bilinear variant)
+def test_upsample_disparity_with_resized_guide(tmp_path, cuda, oracle, guide_size):
+    import cv2
+    import json
+    import os
+    from facebook360_dep_b200 import capi, synth
+    from tests.test_apps import read_pfm, run, write_pfm
+    S, W = 2, 48
+    rig = synth.ring_rig(S, W, W, kind="FTHETA")
+    os.makedirs(tmp_path / "rigs", exist_ok=True)
+    json.dump(rig, open(tmp_path / "rigs" / "rig.json", "w"))
+    rng = np.random.RandomState(3)
+    yy, xx = np.mgrid[0:W, 0:W].astype(np.float32)
+    guides, coarse = {}, {}
+    for cam in rig["cameras"]:
+        g = rng.randint(0, 65536, (guide_size, guide_size, 3)).astype(np.uint16)
+        os.makedirs(tmp_path / "color" / cam["id"], exist_ok=True)
+        assert cv2.imwrite(str(tmp_path / "color" / cam["id"] / "000000.png"), g)
+        guides[cam["id"]] = g
+        d = (0.3 + 0.1 * np.sin(xx / 9.0) * np.cos(yy / 7.0)).astype(np.float32)
+        write_pfm(str(tmp_path / "disparity" / cam["id"] / "000000.pfm"), d)
+        coarse[cam["id"]] = d
+    run("UpsampleDisparity", "--rig=" + str(tmp_path / "rigs" / "rig.json"), "--disparity=" + str(tmp_path / "disparity"),
+        "--output=" + str(tmp_path / "up"), "--resolution=96", "--color=" + str(tmp_path / "color"), "--first=000000", "--last=000000")
+    for cam in rig["cameras"]:
+        up = read_pfm(os.path.join(str(tmp_path / "up"), cam["id"], "000000.pfm"))
+        ref = oracle.upsample_disparity(capi.camera_desc_from_json(cam), coarse[cam["id"]], 96, 96)
+        f = guides[cam["id"]].astype(np.float32) * (np.float32(1.0) / np.float32(65535.0))
+        guide = cv2.resize(f, (96, 96), interpolation=cv2.INTER_AREA)
+        radius = int((96.0 / W) ** 2 + 1)
+        ref = oracle.joint_bilateral_f32(ref, guide, np.ones((96, 96), np.uint8), radius, 0.05, 0.5, 0.5, 1.0)
+        assert (np.abs(up - ref) <= 2e-6 * np.abs(ref) + 2e-7).all()

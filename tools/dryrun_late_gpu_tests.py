@@ -50,6 +50,17 @@ def fake_run(app, *args, check=True):
             os.makedirs(os.path.join(kv["foreground_masks"], cam["id"]), exist_ok=True)
             cv2.imwrite(os.path.join(kv["foreground_masks"], cam["id"], "000007.png"), m * 255)
         return None
+    if app == "UpsampleDisparity":
+        from facebook360_dep_b200 import capi
+        rig = json.load(open(kv["rig"])); R = int(kv["resolution"])
+        for cam in rig["cameras"]:
+            d = TA.read_pfm(os.path.join(kv["disparity"], cam["id"], "000000.pfm"))
+            up = oracle.upsample_disparity(capi.camera_desc_from_json(cam), d, R, R)
+            g = cv2.imread(os.path.join(kv["color"], cam["id"], "000000.png"), cv2.IMREAD_UNCHANGED).astype(np.float32) * (np.float32(1.0) / np.float32(65535.0))
+            g = cv2.resize(g, (R, R), interpolation=cv2.INTER_AREA)
+            out = oracle.joint_bilateral_f32(up, g, np.ones((R, R), np.uint8), int((R / d.shape[1]) ** 2 + 1), 0.05, 0.5, 0.5, 1.0)
+            TA.write_pfm(os.path.join(kv["output"], cam["id"], "000000.pfm"), out)
+        return None
     return real_run(app, *args, check=check)
 
 TA.run = fake_run
@@ -58,7 +69,9 @@ for kind in Z.HARD_KINDS:
     Z.test_gpu_blocks_equal_host_instantiation_hard_surfaces.__wrapped__(cuda, kind) if hasattr(Z.test_gpu_blocks_equal_host_instantiation_hard_surfaces, "__wrapped__") else Z.test_gpu_blocks_equal_host_instantiation_hard_surfaces(cuda, kind)
 print("hard surfaces: test body runs")
 for name, fn, extra in (("raster pfm", Z.test_convert_to_binary_raster_pfm, ()), ("bc7 color_scale", Z.test_convert_to_binary_bc7_with_color_scale, ()),
-                        ("masks r=2", Z.test_generate_foreground_masks_larger_blur, (2,)), ("masks r=3", Z.test_generate_foreground_masks_larger_blur, (3,))):
+                        ("masks r=2", Z.test_generate_foreground_masks_larger_blur, (2,)), ("masks r=3", Z.test_generate_foreground_masks_larger_blur, (3,)),
+                        ("upsample, larger guide", Z.test_upsample_disparity_with_resized_guide, (oracle, 192)),
+                        ("upsample, smaller guide", Z.test_upsample_disparity_with_resized_guide, (oracle, 64))):
     with tempfile.TemporaryDirectory() as d:
         fn(pathlib.Path(d), cuda, *extra)
     print(name + ": test body runs and its assertions hold with the CPU stand-ins")
