@@ -268,8 +268,8 @@ int derp_device_free(int device, void* p);
 int derp_device_copy(int device, void* dst, const void* src, size_t bytes);
 
 /* cv::resize(..., INTER_AREA) of a 3-channel 16-bit image, shrinking only: the resize scripts/render/resize.py:51-85
- * builds every pyramid level with (each level from the FULL-SIZE image, widths scripts/render/config.py:46) and the one
- * cv_util::resizeImage applies to the colour image in UpsampleDisparity.cpp:117.  Bit-identical to OpenCV for integer
+ * builds every pyramid level with (each level from the FULL-SIZE image, widths scripts/render/config.py:46), and the resize of
+ * GenerateForegroundMasks' 16-bit inputs.  Bit-identical to OpenCV for integer
  * ratios (resizeAreaFast_) and general ratios (computeResizeAreaTab / ResizeArea_Invoker<ushort, float>).  src / dst may
  * be host or device memory. */
 int derp_downscale_area(int device, const uint16_t* src, int src_w, int src_h, uint16_t* dst, int dst_w, int dst_h);
